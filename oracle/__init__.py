@@ -1,0 +1,19 @@
+"""CPU oracle for the HYMLS preconditioner hot path -- TEST INFRASTRUCTURE ONLY.
+
+This package is a CPU restatement (numpy / scipy) of the reference algorithm
+(nlesc-smcm/hymls, `src/HYMLS_*.cpp`).  It exists to check the CUDA product
+path and to serve as the timed CPU baseline in `bench.py`.  Only `tests/`,
+`__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / `--impl reference`
+legs may import it.  The product (`hymls_b200/`) never does.
+
+Parity status:
+  * index maps (partitioner / groups): PINNED by the closed-form expectations of
+    the reference's own unit tests (tests/test_oracle_partitioner.py).
+  * matrix generators: PINNED to 1e-14 against the shipped MatrixMarket
+    fixtures (committed, reduced, under tests/golden/).
+  * exact path (Number of Levels = 0): PINNED by the reference's "1 iteration"
+    integration targets on the Stokes fixtures.
+  * approximate path (levels >= 1): the reference ships no golden ApplyInverse
+    vectors; pinned only through iteration-count / residual targets of the
+    reference's integration tests ("parity unpinned" beyond that).
+"""

@@ -1,0 +1,306 @@
+"""ctypes binding of include/hymls_b200.h, shaped like the reference classes.
+
+    HYMLS::Preconditioner(K, params, testVector)  -> Preconditioner(K, params, testvector)
+        Initialize / Compute / ApplyInverse        (src/HYMLS_Preconditioner.hpp:98-254)
+    HYMLS::Solver(K, P, params)::ApplyInverse(b,x) -> Solver(prec).ApplyInverse(b)
+                                                    (src/HYMLS_BaseSolver.cpp:309-359)
+`params` is either the XML text of a Teuchos ParameterList or a nested dict.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+HOST, DEVICE = 0, 1
+MAP_OVERLAPPING, MAP_INTERIOR, MAP_SEPARATOR, MAP_VSUM = 0, 1, 2, 3
+
+
+class HymlsError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("hymls_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class _SolveInfo(C.Structure):
+    _fields_ = [("iterations", C.c_int), ("converged", C.c_int), ("rel_residual", C.c_double),
+                ("explicit_rel_residual", C.c_double), ("solve_seconds", C.c_double), ("history_len", C.c_int)]
+
+
+class _Stats(C.Structure):
+    _fields_ = [("num_initialize", C.c_int), ("num_compute", C.c_int), ("num_apply_inverse", C.c_int),
+                ("time_initialize", C.c_double), ("time_compute", C.c_double), ("time_apply_inverse", C.c_double),
+                ("n", C.c_int64), ("num_interior", C.c_int64), ("num_separator", C.c_int64), ("num_vsum", C.c_int64),
+                ("num_subdomains", C.c_int64), ("num_blocks", C.c_int64), ("sum_nsd_sq", C.c_double),
+                ("bytes_apply", C.c_double), ("flops_compute", C.c_double), ("bytes_a11_level0", C.c_double),
+                ("kernel_launches", C.c_int64), ("device_bytes", C.c_double)]
+
+
+def lib_path():
+    return os.path.join(_HERE, "libhymls_b200.so")
+
+
+def load_library():
+    """Loads the CUDA library; fails loudly if it has not been built (no fallback)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        raise ImportError("hymls_b200: %s is missing -- run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "or `make -C hymls_b200/csrc`; there is no CPU fallback" % path)
+    lib = C.CDLL(path)
+    P = C.POINTER
+    vp, i64, dbl = C.c_void_p, C.c_int64, C.c_double
+    lib.hymls_b200_last_error.restype = C.c_char_p
+    lib.hymls_b200_version.restype = C.c_char_p
+    lib.hymls_b200_create.argtypes = [C.c_char_p, P(vp)]
+    lib.hymls_b200_destroy.argtypes = [vp]
+    lib.hymls_b200_destroy.restype = None
+    lib.hymls_b200_set_stream.argtypes = [vp, vp]
+    lib.hymls_b200_set_matrix_csr.argtypes = [vp, i64, vp, vp, vp, C.c_int]
+    lib.hymls_b200_set_testvector.argtypes = [vp, vp]
+    lib.hymls_b200_initialize.argtypes = [vp]
+    lib.hymls_b200_compute.argtypes = [vp]
+    lib.hymls_b200_apply_inverse.argtypes = [vp, vp, i64, vp, i64, C.c_int, C.c_int]
+    lib.hymls_b200_set_border.argtypes = [vp, vp, vp, vp, C.c_int]
+    lib.hymls_b200_apply_inverse_bordered.argtypes = [vp, vp, i64, vp, vp, i64, vp, C.c_int, C.c_int]
+    lib.hymls_b200_apply_matrix.argtypes = [vp, vp, vp, C.c_int]
+    lib.hymls_b200_solve.argtypes = [vp, vp, vp, C.c_int, C.c_uint64, P(_SolveInfo), vp, C.c_int]
+    lib.hymls_b200_num_levels.argtypes = [vp]
+    lib.hymls_b200_num_subdomains.argtypes = [vp, C.c_int]
+    lib.hymls_b200_get_interior.argtypes = [vp, C.c_int, C.c_int, vp, i64]
+    lib.hymls_b200_get_interior.restype = i64
+    lib.hymls_b200_get_groups.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, i64, P(i64)]
+    lib.hymls_b200_get_map.argtypes = [vp, C.c_int, C.c_int, vp, i64]
+    lib.hymls_b200_get_map.restype = i64
+    lib.hymls_b200_pid_map.argtypes = [C.c_char_p, C.c_int, vp, C.c_int]
+    lib.hymls_b200_get_stats.argtypes = [vp, P(_Stats)]
+    lib.hymls_b200_time_apply.argtypes = [vp, C.c_int, P(dbl), P(dbl)]
+    _LIB = lib
+    return lib
+
+
+def _check(lib, rc):
+    if rc < 0:
+        raise HymlsError(rc, lib.hymls_b200_last_error().decode())
+    return rc
+
+
+def _xml_escape(s):
+    return (str(s).replace("&", "&amp;").replace("<", "&lt;").replace(">", "&gt;").replace('"', "&quot;"))
+
+
+def params_to_xml(params, name="HYMLS"):
+    """nested dict -> Teuchos ParameterList XML (bool/int/float/str leaves)."""
+    if isinstance(params, str):
+        return params
+    out = ['<ParameterList name="%s">' % _xml_escape(name)]
+    for k, v in params.items():
+        if isinstance(v, dict):
+            out.append(params_to_xml(v, k))
+        elif isinstance(v, bool):
+            out.append('<Parameter name="%s" type="bool" value="%s"/>' % (_xml_escape(k), "true" if v else "false"))
+        elif isinstance(v, (int, np.integer)):
+            out.append('<Parameter name="%s" type="int" value="%d"/>' % (_xml_escape(k), int(v)))
+        elif isinstance(v, (float, np.floating)):
+            out.append('<Parameter name="%s" type="double" value="%r"/>' % (_xml_escape(k), float(v)))
+        else:
+            out.append('<Parameter name="%s" type="string" value="%s"/>' % (_xml_escape(k), _xml_escape(v)))
+    out.append("</ParameterList>")
+    return "\n".join(out)
+
+
+def pid_map(params, nprocs):
+    """BasePartitioner::CreatePIDMap for `nprocs` ranks (src/HYMLS_BasePartitioner.cpp:361-586)."""
+    lib = load_library()
+    xml = params_to_xml(params).encode()
+    n = _check(lib, lib.hymls_b200_pid_map(xml, nprocs, None, 0))
+    out = np.zeros(n, dtype=np.int32)
+    _check(lib, lib.hymls_b200_pid_map(xml, nprocs, out.ctypes.data, n))
+    return out
+
+
+def _ptr(a):
+    """host numpy array or torch CUDA tensor -> (pointer, where)"""
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data, HOST
+    if hasattr(a, "data_ptr"):
+        return a.data_ptr(), (DEVICE if a.is_cuda else HOST)
+    raise TypeError("expected a numpy array or a torch tensor")
+
+
+class Preconditioner:
+    """HYMLS::Preconditioner : Ifpack_Preconditioner (src/HYMLS_Preconditioner.hpp:56-254)."""
+
+    def __init__(self, K, params, testvector=None, cuda_stream=None, pattern_only=False):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        self.params_xml = params_to_xml(params)
+        _check(self._lib, self._lib.hymls_b200_create(self.params_xml.encode(), C.byref(self._h)))
+        if cuda_stream is not None:
+            _check(self._lib, self._lib.hymls_b200_set_stream(self._h, C.c_void_p(cuda_stream)))
+        self.n = 0
+        if K is not None:
+            self.SetMatrix(K, pattern_only=pattern_only)
+        if testvector is not None:
+            tv = np.ascontiguousarray(testvector, dtype=np.float64)
+            _check(self._lib, self._lib.hymls_b200_set_testvector(self._h, tv.ctypes.data))
+
+    def __del__(self):
+        try:
+            if self._h:
+                self._lib.hymls_b200_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    # -- Preconditioner::SetMatrix (:250-254): scipy CSR (host) or (rowptr, colidx, values) arrays/tensors
+    def SetMatrix(self, K, pattern_only=False):
+        if isinstance(K, tuple):
+            rowptr, colidx, values = K
+            n = len(rowptr) - 1
+            p_rp, w1 = _ptr(rowptr)
+            p_ci, w2 = _ptr(colidx)
+            p_v, w3 = _ptr(values)
+            assert w1 == w2 == w3
+            self._keep = (rowptr, colidx, values)
+            _check(self._lib, self._lib.hymls_b200_set_matrix_csr(self._h, n, p_rp, p_ci, p_v, w1))
+        else:
+            K = K.tocsr()
+            K.sort_indices()
+            n = K.shape[0]
+            rp = np.ascontiguousarray(K.indptr, dtype=np.int64)
+            ci = np.ascontiguousarray(K.indices, dtype=np.int32)
+            v = np.ascontiguousarray(K.data, dtype=np.float64)
+            _check(self._lib, self._lib.hymls_b200_set_matrix_csr(
+                self._h, n, rp.ctypes.data, ci.ctypes.data, None if pattern_only else v.ctypes.data, HOST))
+        self.n = n
+        return 0
+
+    def Initialize(self):
+        return _check(self._lib, self._lib.hymls_b200_initialize(self._h))
+
+    def Compute(self):
+        return _check(self._lib, self._lib.hymls_b200_compute(self._h))
+
+    def ApplyInverse(self, B, X=None):
+        """X = P^-1 B.  numpy (host) or torch CUDA tensors (device, column major: shape (nvec, n) contiguous
+        or 1-D)."""
+        if isinstance(B, np.ndarray):
+            Bc = np.asfortranarray(B.reshape(self.n, -1), dtype=np.float64)
+            nvec = Bc.shape[1]
+            Xc = np.zeros_like(Bc, order="F")
+            _check(self._lib, self._lib.hymls_b200_apply_inverse(self._h, Bc.ctypes.data, self.n, Xc.ctypes.data,
+                                                                  self.n, nvec, HOST))
+            return Xc.reshape(B.shape) if B.ndim == 1 else Xc
+        import torch
+        assert B.is_cuda and B.dtype == torch.float64 and B.is_contiguous()
+        nvec = 1 if B.dim() == 1 else B.shape[0]
+        if X is None:
+            X = torch.empty_like(B)
+        _check(self._lib, self._lib.hymls_b200_apply_inverse(self._h, B.data_ptr(), self.n, X.data_ptr(), self.n,
+                                                              nvec, DEVICE))
+        return X
+
+    def Apply(self, X, Y):  # Preconditioner::Apply returns -1 (:122-123)
+        return -1
+
+    def SetUseTranspose(self, flag):  # returns -1 (:162-166)
+        return -1
+
+    def SetBorder(self, V, W=None, Cm=None):
+        V = np.asfortranarray(V, dtype=np.float64)
+        m = V.shape[1] if V.ndim > 1 else 1
+        return _check(self._lib, self._lib.hymls_b200_set_border(
+            self._h, V.ctypes.data, None if W is None else np.asfortranarray(W).ctypes.data,
+            None if Cm is None else np.asfortranarray(Cm).ctypes.data, m))
+
+    def ApplyMatrix(self, x):
+        if isinstance(x, np.ndarray):
+            xc = np.ascontiguousarray(x, dtype=np.float64)
+            y = np.zeros_like(xc)
+            _check(self._lib, self._lib.hymls_b200_apply_matrix(self._h, xc.ctypes.data, y.ctypes.data, HOST))
+            return y
+        import torch
+        y = torch.empty_like(x)
+        _check(self._lib, self._lib.hymls_b200_apply_matrix(self._h, x.data_ptr(), y.data_ptr(), DEVICE))
+        return y
+
+    # -- index maps --------------------------------------------------------------------------------
+    def NumLevels(self):
+        return self._lib.hymls_b200_num_levels(self._h)
+
+    def NumMySubdomains(self, level=0):
+        return _check(self._lib, self._lib.hymls_b200_num_subdomains(self._h, level))
+
+    def GetInteriorGroup(self, sd, level=0):
+        n = self._lib.hymls_b200_get_interior(self._h, level, sd, None, 0)
+        _check(self._lib, int(n))
+        out = np.zeros(n, dtype=np.int64)
+        self._lib.hymls_b200_get_interior(self._h, level, sd, out.ctypes.data, n)
+        return out
+
+    def GetSeparatorGroups(self, sd, level=0):
+        """[(type, gids)] in the reference's order (HierarchicalMap::GetSeparatorGroups)."""
+        tot = C.c_int64()
+        ng = _check(self._lib, self._lib.hymls_b200_get_groups(self._h, level, sd, None, None, None, 0, C.byref(tot)))
+        ptr = np.zeros(ng + 1, dtype=np.int64)
+        types = np.zeros(ng, dtype=np.int32)
+        gids = np.zeros(tot.value, dtype=np.int64)
+        _check(self._lib, self._lib.hymls_b200_get_groups(self._h, level, sd, ptr.ctypes.data, types.ctypes.data,
+                                                           gids.ctypes.data, tot.value, C.byref(tot)))
+        return [(int(types[g]), gids[ptr[g]:ptr[g + 1]]) for g in range(ng)]
+
+    def GetMap(self, which, level=0):
+        n = self._lib.hymls_b200_get_map(self._h, level, which, None, 0)
+        _check(self._lib, int(n))
+        out = np.zeros(n, dtype=np.int64)
+        self._lib.hymls_b200_get_map(self._h, level, which, out.ctypes.data, n)
+        return out
+
+    def Stats(self):
+        st = _Stats()
+        _check(self._lib, self._lib.hymls_b200_get_stats(self._h, C.byref(st)))
+        return {k: getattr(st, k) for k, _ in _Stats._fields_}
+
+    def TimeApply(self, reps=20):
+        a, b = C.c_double(), C.c_double()
+        _check(self._lib, self._lib.hymls_b200_time_apply(self._h, reps, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+
+class Solver:
+    """HYMLS::Solver(K, P, params): Krylov solve with the preconditioner (src/HYMLS_Solver.cpp:22-51,148-152).
+    The "Solver" sublist is the one of the parameter list the preconditioner was created with."""
+
+    def __init__(self, prec):
+        self.prec = prec
+        self.num_iter = 0
+        self.info = None
+        self.history = None
+
+    def ApplyInverse(self, b, x=None, seed=43, history_cap=2048):
+        P = self.prec
+        lib = P._lib
+        info = _SolveInfo()
+        hist = np.zeros(history_cap)
+        if isinstance(b, np.ndarray):
+            bc = np.ascontiguousarray(b, dtype=np.float64)
+            xc = np.zeros_like(bc) if x is None else np.ascontiguousarray(x, dtype=np.float64)
+            _check(lib, lib.hymls_b200_solve(P._h, bc.ctypes.data, xc.ctypes.data, HOST, seed, C.byref(info),
+                                             hist.ctypes.data, history_cap))
+        else:
+            import torch
+            xc = torch.zeros_like(b) if x is None else x
+            _check(lib, lib.hymls_b200_solve(P._h, b.data_ptr(), xc.data_ptr(), DEVICE, seed, C.byref(info),
+                                             hist.ctypes.data, history_cap))
+        self.num_iter = info.iterations
+        self.info = {k: getattr(info, k) for k, _ in _SolveInfo._fields_}
+        self.history = hist[:min(info.history_len, history_cap)].copy()
+        return xc
+
+    def getNumIter(self):
+        return self.num_iter

@@ -1,0 +1,304 @@
+// Kernels of Preconditioner::ApplyInverse (src/HYMLS_Preconditioner.cpp:930-1070),
+// SchurPreconditioner::ApplyInverse / ApplyOT / ApplyBlockDiagonal / UpdateVsumRhs
+// (src/HYMLS_SchurPreconditioner.cpp:1010-1093,1236-1265,1311-1346,1435-1459),
+// MatrixBlock::Apply / ApplyInverse (src/HYMLS_MatrixBlock.cpp:294-385) and the vector kernels of the
+// Krylov loop (Belos inside src/HYMLS_BaseSolver.cpp:347-356).  All of them are HBM-bandwidth bound.
+#include <cuda_runtime.h>
+
+#include "device.cuh"
+#include "kernels.hpp"
+
+namespace hymls {
+
+// ---------------------------------------------------------------------------------------------
+// Batched dense mat-vec with the explicit inverses:  y_sd = Ainv_sd * x_sd  for every subdomain.
+// The dominant kernel of ApplyInverse: streams 8 n_sd^2 bytes per subdomain exactly once.
+// Work item = (matrix, slab of GEMV_ROWS rows); one warp per row, lanes stride the row with 16-byte
+// loads, x_sd staged in shared memory.
+//   x_sd[q] = xin[gather ? gather[p] : p],  p = vecOff[mat] + q
+//   mode 0:  out[scatter ? scatter[p] : p] = acc
+//   mode 1:  out[scatter ? scatter[p] : p] = xprev[p] - acc   (second A11 solve of ApplyInverse: fused update + export)
+// ---------------------------------------------------------------------------------------------
+static constexpr int GEMV_ROWS = 32;   // rows per CTA
+static constexpr int GEMV_T = 256;     // 8 warps, 4 rows each
+
+__global__ void __launch_bounds__(GEMV_T)
+k_batched_gemv(GemvArgs a) {
+  const int item = blockIdx.x;
+  const int mat = a.itemMat[item];
+  const int r0 = a.itemRow0[item];
+  const int n = a.n[mat], np = a.np[mat];
+  const int64_t v0 = a.vecOff[mat];  // offset of this matrix' segment in the packed vectors
+  const double* __restrict__ A = a.A + a.matOff[mat];
+  extern __shared__ double sx[];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  for (int q = tid; q < np; q += GEMV_T) {
+    double v = 0.0;
+    if (q < n) v = a.gather ? a.xin[a.gather[v0 + q]] : a.xin[v0 + q];
+    sx[q] = v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int rr = 0; rr < GEMV_ROWS / (GEMV_T / 32); ++rr) {
+    const int r = r0 + wid * (GEMV_ROWS / (GEMV_T / 32)) + rr;
+    if (r >= n) break;
+    const double2* __restrict__ row = reinterpret_cast<const double2*>(A + (int64_t)r * np);
+    const double2* __restrict__ x2 = reinterpret_cast<const double2*>(sx);
+    double acc0 = 0.0, acc1 = 0.0;
+    const int n2 = np >> 1;
+    int q = lane;
+    for (; q + 96 < n2; q += 128) {  // 4 independent 16-byte loads in flight per lane
+      double2 m0 = __ldg(row + q), m1 = __ldg(row + q + 32), m2 = __ldg(row + q + 64), m3 = __ldg(row + q + 96);
+      double2 b0 = x2[q], b1 = x2[q + 32], b2 = x2[q + 64], b3 = x2[q + 96];
+      acc0 += m0.x * b0.x + m1.x * b1.x + m2.x * b2.x + m3.x * b3.x;
+      acc1 += m0.y * b0.y + m1.y * b1.y + m2.y * b2.y + m3.y * b3.y;
+    }
+    for (; q < n2; q += 32) {
+      double2 m0 = __ldg(row + q);
+      double2 b0 = x2[q];
+      acc0 += m0.x * b0.x;
+      acc1 += m0.y * b0.y;
+    }
+    double acc = acc0 + acc1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+      const double v = (a.mode == 0) ? acc : a.xprev[v0 + r] - acc;
+      a.out[a.scatter ? a.scatter[v0 + r] : v0 + r] = v;
+    }
+  }
+}
+
+void batchedGemv(const GemvArgs& a, int numItems, int npMax, cudaStream_t s, int64_t* launches) {
+  if (numItems == 0) return;
+  static size_t smemSet = 48 * 1024;
+  size_t smem = (size_t)npMax * sizeof(double);
+  if (smem > smemSet) {
+    if (smem > 227 * 1024) throw Error(HYMLS_B200_ERR_UNSUPPORTED, "dense block too large for the GEMV kernel");
+    HY_CUDA(cudaFuncSetAttribute(k_batched_gemv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smemSet = smem;
+  }
+  k_batched_gemv<<<numItems, GEMV_T, smem, s>>>(a);
+  ++*launches;
+}
+int gemvRowsPerItem() { return GEMV_ROWS; }
+
+// ---------------------------------------------------------------------------------------------
+// CSR SpMV variants (thread per row; rows have 1..~10 entries on level 0)
+//   y[r] = alpha * (b ? b[bidx ? bidx[r] : r] : 0) + beta * sum_e val[e] x[col[e]]
+// ---------------------------------------------------------------------------------------------
+__global__ void k_spmv(const int64_t* __restrict__ ptr, const int* __restrict__ col, const double* __restrict__ val,
+                       const double* __restrict__ x, double* __restrict__ y, int64_t n, double alpha,
+                       const double* __restrict__ b, const int* __restrict__ bidx, double beta) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  double s = 0.0;
+  for (int64_t e = ptr[r]; e < ptr[r + 1]; ++e) s += val[e] * x[col[e]];
+  double base = 0.0;
+  if (b) base = alpha * b[bidx ? bidx[r] : r];
+  y[r] = base + beta * s;
+}
+void spmv(const int64_t* ptr, const int* col, const double* val, const double* x, double* y, int64_t n, double alpha,
+          const double* b, const int* bidx, double beta, cudaStream_t s, int64_t* launches) {
+  if (n == 0) return;
+  k_spmv<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ptr, col, val, x, y, n, alpha, b, bidx, beta);
+  ++*launches;
+}
+
+__global__ void k_gather_values(const double* __restrict__ src, const int64_t* __restrict__ idx,
+                                double* __restrict__ dst, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[idx[i]];
+}
+void gatherValues(const double* src, const int64_t* idx, double* dst, int64_t n, cudaStream_t s, int64_t* launches) {
+  if (n == 0) return;
+  k_gather_values<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(src, idx, dst, n);
+  ++*launches;
+}
+// dst[dstIdx[i] - dstBase] = src[srcIdx[i]]   (dense fill of the A11 blocks of one chunk)
+__global__ void k_scatter_values(const double* __restrict__ src, const int64_t* __restrict__ srcIdx,
+                                 const int64_t* __restrict__ dstIdx, int64_t dstBase, double* __restrict__ dst,
+                                 int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[dstIdx[i] - dstBase] = src[srcIdx[i]];
+}
+void scatterValues(const double* src, const int64_t* srcIdx, const int64_t* dstIdx, int64_t dstBase, double* dst,
+                   int64_t n, cudaStream_t s, int64_t* launches) {
+  if (n == 0) return;
+  k_scatter_values<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(src, srcIdx, dstIdx, dstBase, dst, n);
+  ++*launches;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Householder transforms on the separator vector, one warp per separator group (ApplyOT):
+//   forward :  z = H rhs ;  vsumRhs[u] = z[first]                      (steps (1) and UpdateVsumRhs)
+//   backward:  y[first] = vsumSol[u];  x2 = H y;  X[sepRow[p]] = x2[p]  (:1078-1081 + export :1052)
+// H = 2 w w' - I with w = 0 for groups whose reflector is degenerate (sparse variant: H = -I).
+// ---------------------------------------------------------------------------------------------
+__global__ void k_householder(const int* __restrict__ uniqStart, int nuniq, const double* __restrict__ w,
+                              const double* __restrict__ in, double* __restrict__ out, double* __restrict__ vsumOut,
+                              const double* __restrict__ vsumIn, double* __restrict__ X, const int* __restrict__ sepRow) {
+  const int u = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (u >= nuniq) return;
+  const int lane = threadIdx.x & 31;
+  const int a = uniqStart[u], z = uniqStart[u + 1];
+  double t = 0.0;
+  for (int p = a + lane; p < z; p += 32) {
+    double v = (vsumIn && p == a) ? vsumIn[u] : in[p];
+    t += w[p] * v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  for (int p = a + lane; p < z; p += 32) {
+    double v = (vsumIn && p == a) ? vsumIn[u] : in[p];
+    double r = 2.0 * w[p] * t - v;
+    out[p] = r;
+    if (vsumOut && p == a) vsumOut[u] = r;
+    if (X) X[sepRow[p]] = r;
+  }
+}
+void householder(const int* uniqStart, int nuniq, const double* w, const double* in, double* out, double* vsumOut,
+                 const double* vsumIn, double* X, const int* sepRow, cudaStream_t s, int64_t* launches) {
+  if (nuniq == 0) return;
+  const int wpb = 8;
+  k_householder<<<(nuniq + wpb - 1) / wpb, wpb * 32, 0, s>>>(uniqStart, nuniq, w, in, out, vsumOut, vsumIn, X, sepRow);
+  ++*launches;
+}
+
+// ---------------------------------------------------------------------------------------------
+// small vector kernels of the Krylov loop
+// ---------------------------------------------------------------------------------------------
+// partial[i * nblk + b] = sum over rows of block b of V_i[r] * w[r],  i = 0..k-1   (one pass over w)
+__global__ void __launch_bounds__(256)
+k_multi_dot(const double* __restrict__ V, int64_t ldv, int k, const double* __restrict__ w, int64_t n,
+            double* __restrict__ partial) {
+  __shared__ double red[8];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int i = 0; i < k; ++i) {
+    const double* v = V + (int64_t)i * ldv;
+    double s = 0.0;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + tid; r < n; r += stride) s += v[r] * w[r];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) red[wid] = s;
+    __syncthreads();
+    if (wid == 0) {
+      s = lane < 8 ? red[lane] : 0.0;
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) partial[(int64_t)i * gridDim.x + blockIdx.x] = s;
+    }
+    __syncthreads();
+  }
+}
+// h[i] (+)= sum_b partial[i*nblk+b]   (fixed order: deterministic)
+__global__ void k_reduce_partials(const double* __restrict__ partial, int nblk, int k, double* __restrict__ h,
+                                  int accumulate) {
+  const int i = blockIdx.x;
+  if (i >= k) return;
+  __shared__ double red[32];
+  double s = 0.0;
+  for (int b = threadIdx.x; b < nblk; b += blockDim.x) s += partial[(int64_t)i * nblk + b];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) red[wid] = s;
+  __syncthreads();
+  if (wid == 0) {
+    s = lane < (blockDim.x >> 5) ? red[lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) h[i] = accumulate ? h[i] + s : s;
+  }
+}
+static const int DOT_BLOCKS = 592;  // 4 x 148 SMs
+void multiDot(const double* V, int64_t ldv, int k, const double* w, int64_t n, double* partial, double* h,
+              int accumulate, cudaStream_t s, int64_t* launches) {
+  if (k == 0) return;
+  k_multi_dot<<<DOT_BLOCKS, 256, 0, s>>>(V, ldv, k, w, n, partial);
+  k_reduce_partials<<<k, 256, 0, s>>>(partial, DOT_BLOCKS, k, h, accumulate);
+  *launches += 2;
+}
+int multiDotBlocks() { return DOT_BLOCKS; }
+
+// w -= sum_i h[i] V_i
+__global__ void k_multi_axpy(const double* __restrict__ V, int64_t ldv, int k, const double* __restrict__ h,
+                             double* __restrict__ w, int64_t n, double sign) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) {
+    double s = 0.0;
+    for (int i = 0; i < k; ++i) s += h[i] * V[(int64_t)i * ldv + r];
+    w[r] += sign * s;
+  }
+}
+void multiAxpy(const double* V, int64_t ldv, int k, const double* h, double* w, int64_t n, double sign,
+               cudaStream_t s, int64_t* launches) {
+  if (k == 0 || n == 0) return;
+  k_multi_axpy<<<DOT_BLOCKS, 256, 0, s>>>(V, ldv, k, h, w, n, sign);
+  ++*launches;
+}
+// y = a*x + b*y   (b == 0 : y = a*x, no read of y)
+__global__ void k_axpby(double a, const double* __restrict__ x, double b, double* __restrict__ y, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride)
+    y[r] = (b == 0.0) ? a * x[r] : a * x[r] + b * y[r];
+}
+void axpby(double a, const double* x, double b, double* y, int64_t n, cudaStream_t s, int64_t* launches) {
+  if (n == 0) return;
+  k_axpby<<<DOT_BLOCKS, 256, 0, s>>>(a, x, b, y, n);
+  ++*launches;
+}
+// y = x * (1 / *dnorm)  with the norm on the device (avoids a host round trip)
+__global__ void k_scale_by_inv(const double* __restrict__ x, const double* __restrict__ nrm2, double* __restrict__ y,
+                               int64_t n) {
+  const double inv = 1.0 / sqrt(*nrm2);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) y[r] = x[r] * inv;
+}
+void scaleByInvNorm(const double* x, const double* nrm2, double* y, int64_t n, cudaStream_t s, int64_t* launches) {
+  if (n == 0) return;
+  k_scale_by_inv<<<DOT_BLOCKS, 256, 0, s>>>(x, nrm2, y, n);
+  ++*launches;
+}
+__global__ void k_set_value(double* x, int64_t idx, double v) { x[idx] = v; }
+void setValue(double* x, int64_t idx, double v, cudaStream_t s, int64_t* launches) {
+  k_set_value<<<1, 1, 0, s>>>(x, idx, v);
+  ++*launches;
+}
+// dense fill of the coarse matrix from CSR (+ FullDiag semantics) and Dirichlet rows/cols (PutDirichlet)
+__global__ void k_csr_to_dense(const int64_t* __restrict__ ptr, const int* __restrict__ col,
+                               const double* __restrict__ val, double* __restrict__ D, int n, int np) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  for (int64_t e = ptr[r]; e < ptr[r + 1]; ++e) D[(int64_t)r * np + col[e]] = val[e];
+}
+__global__ void k_put_dirichlet(double* __restrict__ D, int n, int np, int fix) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  D[(int64_t)fix * np + i] = (i == fix) ? 1.0 : 0.0;
+  if (i != fix) D[(int64_t)i * np + fix] = 0.0;
+}
+void csrToDense(const int64_t* ptr, const int* col, const double* val, double* D, int n, int np, cudaStream_t s,
+                int64_t* launches) {
+  if (n == 0) return;
+  k_csr_to_dense<<<(n + 255) / 256, 256, 0, s>>>(ptr, col, val, D, n, np);
+  ++*launches;
+}
+void putDirichlet(double* D, int n, int np, int fix, cudaStream_t s, int64_t* launches) {
+  k_put_dirichlet<<<(n + 255) / 256, 256, 0, s>>>(D, n, np, fix);
+  ++*launches;
+}
+// y[idx[i]] = x[i]  /  y[i] = x[idx[i]]
+__global__ void k_scatter_vec(const double* __restrict__ x, const int* __restrict__ idx, double* __restrict__ y,
+                              int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[idx[i]] = x[i];
+}
+void scatterVec(const double* x, const int* idx, double* y, int64_t n, cudaStream_t s, int64_t* launches) {
+  if (n == 0) return;
+  k_scatter_vec<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, idx, y, n);
+  ++*launches;
+}
+
+}  // namespace hymls

@@ -1,0 +1,1067 @@
+#include "engine.hpp"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <random>
+
+namespace hymls {
+
+thread_local double g_devBytes = 0;
+
+static const double SMALL_ENTRY = 1e-14;  // HYMLS_SMALL_ENTRY
+
+// ---------------------------------------------------------------------------------------------
+// parameter validation (Preconditioner::getValidParameters, src/HYMLS_Preconditioner.cpp:135-276)
+// ---------------------------------------------------------------------------------------------
+static bool startsWith(const std::string& s, const char* p) { return s.rfind(p, 0) == 0; }
+static void validatePreconditionerList(const ParameterList& prec) {
+  static const char* valid[] = {
+      "Apply Dropping", "Apply Orthogonal Transformation", "B-Grid Transform", "Coarsening Factor",
+      "Coarsening Factor (x)", "Coarsening Factor (y)", "Coarsening Factor (z)", "Dense Solvers on Level",
+      "Eliminate Retained Nodes Together", "Eliminate Velocities Together", "Fix Pressure Level",
+      "Number of Levels", "Partitioner", "Preconditioner Variant", "Separator Length", "Separator Length (x)",
+      "Separator Length (y)", "Separator Length (z)", "Subdivide Separators", "Subdivide based on variable",
+      "Subdomain Solver Num Threads", "Subdomain Solver Type", "Visualize Solver",
+      // extension of this implementation ("Deviations")
+      "Eliminate Tube Pressures With Velocities"};
+  for (const std::string& name : prec.parameterNames()) {
+    bool ok = startsWith(name, "Fix GID ") || startsWith(name, "Retain Nodes");
+    for (const char* v : valid) ok = ok || name == v;
+    if (!ok)
+      throw Error(HYMLS_B200_ERR_ARG, "Error, the parameter {name=\"" + name +
+                                          "\"} in the parameter (sub)list \"Preconditioner\" was not found in the "
+                                          "list of valid parameters");
+  }
+  for (const std::string& name : prec.sublistNames())
+    if (name != "Sparse Solver" && name != "Dense Solver" && name != "Coarse Solver" && name != "Direct Solver")
+      throw Error(HYMLS_B200_ERR_ARG, "unknown sublist \"" + name + "\" in \"Preconditioner\"");
+}
+
+Engine::Engine(const std::string& xml) {
+  params_ = ParameterList::fromXml(xml);
+  int ndev = 0;
+  deviceOk_ = (cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0);
+  if (!deviceOk_) cudaGetLastError();
+  ParameterList& prec = params_.sublist("Preconditioner");
+  validatePreconditionerList(prec);
+  maxLevel_ = prec.get("Number of Levels", 1);
+  std::string method = prec.get("Partitioner", "Cartesian");
+  if (method != "Cartesian")
+    throw Error(HYMLS_B200_ERR_UNSUPPORTED, "Partitioner '" + method + "': only 'Cartesian' is implemented");
+  std::string variant = prec.get("Preconditioner Variant", "Block Diagonal");
+  bool dropping = prec.get("Apply Dropping", true);
+  bool ot = prec.get("Apply Orthogonal Transformation", dropping);
+  if (variant != "Block Diagonal" || !dropping || !ot)
+    throw Error(HYMLS_B200_ERR_UNSUPPORTED,
+                "only 'Block Diagonal' with dropping and orthogonal transformation is implemented");
+  if (deviceOk_) {
+    HY_CUDA(cudaEventCreate(&ev0_));
+    HY_CUDA(cudaEventCreate(&ev1_));
+    HY_CUDA(cudaEventCreate(&evA_));
+    HY_CUDA(cudaEventCreate(&evB_));
+  }
+}
+
+void Engine::needDevice() const {
+  if (!deviceOk_)
+    throw Error(HYMLS_B200_ERR_CUDA, "hymls_b200 needs a CUDA device for this call: there is no CPU fallback");
+}
+
+Engine::~Engine() {
+  if (ev0_) cudaEventDestroy(ev0_);
+  if (ev1_) cudaEventDestroy(ev1_);
+  if (evA_) cudaEventDestroy(evA_);
+  if (evB_) cudaEventDestroy(evB_);
+}
+
+void Engine::setMatrix(int64_t n, const int64_t* rowptr, const int32_t* colidx, const double* values, int where) {
+  if (n <= 0 || !rowptr || !colidx) throw Error(HYMLS_B200_ERR_ARG, "set_matrix_csr: bad arguments");
+  if (where == HYMLS_B200_DEVICE || values) needDevice();  // values live on the device only
+  std::vector<int64_t> rp(n + 1);
+  if (where == HYMLS_B200_DEVICE) {
+    HY_CUDA(cudaMemcpy(rp.data(), rowptr, (n + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost));
+  } else {
+    std::memcpy(rp.data(), rowptr, (n + 1) * sizeof(int64_t));
+  }
+  const int64_t nnz = rp[n];
+  bool samePattern = haveMatrix_ && n == n_ && hRowptr_ == rp;
+  std::vector<int> ci;
+  if (!samePattern || where == HYMLS_B200_HOST) {
+    ci.resize(nnz);
+    if (where == HYMLS_B200_DEVICE) {
+      HY_CUDA(cudaMemcpy(ci.data(), colidx, nnz * sizeof(int), cudaMemcpyDeviceToHost));
+    } else {
+      std::memcpy(ci.data(), colidx, nnz * sizeof(int));
+    }
+    samePattern = samePattern && ci == hColidx_;
+  }
+  if (!samePattern) {
+    n_ = n;
+    hRowptr_.swap(rp);
+    hColidx_.swap(ci);
+    levels_.clear();
+    initialized_ = false;
+    haveMatrix_ = true;
+    levels_.emplace_back(new Level());
+    if (deviceOk_) {
+      Level& L0 = *levels_[0];
+      L0.rowptr.upload(hRowptr_, stream_);
+      L0.colidx.upload(hColidx_, stream_);
+      L0.val.alloc(nnz);
+    }
+  }
+  computed_ = false;
+  if (!values) return;  // pattern only: enough for Initialize (index maps) without a device
+  Level& L0 = *levels_[0];
+  HY_CUDA(cudaMemcpyAsync(L0.val.p, values, nnz * sizeof(double),
+                          where == HYMLS_B200_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, stream_));
+  HY_CUDA(cudaStreamSynchronize(stream_));
+  computed_ = false;
+}
+
+void Engine::setTestVector(const double* tv) {
+  if (!haveMatrix_) throw Error(HYMLS_B200_ERR_STATE, "set the matrix before the test vector");
+  if (tv) hTestVector_.assign(tv, tv + n_); else hTestVector_.clear();
+  initialized_ = false;
+  computed_ = false;
+}
+
+// ---------------------------------------------------------------------------------------------
+void BatchedInverse::setup(const std::vector<int>& n_, const std::vector<int>& np_,
+                           const std::vector<int64_t>& matOff_, const std::vector<int64_t>& vecOff_,
+                           cudaStream_t s) {
+  hN = n_;
+  hNp = np_;
+  hMatOff = matOff_;
+  hVecOff = vecOff_;
+  count = (int)n_.size();
+  npMax = 0;
+  std::vector<int> im, ir;
+  const int rows = gemvRowsPerItem();
+  for (int m = 0; m < count; ++m) {
+    npMax = std::max(npMax, np_[m]);
+    for (int r0 = 0; r0 < n_[m]; r0 += rows) {
+      im.push_back(m);
+      ir.push_back(r0);
+    }
+  }
+  numItems = (int)im.size();
+  n.upload(hN, s);
+  np.upload(hNp, s);
+  matOff.upload(hMatOff, s);
+  vecOff.upload(hVecOff, s);
+  itemMat.upload(im, s);
+  itemRow0.upload(ir, s);
+  F.alloc((size_t)(count ? matOff_[count] : 0));
+  HY_CUDA(cudaStreamSynchronize(s));
+}
+GemvArgs BatchedInverse::args() const {
+  GemvArgs a{};
+  a.itemMat = itemMat.p;
+  a.itemRow0 = itemRow0.p;
+  a.n = n.p;
+  a.np = np.p;
+  a.matOff = matOff.p;
+  a.vecOff = vecOff.p;
+  a.A = F.p;
+  return a;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Initialize: symbolic phase of every level (host) + upload of the index arrays
+// ---------------------------------------------------------------------------------------------
+void Engine::initialize() {
+  if (!haveMatrix_) throw Error(HYMLS_B200_ERR_STATE, "Initialize: no matrix set");
+  auto t0 = std::chrono::steady_clock::now();
+  ParameterList levelParams = params_.deepCopy();
+  levels_.resize(1);
+  const int nlev = std::max(maxLevel_, 1);
+  std::vector<int> gid2row;
+  for (int l = 0; l < nlev; ++l) {
+    if (l > 0) levels_.emplace_back(new Level());
+    Level& L = *levels_[l];
+    LevelSym& S = L.sym;
+    S.level = l;
+    L.exact = (maxLevel_ == 0);
+    CartesianPartitioner part(levelParams, l);
+    if (l == 0) {
+      // write the defaults back like the reference does (Fix GID 1, ...) so later queries see them
+      params_.sublist("Preconditioner") = levelParams.sublist("Preconditioner").deepCopy();
+      params_.sublist("Problem") = levelParams.sublist("Problem").deepCopy();
+      if (part.numGlobalNodes() != n_)
+        throw Error(HYMLS_B200_ERR_ARG, "matrix has " + std::to_string(n_) + " rows but nx*ny*nz*dof = " +
+                                            std::to_string(part.numGlobalNodes()));
+      S.n = n_;
+      S.rowGid.resize(n_);
+      for (int64_t i = 0; i < n_; ++i) S.rowGid[i] = i;
+      S.rowptr = hRowptr_;
+      S.colidx = hColidx_;
+      S.testVector = hTestVector_;
+      gid2row.assign(n_, -1);
+    } else {
+      const LevelSym& P = levels_[l - 1]->sym;
+      S.n = P.nuniq;
+      S.rowGid.resize(S.n);
+      for (int u = 0; u < P.nuniq; ++u) S.rowGid[u] = P.H.sepGid[P.H.uniqPtr[u]];
+      S.rowptr = P.redPtr;
+      S.colidx = P.redCol;
+      S.testVector = P.nextTestVector;
+      std::fill(gid2row.begin(), gid2row.end(), -1);
+    }
+    for (int64_t r = 0; r < S.n; ++r) gid2row[S.rowGid[r]] = (int)r;
+    part.partition();
+    buildLevelSym(S, part, gid2row);
+    // parameters of the next level (SetNextLevelParameters; sx *= cx)
+    part.setNextLevelParameters(levelParams);
+    if (deviceOk_) uploadLevel(L);
+  }
+  if (deviceOk_) HY_CUDA(cudaStreamSynchronize(stream_));
+  initialized_ = true;
+  computed_ = false;
+  stats_.num_initialize++;
+  stats_.time_initialize += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+template <typename T>
+static std::vector<int> toInt(const std::vector<T>& v) {
+  return std::vector<int>(v.begin(), v.end());
+}
+
+void Engine::uploadLevel(Level& L) {
+  LevelSym& S = L.sym;
+  cudaStream_t s = stream_;
+  if (S.level > 0) {
+    L.rowptr.upload(S.rowptr, s);
+    L.colidx.upload(S.colidx, s);
+    L.val.alloc(S.colidx.size());
+  }
+  L.intRow.upload(S.intRow, s);
+  L.sepRow.upload(S.sepRow, s);
+  // A11
+  std::vector<int64_t> vecOffI(S.H.intPtr.begin(), S.H.intPtr.end() - 1);
+  L.a11.setup(S.sdN, S.sdNp, S.a11Off, vecOffI, s);
+  L.a11Src.upload(S.a11Src, s);
+  L.a11Dst.upload(S.a11Dst, s);
+  L.a11ListPtr.assign(S.nsd + 1, 0);
+  for (int sd = 0; sd <= S.nsd; ++sd)
+    L.a11ListPtr[sd] = std::lower_bound(S.a11Dst.begin(), S.a11Dst.end(), S.a11Off[sd]) - S.a11Dst.begin();
+  // A12 / A21 / A22
+  L.p12.upload(S.A12.ptr, s);
+  L.c12.upload(S.A12.col, s);
+  L.src12.upload(S.A12.src, s);
+  L.v12.alloc(S.A12.col.size());
+  L.p21.upload(S.A21.ptr, s);
+  L.c21.upload(S.A21.col, s);
+  L.src21.upload(S.A21.src, s);
+  L.v21.alloc(S.A21.col.size());
+  if (L.exact) {
+    L.p22.upload(S.A22.ptr, s);
+    L.c22.upload(S.A22.col, s);
+    L.src22.upload(S.A22.src, s);
+  }
+  // Schur assembly data
+  const int64_t totalRows = S.sdRowPtr[S.nsd];
+  std::vector<int> rowSd(totalRows), rowInst(totalRows), rowLinkPos(totalRows);
+  std::vector<int64_t> sdLinkPtr(S.nsd + 1, 0);
+  std::vector<int> lnkSd, lnkSize;
+  int maxM = 0, maxG = 0, maxN = 0;
+  size_t maxBlkSmem = 0;
+  for (int sd = 0; sd < S.nsd; ++sd) {
+    const int64_t ia = S.sdInstPtr[sd], iz = S.sdInstPtr[sd + 1];
+    const int nl = S.sdNumLink[sd];
+    std::vector<int> lsz(nl, 0), lcnt(nl, 0);
+    for (int64_t g = ia; g < iz; ++g) {
+      const int l = S.instLink[g];
+      for (int q = 0; q < S.instLen[g]; ++q) {
+        const int64_t R = S.sdRowPtr[sd] + S.instLoc[g] + q;
+        rowSd[R] = sd;
+        rowInst[R] = (int)g;
+        rowLinkPos[R] = lsz[l] + q;
+      }
+      lsz[l] += S.instLen[g];
+      lcnt[l]++;
+    }
+    for (int l = 0; l < nl; ++l) {
+      lnkSd.push_back(sd);
+      lnkSize.push_back(lsz[l]);
+      maxBlkSmem = std::max(maxBlkSmem, (size_t)(2 * (size_t)lsz[l] * lcnt[l] + (size_t)lcnt[l] * lcnt[l]) * 8);
+    }
+    sdLinkPtr[sd + 1] = (int64_t)lnkSd.size();
+    maxM = std::max(maxM, S.sdM[sd]);
+    maxG = std::max(maxG, (int)(iz - ia));
+    maxN = std::max(maxN, S.sdNp[sd]);
+  }
+  L.dLen = maxN;
+  L.rowSmem = (size_t)(maxN + maxM) * sizeof(double);
+  L.blkSmem = maxBlkSmem;
+  // chunks of subdomains whose workspace (C, SV: m*G each; S_LL: sum lsz^2) fits the budget
+  const int64_t budget = (int64_t)96 << 20;  // doubles per array (768 MB)
+  std::vector<int64_t> wsOffC(S.nsd, 0), lnkOff(lnkSd.size(), 0);
+  L.chunks.clear();
+  L.wsCLen = L.wsSLLLen = 0;
+  {
+    int sd0 = 0;
+    int64_t cUsed = 0, lUsed = 0;
+    for (int sd = 0; sd < S.nsd; ++sd) {
+      const int64_t G = S.sdInstPtr[sd + 1] - S.sdInstPtr[sd];
+      const int64_t needC = (int64_t)S.sdM[sd] * G;
+      int64_t needL = 0;
+      for (int64_t lk = sdLinkPtr[sd]; lk < sdLinkPtr[sd + 1]; ++lk) needL += (int64_t)lnkSize[lk] * lnkSize[lk];
+      if (sd > sd0 && (cUsed + needC > budget || lUsed + needL > budget)) {
+        L.chunks.push_back({sd0, sd, S.sdRowPtr[sd0], S.sdRowPtr[sd], sdLinkPtr[sd0], sdLinkPtr[sd]});
+        sd0 = sd;
+        cUsed = lUsed = 0;
+      }
+      wsOffC[sd] = cUsed;
+      cUsed += needC;
+      for (int64_t lk = sdLinkPtr[sd]; lk < sdLinkPtr[sd + 1]; ++lk) {
+        lnkOff[lk] = lUsed;
+        lUsed += (int64_t)lnkSize[lk] * lnkSize[lk];
+      }
+      L.wsCLen = std::max(L.wsCLen, cUsed);
+      L.wsSLLLen = std::max(L.wsSLLLen, lUsed);
+    }
+    if (S.nsd > sd0)
+      L.chunks.push_back({sd0, S.nsd, S.sdRowPtr[sd0], S.sdRowPtr[S.nsd], sdLinkPtr[sd0], sdLinkPtr[S.nsd]});
+  }
+  L.rowSd.upload(rowSd, s);
+  L.rowInst.upload(rowInst, s);
+  L.rowLinkPos.upload(rowLinkPos, s);
+  L.sdSep.upload(S.sdSep, s);
+  L.sdM.upload(S.sdM, s);
+  L.sdRowPtr.upload(S.sdRowPtr, s);
+  L.s21Ptr.upload(S.s21Ptr, s);
+  L.s21Col.upload(S.s21Col, s);
+  L.s21Src.upload(S.s21Src, s);
+  L.s12Ptr.upload(S.s12Ptr, s);
+  L.s12Row.upload(S.s12Row, s);
+  L.s12Src.upload(S.s12Src, s);
+  L.s22Ptr.upload(S.s22Ptr, s);
+  L.s22Col.upload(S.s22Col, s);
+  L.s22Src.upload(S.s22Src, s);
+  L.sdInstPtr.upload(S.sdInstPtr, s);
+  L.instLoc.upload(S.instLoc, s);
+  L.instLen.upload(S.instLen, s);
+  L.instUniq.upload(S.instUniq, s);
+  L.instLink.upload(S.instLink, s);
+  L.sdLinkPtr.upload(sdLinkPtr, s);
+  L.lnkSd.upload(lnkSd, s);
+  L.lnkSize.upload(lnkSize, s);
+  L.lnkOff.upload(lnkOff, s);
+  L.wsOffC.upload(wsOffC, s);
+  L.uniqStart.upload(toInt(S.H.uniqPtr), s);
+  L.uniqBlk.upload(S.uniqBlk, s);
+  L.uniqBlkOff.upload(S.uniqBlkOff, s);
+  L.what.upload(S.what, s);
+  std::vector<double> wd(S.what);
+  for (int u = 0; u < S.nuniq; ++u)
+    if (S.usign[u] < 0)
+      for (int64_t p = S.H.uniqPtr[u]; p < S.H.uniqPtr[u + 1]; ++p) wd[p] = 0.0;
+  L.wd.upload(wd, s);
+  L.usign.upload(S.usign, s);
+  L.redPtr.upload(S.redPtr, s);
+  L.redCol.upload(S.redCol, s);
+  // separator blocks
+  std::vector<int64_t> blkVecOff(S.blkRowPtr.begin(), S.blkRowPtr.end() - 1);
+  L.blk.setup(S.blkN, S.blkNp, S.blkOff, blkVecOff, s);
+  L.blkRows.upload(S.blkRows, s);
+  // work vectors
+  L.x1.alloc(S.nI);
+  L.y1.alloc(S.nI);
+  L.rhsS.alloc(S.nS);
+  L.Z.alloc(S.nS);
+  L.Y.alloc(S.nS);
+  L.vsRhs.alloc(S.nuniq);
+  L.vsSol.alloc(S.nuniq);
+  HY_CUDA(cudaStreamSynchronize(s));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Compute
+// ---------------------------------------------------------------------------------------------
+static void checkInfo(DevBuf<int>& info, cudaStream_t s, const std::string& what) {
+  int h = 0;
+  HY_CUDA(cudaMemcpyAsync(&h, info.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+  HY_CUDA(cudaStreamSynchronize(s));
+  if (h != 0)
+    throw Error(HYMLS_B200_ERR_NUMERIC,
+                what + ": zero pivot (matrix " + std::to_string(h - 1) +
+                    " is exactly singular). For 3D Stokes-C on the Cartesian partitioner the reference's pressure "
+                    "'tube' blocks are identically zero; see 'Eliminate Tube Pressures With Velocities' in DESIGN.md");
+}
+
+void Engine::compute() {
+  needDevice();
+  if (!initialized_) initialize();  // "I'll do it for you", Preconditioner.cpp:403-409
+  HY_CUDA(cudaEventRecord(ev0_, stream_));
+  info_.alloc(1);
+  HY_CUDA(cudaMemsetAsync(info_.p, 0, sizeof(int), stream_));
+  stats_.flops_compute = 0;
+  for (int l = 0; l < (int)levels_.size(); ++l) computeLevel(l);
+  HY_CUDA(cudaEventRecord(ev1_, stream_));
+  HY_CUDA(cudaStreamSynchronize(stream_));
+  float ms = 0;
+  HY_CUDA(cudaEventElapsedTime(&ms, ev0_, ev1_));
+  stats_.time_compute += ms * 1e-3;
+  stats_.num_compute++;
+  // scratch of Compute is not needed by ApplyInverse
+  work_.release();
+  wsC_.release();
+  wsSV_.release();
+  wsSLL_.release();
+  piv_.release();
+  perm_.release();
+  computed_ = true;
+}
+
+// inverts the matrices [m0, m1) of `B` whose dense input has been assembled in W (chunk-relative offsets)
+static void invertRange(BatchedInverse& B, int m0, int m1, double* W, DevBuf<int>& piv, DevBuf<int>& perm,
+                        DevBuf<int64_t>& relOff, int* info, cudaStream_t s, int64_t* launches) {
+  const int cnt = m1 - m0;
+  if (cnt <= 0) return;
+  int npMax = 0;
+  std::vector<int64_t> rel(cnt);
+  for (int m = m0; m < m1; ++m) {
+    npMax = std::max(npMax, B.hNp[m]);
+    rel[m - m0] = B.hMatOff[m] - B.hMatOff[m0];
+  }
+  if (npMax == 0) return;
+  relOff.upload(rel, s);
+  piv.alloc((size_t)cnt * npMax);
+  perm.alloc((size_t)cnt * npMax);
+  invertBatched(W, B.F.p + B.hMatOff[m0], relOff.p, B.n.p + m0, B.np.p + m0, cnt, npMax, piv.p, perm.p, info, s,
+                launches);
+  HY_CUDA(cudaStreamSynchronize(s));  // relOff is reused by the next chunk
+}
+
+void Engine::computeLevel(int l) {
+  Level& L = *levels_[l];
+  LevelSym& S = L.sym;
+  cudaStream_t s = stream_;
+  // (1) off-diagonal blocks: value gathers (MatrixBlock::Compute)
+  gatherValues(L.val.p, L.src12.p, L.v12.p, (int64_t)S.A12.col.size(), s, &launches_);
+  gatherValues(L.val.p, L.src21.p, L.v21.p, (int64_t)S.A21.col.size(), s, &launches_);
+  // (2) A11 blocks: dense fill + batched inversion, in chunks of subdomains (ComputeSubdomainSolvers)
+  {
+    const int64_t budget = (int64_t)1 << 29;  // doubles (4 GB) of inversion workspace
+    DevBuf<int64_t> relOff;
+    int sd0 = 0;
+    while (sd0 < S.nsd) {
+      int sd1 = sd0;
+      int64_t used = 0;
+      while (sd1 < S.nsd && sd1 - sd0 < 16384) {
+        int64_t need = S.a11Off[sd1 + 1] - S.a11Off[sd1];
+        if (sd1 > sd0 && used + need > budget) break;
+        used += need;
+        ++sd1;
+      }
+      if (work_.n < (size_t)used) work_.alloc((size_t)std::max<int64_t>(used, std::min<int64_t>(budget, S.a11Off[S.nsd])));
+      HY_CUDA(cudaMemsetAsync(work_.p, 0, used * sizeof(double), s));
+      const int64_t e0 = L.a11ListPtr[sd0], e1 = L.a11ListPtr[sd1];
+      scatterValues(L.val.p, L.a11Src.p + e0, L.a11Dst.p + e0, S.a11Off[sd0], work_.p, e1 - e0, s, &launches_);
+      invertRange(L.a11, sd0, sd1, work_.p, piv_, perm_, relOff, info_.p, s, &launches_);
+      for (int sd = sd0; sd < sd1; ++sd) stats_.flops_compute += 2.0 * std::pow((double)S.sdN[sd], 3);
+      sd0 = sd1;
+    }
+    checkInfo(info_, s, "subdomain solver (A11) of level " + std::to_string(l));
+  }
+  // (3) Schur complement
+  SchurArgs a{};
+  a.rowSd = L.rowSd.p;
+  a.rowInst = L.rowInst.p;
+  a.rowLinkPos = L.rowLinkPos.p;
+  a.sdSep = L.sdSep.p;
+  a.sdRowPtr = L.sdRowPtr.p;
+  a.sdM = L.sdM.p;
+  a.sdN = L.a11.n.p;
+  a.sdNp = L.a11.np.p;
+  a.a11Off = L.a11.matOff.p;
+  a.Ainv = L.a11.F.p;
+  a.val = L.val.p;
+  a.s21Ptr = L.s21Ptr.p;
+  a.s12Ptr = L.s12Ptr.p;
+  a.s22Ptr = L.s22Ptr.p;
+  a.s21Col = L.s21Col.p;
+  a.s12Row = L.s12Row.p;
+  a.s22Col = L.s22Col.p;
+  a.s21Src = L.s21Src.p;
+  a.s12Src = L.s12Src.p;
+  a.s22Src = L.s22Src.p;
+  a.sdInstPtr = L.sdInstPtr.p;
+  a.instLoc = L.instLoc.p;
+  a.instLen = L.instLen.p;
+  a.instUniq = L.instUniq.p;
+  a.instLink = L.instLink.p;
+  a.sdLinkPtr = L.sdLinkPtr.p;
+  a.lnkSd = L.lnkSd.p;
+  a.lnkSize = L.lnkSize.p;
+  a.lnkOff = L.lnkOff.p;
+  a.uniqStart = L.uniqStart.p;
+  a.uniqBlk = L.uniqBlk.p;
+  a.uniqBlkOff = L.uniqBlkOff.p;
+  a.wd = L.wd.p;
+  a.usign = L.usign.p;
+  a.redPtr = L.redPtr.p;
+  a.redCol = L.redCol.p;
+  a.blkNp = L.blk.np.p;
+  a.blkOff = L.blk.matOff.p;
+  a.wsOffC = L.wsOffC.p;
+  a.dLen = L.dLen;
+  a.info = info_.p;
+
+  if (L.exact) {
+    // Number of Levels = 0: S = A22 - sum_sd A21 A11^-1 A12, dense, solved directly
+    // (Preconditioner::Compute :485-500 -> CoarseSolver)
+    const int nS = (int)S.nS;
+    const int np = (nS + 7) & ~7;
+    std::vector<int> cn(1, nS), cnp(1, np);
+    std::vector<int64_t> off{0, (int64_t)np * np}, voff(1, 0);
+    coarse_.setup(cn, cnp, off, voff, s);
+    work_.alloc((size_t)np * np);
+    HY_CUDA(cudaMemsetAsync(work_.p, 0, (size_t)np * np * sizeof(double), s));
+    // A22 part: gather the values of the A22 block into a temporary and densify
+    DevBuf<double> v22;
+    v22.alloc(S.A22.col.size());
+    gatherValues(L.val.p, L.src22.p, v22.p, (int64_t)S.A22.col.size(), s, &launches_);
+    csrToDense(L.p22.p, L.c22.p, v22.p, work_.p, nS, np, s, &launches_);
+    schurDense(a, 0, S.sdRowPtr[S.nsd], work_.p, np, L.rowSmem, s, &launches_);
+    coarseFix_.clear();
+    ParameterList& prec = params_.sublist("Preconditioner");
+    for (int pos = 1; prec.isParameter("Fix GID " + std::to_string(pos)); ++pos) {
+      gidx g = prec.get("Fix GID " + std::to_string(pos), -1);
+      int row = -1;
+      for (int64_t p = 0; p < S.nS; ++p)
+        if (S.H.sepGid[p] == g) row = (int)p;
+      if (row < 0) throw Error(HYMLS_B200_ERR_ARG, "fix GID: " + std::to_string(g) + " not in matrix row map");
+      coarseFix_.push_back(row);
+      putDirichlet(work_.p, nS, np, row, s, &launches_);
+    }
+    DevBuf<int64_t> relOff;
+    invertRange(coarse_, 0, 1, work_.p, piv_, perm_, relOff, info_.p, s, &launches_);
+    checkInfo(info_, s, "exact Schur complement");
+    stats_.flops_compute += 2.0 * std::pow((double)nS, 3);
+    coarseN_ = nS;
+    coarseRhs_.alloc(nS);
+    v22.release();
+    return;
+  }
+
+  // transformed + dropped Schur complement: reduced matrix on the V-sums (next level) and separator blocks
+  Level* next = (l + 1 < (int)levels_.size()) ? levels_[l + 1].get() : nullptr;
+  DevBuf<double> redValOwn;
+  double* redVal;
+  if (next) {
+    redVal = next->val.p;
+  } else {
+    redValOwn.alloc(S.redCol.size());
+    redVal = redValOwn.p;
+  }
+  HY_CUDA(cudaMemsetAsync(redVal, 0, S.redCol.size() * sizeof(double), s));
+  DevBuf<double> blkW;
+  blkW.alloc((size_t)S.blkOff[S.nblk]);
+  HY_CUDA(cudaMemsetAsync(blkW.p, 0, blkW.bytes(), s));
+  wsC_.alloc((size_t)L.wsCLen);
+  wsSV_.alloc((size_t)L.wsCLen);
+  wsSLL_.alloc((size_t)L.wsSLLLen);
+  a.redVal = redVal;
+  a.blkW = blkW.p;
+  a.wsC = wsC_.p;
+  a.wsSV = wsSV_.p;
+  a.wsSLL = wsSLL_.p;
+  for (int pass = 1; pass <= 2; ++pass)
+    for (const Level::Chunk& c : L.chunks)
+      schurAssemble(a, c.sd0, c.sd1, c.R0, c.R1, c.lk0, c.lk1, pass, L.rowSmem, L.blkSmem, s, &launches_);
+  {
+    int h = 0;
+    HY_CUDA(cudaMemcpyAsync(&h, info_.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    HY_CUDA(cudaStreamSynchronize(s));
+    if (h == -7) throw Error(HYMLS_B200_ERR_UNSUPPORTED, "more than 32 groups in one linked separator set");
+  }
+  // separator blocks (SchurPreconditioner::Compute :284-291)
+  {
+    DevBuf<int64_t> relOff;
+    int b0 = 0;
+    while (b0 < S.nblk) {
+      int b1 = std::min(S.nblk, b0 + 16384);
+      invertRange(L.blk, b0, b1, blkW.p + S.blkOff[b0], piv_, perm_, relOff, info_.p, s, &launches_);
+      b0 = b1;
+    }
+    for (int b = 0; b < S.nblk; ++b) stats_.flops_compute += 2.0 * std::pow((double)S.blkN[b], 3);
+    checkInfo(info_, s, "separator block of level " + std::to_string(l));
+  }
+  // reduced Schur complement: drop (RelDropDiag, ComputeNextLevel :548), then next level or coarse solver
+  diagScratch_.alloc(S.nuniq);
+  dropByValue(redVal, L.redPtr.p, L.redCol.p, diagScratch_.p, S.nuniq, SMALL_ENTRY, s, &launches_);
+  if (!next) {
+    std::vector<gidx> rowGid(S.nuniq);
+    for (int u = 0; u < S.nuniq; ++u) rowGid[u] = S.H.sepGid[S.H.uniqPtr[u]];
+    computeCoarse(L.redPtr.p, L.redCol.p, redVal, S.nuniq, rowGid);
+  }
+  HY_CUDA(cudaStreamSynchronize(s));
+}
+
+// CoarseSolver::Compute (src/HYMLS_CoarseSolver.cpp:131-248): drop (RelFullDiag), Dirichlet rows for the
+// "Fix GID k" entries, dense inverse.
+void Engine::computeCoarse(const int64_t* ptr, const int* col, double* val, int n, const std::vector<gidx>& rowGid) {
+  cudaStream_t s = stream_;
+  const int np = (n + 7) & ~7;
+  std::vector<int> cn(1, n), cnp(1, np);
+  std::vector<int64_t> off{0, (int64_t)np * np}, voff(1, 0);
+  coarse_.setup(cn, cnp, off, voff, s);
+  coarseN_ = n;
+  coarseRhs_.alloc(n);
+  if (n == 0) return;
+  diagScratch_.alloc(n);
+  dropByValue(val, ptr, col, diagScratch_.p, n, SMALL_ENTRY, s, &launches_);
+  work_.alloc((size_t)np * np);
+  HY_CUDA(cudaMemsetAsync(work_.p, 0, (size_t)np * np * sizeof(double), s));
+  csrToDense(ptr, col, val, work_.p, n, np, s, &launches_);
+  coarseFix_.clear();
+  ParameterList& prec = params_.sublist("Preconditioner");
+  for (int pos = 1; prec.isParameter("Fix GID " + std::to_string(pos)); ++pos) {
+    gidx g = prec.get("Fix GID " + std::to_string(pos), -1);
+    int row = -1;
+    for (int r = 0; r < n; ++r)
+      if (rowGid[r] == g) row = r;
+    if (row < 0) throw Error(HYMLS_B200_ERR_ARG, "fix GID: " + std::to_string(g) + " not in matrix row map");
+    coarseFix_.push_back(row);
+    putDirichlet(work_.p, n, np, row, s, &launches_);
+  }
+  DevBuf<int64_t> relOff;
+  invertRange(coarse_, 0, 1, work_.p, piv_, perm_, relOff, info_.p, s, &launches_);
+  checkInfo(info_, s, "coarse solver");
+  stats_.flops_compute += 2.0 * std::pow((double)n, 3);
+}
+
+// ---------------------------------------------------------------------------------------------
+// ApplyInverse
+// ---------------------------------------------------------------------------------------------
+void Engine::applyLevel(int l, const double* B, double* X) {
+  Level& L = *levels_[l];
+  const LevelSym& S = L.sym;
+  cudaStream_t s = stream_;
+  // x1 = A11 \ b1   (b1 gathered from B on the fly)
+  GemvArgs g = L.a11.args();
+  g.xin = B;
+  g.gather = L.intRow.p;
+  g.out = L.x1.p;
+  g.scatter = nullptr;
+  g.mode = 0;
+  const bool timeIt = timeA11_ && l == 0;
+  if (timeIt) HY_CUDA(cudaEventRecord(evA_, s));
+  batchedGemv(g, L.a11.numItems, L.a11.npMax, s, &launches_);
+  if (timeIt) {
+    HY_CUDA(cudaEventRecord(evB_, s));
+    HY_CUDA(cudaEventSynchronize(evB_));
+    float ms = 0;
+    HY_CUDA(cudaEventElapsedTime(&ms, evA_, evB_));
+    a11Ms_ += ms;
+    a11Launches_++;
+  }
+  // schurRhs = b2 - A21 x1
+  spmv(L.p21.p, L.c21.p, L.v21.p, L.x1.p, L.rhsS.p, S.nS, 1.0, B, L.sepRow.p, -1.0, s, &launches_);
+  double* x2 = L.Y.p;
+  if (L.exact) {
+    // direct solve with the dense Schur complement (CoarseSolver::ApplyInverse :268-323)
+    for (int row : coarseFix_)
+      if (row > 0) setValue(L.rhsS.p, row, 0.0, s, &launches_);  // sic: 'lid > 0'
+    GemvArgs c = coarse_.args();
+    c.xin = L.rhsS.p;
+    c.out = x2;
+    c.mode = 0;
+    batchedGemv(c, coarse_.numItems, coarse_.npMax, s, &launches_);
+    scatterVec(x2, L.sepRow.p, X, S.nS, s, &launches_);
+  } else {
+    // B' = H rhs ; V-sum part goes to the next level (ApplyOT + UpdateVsumRhs)
+    householder(L.uniqStart.p, S.nuniq, L.what.p, L.rhsS.p, L.Z.p, L.vsRhs.p, nullptr, nullptr, nullptr, s,
+                &launches_);
+    // non-V-sums: block diagonal solves (ApplyBlockDiagonal)
+    GemvArgs b = L.blk.args();
+    b.xin = L.Z.p;
+    b.gather = L.blkRows.p;
+    b.out = L.Y.p;
+    b.scatter = L.blkRows.p;
+    b.mode = 0;
+    batchedGemv(b, L.blk.numItems, L.blk.npMax, s, &launches_);
+    // V-sums: next level or coarse solver
+    if (l + 1 < (int)levels_.size()) {
+      applyLevel(l + 1, L.vsRhs.p, L.vsSol.p);
+    } else {
+      for (int row : coarseFix_)
+        if (row > 0) setValue(L.vsRhs.p, row, 0.0, s, &launches_);
+      GemvArgs c = coarse_.args();
+      c.xin = L.vsRhs.p;
+      c.out = L.vsSol.p;
+      c.mode = 0;
+      batchedGemv(c, coarse_.numItems, coarse_.npMax, s, &launches_);
+    }
+    // x2 = H [Y(non-V-sum); vsumSol], exported to X
+    householder(L.uniqStart.p, S.nuniq, L.what.p, L.Y.p, L.Y.p, nullptr, L.vsSol.p, X, L.sepRow.p, s, &launches_);
+  }
+  // y1 = A12 x2 ;  X[interior] = x1 - A11 \ y1
+  spmv(L.p12.p, L.c12.p, L.v12.p, x2, L.y1.p, S.nI, 0.0, nullptr, nullptr, 1.0, s, &launches_);
+  g.xin = L.y1.p;
+  g.gather = nullptr;
+  g.xprev = L.x1.p;
+  g.out = X;
+  g.scatter = L.intRow.p;
+  g.mode = 1;
+  if (timeIt) HY_CUDA(cudaEventRecord(evA_, s));
+  batchedGemv(g, L.a11.numItems, L.a11.npMax, s, &launches_);
+  if (timeIt) {
+    HY_CUDA(cudaEventRecord(evB_, s));
+    HY_CUDA(cudaEventSynchronize(evB_));
+    float ms = 0;
+    HY_CUDA(cudaEventElapsedTime(&ms, evA_, evB_));
+    a11Ms_ += ms;
+    a11Launches_++;
+  }
+}
+
+void Engine::applyDevice(const double* dB, double* dX) {
+  applyLevel(0, dB, dX);
+  stats_.num_apply_inverse++;
+}
+
+void Engine::applyInverse(const double* B, int64_t ldb, double* X, int64_t ldx, int nvec, int where) {
+  needDevice();
+  if (!computed_) throw Error(HYMLS_B200_ERR_STATE, "The preconditioner has not yet been computed.");
+  if (!B || !X || nvec < 0 || ldb < n_ || ldx < n_) throw Error(HYMLS_B200_ERR_ARG, "apply_inverse: bad arguments");
+  for (int k = 0; k < nvec; ++k) {
+    const double* b = B + k * ldb;
+    double* x = X + k * ldx;
+    if (where == HYMLS_B200_DEVICE) {
+      applyDevice(b, x);
+    } else {
+      bufB_.alloc(n_);
+      bufX_.alloc(n_);
+      HY_CUDA(cudaMemcpyAsync(bufB_.p, b, n_ * sizeof(double), cudaMemcpyHostToDevice, stream_));
+      applyDevice(bufB_.p, bufX_.p);
+      HY_CUDA(cudaMemcpyAsync(x, bufX_.p, n_ * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+      HY_CUDA(cudaStreamSynchronize(stream_));
+    }
+  }
+}
+
+void Engine::applyMatrix(const double* x, double* y, int where) {
+  needDevice();
+  if (!haveMatrix_) throw Error(HYMLS_B200_ERR_STATE, "no matrix set");
+  Level& L0 = *levels_[0];
+  if (where == HYMLS_B200_DEVICE) {
+    spmv(L0.rowptr.p, L0.colidx.p, L0.val.p, x, y, n_, 0.0, nullptr, nullptr, 1.0, stream_, &launches_);
+  } else {
+    bufB_.alloc(n_);
+    bufX_.alloc(n_);
+    HY_CUDA(cudaMemcpyAsync(bufB_.p, x, n_ * sizeof(double), cudaMemcpyHostToDevice, stream_));
+    spmv(L0.rowptr.p, L0.colidx.p, L0.val.p, bufB_.p, bufX_.p, n_, 0.0, nullptr, nullptr, 1.0, stream_, &launches_);
+    HY_CUDA(cudaMemcpyAsync(y, bufX_.p, n_ * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+    HY_CUDA(cudaStreamSynchronize(stream_));
+  }
+}
+
+void Engine::timeApply(int reps, double* msApply, double* msA11) {
+  needDevice();
+  if (!computed_) throw Error(HYMLS_B200_ERR_STATE, "The preconditioner has not yet been computed.");
+  bufB_.alloc(n_);
+  bufX_.alloc(n_);
+  std::vector<double> h(n_);
+  std::mt19937_64 rng(7);
+  for (auto& v : h) v = (double)(rng() >> 11) * (1.0 / 9007199254740992.0) * 2.0 - 1.0;
+  HY_CUDA(cudaMemcpyAsync(bufB_.p, h.data(), n_ * sizeof(double), cudaMemcpyHostToDevice, stream_));
+  for (int i = 0; i < 3; ++i) applyDevice(bufB_.p, bufX_.p);
+  HY_CUDA(cudaStreamSynchronize(stream_));
+  HY_CUDA(cudaEventRecord(ev0_, stream_));
+  for (int i = 0; i < reps; ++i) applyDevice(bufB_.p, bufX_.p);
+  HY_CUDA(cudaEventRecord(ev1_, stream_));
+  HY_CUDA(cudaStreamSynchronize(stream_));
+  float ms = 0;
+  HY_CUDA(cudaEventElapsedTime(&ms, ev0_, ev1_));
+  if (msApply) *msApply = ms / reps;
+  // second loop with per-launch events around the A11 kernel (serialises the stream: not used for msApply)
+  timeA11_ = true;
+  a11Ms_ = 0;
+  a11Launches_ = 0;
+  for (int i = 0; i < reps; ++i) applyDevice(bufB_.p, bufX_.p);
+  HY_CUDA(cudaStreamSynchronize(stream_));
+  timeA11_ = false;
+  if (msA11) *msA11 = a11Launches_ ? a11Ms_ / a11Launches_ : 0.0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Krylov driver (BaseSolver::ApplyInverse -> Belos BlockGmresSolMgr / BlockCGSolMgr, block size 1)
+// ---------------------------------------------------------------------------------------------
+static double hostScalar(const double* d, cudaStream_t s) {
+  double v;
+  HY_CUDA(cudaMemcpyAsync(&v, d, sizeof(double), cudaMemcpyDeviceToHost, s));
+  HY_CUDA(cudaStreamSynchronize(s));
+  return v;
+}
+
+void Engine::solve(const double* b, double* x, int where, uint64_t seed, hymls_b200_solve_info* info, double* hist,
+                   int histCap) {
+  needDevice();
+  if (!computed_) throw Error(HYMLS_B200_ERR_STATE, "The preconditioner has not yet been computed.");
+  ParameterList& sol = params_.sublist("Solver");
+  ParameterList& it = sol.sublist("Iterative Solver");
+  const std::string method = sol.get("Krylov Method", "GMRES");
+  const std::string side = sol.get("Left or Right Preconditioning", "Right");
+  const std::string startVec = sol.get("Initial Vector", "Random");
+  const int maxIters = it.get("Maximum Iterations", 1000);
+  const double tol = it.get("Convergence Tolerance", 1e-8);
+  int numBlocks = it.get("Num Blocks", 300);
+  const int maxRestarts = it.get("Maximum Restarts", 20);
+  const bool explicitTest = it.get("Explicit Residual Test", false);
+  const std::string impScaling = it.get("Implicit Residual Scaling", "Norm of Preconditioned Initial Residual");
+  const std::string expScaling = it.get("Explicit Residual Scaling", "Norm of Initial Residual");
+  if (sol.get("Use Bordering", false) || sol.get("Use Deflation", false))
+    throw Error(HYMLS_B200_ERR_UNSUPPORTED, "bordered / deflated solvers are not implemented yet");
+  const int64_t n = n_;
+  cudaStream_t s = stream_;
+  Level& L0 = *levels_[0];
+  numBlocks = std::max(1, std::min(numBlocks, maxIters));
+  const int m = numBlocks;
+
+  kX_.alloc(n);
+  kB_.alloc(n);
+  kR_.alloc(n);
+  kW_.alloc(n);
+  kZ_.alloc(n);
+  kH_.alloc(2 * m + 8);
+  kPartial_.alloc((size_t)(m + 2) * multiDotBlocks());
+  const auto kind = where == HYMLS_B200_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  HY_CUDA(cudaMemcpyAsync(kB_.p, b, n * sizeof(double), kind, s));
+  if (startVec == "Random") {
+    // MatrixUtils::Random (src/HYMLS_MatrixUtils.cpp:961-1007): uniform in (-1,1); the reference's
+    // Epetra_Util LCG stream is replaced by a documented 64-bit Mersenne Twister with `seed`.
+    std::vector<double> h(n);
+    std::mt19937_64 rng(seed);
+    for (auto& v : h) v = (double)(rng() >> 11) * (1.0 / 9007199254740992.0) * 2.0 - 1.0;
+    HY_CUDA(cudaMemcpyAsync(kX_.p, h.data(), n * sizeof(double), cudaMemcpyHostToDevice, s));
+    HY_CUDA(cudaStreamSynchronize(s));
+  } else if (startVec == "Zero") {
+    HY_CUDA(cudaMemsetAsync(kX_.p, 0, n * sizeof(double), s));
+  } else {
+    HY_CUDA(cudaMemcpyAsync(kX_.p, x, n * sizeof(double), kind, s));
+  }
+  HY_CUDA(cudaEventRecord(ev0_, s));
+  auto A = [&](const double* in, double* out) {
+    spmv(L0.rowptr.p, L0.colidx.p, L0.val.p, in, out, n, 0.0, nullptr, nullptr, 1.0, s, &launches_);
+  };
+  auto dot = [&](const double* u, const double* v) {
+    multiDot(u, n, 1, v, n, kPartial_.p, kH_.p + 2 * m + 4, 0, s, &launches_);
+    return hostScalar(kH_.p + 2 * m + 4, s);
+  };
+  std::vector<double> history;
+  int iters = 0;
+  bool converged = false;
+  double lastRel = 0;
+  const bool left = side == "Left", right = side == "Right";
+  const double bnorm = std::sqrt(dot(kB_.p, kB_.p));
+
+  if (method == "CG") {
+    // r = b - A x ; z = M r ; p = z
+    DevBuf<double>& P = kW_;
+    DevBuf<double> Ap;
+    Ap.alloc(n);
+    A(kX_.p, kR_.p);
+    axpby(1.0, kB_.p, -1.0, kR_.p, n, s, &launches_);
+    const double r0 = std::sqrt(dot(kR_.p, kR_.p));
+    history.push_back(1.0);
+    if (r0 == 0) {
+      converged = true;
+    } else {
+      applyDevice(kR_.p, kZ_.p);
+      axpby(1.0, kZ_.p, 0.0, P.p, n, s, &launches_);
+      double rz = dot(kR_.p, kZ_.p);
+      while (iters < maxIters) {
+        A(P.p, Ap.p);
+        const double alpha = rz / dot(P.p, Ap.p);
+        axpby(alpha, P.p, 1.0, kX_.p, n, s, &launches_);
+        axpby(-alpha, Ap.p, 1.0, kR_.p, n, s, &launches_);
+        ++iters;
+        lastRel = std::sqrt(dot(kR_.p, kR_.p)) / r0;
+        history.push_back(lastRel);
+        if (lastRel <= tol) {
+          converged = true;
+          break;
+        }
+        applyDevice(kR_.p, kZ_.p);
+        const double rzNew = dot(kR_.p, kZ_.p);
+        axpby(1.0, kZ_.p, rzNew / rz, P.p, n, s, &launches_);
+        rz = rzNew;
+      }
+    }
+  } else if (method == "GMRES") {
+    kV_.alloc((size_t)(m + 1) * n);
+    std::vector<double> H((size_t)(m + 1) * m, 0.0), cs(m), sn(m), g(m + 1), hbuf(2 * m + 8);
+    double* dH1 = kH_.p;              // first Gram-Schmidt pass  (m+1)
+    double* dH2 = kH_.p + (m + 1);    // second pass              (m+1)
+    double* dNrm = kH_.p + 2 * m + 2; // ||w||^2
+    // initial residual
+    A(kX_.p, kR_.p);
+    axpby(1.0, kB_.p, -1.0, kR_.p, n, s, &launches_);  // r = b - A x
+    const double r0norm = std::sqrt(dot(kR_.p, kR_.p));
+    double* r = kR_.p;
+    if (left) {
+      applyDevice(kR_.p, kZ_.p);
+      r = kZ_.p;
+    }
+    const double pr0norm = left ? std::sqrt(dot(r, r)) : r0norm;
+    auto scaleOf = [&](const std::string& k) {
+      double v = 1.0;
+      if (k == "Norm of RHS") v = bnorm;
+      else if (k == "Norm of Initial Residual") v = r0norm;
+      else if (k == "Norm of Preconditioned Initial Residual") v = pr0norm;
+      else if (k == "None") v = 1.0;
+      else throw Error(HYMLS_B200_ERR_ARG, "unknown residual scaling '" + k + "'");
+      return v == 0.0 ? 1.0 : v;
+    };
+    const double impScale = scaleOf(impScaling), expScale = scaleOf(expScaling);
+    double beta = pr0norm;
+    double trueRes = r0norm;
+    for (int restart = 0; restart <= maxRestarts; ++restart) {
+      if (restart == 0) history.push_back(beta / impScale);
+      lastRel = beta / impScale;
+      if (lastRel <= tol && !explicitTest) {
+        converged = true;
+        break;
+      }
+      axpby(1.0 / beta, r, 0.0, kV_.p, n, s, &launches_);  // v0 = r / beta
+      std::fill(g.begin(), g.end(), 0.0);
+      g[0] = beta;
+      int kDone = 0;
+      for (int k = 0; k < m && iters < maxIters; ++k) {
+        double* vk = kV_.p + (size_t)k * n;
+        double* w = kV_.p + (size_t)(k + 1) * n;
+        if (right) {
+          applyDevice(vk, kZ_.p);
+          A(kZ_.p, w);
+        } else if (left) {
+          A(vk, kZ_.p);
+          applyDevice(kZ_.p, w);
+        } else {
+          A(vk, w);
+        }
+        // two passes of classical Gram-Schmidt (Belos ICGS/DGKS), fused multi-dot + multi-axpy
+        multiDot(kV_.p, n, k + 1, w, n, kPartial_.p, dH1, 0, s, &launches_);
+        multiAxpy(kV_.p, n, k + 1, dH1, w, n, -1.0, s, &launches_);
+        multiDot(kV_.p, n, k + 1, w, n, kPartial_.p, dH2, 0, s, &launches_);
+        multiAxpy(kV_.p, n, k + 1, dH2, w, n, -1.0, s, &launches_);
+        multiDot(w, n, 1, w, n, kPartial_.p, dNrm, 0, s, &launches_);
+        scaleByInvNorm(w, dNrm, w, n, s, &launches_);
+        HY_CUDA(cudaMemcpyAsync(hbuf.data(), kH_.p, (2 * m + 3) * sizeof(double), cudaMemcpyDeviceToHost, s));
+        HY_CUDA(cudaStreamSynchronize(s));
+        for (int i = 0; i <= k; ++i) H[(size_t)i * m + k] = hbuf[i] + hbuf[m + 1 + i];
+        const double hn = std::sqrt(hbuf[2 * m + 2]);
+        H[(size_t)(k + 1) * m + k] = hn;
+        for (int i = 0; i < k; ++i) {
+          const double t = cs[i] * H[(size_t)i * m + k] + sn[i] * H[(size_t)(i + 1) * m + k];
+          H[(size_t)(i + 1) * m + k] = -sn[i] * H[(size_t)i * m + k] + cs[i] * H[(size_t)(i + 1) * m + k];
+          H[(size_t)i * m + k] = t;
+        }
+        const double d = std::hypot(H[(size_t)k * m + k], H[(size_t)(k + 1) * m + k]);
+        cs[k] = H[(size_t)k * m + k] / d;
+        sn[k] = H[(size_t)(k + 1) * m + k] / d;
+        H[(size_t)k * m + k] = d;
+        H[(size_t)(k + 1) * m + k] = 0.0;
+        g[k + 1] = -sn[k] * g[k];
+        g[k] = cs[k] * g[k];
+        ++iters;
+        kDone = k + 1;
+        lastRel = std::fabs(g[k + 1]) / impScale;
+        history.push_back(lastRel);
+        if (lastRel <= tol) break;
+      }
+      if (kDone > 0) {
+        // y = triu(H)^-1 g ; x += [M^-1] V y
+        std::vector<double> y(kDone);
+        for (int i = kDone - 1; i >= 0; --i) {
+          double t = g[i];
+          for (int j = i + 1; j < kDone; ++j) t -= H[(size_t)i * m + j] * y[j];
+          y[i] = t / H[(size_t)i * m + i];
+        }
+        HY_CUDA(cudaMemcpyAsync(dH1, y.data(), kDone * sizeof(double), cudaMemcpyHostToDevice, s));
+        HY_CUDA(cudaMemsetAsync(kZ_.p, 0, n * sizeof(double), s));
+        multiAxpy(kV_.p, n, kDone, dH1, kZ_.p, n, 1.0, s, &launches_);
+        HY_CUDA(cudaStreamSynchronize(s));
+        if (right) {
+          applyDevice(kZ_.p, kW_.p);
+          axpby(1.0, kW_.p, 1.0, kX_.p, n, s, &launches_);
+        } else {
+          axpby(1.0, kZ_.p, 1.0, kX_.p, n, s, &launches_);
+        }
+      }
+      A(kX_.p, kR_.p);
+      axpby(1.0, kB_.p, -1.0, kR_.p, n, s, &launches_);
+      trueRes = std::sqrt(dot(kR_.p, kR_.p));
+      r = kR_.p;
+      beta = trueRes;
+      if (left) {
+        applyDevice(kR_.p, kZ_.p);
+        r = kZ_.p;
+        beta = std::sqrt(dot(r, r));
+      }
+      if (history.back() <= tol) {
+        if (!explicitTest || trueRes / expScale <= tol) {
+          converged = true;
+          break;
+        }
+      }
+      if (iters >= maxIters) break;
+    }
+  } else {
+    throw Error(HYMLS_B200_ERR_ARG, "Krylov Method '" + method + "' not supported (GMRES, CG)");
+  }
+  HY_CUDA(cudaEventRecord(ev1_, s));
+  HY_CUDA(cudaStreamSynchronize(s));
+  float ms = 0;
+  HY_CUDA(cudaEventElapsedTime(&ms, ev0_, ev1_));
+  // explicit residual
+  A(kX_.p, kR_.p);
+  axpby(1.0, kB_.p, -1.0, kR_.p, n, s, &launches_);
+  const double res = std::sqrt(dot(kR_.p, kR_.p));
+  const auto back = where == HYMLS_B200_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  HY_CUDA(cudaMemcpyAsync(x, kX_.p, n * sizeof(double), back, s));
+  HY_CUDA(cudaStreamSynchronize(s));
+  if (info) {
+    info->iterations = iters;
+    info->converged = converged ? 1 : 0;
+    info->rel_residual = lastRel;
+    info->explicit_rel_residual = bnorm > 0 ? res / bnorm : res;
+    info->solve_seconds = ms * 1e-3;
+    info->history_len = (int)history.size();
+  }
+  if (hist)
+    for (int i = 0; i < (int)history.size() && i < histCap; ++i) hist[i] = history[i];
+}
+
+void Engine::getStats(hymls_b200_stats* st) {
+  *st = stats_;
+  st->kernel_launches = launches_;
+  if (!levels_.empty() && initialized_) {
+    const LevelSym& S = levels_[0]->sym;
+    st->n = S.n;
+    st->num_interior = S.nI;
+    st->num_separator = S.nS;
+    st->num_vsum = S.nuniq;
+    st->num_subdomains = S.nsd;
+    st->num_blocks = S.nblk;
+    st->sum_nsd_sq = S.sumNsq;
+    st->bytes_a11_level0 = 16.0 * S.sumNsq;
+    // algorithmic bytes of one ApplyInverse, summed over the levels
+    double bytes = 0;
+    for (auto& lp : levels_) {
+      const LevelSym& T = lp->sym;
+      double sb = 0;
+      for (int b = 0; b < T.nblk; ++b) sb += 8.0 * (double)T.blkN[b] * T.blkN[b];
+      bytes += 16.0 * T.sumNsq + 12.0 * (double)(T.A12.nnz() + T.A21.nnz()) + 4.0 * (double)(T.nI + T.nS + 2) + sb +
+               2.0 * 12.0 * (double)T.nS * 2.0 + 8.0 * (10.0 * T.nI + 14.0 * T.nS);
+    }
+    bytes += 8.0 * (double)coarseN_ * coarseN_;
+    st->bytes_apply = bytes;
+  }
+}
+
+}  // namespace hymls

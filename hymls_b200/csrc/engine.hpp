@@ -1,0 +1,125 @@
+// Device-side engine: numeric Compute / ApplyInverse of all levels and the Krylov driver.
+#pragma once
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "device.cuh"
+#include "kernels.hpp"
+#include "symbolic.hpp"
+
+namespace hymls {
+
+struct BatchedInverse {  // a set of dense inverses + the GEMV work list over them
+  DevBuf<double> F;
+  DevBuf<int> n, np, itemMat, itemRow0;
+  DevBuf<int64_t> matOff, vecOff;
+  std::vector<int> hN, hNp;
+  std::vector<int64_t> hMatOff, hVecOff;
+  int count = 0, numItems = 0, npMax = 0;
+  void setup(const std::vector<int>& n_, const std::vector<int>& np_, const std::vector<int64_t>& matOff_,
+             const std::vector<int64_t>& vecOff_, cudaStream_t s);
+  GemvArgs args() const;
+};
+
+struct Level {
+  LevelSym sym;
+  bool exact = false;  // Number of Levels == 0: dense Schur complement instead of transform + drop
+  // matrix of this level
+  DevBuf<int64_t> rowptr;
+  DevBuf<int> colidx;
+  DevBuf<double> val;
+  // orderings
+  DevBuf<int> intRow, sepRow;
+  // A11
+  BatchedInverse a11;
+  DevBuf<int64_t> a11Src, a11Dst;
+  std::vector<int64_t> a11ListPtr;  // per sd: range of the scatter list
+  // off-diagonal blocks
+  DevBuf<int64_t> p12, p21, src12, src21, p22, src22;
+  DevBuf<int> c12, c21, c22;
+  DevBuf<double> v12, v21;
+  // Schur assembly index data
+  DevBuf<int> rowSd, rowInst, rowLinkPos, sdSep, sdM;
+  DevBuf<int64_t> sdRowPtr, s21Ptr, s12Ptr, s22Ptr, s21Src, s12Src, s22Src;
+  DevBuf<int> s21Col, s12Row, s22Col;
+  DevBuf<int64_t> sdInstPtr, sdLinkPtr, lnkOff, wsOffC;
+  DevBuf<int> instLoc, instLen, instUniq, instLink, lnkSd, lnkSize;
+  DevBuf<int> uniqStart, uniqBlk, uniqBlkOff;
+  DevBuf<double> what, wd, usign;
+  DevBuf<int64_t> redPtr;
+  DevBuf<int> redCol;
+  // chunking of the assembly workspace
+  struct Chunk { int sd0, sd1; int64_t R0, R1, lk0, lk1; };
+  std::vector<Chunk> chunks;
+  int64_t wsCLen = 0, wsSLLLen = 0;
+  size_t rowSmem = 0, blkSmem = 0;
+  int dLen = 0;
+  // separator blocks
+  BatchedInverse blk;
+  DevBuf<int> blkRows;
+  // work vectors
+  DevBuf<double> x1, y1, rhsS, Z, Y, vsRhs, vsSol;
+};
+
+class Engine {
+ public:
+  explicit Engine(const std::string& xml);
+  ~Engine();
+  void setStream(cudaStream_t s) { stream_ = s; }
+  void setMatrix(int64_t n, const int64_t* rowptr, const int32_t* colidx, const double* values, int where);
+  void setTestVector(const double* tv);
+  void initialize();
+  void compute();
+  void applyInverse(const double* B, int64_t ldb, double* X, int64_t ldx, int nvec, int where);
+  void applyMatrix(const double* x, double* y, int where);
+  void solve(const double* b, double* x, int where, uint64_t seed, hymls_b200_solve_info* info, double* hist,
+             int histCap);
+  void timeApply(int reps, double* msApply, double* msA11);
+  void getStats(hymls_b200_stats* st);
+
+  int numLevels() const { return (int)levels_.size(); }
+  const LevelSym& sym(int l) const { return levels_.at(l)->sym; }
+  ParameterList& params() { return params_; }
+  bool initialized() const { return initialized_; }
+
+ private:
+  void applyLevel(int l, const double* B, double* X);  // device pointers
+  void computeLevel(int l);
+  void computeCoarse(const int64_t* ptr, const int* col, double* val, int n, const std::vector<gidx>& rowGid);
+  void uploadLevel(Level& L);
+  void applyDevice(const double* dB, double* dX);
+
+  ParameterList params_;
+  cudaStream_t stream_ = 0;
+  int maxLevel_ = 1;
+  int64_t n_ = 0;
+  std::vector<int64_t> hRowptr_;
+  std::vector<int> hColidx_;
+  std::vector<double> hTestVector_;
+  bool haveMatrix_ = false, initialized_ = false, computed_ = false, deviceOk_ = false;
+  void needDevice() const;
+  std::vector<std::unique_ptr<Level>> levels_;
+  // coarse solver (dense inverse)
+  BatchedInverse coarse_;
+  std::vector<int> coarseFix_;  // rows with a Dirichlet condition
+  int coarseN_ = 0;
+  DevBuf<double> coarseRhs_;
+  // scratch
+  DevBuf<double> work_;      // inversion workspace
+  DevBuf<int> piv_, perm_, info_;
+  DevBuf<double> wsC_, wsSV_, wsSLL_, diagScratch_;
+  DevBuf<double> bufB_, bufX_;  // staging for host vectors
+  // Krylov workspace
+  DevBuf<double> kV_, kW_, kZ_, kH_, kPartial_, kX_, kB_, kR_;
+  int kCap_ = 0;
+  // statistics
+  hymls_b200_stats stats_{};
+  int64_t launches_ = 0;
+  cudaEvent_t ev0_ = nullptr, ev1_ = nullptr, evA_ = nullptr, evB_ = nullptr;
+  bool timeA11_ = false;
+  double a11Ms_ = 0;
+  int a11Launches_ = 0;
+};
+
+}  // namespace hymls

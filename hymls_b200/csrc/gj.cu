@@ -1,0 +1,347 @@
+// Batched FP64 dense inversion for the per-subdomain interior blocks A11(sd) and the separator blocks.
+//
+// Replaces Ifpack_DenseContainer / Ifpack_SparseContainer<KLU>::Compute of the reference
+// (src/HYMLS_MatrixBlock.cpp:210-292, src/HYMLS_SchurPreconditioner.cpp:284-291): the factor that
+// ApplyInverse streams is the explicit inverse (8 n^2 bytes, the same as L+U), obtained by a blocked
+// Gauss-Jordan elimination with partial (row) pivoting:
+//   for every panel K of NB columns
+//     (P) LU with partial pivoting of the active panel rows, then the Gauss-Jordan transform block
+//         G' (n x NB):  G'[K] = inv(M[K,K]),  G'[R] = -M[R,K] inv(M[K,K])           (k_gj_panel)
+//     (U) row swaps + trailing update of ALL other columns  M[:,J] += (G' - E_K) M[K,J]
+//         as an FP64 tensor-core GEMM (DMMA m8n8k4), one CTA per column strip          (k_gj_update)
+//   finally the column permutation that undoes the row swaps, written to the final storage (k_gj_gather).
+// 2 n^3 flops per matrix, all but O(n^2 NB) of them in the DMMA update.
+#include <cuda_runtime.h>
+
+#include "device.cuh"
+#include "kernels.hpp"
+
+namespace hymls {
+
+static constexpr int GJ_NB = 32;       // panel width
+static constexpr int GJ_PANEL_T = 512; // threads of the panel kernel
+static constexpr int GJ_TJ = 128;      // column strip of the update kernel
+static constexpr int GJ_TM = 64;       // row tile of the update kernel
+static constexpr int GJ_UPD_T = 256;   // 8 warps: 2 (rows) x 4 (cols), each 4x4 DMMA tiles of 8x8
+
+// ---------------------------------------------------------------------------------------------
+// identity in the padding rows/cols n..np-1 so the padded matrix stays invertible
+// ---------------------------------------------------------------------------------------------
+__global__ void k_pad_identity(double* __restrict__ W, const int64_t* __restrict__ off,
+                               const int* __restrict__ nArr, const int* __restrict__ npArr, int count) {
+  int mat = blockIdx.x;
+  if (mat >= count) return;
+  int n = nArr[mat], np = npArr[mat];
+  double* M = W + off[mat];
+  for (int i = n + threadIdx.x; i < np; i += blockDim.x) M[(int64_t)i * np + i] = 1.0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// panel kernel: one CTA per matrix
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(GJ_PANEL_T)
+k_gj_panel(double* __restrict__ W, const int64_t* __restrict__ off, const int* __restrict__ npArr,
+           int* __restrict__ pivAll, int npMax, int k0, int* __restrict__ info) {
+  const int mat = blockIdx.x;
+  const int np = npArr[mat];
+  if (k0 >= np) return;
+  const int nb = min(GJ_NB, np - k0);
+  double* M = W + off[mat];
+  int* piv = pivAll + (int64_t)mat * npMax;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  constexpr int NW = GJ_PANEL_T / 32;
+
+  __shared__ double sU[GJ_NB];
+  __shared__ double sKK[GJ_NB][GJ_NB + 1];
+  __shared__ double sLinv[GJ_NB][GJ_NB + 1];
+  __shared__ double sDinv[GJ_NB][GJ_NB + 1];
+  __shared__ double sRedV[NW];
+  __shared__ int sRedI[NW];
+  __shared__ int sPiv;
+  __shared__ double sPivVal;
+
+  // ---- (A) LU with partial pivoting on rows [k0, np) x cols [k0, k0+nb) ----
+  for (int j = 0; j < nb; ++j) {
+    const int c = k0 + j;
+    double bestV = -1.0;
+    int bestR = 0x7fffffff;
+    for (int r = c + tid; r < np; r += GJ_PANEL_T) {
+      double v = fabs(M[(int64_t)r * np + c]);
+      if (v > bestV) {  // rows visited in increasing order per thread -> keeps the smallest row on ties
+        bestV = v;
+        bestR = r;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      double ov = __shfl_down_sync(0xffffffffu, bestV, o);
+      int orow = __shfl_down_sync(0xffffffffu, bestR, o);
+      if (ov > bestV || (ov == bestV && orow < bestR)) {
+        bestV = ov;
+        bestR = orow;
+      }
+    }
+    if (lane == 0) {
+      sRedV[wid] = bestV;
+      sRedI[wid] = bestR;
+    }
+    __syncthreads();
+    if (wid == 0) {
+      bestV = lane < NW ? sRedV[lane] : -1.0;
+      bestR = lane < NW ? sRedI[lane] : 0x7fffffff;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        double ov = __shfl_down_sync(0xffffffffu, bestV, o);
+        int orow = __shfl_down_sync(0xffffffffu, bestR, o);
+        if (ov > bestV || (ov == bestV && orow < bestR)) {
+          bestV = ov;
+          bestR = orow;
+        }
+      }
+      if (lane == 0) {
+        if (bestR == 0x7fffffff) bestR = c;  // all-NaN column
+        sPiv = bestR;
+        piv[c] = bestR;
+        if (!(bestV > 0.0)) atomicExch(info, mat + 1);  // exactly singular (or NaN) pivot column
+      }
+    }
+    __syncthreads();
+    const int p = sPiv;
+    // swap rows c and p inside the panel; publish the pivot row
+    if (tid < nb) {
+      double a = M[(int64_t)c * np + k0 + tid];
+      double b = M[(int64_t)p * np + k0 + tid];
+      M[(int64_t)c * np + k0 + tid] = b;
+      M[(int64_t)p * np + k0 + tid] = a;
+      sU[tid] = b;
+      if (tid == j) sPivVal = b;
+    }
+    __syncthreads();
+    const double rp = 1.0 / sPivVal;
+    for (int r = c + 1 + tid; r < np; r += GJ_PANEL_T) {
+      double* row = M + (int64_t)r * np + k0;
+      double l = row[j] * rp;
+      row[j] = l;
+      for (int q = j + 1; q < nb; ++q) row[q] -= l * sU[q];
+    }
+    __syncthreads();
+  }
+  // ---- (B) Linv = inv(L_KK) (unit lower), Dinv = inv(U) * Linv ----
+  for (int e = tid; e < nb * nb; e += GJ_PANEL_T) sKK[e / nb][e % nb] = M[(int64_t)(k0 + e / nb) * np + k0 + e % nb];
+  __syncthreads();
+  if (tid < nb) {
+    const int t = tid;  // column t of the inverses
+    for (int i = 0; i < nb; ++i) {
+      double x = (i == t) ? 1.0 : 0.0;
+      for (int k = t; k < i; ++k) x -= sKK[i][k] * sLinv[k][t];
+      sLinv[i][t] = (i < t) ? 0.0 : x;
+    }
+    for (int i = nb - 1; i >= 0; --i) {
+      double x = sLinv[i][t];
+      for (int k = i + 1; k < nb; ++k) x -= sKK[i][k] * sDinv[k][t];
+      sDinv[i][t] = x / sKK[i][i];
+    }
+  }
+  __syncthreads();
+  // ---- (C) the Gauss-Jordan transform block G' overwrites the panel columns ----
+  for (int r = tid; r < np; r += GJ_PANEL_T) {
+    double* row = M + (int64_t)r * np + k0;
+    if (r >= k0 && r < k0 + nb) {
+      for (int q = 0; q < nb; ++q) row[q] = sDinv[r - k0][q];
+      continue;
+    }
+    const bool above = r < k0;
+    double a[GJ_NB];
+#pragma unroll
+    for (int q = 0; q < GJ_NB; ++q) a[q] = q < nb ? row[q] : 0.0;
+    for (int q = 0; q < nb; ++q) {
+      double s = 0.0;
+      if (above) {
+#pragma unroll
+        for (int k = 0; k < GJ_NB; ++k) s += (k < nb) ? a[k] * sDinv[k][q] : 0.0;
+      } else {
+#pragma unroll
+        for (int k = 0; k < GJ_NB; ++k) s += (k < nb) ? a[k] * sLinv[k][q] : 0.0;
+      }
+      row[q] = -s;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// DMMA m8n8k4 (FP64 tensor core): D(8x8) += A(8x4, row) * B(4x8, col)
+//   a : A[lane/4][lane%4]        b : B[lane%4][lane/4]        c0,c1 : C[lane/4][2*(lane%4) + {0,1}]
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// update kernel: grid (column strips, matrices)
+__global__ void __launch_bounds__(GJ_UPD_T)
+k_gj_update(double* __restrict__ W, const int64_t* __restrict__ off, const int* __restrict__ npArr,
+            const int* __restrict__ pivAll, int npMax, int k0) {
+  const int mat = blockIdx.y;
+  const int np = npArr[mat];
+  if (k0 >= np) return;
+  const int j0 = blockIdx.x * GJ_TJ;
+  if (j0 >= np) return;
+  const int nb = min(GJ_NB, np - k0);
+  double* M = W + off[mat];
+  const int* piv = pivAll + (int64_t)mat * npMax;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int jw = min(GJ_TJ, np - j0);  // np is a multiple of 8, so jw is too
+
+  constexpr int SB = GJ_TJ + 4;  // stride = 4 mod 16 doubles -> conflict-free fragment loads
+  constexpr int SA = GJ_NB + 4;
+  extern __shared__ double gjSmem[];
+  double* sB = gjSmem;                // GJ_NB x SB
+  double* sA = gjSmem + GJ_NB * SB;   // GJ_TM x SA
+
+  // (1) row swaps of this strip (each thread owns one column, so the sequence needs no barrier)
+  if (tid < jw) {
+    const int col = j0 + tid;
+    if (col < k0 || col >= k0 + nb) {
+      for (int j = 0; j < nb; ++j) {
+        const int c = k0 + j, p = piv[c];
+        if (p != c) {
+          double a = M[(int64_t)c * np + col];
+          double b = M[(int64_t)p * np + col];
+          M[(int64_t)c * np + col] = b;
+          M[(int64_t)p * np + col] = a;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // (2) B = old M[K, strip]  (zero-padded to GJ_NB x GJ_TJ)
+  for (int e = tid; e < GJ_NB * GJ_TJ; e += GJ_UPD_T) {
+    const int k = e / GJ_TJ, c = e % GJ_TJ;
+    sB[k * SB + c] = (k < nb && c < jw) ? M[(int64_t)(k0 + k) * np + j0 + c] : 0.0;
+  }
+  __syncthreads();
+  // warp layout: 2 x 4 warps, each 4 x 4 tiles of 8 x 8 -> CTA tile 64 x 128
+  const int wr = wid >> 2, wc = wid & 3;
+  const int fr = lane >> 2, fk = lane & 3;
+
+  for (int r0 = 0; r0 < np; r0 += GJ_TM) {
+    // (3a) stage G'[r0 : r0+64, K] in shared memory
+    for (int e = tid; e < GJ_TM * GJ_NB; e += GJ_UPD_T) {
+      const int r = e / GJ_NB, k = e % GJ_NB;
+      sA[r * SA + k] = (r0 + r < np && k < nb) ? M[(int64_t)(r0 + r) * np + k0 + k] : 0.0;
+    }
+    __syncthreads();
+    double acc[4][4][2];
+#pragma unroll
+    for (int ti = 0; ti < 4; ++ti) {
+      const int row = r0 + (wr * 4 + ti) * 8 + fr;
+      const bool inK = (row >= k0 && row < k0 + nb);  // rows of the panel are replaced, not accumulated
+#pragma unroll
+      for (int tj = 0; tj < 4; ++tj) {
+        const int col = j0 + (wc * 4 + tj) * 8 + 2 * fk;
+        const bool ok = row < np && col < j0 + jw && !inK;
+        acc[ti][tj][0] = ok ? M[(int64_t)row * np + col] : 0.0;
+        acc[ti][tj][1] = ok ? M[(int64_t)row * np + col + 1] : 0.0;
+      }
+    }
+#pragma unroll
+    for (int kk = 0; kk < GJ_NB / 4; ++kk) {
+      double a[4], b[4];
+#pragma unroll
+      for (int ti = 0; ti < 4; ++ti) a[ti] = sA[((wr * 4 + ti) * 8 + fr) * SA + kk * 4 + fk];
+#pragma unroll
+      for (int tj = 0; tj < 4; ++tj) b[tj] = sB[(kk * 4 + fk) * SB + (wc * 4 + tj) * 8 + fr];
+#pragma unroll
+      for (int ti = 0; ti < 4; ++ti)
+#pragma unroll
+        for (int tj = 0; tj < 4; ++tj) dmma884(acc[ti][tj][0], acc[ti][tj][1], a[ti], b[tj]);
+    }
+#pragma unroll
+    for (int ti = 0; ti < 4; ++ti) {
+      const int row = r0 + (wr * 4 + ti) * 8 + fr;
+#pragma unroll
+      for (int tj = 0; tj < 4; ++tj) {
+        const int col = j0 + (wc * 4 + tj) * 8 + 2 * fk;
+        // the panel's own columns hold G' and are left alone
+        if (row < np && col < j0 + jw && (col < k0 || col >= k0 + nb)) {
+          M[(int64_t)row * np + col] = acc[ti][tj][0];
+          M[(int64_t)row * np + col + 1] = acc[ti][tj][1];
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// column permutation that undoes the row interchanges: idx = arange; for c = np-1..0 swap(idx[c], idx[piv[c]])
+__global__ void k_gj_perm(const int* __restrict__ npArr, const int* __restrict__ pivAll, int* __restrict__ permAll,
+                          int npMax, int count) {
+  const int mat = blockIdx.x;
+  if (mat >= count) return;
+  extern __shared__ int sIdx[];
+  const int np = npArr[mat];
+  const int* piv = pivAll + (int64_t)mat * npMax;
+  int* perm = permAll + (int64_t)mat * npMax;
+  for (int i = threadIdx.x; i < np; i += blockDim.x) sIdx[i] = i;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int c = np - 1; c >= 0; --c) {
+      int p = piv[c];
+      if (p != c) {
+        int t = sIdx[c];
+        sIdx[c] = sIdx[p];
+        sIdx[p] = t;
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < np; i += blockDim.x) perm[i] = sIdx[i];
+}
+
+// F[r][j] = W[r][perm[j]]   grid (row tiles of 8, matrices)
+__global__ void k_gj_gather(const double* __restrict__ W, double* __restrict__ F, const int64_t* __restrict__ off,
+                            const int* __restrict__ npArr, const int* __restrict__ permAll, int npMax) {
+  const int mat = blockIdx.y;
+  const int np = npArr[mat];
+  const int r0 = blockIdx.x * 8;
+  if (r0 >= np) return;
+  const int* perm = permAll + (int64_t)mat * npMax;
+  const double* Wm = W + off[mat];
+  double* Fm = F + off[mat];
+  for (int j = threadIdx.x; j < np; j += blockDim.x) {
+    const int pj = perm[j];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) Fm[(int64_t)(r0 + r) * np + j] = Wm[(int64_t)(r0 + r) * np + pj];
+  }
+}
+
+static constexpr size_t GJ_UPD_SMEM = (size_t)(GJ_NB * (GJ_TJ + 4) + GJ_TM * (GJ_NB + 4)) * sizeof(double);
+
+void invertBatched(double* W, double* F, const int64_t* dOff, const int* dN, const int* dNp, int count, int npMax,
+                   int* dPiv, int* dPerm, int* dInfo, cudaStream_t s, int64_t* launches) {
+  if (count == 0 || npMax == 0) return;
+  static bool attrSet = false;
+  if (!attrSet) {
+    HY_CUDA(cudaFuncSetAttribute(k_gj_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GJ_UPD_SMEM));
+    HY_CUDA(cudaFuncSetAttribute(k_gj_perm, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attrSet = true;
+  }
+  if ((size_t)npMax * sizeof(int) > 200 * 1024)
+    throw Error(HYMLS_B200_ERR_UNSUPPORTED, "dense block larger than 51200 rows");
+  k_pad_identity<<<count, 64, 0, s>>>(W, dOff, dN, dNp, count);
+  ++*launches;
+  for (int k0 = 0; k0 < npMax; k0 += GJ_NB) {
+    k_gj_panel<<<count, GJ_PANEL_T, 0, s>>>(W, dOff, dNp, dPiv, npMax, k0, dInfo);
+    dim3 g((npMax + GJ_TJ - 1) / GJ_TJ, count);
+    k_gj_update<<<g, GJ_UPD_T, GJ_UPD_SMEM, s>>>(W, dOff, dNp, dPiv, npMax, k0);
+    *launches += 2;
+  }
+  k_gj_perm<<<count, 256, npMax * sizeof(int), s>>>(dNp, dPiv, dPerm, npMax, count);
+  dim3 g2((npMax + 7) / 8, count);
+  k_gj_gather<<<g2, 256, 0, s>>>(W, F, dOff, dNp, dPerm, npMax);
+  *launches += 2;
+  HY_CUDA(cudaGetLastError());
+}
+
+}  // namespace hymls

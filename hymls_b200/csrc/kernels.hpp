@@ -1,0 +1,98 @@
+// Host-callable launchers of the CUDA kernels (definitions in gj.cu, schur.cu, apply.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace hymls {
+
+// ---- gj.cu: batched dense inversion, W (workspace, destroyed) -> F (inverse), same offsets ----
+void invertBatched(double* W, double* F, const int64_t* dOff, const int* dN, const int* dNp, int count, int npMax,
+                   int* dPiv, int* dPerm, int* dInfo, cudaStream_t s, int64_t* launches);
+
+// ---- schur.cu ----
+struct SchurArgs {
+  // per local separator row R (row i of subdomain sd: R = sdRowPtr[sd] + i)
+  const int* rowSd;
+  const int* rowInst;      // group instance (global index) the row belongs to
+  const int* rowLinkPos;   // position of the row inside its linked set
+  const int* sdSep;        // separator position of the row
+  const int64_t* sdRowPtr;
+  const int *sdM, *sdN, *sdNp;
+  const int64_t* a11Off;
+  const double* Ainv;
+  const double* val;       // values of this level's matrix
+  const int64_t *s21Ptr, *s12Ptr, *s22Ptr;
+  const int *s21Col, *s12Row, *s22Col;
+  const int64_t *s21Src, *s12Src, *s22Src;
+  // group instances
+  const int64_t* sdInstPtr;
+  const int *instLoc, *instLen, *instUniq, *instLink;
+  // linked sets per subdomain
+  const int64_t* sdLinkPtr;  // nsd+1
+  const int* lnkSd;
+  const int* lnkSize;
+  const int64_t* lnkOff;     // offset of the S_LL block in wsSLL (chunk relative)
+  // unique groups
+  const int* uniqStart;      // nuniq+1 (separator positions)
+  const int *uniqBlk, *uniqBlkOff;
+  const double* wd;          // reflector used for the matrix transform (0 where the dense variant is the identity)
+  const double* usign;
+  // outputs
+  const int64_t* redPtr;
+  const int* redCol;
+  double* redVal;
+  const int* blkNp;
+  const int64_t* blkOff;
+  double* blkW;
+  // workspace (per chunk)
+  const int64_t* wsOffC;     // per subdomain: offset of its m x G arrays C and SV
+  double *wsC, *wsSV, *wsSLL;
+  int dLen;                  // doubles reserved for the A21*Ainv row in shared memory
+  int* info;
+};
+void schurAssemble(const SchurArgs& a, int sd0, int sd1, int64_t R0, int64_t R1, int64_t lk0, int64_t lk1, int pass,
+                   size_t rowSmem, size_t blkSmem, cudaStream_t s, int64_t* launches);
+void schurDense(const SchurArgs& a, int64_t R0, int64_t R1, double* denseS, int64_t ldS, size_t rowSmem,
+                cudaStream_t s, int64_t* launches);
+void dropByValue(double* val, const int64_t* ptr, const int* col, double* diagScratch, int n, double tol,
+                 cudaStream_t s, int64_t* launches);
+
+// ---- apply.cu ----
+struct GemvArgs {
+  const int* itemMat;
+  const int* itemRow0;
+  const int *n, *np;
+  const int64_t* matOff;   // offset of each matrix in A
+  const int64_t* vecOff;   // offset of each matrix' segment in the packed vectors
+  const double* A;
+  const double* xin;
+  const int* gather;
+  const double* xprev;
+  double* out;
+  const int* scatter;
+  int mode;
+};
+void batchedGemv(const GemvArgs& a, int numItems, int npMax, cudaStream_t s, int64_t* launches);
+int gemvRowsPerItem();
+void spmv(const int64_t* ptr, const int* col, const double* val, const double* x, double* y, int64_t n, double alpha,
+          const double* b, const int* bidx, double beta, cudaStream_t s, int64_t* launches);
+void gatherValues(const double* src, const int64_t* idx, double* dst, int64_t n, cudaStream_t s, int64_t* launches);
+void scatterValues(const double* src, const int64_t* srcIdx, const int64_t* dstIdx, int64_t dstBase, double* dst,
+                   int64_t n, cudaStream_t s, int64_t* launches);
+void householder(const int* uniqStart, int nuniq, const double* w, const double* in, double* out, double* vsumOut,
+                 const double* vsumIn, double* X, const int* sepRow, cudaStream_t s, int64_t* launches);
+void multiDot(const double* V, int64_t ldv, int k, const double* w, int64_t n, double* partial, double* h,
+              int accumulate, cudaStream_t s, int64_t* launches);
+int multiDotBlocks();
+void multiAxpy(const double* V, int64_t ldv, int k, const double* h, double* w, int64_t n, double sign,
+               cudaStream_t s, int64_t* launches);
+void axpby(double a, const double* x, double b, double* y, int64_t n, cudaStream_t s, int64_t* launches);
+void scaleByInvNorm(const double* x, const double* nrm2, double* y, int64_t n, cudaStream_t s, int64_t* launches);
+void setValue(double* x, int64_t idx, double v, cudaStream_t s, int64_t* launches);
+void csrToDense(const int64_t* ptr, const int* col, const double* val, double* D, int n, int np, cudaStream_t s,
+                int64_t* launches);
+void putDirichlet(double* D, int n, int np, int fix, cudaStream_t s, int64_t* launches);
+void scatterVec(const double* x, const int* idx, double* y, int64_t n, cudaStream_t s, int64_t* launches);
+
+}  // namespace hymls

@@ -1,0 +1,265 @@
+// Schur-complement assembly with on-the-fly orthogonal transformation and dropping.
+//
+// Reference: SchurComplement::Construct11/Construct22 (src/HYMLS_SchurComplement.cpp:131-306),
+// SchurPreconditioner::AssembleTransformAndDrop / ConstructSCPart (src/HYMLS_SchurPreconditioner.cpp:698-986),
+// RestrictedOT::Apply (src/HYMLS_RestrictedOT.hpp:21-36), Householder::Apply/ApplyR (src/HYMLS_Householder.cpp:38-126).
+//
+// The reference builds, per subdomain, the dense m x m matrix Sk (A22 part, then -A21 A11^-1 A12 with m
+// right-hand sides), applies H_g from the left and right for every separator group g and keeps only
+//   (a) the V-sum x V-sum entries (first node of every group)  and
+//   (b) the non-V-sum x non-V-sum entries inside each linked set of groups.
+// With the explicit inverse of A11 at hand, row i of Sk is a sparse combination of a few rows of A11^-1
+// followed by a sparse column gather, and the kept entries of H Sk H are bilinear forms in
+//   C = Sk W (m x G),  SV = Sk[:, first] (m x G),  and the diagonal blocks S_LL of the linked sets,
+// where W = blockdiag(w_g) holds the normalised reflectors (H_g = s_g (2 w_g w_g' - I), s_g = -1 and
+// w_g = 0 for the degenerate groups the reference leaves untouched):
+//   (H Sk H)[i,j] = s_i s_j ( Sk[i,j] - 2 w_i (W'Sk)[g(i),j] - 2 (Sk W)[i,g(j)] w_j + 4 w_i w_j (W'Sk W)[g(i),g(j)] ).
+// Pass 1 (A22 part) stores, pass 2 (-A21 A11^-1 A12 part) adds -- ReplaceGlobalValues / SumIntoGlobalValues.
+#include <cuda_runtime.h>
+
+#include "device.cuh"
+#include "kernels.hpp"
+
+namespace hymls {
+
+// one CTA per local separator row of a subdomain
+__global__ void __launch_bounds__(128)
+k_schur_rows(SchurArgs a, int64_t R0, int pass, double* __restrict__ denseS, int64_t ldS) {
+  const int64_t R = R0 + blockIdx.x;
+  const int sd = a.rowSd[R];
+  const int64_t base = a.sdRowPtr[sd];
+  const int i = (int)(R - base);
+  const int m = a.sdM[sd], n = a.sdN[sd], np = a.sdNp[sd];
+  const int tid = threadIdx.x, T = blockDim.x;
+  extern __shared__ double sm[];
+  double* d = sm;            // n   : row i of A21(sd) * A11^-1
+  double* sk = sm + a.dLen;  // m   : row i of Sk
+
+  if (pass == 2) {
+    for (int q = tid; q < n; q += T) d[q] = 0.0;
+    __syncthreads();
+    const double* Ainv = a.Ainv + a.a11Off[sd];
+    for (int64_t e = a.s21Ptr[R]; e < a.s21Ptr[R + 1]; ++e) {
+      const double v = a.val[a.s21Src[e]];
+      const double* row = Ainv + (int64_t)a.s21Col[e] * np;
+      for (int q = tid; q < n; q += T) d[q] += v * row[q];
+    }
+    __syncthreads();
+    for (int j = tid; j < m; j += T) {
+      double s = 0.0;
+      for (int64_t e = a.s12Ptr[base + j]; e < a.s12Ptr[base + j + 1]; ++e) s += d[a.s12Row[e]] * a.val[a.s12Src[e]];
+      sk[j] = -s;
+    }
+  } else {
+    for (int j = tid; j < m; j += T) sk[j] = 0.0;
+    __syncthreads();
+    for (int64_t e = a.s22Ptr[R] + tid; e < a.s22Ptr[R + 1]; e += T) sk[a.s22Col[e]] = a.val[a.s22Src[e]];
+  }
+  __syncthreads();
+
+  if (denseS != nullptr) {  // Number of Levels = 0: the full Schur complement, dense (Construct :88-129)
+    const int64_t prow = a.sdSep[base + i];
+    for (int j = tid; j < m; j += T)
+      if (sk[j] != 0.0) atomicAdd(&denseS[prow * ldS + a.sdSep[base + j]], sk[j]);
+    return;
+  }
+
+  const int64_t ia = a.sdInstPtr[sd];
+  const int G = (int)(a.sdInstPtr[sd + 1] - ia);
+  double* C = a.wsC + a.wsOffC[sd] + (int64_t)i * G;
+  double* SV = a.wsSV + a.wsOffC[sd] + (int64_t)i * G;
+  for (int h = tid; h < G; h += T) {
+    const int loc = a.instLoc[ia + h], len = a.instLen[ia + h];
+    const double* w = a.wd + a.uniqStart[a.instUniq[ia + h]];
+    double c = 0.0;
+    for (int q = 0; q < len; ++q) c += sk[loc + q] * w[q];
+    C[h] = c;
+    SV[h] = sk[loc];
+  }
+  const int myLink = a.instLink[a.rowInst[R]];
+  const int64_t lk = a.sdLinkPtr[sd] + myLink;
+  const int lsz = a.lnkSize[lk];
+  double* SLL = a.wsSLL + a.lnkOff[lk] + (int64_t)a.rowLinkPos[R] * lsz;
+  for (int j = tid; j < m; j += T)
+    if (a.instLink[a.rowInst[base + j]] == myLink) SLL[a.rowLinkPos[base + j]] = sk[j];
+}
+
+__device__ __forceinline__ int64_t findCol(const int* __restrict__ col, int64_t lo, int64_t hi, int c) {
+  while (lo < hi) {
+    int64_t mid = (lo + hi) >> 1;
+    if (col[mid] < c) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// (a) V-sum x V-sum entries: one CTA per subdomain
+__global__ void __launch_bounds__(256)
+k_schur_vsum(SchurArgs a, int sd0, int pass) {
+  const int sd = sd0 + blockIdx.x;
+  const int64_t ia = a.sdInstPtr[sd];
+  const int G = (int)(a.sdInstPtr[sd + 1] - ia);
+  const double* C = a.wsC + a.wsOffC[sd];
+  const double* SV = a.wsSV + a.wsOffC[sd];
+  for (int idx = threadIdx.x; idx < G * G; idx += blockDim.x) {
+    const int g = idx / G, h = idx % G;
+    const int locg = a.instLoc[ia + g], leng = a.instLen[ia + g], ug = a.instUniq[ia + g];
+    const int uh = a.instUniq[ia + h];
+    const double* wg = a.wd + a.uniqStart[ug];
+    double Mgh = 0.0, RV = 0.0;
+    for (int q = 0; q < leng; ++q) {
+      Mgh += wg[q] * C[(int64_t)(locg + q) * G + h];
+      RV += wg[q] * SV[(int64_t)(locg + q) * G + h];
+    }
+    const double w0g = wg[0], w0h = a.wd[a.uniqStart[uh]];
+    double v = SV[(int64_t)locg * G + h] - 2.0 * w0g * RV - 2.0 * C[(int64_t)locg * G + h] * w0h +
+               4.0 * w0g * w0h * Mgh;
+    v *= a.usign[ug] * a.usign[uh];
+    const int64_t pos = findCol(a.redCol, a.redPtr[ug], a.redPtr[ug + 1], uh);
+    if (pass == 1) a.redVal[pos] = v; else atomicAdd(&a.redVal[pos], v);
+  }
+}
+
+// (b) non-V-sum entries of one linked set: one CTA per (subdomain, linked set)
+static constexpr int MAX_LINK_INST = 32;
+__global__ void __launch_bounds__(256)
+k_schur_blocks(SchurArgs a, int64_t lk0, int pass) {
+  const int64_t lk = lk0 + blockIdx.x;
+  const int sd = a.lnkSd[lk];
+  const int link = (int)(lk - a.sdLinkPtr[sd]);
+  const int lsz = a.lnkSize[lk];
+  const int64_t ia = a.sdInstPtr[sd];
+  const int G = (int)(a.sdInstPtr[sd + 1] - ia);
+  const double* SLL = a.wsSLL + a.lnkOff[lk];
+  const int tid = threadIdx.x, T = blockDim.x;
+
+  __shared__ int sStart[MAX_LINK_INST], sLen[MAX_LINK_INST], sU[MAX_LINK_INST], sW0[MAX_LINK_INST];
+  __shared__ int sT;
+  extern __shared__ double sm[];
+  if (tid == 0) {
+    int t = 0, off = 0;
+    for (int g = 0; g < G; ++g)
+      if (a.instLink[ia + g] == link) {
+        if (t < MAX_LINK_INST) {
+          sStart[t] = off;
+          sLen[t] = a.instLen[ia + g];
+          sU[t] = a.instUniq[ia + g];
+          sW0[t] = a.uniqStart[sU[t]];
+        }
+        off += a.instLen[ia + g];
+        ++t;
+      }
+    sT = t;
+  }
+  __syncthreads();
+  const int nt = sT;
+  if (nt > MAX_LINK_INST) { if (tid == 0) atomicExch(a.info, -7); return; }
+  if (lsz <= nt) return;  // only V-sums in this set: nothing to keep
+  double* CL = sm;                 // lsz x nt
+  double* RL = sm + (int64_t)lsz * nt;  // nt x lsz
+  double* ML = RL + (int64_t)lsz * nt;  // nt x nt
+  for (int e = tid; e < lsz * nt; e += T) {
+    const int i = e / nt, t = e % nt;
+    const double* w = a.wd + sW0[t];
+    double c = 0.0, r = 0.0;
+    for (int q = 0; q < sLen[t]; ++q) {
+      c += SLL[(int64_t)i * lsz + sStart[t] + q] * w[q];
+      r += w[q] * SLL[(int64_t)(sStart[t] + q) * lsz + i];
+    }
+    CL[i * nt + t] = c;
+    RL[t * lsz + i] = r;
+  }
+  __syncthreads();
+  for (int e = tid; e < nt * nt; e += T) {
+    const int t = e / nt, t2 = e % nt;
+    const double* w = a.wd + sW0[t];
+    double s = 0.0;
+    for (int q = 0; q < sLen[t]; ++q) s += w[q] * CL[(sStart[t] + q) * nt + t2];
+    ML[e] = s;
+  }
+  __syncthreads();
+  for (int e = tid; e < lsz * lsz; e += T) {
+    const int i = e / lsz, j = e % lsz;
+    int ti = 0, tj = 0;
+    while (ti + 1 < nt && sStart[ti + 1] <= i) ++ti;
+    while (tj + 1 < nt && sStart[tj + 1] <= j) ++tj;
+    const int qi = i - sStart[ti], qj = j - sStart[tj];
+    if (qi == 0 || qj == 0) continue;  // V-sum rows/cols are not part of the block
+    const int ui = sU[ti], uj = sU[tj];
+    const int b = a.uniqBlk[ui];
+    if (b != a.uniqBlk[uj]) continue;  // pattern entry no block solver ever reads
+    const double wi = a.wd[sW0[ti] + qi], wj = a.wd[sW0[tj] + qj];
+    double v = SLL[(int64_t)i * lsz + j] - 2.0 * wi * RL[ti * lsz + j] - 2.0 * CL[i * nt + tj] * wj +
+               4.0 * wi * wj * ML[ti * nt + tj];
+    v *= a.usign[ui] * a.usign[uj];
+    const int npb = a.blkNp[b];
+    double* dst = a.blkW + a.blkOff[b] + (int64_t)(a.uniqBlkOff[ui] + qi - 1) * npb + (a.uniqBlkOff[uj] + qj - 1);
+    if (pass == 1) *dst = v; else atomicAdd(dst, v);
+  }
+}
+
+// RelDropDiag / RelFullDiag value dropping (MatrixUtils::DropByValue :1010-1194) applied in place:
+// entries |a_ij| <= 1e-14 * max(|a_ii|,|a_jj|) (or <= 1e-14) become exact zeros; the pattern is kept.
+__global__ void k_drop_by_value(double* __restrict__ val, const int64_t* __restrict__ ptr, const int* __restrict__ col,
+                                const double* __restrict__ diag, int n, double tol) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const double di = fabs(diag[r]);
+  for (int64_t e = ptr[r]; e < ptr[r + 1]; ++e) {
+    const int c = col[e];
+    const double v = fabs(val[e]);
+    const double scal = (c == r) ? 1.0 : fmax(di, fabs(diag[c]));
+    if (!(v > scal * tol && v > tol)) val[e] = 0.0;
+  }
+}
+__global__ void k_extract_diag(const double* __restrict__ val, const int64_t* __restrict__ ptr,
+                               const int* __restrict__ col, double* __restrict__ diag, int n) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  double d = 0.0;
+  for (int64_t e = ptr[r]; e < ptr[r + 1]; ++e)
+    if (col[e] == r) d = val[e];
+  diag[r] = d;
+}
+
+void dropByValue(double* val, const int64_t* ptr, const int* col, double* diagScratch, int n, double tol,
+                 cudaStream_t s, int64_t* launches) {
+  if (n == 0) return;
+  k_extract_diag<<<(n + 255) / 256, 256, 0, s>>>(val, ptr, col, diagScratch, n);
+  k_drop_by_value<<<(n + 255) / 256, 256, 0, s>>>(val, ptr, col, diagScratch, n, tol);
+  *launches += 2;
+}
+
+void schurAssemble(const SchurArgs& a, int sd0, int sd1, int64_t R0, int64_t R1, int64_t lk0, int64_t lk1, int pass,
+                   size_t rowSmem, size_t blkSmem, cudaStream_t s, int64_t* launches) {
+  static size_t rowSet = 0, blkSet = 0;
+  if (rowSmem > rowSet) {
+    if (rowSmem > 227 * 1024)
+      throw Error(HYMLS_B200_ERR_UNSUPPORTED, "subdomain too large for the Schur row kernel (n + m > 29000)");
+    HY_CUDA(cudaFuncSetAttribute(k_schur_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rowSmem));
+    rowSet = rowSmem;
+  }
+  if (blkSmem > blkSet) {
+    if (blkSmem > 200 * 1024)
+      throw Error(HYMLS_B200_ERR_UNSUPPORTED, "linked separator set too large for the block kernel");
+    HY_CUDA(cudaFuncSetAttribute(k_schur_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blkSmem));
+    blkSet = blkSmem;
+  }
+  if (R1 > R0) {
+    k_schur_rows<<<(unsigned)(R1 - R0), 128, rowSmem, s>>>(a, R0, pass, nullptr, 0);
+    k_schur_vsum<<<sd1 - sd0, 256, 0, s>>>(a, sd0, pass);
+    k_schur_blocks<<<(unsigned)(lk1 - lk0), 256, blkSmem, s>>>(a, lk0, pass);
+    *launches += 3;
+  }
+  HY_CUDA(cudaGetLastError());
+}
+
+void schurDense(const SchurArgs& a, int64_t R0, int64_t R1, double* denseS, int64_t ldS, size_t rowSmem,
+                cudaStream_t s, int64_t* launches) {
+  if (R1 <= R0) return;
+  HY_CUDA(cudaFuncSetAttribute(k_schur_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rowSmem));
+  k_schur_rows<<<(unsigned)(R1 - R0), 128, rowSmem, s>>>(a, R0, 2, denseS, ldS);
+  ++*launches;
+  HY_CUDA(cudaGetLastError());
+}
+
+}  // namespace hymls

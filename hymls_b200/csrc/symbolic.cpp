@@ -1,0 +1,334 @@
+#include "symbolic.hpp"
+
+#include <algorithm>
+#include <cmath>
+
+#include "../../include/hymls_b200.h"
+
+namespace hymls {
+
+static const double SMALL_ENTRY = 1e-14;  // HYMLS_SMALL_ENTRY, src/HYMLS_Macros.hpp:29
+
+static inline int roundUp8(int n) { return (n + 7) & ~7; }
+static inline double hsign(double x) { return (x < 0) ? -1.0 : (x > 0 ? 1.0 : 0.0); }  // Householder.cpp:15-18
+
+void buildLevelSym(LevelSym& L, const CartesianPartitioner& part, const std::vector<int>& gid2row) {
+  std::vector<char> present;
+  if (L.level > 0) {
+    present.assign(gid2row.size(), 0);
+    for (gidx g : L.rowGid) present[g] = 1;
+  }
+  buildHierarchicalMap(part, present, L.H);
+  const HierarchicalMap& H = L.H;
+  L.nsd = H.nsd;
+  L.nuniq = H.numUnique();
+  L.nI = H.numInterior();
+  L.nS = H.numSeparator();
+  if (L.nI + L.nS != L.n)
+    throw Error(HYMLS_B200_ERR_ARG, "partition does not cover the row map of level " + std::to_string(L.level) +
+                                        " (interior " + std::to_string(L.nI) + " + separators " +
+                                        std::to_string(L.nS) + " != " + std::to_string(L.n) + ")");
+  // ---- orderings ----
+  L.intRow.resize(L.nI);
+  L.sepRow.resize(L.nS);
+  L.rowPos.assign(L.n, INT32_MIN);
+  for (int64_t p = 0; p < L.nI; ++p) {
+    int r = gid2row[H.intGid[p]];
+    if (r < 0 || L.rowPos[r] != INT32_MIN) throw Error(HYMLS_B200_ERR_ARG, "interior node not in map / listed twice");
+    L.intRow[p] = r;
+    L.rowPos[r] = (int)p;
+  }
+  for (int64_t p = 0; p < L.nS; ++p) {
+    int r = gid2row[H.sepGid[p]];
+    if (r < 0 || L.rowPos[r] != INT32_MIN) throw Error(HYMLS_B200_ERR_ARG, "separator node not in map / listed twice");
+    L.sepRow[p] = r;
+    L.rowPos[r] = -(int)p - 1;
+  }
+  // ---- A11 blocks ----
+  L.sdN.resize(L.nsd);
+  L.sdNp.resize(L.nsd);
+  L.a11Off.assign(L.nsd + 1, 0);
+  L.sumNsq = 0;
+  std::vector<int> sdOfInt(L.nI);
+  for (int sd = 0; sd < L.nsd; ++sd) {
+    int n = (int)(H.intPtr[sd + 1] - H.intPtr[sd]);
+    L.sdN[sd] = n;
+    L.sdNp[sd] = roundUp8(n);
+    L.a11Off[sd + 1] = L.a11Off[sd] + (int64_t)L.sdNp[sd] * L.sdNp[sd];
+    L.sumNsq += (double)n * n;
+    for (int64_t p = H.intPtr[sd]; p < H.intPtr[sd + 1]; ++p) sdOfInt[p] = sd;
+  }
+  // ---- split the matrix into A11 (dense scatter list), A12, A21, A22 ----
+  L.A12.ptr.assign(L.nI + 1, 0);
+  L.A21.ptr.assign(L.nS + 1, 0);
+  L.A22.ptr.assign(L.nS + 1, 0);
+  L.ignoredInteriorCouplings = 0;
+  for (int pass = 0; pass < 2; ++pass) {
+    if (pass == 1) {
+      for (int64_t p = 0; p < L.nI; ++p) L.A12.ptr[p + 1] += L.A12.ptr[p];
+      for (int64_t p = 0; p < L.nS; ++p) L.A21.ptr[p + 1] += L.A21.ptr[p];
+      for (int64_t p = 0; p < L.nS; ++p) L.A22.ptr[p + 1] += L.A22.ptr[p];
+      L.A12.col.resize(L.A12.ptr[L.nI]);
+      L.A12.src.resize(L.A12.ptr[L.nI]);
+      L.A21.col.resize(L.A21.ptr[L.nS]);
+      L.A21.src.resize(L.A21.ptr[L.nS]);
+      L.A22.col.resize(L.A22.ptr[L.nS]);
+      L.A22.src.resize(L.A22.ptr[L.nS]);
+    }
+    std::vector<int64_t> f12, f21, f22;
+    if (pass == 1) {
+      f12.assign(L.A12.ptr.begin(), L.A12.ptr.end() - 1);
+      f21.assign(L.A21.ptr.begin(), L.A21.ptr.end() - 1);
+      f22.assign(L.A22.ptr.begin(), L.A22.ptr.end() - 1);
+    }
+    for (int64_t p = 0; p < L.nI; ++p) {
+      int r = L.intRow[p];
+      int sd = sdOfInt[p];
+      for (int64_t e = L.rowptr[r]; e < L.rowptr[r + 1]; ++e) {
+        int cp = L.rowPos[L.colidx[e]];
+        if (cp >= 0) {
+          if (sdOfInt[cp] == sd) {
+            if (pass == 1) {
+              int64_t li = p - H.intPtr[sd], lj = cp - H.intPtr[sd];
+              L.a11Src.push_back(e);
+              L.a11Dst.push_back(L.a11Off[sd] + li * L.sdNp[sd] + lj);
+            }
+          } else if (pass == 0) {
+            L.ignoredInteriorCouplings++;
+          }
+        } else {
+          int ps = -cp - 1;
+          if (pass == 0) {
+            L.A12.ptr[p + 1]++;
+          } else {
+            L.A12.col[f12[p]] = ps;
+            L.A12.src[f12[p]++] = e;
+          }
+        }
+      }
+    }
+    for (int64_t p = 0; p < L.nS; ++p) {
+      int r = L.sepRow[p];
+      for (int64_t e = L.rowptr[r]; e < L.rowptr[r + 1]; ++e) {
+        int cp = L.rowPos[L.colidx[e]];
+        if (cp >= 0) {
+          if (pass == 0) {
+            L.A21.ptr[p + 1]++;
+          } else {
+            L.A21.col[f21[p]] = cp;
+            L.A21.src[f21[p]++] = e;
+          }
+        } else {
+          if (pass == 0) {
+            L.A22.ptr[p + 1]++;
+          } else {
+            L.A22.col[f22[p]] = -cp - 1;
+            L.A22.src[f22[p]++] = e;
+          }
+        }
+      }
+    }
+  }
+  // ---- group instances, per-subdomain separator lists ----
+  L.sdM.resize(L.nsd);
+  L.sdRowPtr.assign(L.nsd + 1, 0);
+  L.sdInstPtr.assign(L.nsd + 1, 0);
+  L.sdNumLink.resize(L.nsd);
+  for (int sd = 0; sd < L.nsd; ++sd) {
+    int m = 0;
+    std::vector<int> types;
+    for (int64_t g = H.sdGrpPtr[sd]; g < H.sdGrpPtr[sd + 1]; ++g) {
+      int len = (int)(H.grpPtr[g + 1] - H.grpPtr[g]);
+      int u = H.grpUnique[g];
+      L.instLoc.push_back(m);
+      L.instLen.push_back(len);
+      L.instUniq.push_back(u);
+      types.push_back(H.grpType[g]);
+      for (int q = 0; q < len; ++q) L.sdSep.push_back((int)(H.uniqPtr[u] + q));
+      m += len;
+    }
+    // linked sets as seen from this subdomain (hid_->GetLinkedSeparatorGroups(sd))
+    std::vector<std::vector<int>> linked = linkGroups(types);
+    std::vector<int> linkOf(types.size());
+    for (size_t l = 0; l < linked.size(); ++l)
+      for (int gi : linked[l]) linkOf[gi] = (int)l;
+    for (int v : linkOf) L.instLink.push_back(v);
+    L.sdNumLink[sd] = (int)linked.size();
+    L.sdM[sd] = m;
+    L.sdRowPtr[sd + 1] = L.sdRowPtr[sd] + m;
+    L.sdInstPtr[sd + 1] = (int64_t)L.instLoc.size();
+  }
+  // ---- blocks: per owner subdomain, linked sets among the groups it owns (InitializeBlocks :301-340) ----
+  L.uniqBlk.assign(L.nuniq, -1);
+  L.uniqBlkOff.assign(L.nuniq, 0);
+  L.blkOff.assign(1, 0);
+  L.blkRowPtr.assign(1, 0);
+  L.sepBlk.assign(L.nS, -1);
+  L.sepBlkIdx.assign(L.nS, -1);
+  {
+    int u = 0;
+    while (u < L.nuniq) {
+      int sd = H.uniqOwnerSd[u];
+      int e = u;
+      while (e < L.nuniq && H.uniqOwnerSd[e] == sd) ++e;  // unique groups of one owner are consecutive
+      std::vector<int> types(H.uniqType.begin() + u, H.uniqType.begin() + e);
+      for (auto& lg : linkGroups(types)) {
+        int b = (int)L.blkN.size();
+        int rows = 0;
+        for (int gi : lg) {
+          int uu = u + gi;
+          L.uniqBlk[uu] = b;
+          L.uniqBlkOff[uu] = rows;
+          int64_t a = H.uniqPtr[uu], z = H.uniqPtr[uu + 1];
+          for (int64_t p = a + 1; p < z; ++p) {
+            L.sepBlk[p] = b;
+            L.sepBlkIdx[p] = rows++;
+            L.blkRows.push_back((int)p);
+          }
+        }
+        L.blkN.push_back(rows);
+        L.blkNp.push_back(roundUp8(rows));
+        L.blkOff.push_back(L.blkOff.back() + (int64_t)roundUp8(rows) * roundUp8(rows));
+        L.blkRowPtr.push_back((int64_t)L.blkRows.size());
+      }
+      u = e;
+    }
+  }
+  L.nblk = (int)L.blkN.size();
+  // ---- per-subdomain local sparse pieces (Construct11 / Construct22 index work) ----
+  {
+    const int64_t totalRows = L.sdRowPtr[L.nsd];
+    L.s21Ptr.assign(totalRows + 1, 0);
+    L.s22Ptr.assign(totalRows + 1, 0);
+    L.s12Ptr.assign(totalRows + 1, 0);
+    std::vector<int> loc(L.nS, -1);
+    // counting pass then fill pass
+    for (int pass = 0; pass < 2; ++pass) {
+      if (pass == 1) {
+        for (int64_t i = 0; i < totalRows; ++i) {
+          L.s21Ptr[i + 1] += L.s21Ptr[i];
+          L.s22Ptr[i + 1] += L.s22Ptr[i];
+          L.s12Ptr[i + 1] += L.s12Ptr[i];
+        }
+        L.s21Col.resize(L.s21Ptr[totalRows]);
+        L.s21Src.resize(L.s21Ptr[totalRows]);
+        L.s22Col.resize(L.s22Ptr[totalRows]);
+        L.s22Src.resize(L.s22Ptr[totalRows]);
+        L.s12Row.resize(L.s12Ptr[totalRows]);
+        L.s12Src.resize(L.s12Ptr[totalRows]);
+      }
+      std::vector<int64_t> f21, f22, f12;
+      if (pass == 1) {
+        f21.assign(L.s21Ptr.begin(), L.s21Ptr.end() - 1);
+        f22.assign(L.s22Ptr.begin(), L.s22Ptr.end() - 1);
+        f12.assign(L.s12Ptr.begin(), L.s12Ptr.end() - 1);
+      }
+      for (int sd = 0; sd < L.nsd; ++sd) {
+        const int64_t base = L.sdRowPtr[sd];
+        const int m = L.sdM[sd];
+        const int64_t i0 = H.intPtr[sd], i1 = H.intPtr[sd + 1];
+        for (int i = 0; i < m; ++i) loc[L.sdSep[base + i]] = i;
+        for (int i = 0; i < m; ++i) {
+          int ps = L.sdSep[base + i];
+          for (int64_t e = L.A21.ptr[ps]; e < L.A21.ptr[ps + 1]; ++e) {
+            int c = L.A21.col[e];
+            if (c >= i0 && c < i1) {
+              if (pass == 0) {
+                L.s21Ptr[base + i + 1]++;
+              } else {
+                L.s21Col[f21[base + i]] = (int)(c - i0);
+                L.s21Src[f21[base + i]++] = L.A21.src[e];
+              }
+            }
+          }
+          for (int64_t e = L.A22.ptr[ps]; e < L.A22.ptr[ps + 1]; ++e) {
+            int j = loc[L.A22.col[e]];
+            if (j >= 0) {
+              if (pass == 0) {
+                L.s22Ptr[base + i + 1]++;
+              } else {
+                L.s22Col[f22[base + i]] = j;
+                L.s22Src[f22[base + i]++] = L.A22.src[e];
+              }
+            }
+          }
+        }
+        for (int64_t p = i0; p < i1; ++p) {
+          for (int64_t e = L.A12.ptr[p]; e < L.A12.ptr[p + 1]; ++e) {
+            int j = loc[L.A12.col[e]];
+            if (j < 0) continue;  // coupling to a separator that does not surround this subdomain
+            if (pass == 0) {
+              L.s12Ptr[base + j + 1]++;
+            } else {
+              L.s12Row[f12[base + j]] = (int)(p - i0);
+              L.s12Src[f12[base + j]++] = L.A12.src[e];
+            }
+          }
+        }
+        for (int i = 0; i < m; ++i) loc[L.sdSep[base + i]] = -1;
+      }
+    }
+  }
+  // ---- reduced Schur pattern on the V-sums: union of per-subdomain cliques (:737-787) ----
+  {
+    std::vector<std::vector<int>> rows(L.nuniq);
+    for (int sd = 0; sd < L.nsd; ++sd) {
+      int64_t a = L.sdInstPtr[sd], z = L.sdInstPtr[sd + 1];
+      for (int64_t g = a; g < z; ++g) {
+        std::vector<int>& r = rows[L.instUniq[g]];
+        for (int64_t h = a; h < z; ++h) r.push_back(L.instUniq[h]);
+      }
+    }
+    L.redPtr.assign(L.nuniq + 1, 0);
+    for (int u = 0; u < L.nuniq; ++u) {
+      std::vector<int>& r = rows[u];
+      std::sort(r.begin(), r.end());
+      r.erase(std::unique(r.begin(), r.end()), r.end());
+      L.redPtr[u + 1] = L.redPtr[u] + (int64_t)r.size();
+    }
+    L.redCol.resize(L.redPtr[L.nuniq]);
+    for (int u = 0; u < L.nuniq; ++u) std::copy(rows[u].begin(), rows[u].end(), L.redCol.begin() + L.redPtr[u]);
+  }
+  // ---- Householder reflectors from the test vector (InitializeOT :384-467, Householder::Construct) ----
+  if ((int64_t)L.testVector.size() != L.n) L.testVector.assign(L.n, 1.0);
+  L.what.assign(L.nS, 0.0);
+  L.usign.assign(L.nuniq, 1.0);
+  L.nextTestVector.assign(L.nuniq, 0.0);
+  std::vector<double> v;
+  for (int u = 0; u < L.nuniq; ++u) {
+    int64_t a = H.uniqPtr[u], z = H.uniqPtr[u + 1];
+    int len = (int)(z - a);
+    v.resize(len);
+    double nrm2 = 0;
+    for (int q = 0; q < len; ++q) {
+      v[q] = L.testVector[L.sepRow[a + q]];
+      nrm2 += v[q] * v[q];
+    }
+    const double nrm = std::sqrt(nrm2);
+    const double s = hsign(v[0]);
+    for (int q = 0; q < len; ++q) v[q] *= s;
+    // dense variant (Householder::Apply/ApplyR :38-126): identity when degenerate
+    double nrmv2 = 0;
+    for (int q = 0; q < len; ++q) nrmv2 += v[q] * v[q];
+    const double nrmv = std::sqrt(nrmv2);
+    const double v1 = v[0] + nrmv;
+    const bool denseDegenerate = std::fabs(v1) < SMALL_ENTRY || nrmv < SMALL_ENTRY;
+    L.usign[u] = denseDegenerate ? -1.0 : 1.0;
+    // sparse variant (Householder::Construct :128-163): norm taken BEFORE the sign scaling
+    v[0] += nrm;
+    double n2 = 0;
+    for (int q = 0; q < len; ++q) n2 += v[q] * v[q];
+    n2 = std::sqrt(n2);
+    double dotv = 0;
+    if (n2 >= SMALL_ENTRY) {
+      for (int q = 0; q < len; ++q) {
+        L.what[a + q] = v[q] / n2;
+        dotv += L.what[a + q] * L.testVector[L.sepRow[a + q]];
+      }
+    }
+    // next level test vector = V-sum part of H*tv with H = 2ww'-I (ComputeNextLevel :569-573)
+    L.nextTestVector[u] = 2.0 * L.what[a] * dotv - L.testVector[L.sepRow[a]];
+  }
+}
+
+}  // namespace hymls

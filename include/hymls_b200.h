@@ -1,0 +1,156 @@
+/*
+ * hymls_b200 -- C ABI of the B200-native HYMLS preconditioner hot path.
+ *
+ * Drop-in boundary for HYMLS::Preconditioner (reference: src/HYMLS_Preconditioner.hpp:56-254)
+ * and for the Krylov driver HYMLS::Solver/BaseSolver (src/HYMLS_Solver.hpp, src/HYMLS_BaseSolver.cpp:309-359).
+ * Plain pointers and sizes only; every function returns 0 on success and a negative code on
+ * failure (hymls_b200_last_error() gives the message) -- the reference's convention
+ * (`int` return, 0 = OK, src/HYMLS_Macros.hpp:147-158), with no exception crossing the boundary.
+ *
+ * A handle is not thread safe (same as the reference object): one call at a time per handle.
+ * All compute runs on the CUDA device that is current when hymls_b200_create() is called, on the
+ * stream set with hymls_b200_set_stream() (default: the legacy default stream).
+ * There is no CPU fallback: every entry point that computes (set values on the device, Compute,
+ * ApplyInverse, solve, ...) fails with HYMLS_B200_ERR_CUDA when no device is usable.  Only the integer
+ * host work of Initialize (partitioning, index maps) runs without a device, so that the maps can be
+ * compared with the reference anywhere.
+ */
+#ifndef HYMLS_B200_H
+#define HYMLS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hymls_b200 hymls_b200_t;
+
+enum {
+  HYMLS_B200_OK = 0,
+  HYMLS_B200_ERR_ARG = -1,      /* bad argument / bad parameter list (Tools::Error in the reference) */
+  HYMLS_B200_ERR_STATE = -2,    /* call order: ApplyInverse before Compute (Preconditioner.cpp:936-939) */
+  HYMLS_B200_ERR_CUDA = -3,     /* CUDA failure or no device */
+  HYMLS_B200_ERR_NUMERIC = -4,  /* singular block met during Compute */
+  HYMLS_B200_ERR_UNSUPPORTED = -99 /* same code the reference returns for unimplemented paths */
+};
+
+/* where a vector/matrix argument lives */
+enum { HYMLS_B200_HOST = 0, HYMLS_B200_DEVICE = 1 };
+
+/* Message of the last failure on this thread ("" if none). */
+const char* hymls_b200_last_error(void);
+
+/* Library version string and the device it is bound to (NULL if no CUDA device). */
+const char* hymls_b200_version(void);
+
+/*
+ * Constructor -- HYMLS::Preconditioner::Preconditioner(K, params, testVector, myLevel=0)
+ * (src/HYMLS_Preconditioner.hpp:80-84).  `xml` is a Teuchos XML parameter list (the text, not a
+ * file name) with the sublists "Problem" and "Preconditioner" (and optionally "Solver"), exactly as
+ * in the reference's testSuite XML files; unknown entries in "Preconditioner" are rejected like
+ * validateParameters does (src/HYMLS_Preconditioner.cpp:126-130) unless they are listed in
+ * DESIGN.md as extensions.
+ */
+int hymls_b200_create(const char* xml, hymls_b200_t** out);
+void hymls_b200_destroy(hymls_b200_t* h);
+
+/* CUDA stream (cudaStream_t passed as void*) used for every launch of this handle. */
+int hymls_b200_set_stream(hymls_b200_t* h, void* cuda_stream);
+
+/*
+ * Matrix K as CSR with 0-based indices, rows in global (GID) order: row i <-> GID i
+ * (Epetra_CrsMatrix::ExtractMyRowView on a linear map).  `where` says whether the three arrays are
+ * host or device pointers.  The pattern is fixed by the first call; later calls with the same
+ * pattern only replace values (SetMatrix + Compute recompute path, Preconditioner.hpp:244-254).
+ */
+int hymls_b200_set_matrix_csr(hymls_b200_t* h, int64_t n, const int64_t* rowptr, const int32_t* colidx,
+                              const double* values, int where);
+
+/* Test vector (length n, host); NULL = ones (Preconditioner::CreateTestVector, .cpp:780-790). */
+int hymls_b200_set_testvector(hymls_b200_t* h, const double* tv);
+
+/* Preconditioner::Initialize / Compute (src/HYMLS_Preconditioner.cpp:279-394, 400-517). */
+int hymls_b200_initialize(hymls_b200_t* h);
+int hymls_b200_compute(hymls_b200_t* h);
+
+/*
+ * Preconditioner::ApplyInverse(B, X) (src/HYMLS_Preconditioner.cpp:594-605, 930-1070).
+ * B, X: nvec columns of length n, column stride ldb / ldx (Epetra_MultiVector::Values()/Stride()).
+ */
+int hymls_b200_apply_inverse(hymls_b200_t* h, const double* B, int64_t ldb, double* X, int64_t ldx,
+                             int nvec, int where);
+
+/*
+ * BorderedOperator interface (src/HYMLS_Preconditioner.cpp:844-918): V, W are n x m (column major,
+ * host), C is m x m; W == NULL means W = V, C == NULL means 0.  V == NULL removes the border.
+ * Compute() must be called afterwards.
+ */
+int hymls_b200_set_border(hymls_b200_t* h, const double* V, const double* W, const double* C, int m);
+/* [X;S] = [K V; W' C]^-1 [B;T]  (Preconditioner.cpp:930-1070); T, S are m x nvec column major. */
+int hymls_b200_apply_inverse_bordered(hymls_b200_t* h, const double* B, int64_t ldb, const double* T,
+                                      double* X, int64_t ldx, double* S, int nvec, int where);
+
+/* y = K x with the matrix held by the handle (Epetra_CrsMatrix::Apply). */
+int hymls_b200_apply_matrix(hymls_b200_t* h, const double* x, double* y, int where);
+
+/*
+ * Krylov driver -- HYMLS::Solver(K, P, params)::ApplyInverse(b, x) (src/HYMLS_BaseSolver.cpp:309-359).
+ * Uses the "Solver" sublist of the XML given at creation (Krylov Method GMRES|CG, Left or Right
+ * Preconditioning, Initial Vector Zero|Random|Previous, "Iterative Solver": Maximum Iterations,
+ * Num Blocks, Maximum Restarts, Convergence Tolerance, Explicit Residual Test, *Residual Scaling).
+ * x holds the initial guess when Initial Vector = Previous and receives the solution.
+ * If a border is set the bordered system is solved (HYMLS::BorderedSolver) with right-hand side [b;0].
+ * resid_history (may be NULL) receives up to history_cap relative implicit residuals, iteration 0 first.
+ */
+typedef struct {
+  int iterations;
+  int converged;
+  double rel_residual;        /* last implicit relative residual */
+  double explicit_rel_residual; /* ||b - K x|| / ||b|| evaluated at the end */
+  double solve_seconds;       /* device time of the whole solve (CUDA events) */
+  int history_len;
+} hymls_b200_solve_info;
+int hymls_b200_solve(hymls_b200_t* h, const double* b, double* x, int where, uint64_t random_seed,
+                     hymls_b200_solve_info* info, double* resid_history, int history_cap);
+
+/* ---- index maps, for bit-exact comparison with the reference (HierarchicalMap) ---- */
+int hymls_b200_num_levels(hymls_b200_t* h);
+int hymls_b200_num_subdomains(hymls_b200_t* h, int level);
+/* interior group of subdomain sd: GIDs ascending (HierarchicalMap::GetInteriorGroup). cap<len -> len returned, nothing written */
+int64_t hymls_b200_get_interior(hymls_b200_t* h, int level, int sd, int64_t* gids, int64_t cap);
+/* separator groups of sd in reference order: ptr has ngroups+1 entries, types ngroups; returns ngroups.
+   Call with NULL pointers to query sizes: *total_len receives the number of GIDs. */
+int hymls_b200_get_groups(hymls_b200_t* h, int level, int sd, int64_t* ptr, int32_t* types,
+                          int64_t* gids, int64_t cap, int64_t* total_len);
+/* overlapping (row) map, separator map and V-sum map of a level (GIDs); returns length */
+int64_t hymls_b200_get_map(hymls_b200_t* h, int level, int which, int64_t* gids, int64_t cap);
+enum { HYMLS_B200_MAP_OVERLAPPING = 0, HYMLS_B200_MAP_INTERIOR = 1, HYMLS_B200_MAP_SEPARATOR = 2,
+       HYMLS_B200_MAP_VSUM = 3 };
+/* subdomain -> rank map of BasePartitioner::CreatePIDMap for `nprocs` ranks (level 0), length = #subdomains */
+int hymls_b200_pid_map(const char* xml, int nprocs, int32_t* pid, int cap);
+
+/* ---- statistics (Ifpack-style counters, src/HYMLS_Preconditioner.cpp:612-717) ---- */
+typedef struct {
+  int num_initialize, num_compute, num_apply_inverse;
+  double time_initialize, time_compute, time_apply_inverse; /* seconds (host wall for init, CUDA events else) */
+  int64_t n, num_interior, num_separator, num_vsum;          /* level 0 */
+  int64_t num_subdomains, num_blocks;
+  double sum_nsd_sq;            /* sum over subdomains of n_sd^2 (level 0), the roofline figure of SURVEY 8(d) */
+  double bytes_apply;           /* algorithmic bytes of one ApplyInverse (all levels), SURVEY 8(d) formula */
+  double flops_compute;         /* algorithmic flops of Compute (inversions: 2 n^3) */
+  double bytes_a11_level0;      /* 8 * sum n_sd^2 * 2 : the two A11 passes of one ApplyInverse */
+  int64_t kernel_launches;      /* launches issued by this handle so far */
+  double device_bytes;          /* device memory held */
+} hymls_b200_stats;
+int hymls_b200_get_stats(hymls_b200_t* h, hymls_b200_stats* st);
+
+/* Timed loop helpers used by bench.py: run ApplyInverse `reps` times on device-resident vectors and
+   return the average CUDA-event time per call of (a) the whole call, (b) the dominant kernel
+   (batched A11^-1 apply, both passes). */
+int hymls_b200_time_apply(hymls_b200_t* h, int reps, double* ms_per_apply, double* ms_a11_kernel_per_launch);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

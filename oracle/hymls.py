@@ -28,7 +28,8 @@ SMALL = 1e-14  # HYMLS_SMALL_ENTRY, src/HYMLS_Macros.hpp:29
 
 
 def sign(x):
-    return 1.0 if x >= 0 else -1.0
+    # src/HYMLS_Householder.cpp:15-18 -- note sign(0) == 0
+    return -1.0 if x < 0 else (1.0 if x > 0 else 0.0)
 
 
 # ---------------------------------------------------------------------------

@@ -1,0 +1,108 @@
+"""Bit-exact index maps: the C++ host partitioner (through the C ABI, no GPU needed) against the oracle,
+which tests/test_oracle_partitioner.py pins to the reference's own unit-test expectations."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import hymls_b200 as hb
+from hymls_b200 import api
+from oracle import hymls as ohymls
+from oracle.partitioner import CartesianPartitioner
+from tests.common import make_params
+
+
+def _dictify(p):
+    return {k: (_dictify(v) if isinstance(v, dict) else v) for k, v in p.items()}
+
+
+def test_library_exports_every_declared_symbol():
+    lib = hb.load_library()
+    header = open(os.path.join(os.path.dirname(api._HERE), "include", "hymls_b200.h")).read()
+    names = set(re.findall(r"\b(hymls_b200_[a-z_0-9]+)\s*\(", header))
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), n
+
+
+def test_compute_without_device_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    p = make_params("Laplace", 2, 8, 4, 1)
+    A = hb.galeri.create_matrix("Laplace", 2, 8)
+    with pytest.raises(hb.HymlsError) as e:
+        hb.Preconditioner(A, _dictify(p))  # values need the device
+    assert e.value.code == -3 and "no CPU fallback" in str(e.value)
+    P = hb.Preconditioner(A, _dictify(p), pattern_only=True)
+    P.Initialize()
+    with pytest.raises(hb.HymlsError) as e:
+        P.Compute()
+    assert e.value.code == -3
+
+
+def test_unknown_preconditioner_parameter_is_rejected():
+    # validateParameters, src/HYMLS_Preconditioner.cpp:126-130 (this is what makes testSuite/cavity.xml stale)
+    p = _dictify(make_params("Stokes-C", 2, 8, 4, 1))
+    p["Preconditioner"]["Classifier"] = "Stokes"
+    with pytest.raises(hb.HymlsError) as e:
+        hb.Preconditioner(None, p)
+    assert "Classifier" in str(e.value)
+
+
+CASES = [
+    ("Laplace", 2, 32, 4, 2, None),
+    ("Laplace", 3, 16, 4, 2, None),
+    ("Stokes-C", 2, 32, 4, 3, 2),
+    ("Stokes-C", 2, 24, 4, 1, None),      # ragged: 24 = 6 subdomains of 4
+    ("Stokes-C", 3, 16, 4, 2, 2),
+    ("Stokes-C", 3, 16, 8, 1, None),
+    ("Stokes-C", 3, 12, 4, 1, None),
+]
+
+
+@pytest.mark.parametrize("eqn,dim,nx,sx,levels,cx", CASES)
+def test_maps_match_oracle_on_every_level(eqn, dim, nx, sx, levels, cx):
+    extra = {"Eliminate_Tube_Pressures_With_Velocities": True} if (eqn == "Stokes-C" and dim == 3) else {}
+    p = make_params(eqn, dim, nx, sx, levels, cx, **extra)
+    A = hb.galeri.create_matrix(eqn, dim, nx)
+    if eqn == "Stokes-C":
+        A = -A
+    tv = hb.galeri.create_testvector(A)
+    P = hb.Preconditioner(A, _dictify(p), tv, pattern_only=True)
+    P.Initialize()
+    O = ohymls.Preconditioner(A, p.copy(), tv)
+    O.initialize()
+    assert P.NumLevels() == max(levels, 1)
+    lvl = O
+    for l in range(P.NumLevels()):
+        hid = lvl.hid
+        assert P.NumMySubdomains(l) == hid.num_subdomains()
+        for sd in range(hid.num_subdomains()):
+            assert np.array_equal(P.GetInteriorGroup(sd, l), np.asarray(hid.interior[sd], dtype=np.int64))
+            got = P.GetSeparatorGroups(sd, l)
+            assert len(got) == len(hid.groups[sd])
+            for (t, g), (to, go) in zip(got, hid.groups[sd]):
+                assert t == to and np.array_equal(g, np.asarray(go, dtype=np.int64))
+        assert np.array_equal(P.GetMap(api.MAP_OVERLAPPING, l), hid.overlapping_map)
+        assert np.array_equal(P.GetMap(api.MAP_INTERIOR, l), hid.interior_map())
+        assert np.array_equal(P.GetMap(api.MAP_SEPARATOR, l), hid.separator_map())
+        assert np.array_equal(P.GetMap(api.MAP_VSUM, l), lvl.schur_prec.vsum_gids)
+        if l + 1 < P.NumLevels():
+            # the oracle builds deeper levels during compute(); do the symbolic part by hand
+            sp_ = lvl.schur_prec
+            import scipy.sparse as sps
+            nv = len(sp_.vsum_gids)
+            lvl = ohymls.Preconditioner(sps.identity(nv, format="csr"), p.copy(), np.ones(nv), l + 1,
+                                        sp_.next_hid, gids=sp_.vsum_gids)
+            lvl.initialize()
+
+
+@pytest.mark.parametrize("nx,sx,nprocs", [(64, 4, 8), (64, 4, 2), (64, 4, 4), (32, 4, 64), (64, 8, 8), (32, 4, 3)])
+def test_pid_map_matches_oracle(nx, sx, nprocs):
+    p = make_params("Stokes-C", 3, nx, sx, 1)
+    got = hb.pid_map(_dictify(p), nprocs)
+    ref = CartesianPartitioner(p.copy(), 0, nprocs, 0).partition().pid_map
+    assert np.array_equal(got, np.asarray(ref, dtype=np.int32))

@@ -79,6 +79,8 @@ def load_library():
     lib.hymls_b200_pid_map.argtypes = [C.c_char_p, C.c_int, vp, C.c_int]
     lib.hymls_b200_get_stats.argtypes = [vp, P(_Stats)]
     lib.hymls_b200_time_apply.argtypes = [vp, C.c_int, P(dbl), P(dbl)]
+    lib.hymls_b200_debug_copy.argtypes = [vp, C.c_int, C.c_char_p, vp, i64]
+    lib.hymls_b200_debug_copy.restype = i64
     _LIB = lib
     return lib
 
@@ -259,6 +261,14 @@ class Preconditioner:
         _check(self._lib, int(n))
         out = np.zeros(n, dtype=np.int64)
         self._lib.hymls_b200_get_map(self._h, level, which, out.ctypes.data, n)
+        return out
+
+    def DebugArray(self, name, level=0):
+        n = self._lib.hymls_b200_debug_copy(self._h, level, name.encode(), None, 0)
+        _check(self._lib, int(n))
+        out = np.zeros(n)
+        if n:
+            _check(self._lib, int(self._lib.hymls_b200_debug_copy(self._h, level, name.encode(), out.ctypes.data, n)))
         return out
 
     def Stats(self):

@@ -205,6 +205,12 @@ int hymls_b200_get_stats(hymls_b200_t* h, hymls_b200_stats* st) {
   HY_CATCH
 }
 
+int64_t hymls_b200_debug_copy(hymls_b200_t* h, int level, const char* name, double* out, int64_t cap) {
+  HY_TRY
+  return h->eng->debugCopy(level, name, out, cap);
+  HY_CATCH
+}
+
 int hymls_b200_time_apply(hymls_b200_t* h, int reps, double* msApply, double* msA11) {
   HY_TRY
   h->eng->timeApply(reps, msApply, msA11);

@@ -550,13 +550,12 @@ void Engine::computeLevel(int l) {
 
   // transformed + dropped Schur complement: reduced matrix on the V-sums (next level) and separator blocks
   Level* next = (l + 1 < (int)levels_.size()) ? levels_[l + 1].get() : nullptr;
-  DevBuf<double> redValOwn;
   double* redVal;
   if (next) {
     redVal = next->val.p;
   } else {
-    redValOwn.alloc(S.redCol.size());
-    redVal = redValOwn.p;
+    L.redValLast.alloc(S.redCol.size());
+    redVal = L.redValLast.p;
   }
   HY_CUDA(cudaMemsetAsync(redVal, 0, S.redCol.size() * sizeof(double), s));
   DevBuf<double> blkW;
@@ -1035,6 +1034,41 @@ void Engine::solve(const double* b, double* x, int where, uint64_t seed, hymls_b
   }
   if (hist)
     for (int i = 0; i < (int)history.size() && i < histCap; ++i) hist[i] = history[i];
+}
+
+// test hook: copies a device array to the host (doubles). Returns its length.
+int64_t Engine::debugCopy(int level, const std::string& name, double* out, int64_t cap) {
+  needDevice();
+  Level& L = *levels_.at(level);
+  const double* p = nullptr;
+  int64_t n = 0;
+  if (name == "a11inv") { p = L.a11.F.p; n = (int64_t)L.a11.F.n; }
+  else if (name == "blkinv") { p = L.blk.F.p; n = (int64_t)L.blk.F.n; }
+  else if (name == "coarseinv") { p = coarse_.F.p; n = (int64_t)coarse_.F.n; }
+  else if (name == "redval") {
+    if (level + 1 < (int)levels_.size()) { p = levels_[level + 1]->val.p; n = (int64_t)levels_[level + 1]->val.n; }
+    else { p = L.redValLast.p; n = (int64_t)L.redValLast.n; }
+  }
+  else if (name == "v12") { p = L.v12.p; n = (int64_t)L.v12.n; }
+  else if (name == "v21") { p = L.v21.p; n = (int64_t)L.v21.n; }
+  else if (name == "what") { p = L.what.p; n = (int64_t)L.what.n; }
+  else if (name == "redptr" || name == "redcol" || name == "a11off" || name == "blkoff" || name == "blkrows") {
+    const LevelSym& S = L.sym;
+    std::vector<double> v;
+    if (name == "redptr") v.assign(S.redPtr.begin(), S.redPtr.end());
+    else if (name == "redcol") v.assign(S.redCol.begin(), S.redCol.end());
+    else if (name == "a11off") v.assign(S.a11Off.begin(), S.a11Off.end());
+    else if (name == "blkoff") v.assign(S.blkOff.begin(), S.blkOff.end());
+    else v.assign(S.blkRows.begin(), S.blkRows.end());
+    if (out && cap >= (int64_t)v.size()) std::copy(v.begin(), v.end(), out);
+    return (int64_t)v.size();
+  }
+  else throw Error(HYMLS_B200_ERR_ARG, "debug_copy: unknown array '" + name + "'");
+  if (out && cap >= n && n > 0) {
+    HY_CUDA(cudaMemcpyAsync(out, p, n * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+    HY_CUDA(cudaStreamSynchronize(stream_));
+  }
+  return n;
 }
 
 void Engine::getStats(hymls_b200_stats* st) {

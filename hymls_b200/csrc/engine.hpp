@@ -60,6 +60,7 @@ struct Level {
   DevBuf<int> blkRows;
   // work vectors
   DevBuf<double> x1, y1, rhsS, Z, Y, vsRhs, vsSol;
+  DevBuf<double> redValLast;  // reduced Schur values when this is the last level (kept for inspection)
 };
 
 class Engine {
@@ -77,6 +78,7 @@ class Engine {
              int histCap);
   void timeApply(int reps, double* msApply, double* msA11);
   void getStats(hymls_b200_stats* st);
+  int64_t debugCopy(int level, const std::string& name, double* out, int64_t cap);
 
   int numLevels() const { return (int)levels_.size(); }
   const LevelSym& sym(int l) const { return levels_.at(l)->sym; }

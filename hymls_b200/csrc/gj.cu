@@ -321,10 +321,9 @@ static constexpr size_t GJ_UPD_SMEM = (size_t)(GJ_NB * (GJ_TJ + 4) + GJ_TM * (GJ
 void invertBatched(double* W, double* F, const int64_t* dOff, const int* dN, const int* dNp, int count, int npMax,
                    int* dPiv, int* dPerm, int* dInfo, cudaStream_t s, int64_t* launches) {
   if (count == 0 || npMax == 0) return;
-  static bool attrSet = false;
+  static bool attrSet = false, permAttrSet = false;
   if (!attrSet) {
     HY_CUDA(cudaFuncSetAttribute(k_gj_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GJ_UPD_SMEM));
-    HY_CUDA(cudaFuncSetAttribute(k_gj_perm, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attrSet = true;
   }
   if ((size_t)npMax * sizeof(int) > 200 * 1024)
@@ -336,6 +335,10 @@ void invertBatched(double* W, double* F, const int64_t* dOff, const int* dN, con
     dim3 g((npMax + GJ_TJ - 1) / GJ_TJ, count);
     k_gj_update<<<g, GJ_UPD_T, GJ_UPD_SMEM, s>>>(W, dOff, dNp, dPiv, npMax, k0);
     *launches += 2;
+  }
+  if ((size_t)npMax * sizeof(int) > 48 * 1024 && !permAttrSet) {
+    HY_CUDA(cudaFuncSetAttribute(k_gj_perm, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    permAttrSet = true;
   }
   k_gj_perm<<<count, 256, npMax * sizeof(int), s>>>(dNp, dPiv, dPerm, npMax, count);
   dim3 g2((npMax + 7) / 8, count);

@@ -229,20 +229,24 @@ void dropByValue(double* val, const int64_t* ptr, const int* col, double* diagSc
   *launches += 2;
 }
 
+// the opt-in dynamic shared memory limit of a kernel only ever grows (it caps launches, also below 48 KB)
+static size_t g_rowSmemSet = 48 * 1024, g_blkSmemSet = 48 * 1024;
+static void ensureRowSmem(size_t rowSmem) {
+  if (rowSmem <= g_rowSmemSet) return;
+  if (rowSmem > 227 * 1024)
+    throw Error(HYMLS_B200_ERR_UNSUPPORTED, "subdomain too large for the Schur row kernel (n + m > 29000)");
+  HY_CUDA(cudaFuncSetAttribute(k_schur_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rowSmem));
+  g_rowSmemSet = rowSmem;
+}
+
 void schurAssemble(const SchurArgs& a, int sd0, int sd1, int64_t R0, int64_t R1, int64_t lk0, int64_t lk1, int pass,
                    size_t rowSmem, size_t blkSmem, cudaStream_t s, int64_t* launches) {
-  static size_t rowSet = 0, blkSet = 0;
-  if (rowSmem > rowSet) {
-    if (rowSmem > 227 * 1024)
-      throw Error(HYMLS_B200_ERR_UNSUPPORTED, "subdomain too large for the Schur row kernel (n + m > 29000)");
-    HY_CUDA(cudaFuncSetAttribute(k_schur_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rowSmem));
-    rowSet = rowSmem;
-  }
-  if (blkSmem > blkSet) {
+  ensureRowSmem(rowSmem);
+  if (blkSmem > g_blkSmemSet) {
     if (blkSmem > 200 * 1024)
       throw Error(HYMLS_B200_ERR_UNSUPPORTED, "linked separator set too large for the block kernel");
     HY_CUDA(cudaFuncSetAttribute(k_schur_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blkSmem));
-    blkSet = blkSmem;
+    g_blkSmemSet = blkSmem;
   }
   if (R1 > R0) {
     k_schur_rows<<<(unsigned)(R1 - R0), 128, rowSmem, s>>>(a, R0, pass, nullptr, 0);
@@ -256,7 +260,7 @@ void schurAssemble(const SchurArgs& a, int sd0, int sd1, int64_t R0, int64_t R1,
 void schurDense(const SchurArgs& a, int64_t R0, int64_t R1, double* denseS, int64_t ldS, size_t rowSmem,
                 cudaStream_t s, int64_t* launches) {
   if (R1 <= R0) return;
-  HY_CUDA(cudaFuncSetAttribute(k_schur_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rowSmem));
+  ensureRowSmem(rowSmem);
   k_schur_rows<<<(unsigned)(R1 - R0), 128, rowSmem, s>>>(a, R0, 2, denseS, ldS);
   ++*launches;
   HY_CUDA(cudaGetLastError());

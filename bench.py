@@ -36,7 +36,7 @@ def parse():
     ap.add_argument("--nx", type=int, default=int(os.environ.get("HYMLS_BENCH_NX", 64)))
     ap.add_argument("--sx", type=int, default=int(os.environ.get("HYMLS_BENCH_SX", 8)))
     ap.add_argument("--levels", type=int, default=2)
-    ap.add_argument("--cx", type=int, default=0, help="coarsening factor (0: nx/(2*sx), at least 2)")
+    ap.add_argument("--cx", type=int, default=4, help="coarsening factor between levels")
     ap.add_argument("--no-solve", action="store_true", help="skip the GMRES solve")
     ap.add_argument("--cpu-sample-nx", type=int, default=16)
     return ap.parse_args()
@@ -142,7 +142,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     nx, sx = args.nx, args.sx
-    cx = args.cx if args.cx else max(2, nx // (2 * sx))
+    cx = args.cx
     nsd_full = (nx // sx) ** 3
     workload = "synthetic 3D lid-driven cavity (Stokes-C, GaleriExt::Stokes3D a=nx^2 b=1) %d^3, dof 4, sx=%d, %d levels, cx=%d" % (
         nx, sx, args.levels, cx)

@@ -436,10 +436,29 @@ static void invertRange(BatchedInverse& B, int m0, int m1, double* W, DevBuf<int
   HY_CUDA(cudaStreamSynchronize(s));  // relOff is reused by the next chunk
 }
 
+struct PhaseTimer {
+  cudaStream_t s;
+  bool on;
+  int level;
+  std::chrono::steady_clock::time_point t0;
+  PhaseTimer(cudaStream_t st, int lvl) : s(st), on(getenv("HYMLS_B200_VERBOSE") != nullptr), level(lvl) {
+    if (on) { cudaStreamSynchronize(s); t0 = std::chrono::steady_clock::now(); }
+  }
+  void lap(const char* what) {
+    if (!on) return;
+    cudaStreamSynchronize(s);
+    auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[hymls_b200] level %d %-28s %9.3f ms\n", level, what,
+            std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+};
+
 void Engine::computeLevel(int l) {
   Level& L = *levels_[l];
   LevelSym& S = L.sym;
   cudaStream_t s = stream_;
+  PhaseTimer pt(s, l);
   // (1) off-diagonal blocks: value gathers (MatrixBlock::Compute)
   gatherValues(L.val.p, L.src12.p, L.v12.p, (int64_t)S.A12.col.size(), s, &launches_);
   gatherValues(L.val.p, L.src21.p, L.v21.p, (int64_t)S.A21.col.size(), s, &launches_);
@@ -467,6 +486,7 @@ void Engine::computeLevel(int l) {
     }
     checkInfo(info_, s, "subdomain solver (A11) of level " + std::to_string(l));
   }
+  pt.lap("A11 fill + inversion");
   // (3) Schur complement
   SchurArgs a{};
   a.rowSd = L.rowSd.p;
@@ -572,6 +592,7 @@ void Engine::computeLevel(int l) {
   for (int pass = 1; pass <= 2; ++pass)
     for (const Level::Chunk& c : L.chunks)
       schurAssemble(a, c.sd0, c.sd1, c.R0, c.R1, c.lk0, c.lk1, pass, L.rowSmem, L.blkSmem, s, &launches_);
+  pt.lap("Schur assembly (2 passes)");
   {
     int h = 0;
     HY_CUDA(cudaMemcpyAsync(&h, info_.p, sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -590,6 +611,7 @@ void Engine::computeLevel(int l) {
     for (int b = 0; b < S.nblk; ++b) stats_.flops_compute += 2.0 * std::pow((double)S.blkN[b], 3);
     checkInfo(info_, s, "separator block of level " + std::to_string(l));
   }
+  pt.lap("separator block inversion");
   // reduced Schur complement: drop (RelDropDiag, ComputeNextLevel :548), then next level or coarse solver
   diagScratch_.alloc(S.nuniq);
   dropByValue(redVal, L.redPtr.p, L.redCol.p, diagScratch_.p, S.nuniq, SMALL_ENTRY, s, &launches_);
@@ -598,6 +620,7 @@ void Engine::computeLevel(int l) {
     for (int u = 0; u < S.nuniq; ++u) rowGid[u] = S.H.sepGid[S.H.uniqPtr[u]];
     computeCoarse(L.redPtr.p, L.redCol.p, redVal, S.nuniq, rowGid);
   }
+  pt.lap("drop + coarse solver");
   HY_CUDA(cudaStreamSynchronize(s));
 }
 

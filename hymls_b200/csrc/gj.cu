@@ -13,6 +13,8 @@
 // 2 n^3 flops per matrix, all but O(n^2 NB) of them in the DMMA update.
 #include <cuda_runtime.h>
 
+#include <algorithm>
+
 #include "device.cuh"
 #include "kernels.hpp"
 
@@ -20,7 +22,8 @@ namespace hymls {
 
 static constexpr int GJ_NB = 32;       // panel width
 static constexpr int GJ_PANEL_T = 512; // threads of the panel kernel
-static constexpr int GJ_TJ = 128;      // column strip of the update kernel
+static constexpr int GJ_TJ = 64;       // column strip of the update kernel
+static constexpr int GJ_CS = GJ_TJ / 32; // 8x8 tiles per warp along the strip (4 warps across)
 static constexpr int GJ_TM = 64;       // row tile of the update kernel
 static constexpr int GJ_UPD_T = 256;   // 8 warps: 2 (rows) x 4 (cols), each 4x4 DMMA tiles of 8x8
 
@@ -41,10 +44,11 @@ __global__ void k_pad_identity(double* __restrict__ W, const int64_t* __restrict
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(GJ_PANEL_T)
 k_gj_panel(double* __restrict__ W, const int64_t* __restrict__ off, const int* __restrict__ npArr,
-           int* __restrict__ pivAll, int npMax, int k0, int* __restrict__ info) {
+           int* __restrict__ pivAll, int npMax, int k0, int* __restrict__ info, int rowsCap) {
   const int mat = blockIdx.x;
   const int np = npArr[mat];
   if (k0 >= np) return;
+  if (np - k0 <= rowsCap) return;  // handled by the shared-memory kernel
   const int nb = min(GJ_NB, np - k0);
   double* M = W + off[mat];
   int* piv = pivAll + (int64_t)mat * npMax;
@@ -168,6 +172,209 @@ k_gj_panel(double* __restrict__ W, const int64_t* __restrict__ off, const int* _
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// panel kernel, shared-memory version: the 32-column panel is factored as four 8-column sub-panels
+// that live in shared memory (column-major, [8][rows]) while the column-by-column pivot search / swap /
+// rank-1 update runs; each finished sub-panel updates the rest of the panel in global memory (L2) once.
+// Falls back to k_gj_panel when the active part of a matrix does not fit (rows > GJ_SMEM_ROWS).
+// ---------------------------------------------------------------------------------------------
+static constexpr int GJ_SW = 8;            // sub-panel width
+static constexpr int GJ_SMEM_ROWS = 3072;  // 8 * 3072 * 8 B = 192 KB
+
+__global__ void __launch_bounds__(GJ_PANEL_T)
+k_gj_panel_smem(double* __restrict__ W, const int64_t* __restrict__ off, const int* __restrict__ npArr,
+                int* __restrict__ pivAll, int npMax, int k0, int* __restrict__ info, int rowsCap) {
+  const int mat = blockIdx.x;
+  const int np = npArr[mat];
+  if (k0 >= np) return;
+  if (np - k0 > rowsCap) return;  // handled by the generic kernel
+  const int nb = min(GJ_NB, np - k0);
+  double* M = W + off[mat];
+  int* piv = pivAll + (int64_t)mat * npMax;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  constexpr int NW = GJ_PANEL_T / 32;
+
+  extern __shared__ double sS[];  // [GJ_SW][rs] sub-panel, column major
+  __shared__ double sU[GJ_SW];
+  __shared__ double sUn[GJ_SW][GJ_NB];  // freshly solved U rows of the columns right of the sub-panel
+  __shared__ double sKK[GJ_NB][GJ_NB + 1];
+  __shared__ double sLinv[GJ_NB][GJ_NB + 1];
+  __shared__ double sDinv[GJ_NB][GJ_NB + 1];
+  __shared__ double sRedV[NW];
+  __shared__ int sRedI[NW];
+  __shared__ int sPiv;
+  __shared__ double sPivVal;
+  const int rs = (np - k0) | 1;  // odd stride: column-wise and row-wise accesses both conflict-light
+
+  for (int c0 = k0; c0 < k0 + nb; c0 += GJ_SW) {
+    const int w = min(GJ_SW, k0 + nb - c0);
+    const int R = np - c0;  // active rows of this sub-panel (local row r <-> global row c0 + r)
+    // load
+    for (int e = tid; e < R * w; e += GJ_PANEL_T) {
+      const int r = e / w, q = e % w;
+      sS[q * rs + r] = M[(int64_t)(c0 + r) * np + c0 + q];
+    }
+    __syncthreads();
+    for (int j = 0; j < w; ++j) {
+      // pivot search in column j, local rows j..R-1
+      double bestV = -1.0;
+      int bestR = 0x7fffffff;
+      for (int r = j + tid; r < R; r += GJ_PANEL_T) {
+        const double v = fabs(sS[j * rs + r]);
+        if (v > bestV) {
+          bestV = v;
+          bestR = r;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_down_sync(0xffffffffu, bestV, o);
+        const int orow = __shfl_down_sync(0xffffffffu, bestR, o);
+        if (ov > bestV || (ov == bestV && orow < bestR)) {
+          bestV = ov;
+          bestR = orow;
+        }
+      }
+      if (lane == 0) {
+        sRedV[wid] = bestV;
+        sRedI[wid] = bestR;
+      }
+      __syncthreads();
+      if (wid == 0) {
+        bestV = lane < NW ? sRedV[lane] : -1.0;
+        bestR = lane < NW ? sRedI[lane] : 0x7fffffff;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const double ov = __shfl_down_sync(0xffffffffu, bestV, o);
+          const int orow = __shfl_down_sync(0xffffffffu, bestR, o);
+          if (ov > bestV || (ov == bestV && orow < bestR)) {
+            bestV = ov;
+            bestR = orow;
+          }
+        }
+        if (lane == 0) {
+          if (bestR == 0x7fffffff) bestR = j;
+          sPiv = bestR;
+          piv[c0 + j] = c0 + bestR;
+          if (!(bestV > 0.0)) atomicExch(info, mat + 1);
+        }
+      }
+      __syncthreads();
+      const int p = sPiv;
+      if (tid < w) {
+        const double a = sS[tid * rs + j];
+        const double b = sS[tid * rs + p];
+        sS[tid * rs + j] = b;
+        sS[tid * rs + p] = a;
+        sU[tid] = b;
+        if (tid == j) sPivVal = b;
+      }
+      __syncthreads();
+      const double rp = 1.0 / sPivVal;
+      for (int r = j + 1 + tid; r < R; r += GJ_PANEL_T) {
+        const double l = sS[j * rs + r] * rp;
+        sS[j * rs + r] = l;
+        for (int q = j + 1; q < w; ++q) sS[q * rs + r] -= l * sU[q];
+      }
+      __syncthreads();
+    }
+    // store the factored sub-panel
+    for (int e = tid; e < R * w; e += GJ_PANEL_T) {
+      const int r = e / w, q = e % w;
+      M[(int64_t)(c0 + r) * np + c0 + q] = sS[q * rs + r];
+    }
+    // row swaps of this sub-panel applied to the other panel columns (one thread per column)
+    const int nOther = nb - w;
+    if (tid < nOther) {
+      const int col = (tid < c0 - k0) ? k0 + tid : c0 + w + (tid - (c0 - k0));
+      for (int j = 0; j < w; ++j) {
+        const int a = c0 + j, b = piv[c0 + j];
+        if (a != b) {
+          const double x = M[(int64_t)a * np + col];
+          const double y = M[(int64_t)b * np + col];
+          M[(int64_t)a * np + col] = y;
+          M[(int64_t)b * np + col] = x;
+        }
+      }
+    }
+    __syncthreads();
+    // columns to the right of the sub-panel: U rows by forward substitution with the unit-lower w x w
+    // block, then the rank-w update of all rows below
+    const int nRight = k0 + nb - (c0 + w);
+    if (nRight > 0) {
+      if (tid < nRight) {
+        const int col = c0 + w + tid;
+        double u[GJ_SW];
+#pragma unroll
+        for (int i = 0; i < GJ_SW; ++i) {
+          if (i < w) {
+            double x = M[(int64_t)(c0 + i) * np + col];
+            for (int t = 0; t < i; ++t) x -= sS[t * rs + i] * u[t];
+            u[i] = x;
+            M[(int64_t)(c0 + i) * np + col] = x;
+            sUn[i][tid] = x;
+          }
+        }
+      }
+      __syncthreads();
+      for (int r = w + tid; r < R; r += GJ_PANEL_T) {
+        double l[GJ_SW];
+#pragma unroll
+        for (int t = 0; t < GJ_SW; ++t) l[t] = t < w ? sS[t * rs + r] : 0.0;
+        double* row = M + (int64_t)(c0 + r) * np + c0 + w;
+        for (int q = 0; q < nRight; ++q) {
+          double x = row[q];
+#pragma unroll
+          for (int t = 0; t < GJ_SW; ++t) x -= l[t] * sUn[t][q];
+          row[q] = x;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // ---- (B) Linv = inv(L_KK) (unit lower), Dinv = inv(U) * Linv ----
+  for (int e = tid; e < nb * nb; e += GJ_PANEL_T) sKK[e / nb][e % nb] = M[(int64_t)(k0 + e / nb) * np + k0 + e % nb];
+  __syncthreads();
+  if (tid < nb) {
+    const int t = tid;
+    for (int i = 0; i < nb; ++i) {
+      double x = (i == t) ? 1.0 : 0.0;
+      for (int k = t; k < i; ++k) x -= sKK[i][k] * sLinv[k][t];
+      sLinv[i][t] = (i < t) ? 0.0 : x;
+    }
+    for (int i = nb - 1; i >= 0; --i) {
+      double x = sLinv[i][t];
+      for (int k = i + 1; k < nb; ++k) x -= sKK[i][k] * sDinv[k][t];
+      sDinv[i][t] = x / sKK[i][i];
+    }
+  }
+  __syncthreads();
+  // ---- (C) G' overwrites the panel columns ----
+  for (int r = tid; r < np; r += GJ_PANEL_T) {
+    double* row = M + (int64_t)r * np + k0;
+    if (r >= k0 && r < k0 + nb) {
+      for (int q = 0; q < nb; ++q) row[q] = sDinv[r - k0][q];
+      continue;
+    }
+    const bool above = r < k0;
+    double a[GJ_NB];
+#pragma unroll
+    for (int q = 0; q < GJ_NB; ++q) a[q] = q < nb ? row[q] : 0.0;
+    for (int q = 0; q < nb; ++q) {
+      double s = 0.0;
+      if (above) {
+#pragma unroll
+        for (int k = 0; k < GJ_NB; ++k) s += (k < nb) ? a[k] * sDinv[k][q] : 0.0;
+      } else {
+#pragma unroll
+        for (int k = 0; k < GJ_NB; ++k) s += (k < nb) ? a[k] * sLinv[k][q] : 0.0;
+      }
+      row[q] = -s;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // DMMA m8n8k4 (FP64 tensor core): D(8x8) += A(8x4, row) * B(4x8, col)
 //   a : A[lane/4][lane%4]        b : B[lane%4][lane/4]        c0,c1 : C[lane/4][2*(lane%4) + {0,1}]
@@ -179,7 +386,7 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 }
 
 // update kernel: grid (column strips, matrices)
-__global__ void __launch_bounds__(GJ_UPD_T)
+__global__ void __launch_bounds__(GJ_UPD_T, 3)
 k_gj_update(double* __restrict__ W, const int64_t* __restrict__ off, const int* __restrict__ npArr,
             const int* __restrict__ pivAll, int npMax, int k0) {
   const int mat = blockIdx.y;
@@ -232,14 +439,14 @@ k_gj_update(double* __restrict__ W, const int64_t* __restrict__ off, const int* 
       sA[r * SA + k] = (r0 + r < np && k < nb) ? M[(int64_t)(r0 + r) * np + k0 + k] : 0.0;
     }
     __syncthreads();
-    double acc[4][4][2];
+    double acc[4][GJ_CS][2];
 #pragma unroll
     for (int ti = 0; ti < 4; ++ti) {
       const int row = r0 + (wr * 4 + ti) * 8 + fr;
       const bool inK = (row >= k0 && row < k0 + nb);  // rows of the panel are replaced, not accumulated
 #pragma unroll
-      for (int tj = 0; tj < 4; ++tj) {
-        const int col = j0 + (wc * 4 + tj) * 8 + 2 * fk;
+      for (int tj = 0; tj < GJ_CS; ++tj) {
+        const int col = j0 + (wc * GJ_CS + tj) * 8 + 2 * fk;
         const bool ok = row < np && col < j0 + jw && !inK;
         acc[ti][tj][0] = ok ? M[(int64_t)row * np + col] : 0.0;
         acc[ti][tj][1] = ok ? M[(int64_t)row * np + col + 1] : 0.0;
@@ -247,22 +454,22 @@ k_gj_update(double* __restrict__ W, const int64_t* __restrict__ off, const int* 
     }
 #pragma unroll
     for (int kk = 0; kk < GJ_NB / 4; ++kk) {
-      double a[4], b[4];
+      double a[4], b[GJ_CS];
 #pragma unroll
       for (int ti = 0; ti < 4; ++ti) a[ti] = sA[((wr * 4 + ti) * 8 + fr) * SA + kk * 4 + fk];
 #pragma unroll
-      for (int tj = 0; tj < 4; ++tj) b[tj] = sB[(kk * 4 + fk) * SB + (wc * 4 + tj) * 8 + fr];
+      for (int tj = 0; tj < GJ_CS; ++tj) b[tj] = sB[(kk * 4 + fk) * SB + (wc * GJ_CS + tj) * 8 + fr];
 #pragma unroll
       for (int ti = 0; ti < 4; ++ti)
 #pragma unroll
-        for (int tj = 0; tj < 4; ++tj) dmma884(acc[ti][tj][0], acc[ti][tj][1], a[ti], b[tj]);
+        for (int tj = 0; tj < GJ_CS; ++tj) dmma884(acc[ti][tj][0], acc[ti][tj][1], a[ti], b[tj]);
     }
 #pragma unroll
     for (int ti = 0; ti < 4; ++ti) {
       const int row = r0 + (wr * 4 + ti) * 8 + fr;
 #pragma unroll
-      for (int tj = 0; tj < 4; ++tj) {
-        const int col = j0 + (wc * 4 + tj) * 8 + 2 * fk;
+      for (int tj = 0; tj < GJ_CS; ++tj) {
+        const int col = j0 + (wc * GJ_CS + tj) * 8 + 2 * fk;
         // the panel's own columns hold G' and are left alone
         if (row < np && col < j0 + jw && (col < k0 || col >= k0 + nb)) {
           M[(int64_t)row * np + col] = acc[ti][tj][0];
@@ -324,6 +531,8 @@ void invertBatched(double* W, double* F, const int64_t* dOff, const int* dN, con
   static bool attrSet = false, permAttrSet = false;
   if (!attrSet) {
     HY_CUDA(cudaFuncSetAttribute(k_gj_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GJ_UPD_SMEM));
+    HY_CUDA(cudaFuncSetAttribute(k_gj_panel_smem, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)((size_t)GJ_SW * (GJ_SMEM_ROWS | 1) * sizeof(double))));
     attrSet = true;
   }
   if ((size_t)npMax * sizeof(int) > 200 * 1024)
@@ -331,7 +540,14 @@ void invertBatched(double* W, double* F, const int64_t* dOff, const int* dN, con
   k_pad_identity<<<count, 64, 0, s>>>(W, dOff, dN, dNp, count);
   ++*launches;
   for (int k0 = 0; k0 < npMax; k0 += GJ_NB) {
-    k_gj_panel<<<count, GJ_PANEL_T, 0, s>>>(W, dOff, dNp, dPiv, npMax, k0, dInfo);
+    const int activeMax = npMax - k0;
+    const int rowsCap = GJ_SMEM_ROWS;
+    const size_t psm = (size_t)GJ_SW * ((std::min(activeMax, rowsCap)) | 1) * sizeof(double);
+    k_gj_panel_smem<<<count, GJ_PANEL_T, psm, s>>>(W, dOff, dNp, dPiv, npMax, k0, dInfo, rowsCap);
+    if (activeMax > rowsCap) {
+      k_gj_panel<<<count, GJ_PANEL_T, 0, s>>>(W, dOff, dNp, dPiv, npMax, k0, dInfo, rowsCap);
+      ++*launches;
+    }
     dim3 g((npMax + GJ_TJ - 1) / GJ_TJ, count);
     k_gj_update<<<g, GJ_UPD_T, GJ_UPD_SMEM, s>>>(W, dOff, dNp, dPiv, npMax, k0);
     *launches += 2;

@@ -60,6 +60,10 @@ def load_library():
     lib.hymls_b200_destroy.argtypes = [vp]
     lib.hymls_b200_destroy.restype = None
     lib.hymls_b200_set_stream.argtypes = [vp, vp]
+    lib.hymls_b200_comm_get_unique_id.argtypes = [vp]
+    lib.hymls_b200_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
+    lib.hymls_b200_set_rank.argtypes = [vp, C.c_int, C.c_int]
+    lib.hymls_b200_get_owned_subdomains.argtypes = [vp, C.c_int, vp, C.c_int]
     lib.hymls_b200_set_matrix_csr.argtypes = [vp, i64, vp, vp, vp, C.c_int]
     lib.hymls_b200_set_testvector.argtypes = [vp, vp]
     lib.hymls_b200_initialize.argtypes = [vp]
@@ -181,6 +185,28 @@ class Preconditioner:
                 self._h, n, rp.ctypes.data, ci.ctypes.data, None if pattern_only else v.ctypes.data, HOST))
         self.n = n
         return 0
+
+    # -- multi-GPU (one process per GPU) -------------------------------------------------------------
+    @staticmethod
+    def CommUniqueId():
+        lib = load_library()
+        buf = (C.c_char * 128)()
+        _check(lib, lib.hymls_b200_comm_get_unique_id(buf))
+        return bytes(buf)
+
+    def CommInit(self, unique_id, rank, nranks):
+        buf = (C.c_char * 128).from_buffer_copy(unique_id)
+        return _check(self._lib, self._lib.hymls_b200_comm_init(self._h, buf, rank, nranks))
+
+    def SetRank(self, rank, nranks):
+        return _check(self._lib, self._lib.hymls_b200_set_rank(self._h, rank, nranks))
+
+    def OwnedSubdomains(self, level=0):
+        n = _check(self._lib, self._lib.hymls_b200_get_owned_subdomains(self._h, level, None, 0))
+        out = np.zeros(n, dtype=np.int32)
+        if n:
+            _check(self._lib, self._lib.hymls_b200_get_owned_subdomains(self._h, level, out.ctypes.data, n))
+        return out
 
     def Initialize(self):
         return _check(self._lib, self._lib.hymls_b200_initialize(self._h))

@@ -261,6 +261,18 @@ void scaleByInvNorm(const double* x, const double* nrm2, double* y, int64_t n, c
   k_scale_by_inv<<<DOT_BLOCKS, 256, 0, s>>>(x, nrm2, y, n);
   ++*launches;
 }
+// y[i] = b[idx[i]] + t[i]
+__global__ void k_gather_add(const double* __restrict__ b, const int* __restrict__ idx, const double* __restrict__ t,
+                             double* __restrict__ y, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = b[idx[i]] + t[i];
+}
+void gatherAdd(const double* b, const int* idx, const double* t, double* y, int64_t n, cudaStream_t s,
+               int64_t* launches) {
+  if (n == 0) return;
+  k_gather_add<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(b, idx, t, y, n);
+  ++*launches;
+}
 __global__ void k_set_value(double* x, int64_t idx, double v) { x[idx] = v; }
 void setValue(double* x, int64_t idx, double v, cudaStream_t s, int64_t* launches) {
   k_set_value<<<1, 1, 0, s>>>(x, idx, v);

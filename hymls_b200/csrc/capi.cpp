@@ -66,6 +66,37 @@ int hymls_b200_set_stream(hymls_b200_t* h, void* s) {
   HY_CATCH
 }
 
+int hymls_b200_comm_get_unique_id(void* id128) {
+  HY_TRY
+  if (!id128) throw Error(HYMLS_B200_ERR_ARG, "null id");
+  Comm::uniqueId(id128);
+  return 0;
+  HY_CATCH
+}
+
+int hymls_b200_comm_init(hymls_b200_t* h, const void* id128, int rank, int nranks) {
+  HY_TRY
+  h->eng->commInit(id128, rank, nranks);
+  return 0;
+  HY_CATCH
+}
+
+int hymls_b200_set_rank(hymls_b200_t* h, int rank, int nranks) {
+  HY_TRY
+  h->eng->setRankOnly(rank, nranks);
+  return 0;
+  HY_CATCH
+}
+
+int hymls_b200_get_owned_subdomains(hymls_b200_t* h, int level, int32_t* sd, int cap) {
+  HY_TRY
+  if (!h->eng->initialized()) throw Error(HYMLS_B200_ERR_STATE, "not initialized");
+  const std::vector<int>& v = h->eng->ownedSubdomains(level);
+  if (sd && cap >= (int)v.size()) std::memcpy(sd, v.data(), v.size() * sizeof(int));
+  return (int)v.size();
+  HY_CATCH
+}
+
 int hymls_b200_set_matrix_csr(hymls_b200_t* h, int64_t n, const int64_t* rowptr, const int32_t* colidx,
                               const double* values, int where) {
   HY_TRY

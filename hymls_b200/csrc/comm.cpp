@@ -1,0 +1,91 @@
+#include "comm.hpp"
+
+#include <dlfcn.h>
+
+#include <cstdlib>
+#include <string>
+
+#include "../../include/hymls_b200.h"
+#include "params.hpp"
+
+namespace hymls {
+
+namespace {
+typedef struct { char internal[128]; } NcclUniqueId;
+typedef int (*GetUniqueIdFn)(NcclUniqueId*);
+typedef int (*CommInitRankFn)(void**, int, NcclUniqueId, int);
+typedef int (*AllReduceFn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*CommDestroyFn)(void*);
+typedef int (*BroadcastFn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef const char* (*GetErrorStringFn)(int);
+
+struct Api {
+  void* lib = nullptr;
+  GetUniqueIdFn getUniqueId = nullptr;
+  CommInitRankFn commInitRank = nullptr;
+  AllReduceFn allReduce = nullptr;
+  CommDestroyFn commDestroy = nullptr;
+  BroadcastFn broadcast = nullptr;
+  GetErrorStringFn errorString = nullptr;
+};
+
+Api& api() {
+  static Api a;
+  if (a.lib) return a;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) {
+    a.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (a.lib) break;
+  }
+  if (!a.lib) throw Error(HYMLS_B200_ERR_CUDA, std::string("cannot load NCCL (libnccl.so.2): ") + dlerror());
+  a.getUniqueId = (GetUniqueIdFn)dlsym(a.lib, "ncclGetUniqueId");
+  a.commInitRank = (CommInitRankFn)dlsym(a.lib, "ncclCommInitRank");
+  a.allReduce = (AllReduceFn)dlsym(a.lib, "ncclAllReduce");
+  a.commDestroy = (CommDestroyFn)dlsym(a.lib, "ncclCommDestroy");
+  a.broadcast = (BroadcastFn)dlsym(a.lib, "ncclBroadcast");
+  a.errorString = (GetErrorStringFn)dlsym(a.lib, "ncclGetErrorString");
+  if (!a.getUniqueId || !a.commInitRank || !a.allReduce || !a.commDestroy || !a.broadcast)
+    throw Error(HYMLS_B200_ERR_CUDA, "NCCL library lacks the expected symbols");
+  return a;
+}
+
+void check(int rc, const char* what) {
+  if (rc != 0) {
+    Api& a = api();
+    throw Error(HYMLS_B200_ERR_CUDA,
+                std::string("NCCL error in ") + what + ": " + (a.errorString ? a.errorString(rc) : "?"));
+  }
+}
+}  // namespace
+
+Comm::~Comm() {
+  if (comm_) api().commDestroy(comm_);
+}
+
+void Comm::uniqueId(void* id128) { check(api().getUniqueId((NcclUniqueId*)id128), "ncclGetUniqueId"); }
+
+void Comm::init(const void* id128, int rank, int nranks) {
+  NcclUniqueId id = *(const NcclUniqueId*)id128;
+  check(api().commInitRank(&comm_, nranks, id, rank), "ncclCommInitRank");
+  rank_ = rank;
+  nranks_ = nranks;
+}
+
+void Comm::allReduceSum(double* buf, size_t count, cudaStream_t s) const {
+  if (!comm_ || count == 0) return;
+  const int ncclDouble = 8, ncclSum = 0;  // ncclFloat64, ncclSum (nccl.h enums, stable across 2.x)
+  static const bool syncEach = getenv("HYMLS_B200_SYNC_NCCL") != nullptr;
+  if (syncEach) cudaStreamSynchronize(s);
+  check(api().allReduce(buf, buf, count, ncclDouble, ncclSum, comm_, s), "ncclAllReduce");
+  if (syncEach) cudaStreamSynchronize(s);
+}
+
+}  // namespace hymls
+
+namespace hymls {
+void Comm::broadcast(double* buf, size_t count, int root, cudaStream_t s) const {
+  if (!comm_ || count == 0) return;
+  const int ncclDouble = 8;
+  check(api().broadcast(buf, buf, count, ncclDouble, root, comm_, s), "ncclBroadcast");
+}
+}  // namespace hymls

@@ -64,6 +64,20 @@ Engine::Engine(const std::string& xml) {
   }
 }
 
+void Engine::commInit(const void* id128, int rank, int nranks) {
+  needDevice();
+  if (nranks < 1 || rank < 0 || rank >= nranks) throw Error(HYMLS_B200_ERR_ARG, "comm_init: bad rank");
+  if (nranks > 1) comm_.init(id128, rank, nranks); else comm_.setRankOnly(0, 1);
+  initialized_ = false;
+  computed_ = false;
+}
+void Engine::setRankOnly(int rank, int nranks) {
+  if (nranks < 1 || rank < 0 || rank >= nranks) throw Error(HYMLS_B200_ERR_ARG, "set_rank: bad rank");
+  comm_.setRankOnly(rank, nranks);
+  initialized_ = false;
+  computed_ = false;
+}
+
 void Engine::needDevice() const {
   if (!deviceOk_)
     throw Error(HYMLS_B200_ERR_CUDA, "hymls_b200 needs a CUDA device for this call: there is no CPU fallback");
@@ -213,6 +227,21 @@ void Engine::initialize() {
     for (int64_t r = 0; r < S.n; ++r) gid2row[S.rowGid[r]] = (int)r;
     part.partition();
     buildLevelSym(S, part, gid2row);
+    // ownership: level 0 is sharded by the reference's subdomain -> rank map (CreatePIDMap); the
+    // (much smaller) deeper levels are replicated on every rank
+    L.ownSd.clear();
+    L.sharded = (l == 0 && comm_.size() > 1);
+    if (L.sharded) {
+      if (maxLevel_ == 0) throw Error(HYMLS_B200_ERR_UNSUPPORTED, "Number of Levels = 0 is single-GPU only");
+      ParameterList pp = params_.deepCopy();
+      CartesianPartitioner pidPart(pp, 0, comm_.size(), comm_.rank());
+      pidPart.partition();
+      const std::vector<int>& pm = pidPart.pidMap();
+      for (int sd = 0; sd < S.nsd; ++sd)
+        if (pm[part.globalSubdomain(sd)] == comm_.rank()) L.ownSd.push_back(sd);
+    } else {
+      for (int sd = 0; sd < S.nsd; ++sd) L.ownSd.push_back(sd);
+    }
     // parameters of the next level (SetNextLevelParameters; sx *= cx)
     part.setNextLevelParameters(levelParams);
     if (deviceOk_) uploadLevel(L);
@@ -239,23 +268,73 @@ void Engine::uploadLevel(Level& L) {
   }
   L.intRow.upload(S.intRow, s);
   L.sepRow.upload(S.sepRow, s);
-  // A11
-  std::vector<int64_t> vecOffI(S.H.intPtr.begin(), S.H.intPtr.end() - 1);
-  L.a11.setup(S.sdN, S.sdNp, S.a11Off, vecOffI, s);
-  L.a11Src.upload(S.a11Src, s);
-  L.a11Dst.upload(S.a11Dst, s);
-  L.a11ListPtr.assign(S.nsd + 1, 0);
-  for (int sd = 0; sd <= S.nsd; ++sd)
-    L.a11ListPtr[sd] = std::lower_bound(S.a11Dst.begin(), S.a11Dst.end(), S.a11Off[sd]) - S.a11Dst.begin();
-  // A12 / A21 / A22
+  // A11: compact storage of the owned subdomains
+  const int nown = (int)L.ownSd.size();
+  std::vector<char> isOwn(S.nsd, 0);
+  std::vector<int> on(nown), onp(nown);
+  std::vector<int64_t> ovec(nown), a11OffG(S.nsd, -1);
+  L.ownOff.assign(nown + 1, 0);
+  for (int k = 0; k < nown; ++k) {
+    const int sd = L.ownSd[k];
+    isOwn[sd] = 1;
+    on[k] = S.sdN[sd];
+    onp[k] = S.sdNp[sd];
+    ovec[k] = S.H.intPtr[sd];
+    a11OffG[sd] = L.ownOff[k];
+    L.ownOff[k + 1] = L.ownOff[k] + (int64_t)onp[k] * onp[k];
+  }
+  L.a11.setup(on, onp, L.ownOff, ovec, s);
+  L.sdNG.upload(S.sdN, s);
+  L.sdNpG.upload(S.sdNp, s);
+  L.a11OffG.upload(a11OffG, s);
+  {
+    // dense-fill scatter list restricted to the owned subdomains, destinations in compact numbering
+    std::vector<int64_t> src, dst;
+    L.a11ListPtr.assign(nown + 1, 0);
+    for (int k = 0; k < nown; ++k) {
+      const int sd = L.ownSd[k];
+      const int64_t e0 = std::lower_bound(S.a11Dst.begin(), S.a11Dst.end(), S.a11Off[sd]) - S.a11Dst.begin();
+      const int64_t e1 = std::lower_bound(S.a11Dst.begin(), S.a11Dst.end(), S.a11Off[sd + 1]) - S.a11Dst.begin();
+      for (int64_t e = e0; e < e1; ++e) {
+        src.push_back(S.a11Src[e]);
+        dst.push_back(S.a11Dst[e] - S.a11Off[sd] + L.ownOff[k]);
+      }
+      L.a11ListPtr[k + 1] = (int64_t)src.size();
+    }
+    L.a11Src.upload(src, s);
+    L.a11Dst.upload(dst, s);
+  }
+  // A12 / A21 / A22 (A21 restricted to the columns of owned interiors when sharded: partial products
+  // are summed over the ranks)
   L.p12.upload(S.A12.ptr, s);
   L.c12.upload(S.A12.col, s);
   L.src12.upload(S.A12.src, s);
   L.v12.alloc(S.A12.col.size());
-  L.p21.upload(S.A21.ptr, s);
-  L.c21.upload(S.A21.col, s);
-  L.src21.upload(S.A21.src, s);
-  L.v21.alloc(S.A21.col.size());
+  if (!L.sharded) {
+    L.p21.upload(S.A21.ptr, s);
+    L.c21.upload(S.A21.col, s);
+    L.src21.upload(S.A21.src, s);
+    L.v21.alloc(S.A21.col.size());
+  } else {
+    std::vector<char> ownInt(S.nI, 0);
+    for (int sd : L.ownSd)
+      for (int64_t p = S.H.intPtr[sd]; p < S.H.intPtr[sd + 1]; ++p) ownInt[p] = 1;
+    std::vector<int64_t> ptr(S.nS + 1, 0), src;
+    std::vector<int> col;
+    for (int64_t p = 0; p < S.nS; ++p) {
+      for (int64_t e = S.A21.ptr[p]; e < S.A21.ptr[p + 1]; ++e)
+        if (ownInt[S.A21.col[e]]) {
+          col.push_back(S.A21.col[e]);
+          src.push_back(S.A21.src[e]);
+        }
+      ptr[p + 1] = (int64_t)col.size();
+    }
+    L.p21.upload(ptr, s);
+    L.c21.upload(col, s);
+    L.src21.upload(src, s);
+    L.v21.alloc(col.size());
+    L.xI.alloc(S.nI);
+  }
   if (L.exact) {
     L.p22.upload(S.A22.ptr, s);
     L.c22.upload(S.A22.col, s);
@@ -325,6 +404,28 @@ void Engine::uploadLevel(Level& L) {
     }
     if (S.nsd > sd0)
       L.chunks.push_back({sd0, S.nsd, S.sdRowPtr[sd0], S.sdRowPtr[S.nsd], sdLinkPtr[sd0], sdLinkPtr[S.nsd]});
+  }
+  if (L.sharded) {
+    std::vector<int64_t> rows, links;
+    const size_t nch = L.chunks.size();
+    L.chunkOwnSd.assign(nch + 1, 0);
+    L.chunkOwnRow.assign(nch + 1, 0);
+    L.chunkOwnLink.assign(nch + 1, 0);
+    size_t k = 0;
+    for (size_t c = 0; c < nch; ++c) {
+      while (k < L.ownSd.size() && L.ownSd[k] < L.chunks[c].sd1) {
+        const int sd = L.ownSd[k];
+        for (int64_t R = S.sdRowPtr[sd]; R < S.sdRowPtr[sd + 1]; ++R) rows.push_back(R);
+        for (int64_t lk = sdLinkPtr[sd]; lk < sdLinkPtr[sd + 1]; ++lk) links.push_back(lk);
+        ++k;
+      }
+      L.chunkOwnSd[c + 1] = (int64_t)k;
+      L.chunkOwnRow[c + 1] = (int64_t)rows.size();
+      L.chunkOwnLink[c + 1] = (int64_t)links.size();
+    }
+    L.ownSdList.upload(L.ownSd, s);
+    L.ownRowList.upload(rows, s);
+    L.ownLinkList.upload(links, s);
   }
   L.rowSd.upload(rowSd, s);
   L.rowInst.upload(rowInst, s);
@@ -461,28 +562,29 @@ void Engine::computeLevel(int l) {
   PhaseTimer pt(s, l);
   // (1) off-diagonal blocks: value gathers (MatrixBlock::Compute)
   gatherValues(L.val.p, L.src12.p, L.v12.p, (int64_t)S.A12.col.size(), s, &launches_);
-  gatherValues(L.val.p, L.src21.p, L.v21.p, (int64_t)S.A21.col.size(), s, &launches_);
-  // (2) A11 blocks: dense fill + batched inversion, in chunks of subdomains (ComputeSubdomainSolvers)
+  gatherValues(L.val.p, L.src21.p, L.v21.p, (int64_t)L.v21.n, s, &launches_);
+  // (2) A11 blocks: dense fill + batched inversion, in chunks of (owned) subdomains (ComputeSubdomainSolvers)
   {
+    const int nown = (int)L.ownSd.size();
     const int64_t budget = (int64_t)1 << 29;  // doubles (4 GB) of inversion workspace
     DevBuf<int64_t> relOff;
-    int sd0 = 0;
-    while (sd0 < S.nsd) {
-      int sd1 = sd0;
+    int k0 = 0;
+    while (k0 < nown) {
+      int k1 = k0;
       int64_t used = 0;
-      while (sd1 < S.nsd && sd1 - sd0 < 16384) {
-        int64_t need = S.a11Off[sd1 + 1] - S.a11Off[sd1];
-        if (sd1 > sd0 && used + need > budget) break;
+      while (k1 < nown && k1 - k0 < 16384) {
+        int64_t need = L.ownOff[k1 + 1] - L.ownOff[k1];
+        if (k1 > k0 && used + need > budget) break;
         used += need;
-        ++sd1;
+        ++k1;
       }
-      if (work_.n < (size_t)used) work_.alloc((size_t)std::max<int64_t>(used, std::min<int64_t>(budget, S.a11Off[S.nsd])));
+      if (work_.n < (size_t)used) work_.alloc((size_t)std::max<int64_t>(used, std::min<int64_t>(budget, L.ownOff[nown])));
       HY_CUDA(cudaMemsetAsync(work_.p, 0, used * sizeof(double), s));
-      const int64_t e0 = L.a11ListPtr[sd0], e1 = L.a11ListPtr[sd1];
-      scatterValues(L.val.p, L.a11Src.p + e0, L.a11Dst.p + e0, S.a11Off[sd0], work_.p, e1 - e0, s, &launches_);
-      invertRange(L.a11, sd0, sd1, work_.p, piv_, perm_, relOff, info_.p, s, &launches_);
-      for (int sd = sd0; sd < sd1; ++sd) stats_.flops_compute += 2.0 * std::pow((double)S.sdN[sd], 3);
-      sd0 = sd1;
+      const int64_t e0 = L.a11ListPtr[k0], e1 = L.a11ListPtr[k1];
+      scatterValues(L.val.p, L.a11Src.p + e0, L.a11Dst.p + e0, L.ownOff[k0], work_.p, e1 - e0, s, &launches_);
+      invertRange(L.a11, k0, k1, work_.p, piv_, perm_, relOff, info_.p, s, &launches_);
+      for (int k = k0; k < k1; ++k) stats_.flops_compute += 2.0 * std::pow((double)L.a11.hN[k], 3);
+      k0 = k1;
     }
     checkInfo(info_, s, "subdomain solver (A11) of level " + std::to_string(l));
   }
@@ -495,9 +597,9 @@ void Engine::computeLevel(int l) {
   a.sdSep = L.sdSep.p;
   a.sdRowPtr = L.sdRowPtr.p;
   a.sdM = L.sdM.p;
-  a.sdN = L.a11.n.p;
-  a.sdNp = L.a11.np.p;
-  a.a11Off = L.a11.matOff.p;
+  a.sdN = L.sdNG.p;
+  a.sdNp = L.sdNpG.p;
+  a.a11Off = L.a11OffG.p;
   a.Ainv = L.a11.F.p;
   a.val = L.val.p;
   a.s21Ptr = L.s21Ptr.p;
@@ -589,9 +691,34 @@ void Engine::computeLevel(int l) {
   a.wsC = wsC_.p;
   a.wsSV = wsSV_.p;
   a.wsSLL = wsSLL_.p;
-  for (int pass = 1; pass <= 2; ++pass)
+  if (!L.sharded) {
+    for (int pass = 1; pass <= 2; ++pass)
+      for (const Level::Chunk& c : L.chunks)
+        schurAssemble(a, c.sd0, c.sd1, c.R0, c.R1, c.lk0, c.lk1, pass, L.rowSmem, L.blkSmem, s, &launches_);
+  } else {
+    // pass 1 (A22 part, no A11 needed) for every subdomain on every rank; pass 2 (-A21 A11^-1 A12) for the
+    // owned subdomains into zeroed buffers that are summed over the ranks (FECrsMatrix::GlobalAssemble)
     for (const Level::Chunk& c : L.chunks)
-      schurAssemble(a, c.sd0, c.sd1, c.R0, c.R1, c.lk0, c.lk1, pass, L.rowSmem, L.blkSmem, s, &launches_);
+      schurAssemble(a, c.sd0, c.sd1, c.R0, c.R1, c.lk0, c.lk1, 1, L.rowSmem, L.blkSmem, s, &launches_);
+    DevBuf<double> red2, blk2;
+    red2.alloc(S.redCol.size());
+    blk2.alloc((size_t)S.blkOff[S.nblk]);
+    HY_CUDA(cudaMemsetAsync(red2.p, 0, red2.bytes(), s));
+    HY_CUDA(cudaMemsetAsync(blk2.p, 0, blk2.bytes(), s));
+    SchurArgs a2 = a;
+    a2.redVal = red2.p;
+    a2.blkW = blk2.p;
+    for (size_t c = 0; c < L.chunks.size(); ++c)
+      schurAssemble(a2, (int)L.chunkOwnSd[c], (int)L.chunkOwnSd[c + 1], L.chunkOwnRow[c], L.chunkOwnRow[c + 1],
+                    L.chunkOwnLink[c], L.chunkOwnLink[c + 1], 2, L.rowSmem, L.blkSmem, s, &launches_,
+                    L.ownSdList.p, L.ownRowList.p, L.ownLinkList.p);
+    HY_CUDA(cudaStreamSynchronize(s));  // surface kernel faults here rather than inside NCCL
+    comm_.allReduceSum(red2.p, red2.n, s);
+    comm_.allReduceSum(blk2.p, blk2.n, s);
+    axpby(1.0, red2.p, 1.0, redVal, (int64_t)red2.n, s, &launches_);
+    axpby(1.0, blk2.p, 1.0, blkW.p, (int64_t)blk2.n, s, &launches_);
+    HY_CUDA(cudaStreamSynchronize(s));
+  }
   pt.lap("Schur assembly (2 passes)");
   {
     int h = 0;
@@ -683,7 +810,15 @@ void Engine::applyLevel(int l, const double* B, double* X) {
     a11Launches_++;
   }
   // schurRhs = b2 - A21 x1
-  spmv(L.p21.p, L.c21.p, L.v21.p, L.x1.p, L.rhsS.p, S.nS, 1.0, B, L.sepRow.p, -1.0, s, &launches_);
+  if (!L.sharded) {
+    spmv(L.p21.p, L.c21.p, L.v21.p, L.x1.p, L.rhsS.p, S.nS, 1.0, B, L.sepRow.p, -1.0, s, &launches_);
+  } else {
+    // each rank multiplies with the columns of its own interiors; the partial products are summed
+    // (the separator-halo exchange of the reference's Epetra_CrsMatrix::Apply / Import)
+    spmv(L.p21.p, L.c21.p, L.v21.p, L.x1.p, L.Z.p, S.nS, 0.0, nullptr, nullptr, -1.0, s, &launches_);
+    comm_.allReduceSum(L.Z.p, (size_t)S.nS, s);
+    gatherAdd(B, L.sepRow.p, L.Z.p, L.rhsS.p, S.nS, s, &launches_);
+  }
   double* x2 = L.Y.p;
   if (L.exact) {
     // direct solve with the dense Schur complement (CoarseSolver::ApplyInverse :268-323)
@@ -720,7 +855,17 @@ void Engine::applyLevel(int l, const double* B, double* X) {
       batchedGemv(c, coarse_.numItems, coarse_.npMax, s, &launches_);
     }
     // x2 = H [Y(non-V-sum); vsumSol], exported to X
-    householder(L.uniqStart.p, S.nuniq, L.what.p, L.Y.p, L.Y.p, nullptr, L.vsSol.p, X, L.sepRow.p, s, &launches_);
+    if (!L.sharded) {
+      householder(L.uniqStart.p, S.nuniq, L.what.p, L.Y.p, L.Y.p, nullptr, L.vsSol.p, X, L.sepRow.p, s, &launches_);
+    } else {
+      // The separator part is computed redundantly on every rank; the replicas may differ in the last
+      // bit (atomic accumulation order in Compute), which a Krylov method that mixes per-rank partial
+      // results would amplify.  Rank 0's copy is made the common one.
+      householder(L.uniqStart.p, S.nuniq, L.what.p, L.Y.p, L.Y.p, nullptr, L.vsSol.p, nullptr, nullptr, s,
+                  &launches_);
+      comm_.broadcast(L.Y.p, (size_t)S.nS, 0, s);
+      scatterVec(L.Y.p, L.sepRow.p, X, S.nS, s, &launches_);
+    }
   }
   // y1 = A12 x2 ;  X[interior] = x1 - A11 \ y1
   spmv(L.p12.p, L.c12.p, L.v12.p, x2, L.y1.p, S.nI, 0.0, nullptr, nullptr, 1.0, s, &launches_);
@@ -730,6 +875,11 @@ void Engine::applyLevel(int l, const double* B, double* X) {
   g.out = X;
   g.scatter = L.intRow.p;
   g.mode = 1;
+  if (L.sharded) {  // owned interiors into a packed zeroed vector, summed over the ranks, then exported
+    HY_CUDA(cudaMemsetAsync(L.xI.p, 0, (size_t)S.nI * sizeof(double), s));
+    g.out = L.xI.p;
+    g.scatter = nullptr;
+  }
   if (timeIt) HY_CUDA(cudaEventRecord(evA_, s));
   batchedGemv(g, L.a11.numItems, L.a11.npMax, s, &launches_);
   if (timeIt) {
@@ -739,6 +889,10 @@ void Engine::applyLevel(int l, const double* B, double* X) {
     HY_CUDA(cudaEventElapsedTime(&ms, evA_, evB_));
     a11Ms_ += ms;
     a11Launches_++;
+  }
+  if (L.sharded) {
+    comm_.allReduceSum(L.xI.p, (size_t)S.nI, s);
+    scatterVec(L.xI.p, L.intRow.p, X, S.nI, s, &launches_);
   }
 }
 
@@ -1106,7 +1260,12 @@ void Engine::getStats(hymls_b200_stats* st) {
     st->num_subdomains = S.nsd;
     st->num_blocks = S.nblk;
     st->sum_nsd_sq = S.sumNsq;
-    st->bytes_a11_level0 = 16.0 * S.sumNsq;
+    {
+      double own = 0;
+      for (int v : levels_[0]->a11.hN) own += (double)v * v;
+      if (levels_[0]->a11.hN.empty()) for (int sd : levels_[0]->ownSd) own += (double)S.sdN[sd] * S.sdN[sd];
+      st->bytes_a11_level0 = 16.0 * own;  // this rank's share when sharded
+    }
     // algorithmic bytes of one ApplyInverse, summed over the levels
     double bytes = 0;
     for (auto& lp : levels_) {

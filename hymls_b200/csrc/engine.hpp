@@ -4,6 +4,7 @@
 #include <string>
 #include <vector>
 
+#include "comm.hpp"
 #include "device.cuh"
 #include "kernels.hpp"
 #include "symbolic.hpp"
@@ -31,10 +32,19 @@ struct Level {
   DevBuf<double> val;
   // orderings
   DevBuf<int> intRow, sepRow;
-  // A11
+  // A11: inverses of the subdomains this rank owns (all of them on one GPU), compact storage
   BatchedInverse a11;
+  std::vector<int> ownSd;           // owned subdomains, ascending
+  std::vector<int64_t> ownOff;      // compact offsets (doubles) of the owned matrices, ownSd.size()+1
+  DevBuf<int> sdNG, sdNpG;          // per (global) subdomain: n, np
+  DevBuf<int64_t> a11OffG;          // per (global) subdomain: compact offset (undefined if not owned)
   DevBuf<int64_t> a11Src, a11Dst;
-  std::vector<int64_t> a11ListPtr;  // per sd: range of the scatter list
+  std::vector<int64_t> a11ListPtr;  // per owned sd: range of the scatter list
+  bool sharded = false;
+  DevBuf<int> ownSdList;            // device copies of the owned lists for the pass-2 Schur kernels
+  DevBuf<int64_t> ownRowList, ownLinkList;
+  std::vector<int64_t> chunkOwnSd, chunkOwnRow, chunkOwnLink;  // per chunk: ranges in the lists (nchunks+1)
+  DevBuf<double> xI;                // packed interior result (sharded apply: all-reduced)
   // off-diagonal blocks
   DevBuf<int64_t> p12, p21, src12, src21, p22, src22;
   DevBuf<int> c12, c21, c22;
@@ -68,6 +78,9 @@ class Engine {
   explicit Engine(const std::string& xml);
   ~Engine();
   void setStream(cudaStream_t s) { stream_ = s; }
+  void commInit(const void* id128, int rank, int nranks);
+  void setRankOnly(int rank, int nranks);
+  const std::vector<int>& ownedSubdomains(int level) const { return levels_.at(level)->ownSd; }
   void setMatrix(int64_t n, const int64_t* rowptr, const int32_t* colidx, const double* values, int where);
   void setTestVector(const double* tv);
   void initialize();
@@ -93,6 +106,7 @@ class Engine {
   void applyDevice(const double* dB, double* dX);
 
   ParameterList params_;
+  Comm comm_;
   cudaStream_t stream_ = 0;
   int maxLevel_ = 1;
   int64_t n_ = 0;

@@ -52,7 +52,8 @@ struct SchurArgs {
   int* info;
 };
 void schurAssemble(const SchurArgs& a, int sd0, int sd1, int64_t R0, int64_t R1, int64_t lk0, int64_t lk1, int pass,
-                   size_t rowSmem, size_t blkSmem, cudaStream_t s, int64_t* launches);
+                   size_t rowSmem, size_t blkSmem, cudaStream_t s, int64_t* launches, const int* sdList = nullptr,
+                   const int64_t* rowList = nullptr, const int64_t* lkList = nullptr);
 void schurDense(const SchurArgs& a, int64_t R0, int64_t R1, double* denseS, int64_t ldS, size_t rowSmem,
                 cudaStream_t s, int64_t* launches);
 void dropByValue(double* val, const int64_t* ptr, const int* col, double* diagScratch, int n, double tol,
@@ -93,6 +94,8 @@ void setValue(double* x, int64_t idx, double v, cudaStream_t s, int64_t* launche
 void csrToDense(const int64_t* ptr, const int* col, const double* val, double* D, int n, int np, cudaStream_t s,
                 int64_t* launches);
 void putDirichlet(double* D, int n, int np, int fix, cudaStream_t s, int64_t* launches);
+void gatherAdd(const double* b, const int* idx, const double* t, double* y, int64_t n, cudaStream_t s,
+               int64_t* launches);
 void scatterVec(const double* x, const int* idx, double* y, int64_t n, cudaStream_t s, int64_t* launches);
 
 }  // namespace hymls

@@ -24,8 +24,9 @@ namespace hymls {
 
 // one CTA per local separator row of a subdomain
 __global__ void __launch_bounds__(128)
-k_schur_rows(SchurArgs a, int64_t R0, int pass, double* __restrict__ denseS, int64_t ldS) {
-  const int64_t R = R0 + blockIdx.x;
+k_schur_rows(SchurArgs a, int64_t R0, int pass, double* __restrict__ denseS, int64_t ldS,
+             const int64_t* __restrict__ rowList) {
+  const int64_t R = rowList ? rowList[R0 + blockIdx.x] : R0 + blockIdx.x;
   const int sd = a.rowSd[R];
   const int64_t base = a.sdRowPtr[sd];
   const int i = (int)(R - base);
@@ -94,8 +95,8 @@ __device__ __forceinline__ int64_t findCol(const int* __restrict__ col, int64_t 
 
 // (a) V-sum x V-sum entries: one CTA per subdomain
 __global__ void __launch_bounds__(256)
-k_schur_vsum(SchurArgs a, int sd0, int pass) {
-  const int sd = sd0 + blockIdx.x;
+k_schur_vsum(SchurArgs a, int sd0, int pass, const int* __restrict__ sdList) {
+  const int sd = sdList ? sdList[sd0 + blockIdx.x] : sd0 + blockIdx.x;
   const int64_t ia = a.sdInstPtr[sd];
   const int G = (int)(a.sdInstPtr[sd + 1] - ia);
   const double* C = a.wsC + a.wsOffC[sd];
@@ -122,8 +123,8 @@ k_schur_vsum(SchurArgs a, int sd0, int pass) {
 // (b) non-V-sum entries of one linked set: one CTA per (subdomain, linked set)
 static constexpr int MAX_LINK_INST = 32;
 __global__ void __launch_bounds__(256)
-k_schur_blocks(SchurArgs a, int64_t lk0, int pass) {
-  const int64_t lk = lk0 + blockIdx.x;
+k_schur_blocks(SchurArgs a, int64_t lk0, int pass, const int64_t* __restrict__ lkList) {
+  const int64_t lk = lkList ? lkList[lk0 + blockIdx.x] : lk0 + blockIdx.x;
   const int sd = a.lnkSd[lk];
   const int link = (int)(lk - a.sdLinkPtr[sd]);
   const int lsz = a.lnkSize[lk];
@@ -240,7 +241,8 @@ static void ensureRowSmem(size_t rowSmem) {
 }
 
 void schurAssemble(const SchurArgs& a, int sd0, int sd1, int64_t R0, int64_t R1, int64_t lk0, int64_t lk1, int pass,
-                   size_t rowSmem, size_t blkSmem, cudaStream_t s, int64_t* launches) {
+                   size_t rowSmem, size_t blkSmem, cudaStream_t s, int64_t* launches, const int* sdList,
+                   const int64_t* rowList, const int64_t* lkList) {
   ensureRowSmem(rowSmem);
   if (blkSmem > g_blkSmemSet) {
     if (blkSmem > 200 * 1024)
@@ -249,9 +251,9 @@ void schurAssemble(const SchurArgs& a, int sd0, int sd1, int64_t R0, int64_t R1,
     g_blkSmemSet = blkSmem;
   }
   if (R1 > R0) {
-    k_schur_rows<<<(unsigned)(R1 - R0), 128, rowSmem, s>>>(a, R0, pass, nullptr, 0);
-    k_schur_vsum<<<sd1 - sd0, 256, 0, s>>>(a, sd0, pass);
-    k_schur_blocks<<<(unsigned)(lk1 - lk0), 256, blkSmem, s>>>(a, lk0, pass);
+    k_schur_rows<<<(unsigned)(R1 - R0), 128, rowSmem, s>>>(a, R0, pass, nullptr, 0, rowList);
+    k_schur_vsum<<<sd1 - sd0, 256, 0, s>>>(a, sd0, pass, sdList);
+    k_schur_blocks<<<(unsigned)(lk1 - lk0), 256, blkSmem, s>>>(a, lk0, pass, lkList);
     *launches += 3;
   }
   HY_CUDA(cudaGetLastError());
@@ -261,7 +263,7 @@ void schurDense(const SchurArgs& a, int64_t R0, int64_t R1, double* denseS, int6
                 cudaStream_t s, int64_t* launches) {
   if (R1 <= R0) return;
   ensureRowSmem(rowSmem);
-  k_schur_rows<<<(unsigned)(R1 - R0), 128, rowSmem, s>>>(a, R0, 2, denseS, ldS);
+  k_schur_rows<<<(unsigned)(R1 - R0), 128, rowSmem, s>>>(a, R0, 2, denseS, ldS, nullptr);
   ++*launches;
   HY_CUDA(cudaGetLastError());
 }

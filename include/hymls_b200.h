@@ -59,6 +59,21 @@ void hymls_b200_destroy(hymls_b200_t* h);
 int hymls_b200_set_stream(hymls_b200_t* h, void* cuda_stream);
 
 /*
+ * Multi-GPU: one process per GPU, one handle per process.  Level-0 subdomains are sharded by the
+ * reference's subdomain -> rank map (BasePartitioner::CreatePIDMap, src/HYMLS_BasePartitioner.cpp:361-586);
+ * the exchanges of the reference's Epetra Import/Export/SumAll become NCCL all-reduces on the handle's
+ * stream.  Rank 0 creates the id (128 bytes, ncclUniqueId) and ships it to the others (e.g. with
+ * torch.distributed); comm_init is collective and must precede Initialize().  After it, set_matrix,
+ * Initialize, Compute, ApplyInverse and solve are collective calls with replicated arguments.
+ * hymls_b200_set_rank only records (rank, nranks) for the host-side ownership logic (no NCCL, no GPU).
+ */
+int hymls_b200_comm_get_unique_id(void* id128);
+int hymls_b200_comm_init(hymls_b200_t* h, const void* id128, int rank, int nranks);
+int hymls_b200_set_rank(hymls_b200_t* h, int rank, int nranks);
+/* local subdomain ids (level numbering of hymls_b200_get_interior) owned by this rank; returns the count */
+int hymls_b200_get_owned_subdomains(hymls_b200_t* h, int level, int32_t* sd, int cap);
+
+/*
  * Matrix K as CSR with 0-based indices, rows in global (GID) order: row i <-> GID i
  * (Epetra_CrsMatrix::ExtractMyRowView on a linear map).  `where` says whether the three arrays are
  * host or device pointers.  The pattern is fixed by the first call; later calls with the same

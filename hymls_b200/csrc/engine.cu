@@ -227,14 +227,14 @@ void Engine::initialize() {
     for (int64_t r = 0; r < S.n; ++r) gid2row[S.rowGid[r]] = (int)r;
     part.partition();
     buildLevelSym(S, part, gid2row);
-    // ownership: level 0 is sharded by the reference's subdomain -> rank map (CreatePIDMap); the
-    // (much smaller) deeper levels are replicated on every rank
+    // ownership: every level is sharded by the reference's subdomain -> rank map of that level
+    // (BasePartitioner::CreatePIDMap); with fewer subdomains than ranks some ranks own nothing there
     L.ownSd.clear();
-    L.sharded = (l == 0 && comm_.size() > 1);
+    L.sharded = comm_.size() > 1;
     if (L.sharded) {
       if (maxLevel_ == 0) throw Error(HYMLS_B200_ERR_UNSUPPORTED, "Number of Levels = 0 is single-GPU only");
-      ParameterList pp = params_.deepCopy();
-      CartesianPartitioner pidPart(pp, 0, comm_.size(), comm_.rank());
+      ParameterList pp = levelParams.deepCopy();
+      CartesianPartitioner pidPart(pp, l, comm_.size(), comm_.rank());
       pidPart.partition();
       const std::vector<int>& pm = pidPart.pidMap();
       for (int sd = 0; sd < S.nsd; ++sd)

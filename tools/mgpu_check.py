@@ -19,7 +19,7 @@ def main():
     sx = int(sys.argv[2]) if len(sys.argv) > 2 else 4
     levels = int(sys.argv[3]) if len(sys.argv) > 3 else 2
     params = {"Problem": {"Equations": "Stokes-C", "Dimension": 3, "nx": nx, "ny": nx, "nz": nx},
-              "Preconditioner": {"Separator Length": sx, "Number of Levels": levels, "Coarsening Factor": 2,
+              "Preconditioner": {"Separator Length": sx, "Number of Levels": levels, "Coarsening Factor": int(sys.argv[4]) if len(sys.argv) > 4 else 2,
                                  "Eliminate Tube Pressures With Velocities": True},
               "Solver": {"Krylov Method": "GMRES", "Initial Vector": "Zero",
                          "Iterative Solver": {"Maximum Iterations": 300, "Convergence Tolerance": 1e-8}}}

@@ -16,6 +16,7 @@ typedef int (*GetUniqueIdFn)(NcclUniqueId*);
 typedef int (*CommInitRankFn)(void**, int, NcclUniqueId, int);
 typedef int (*AllReduceFn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
 typedef int (*CommDestroyFn)(void*);
+typedef int (*AllGatherFn)(const void*, void*, size_t, int, void*, cudaStream_t);
 typedef int (*BroadcastFn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
 typedef const char* (*GetErrorStringFn)(int);
 
@@ -26,6 +27,7 @@ struct Api {
   AllReduceFn allReduce = nullptr;
   CommDestroyFn commDestroy = nullptr;
   BroadcastFn broadcast = nullptr;
+  AllGatherFn allGather = nullptr;
   GetErrorStringFn errorString = nullptr;
 };
 
@@ -43,8 +45,9 @@ Api& api() {
   a.allReduce = (AllReduceFn)dlsym(a.lib, "ncclAllReduce");
   a.commDestroy = (CommDestroyFn)dlsym(a.lib, "ncclCommDestroy");
   a.broadcast = (BroadcastFn)dlsym(a.lib, "ncclBroadcast");
+  a.allGather = (AllGatherFn)dlsym(a.lib, "ncclAllGather");
   a.errorString = (GetErrorStringFn)dlsym(a.lib, "ncclGetErrorString");
-  if (!a.getUniqueId || !a.commInitRank || !a.allReduce || !a.commDestroy || !a.broadcast)
+  if (!a.getUniqueId || !a.commInitRank || !a.allReduce || !a.commDestroy || !a.broadcast || !a.allGather)
     throw Error(HYMLS_B200_ERR_CUDA, "NCCL library lacks the expected symbols");
   return a;
 }
@@ -83,6 +86,11 @@ void Comm::allReduceSum(double* buf, size_t count, cudaStream_t s) const {
 }  // namespace hymls
 
 namespace hymls {
+void Comm::allGather(const double* send, double* recv, size_t count, cudaStream_t s) const {
+  if (!comm_ || count == 0) return;
+  const int ncclDouble = 8;
+  check(api().allGather(send, recv, count, ncclDouble, comm_, s), "ncclAllGather");
+}
 void Comm::broadcast(double* buf, size_t count, int root, cudaStream_t s) const {
   if (!comm_ || count == 0) return;
   const int ncclDouble = 8;

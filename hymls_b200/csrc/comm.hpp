@@ -22,6 +22,8 @@ class Comm {
   bool active() const { return comm_ != nullptr; }
   void allReduceSum(double* buf, size_t count, cudaStream_t s) const;  // in place
   void broadcast(double* buf, size_t count, int root, cudaStream_t s) const;  // in place
+  // recv[rank * count + i] = send_rank[i]; recv may alias send at offset rank*count
+  void allGather(const double* send, double* recv, size_t count, cudaStream_t s) const;
 
  private:
   void* comm_ = nullptr;

@@ -1070,12 +1070,37 @@ void Engine::solve(const double* b, double* x, int where, uint64_t seed, hymls_b
       }
     }
   } else if (method == "GMRES") {
-    kV_.alloc((size_t)(m + 1) * n);
+    // Krylov basis row-sharded over the ranks: rank r keeps rows [r*chunk, (r+1)*chunk) of every basis
+    // vector; dots are local partial sums + one all-reduce of (k+1) doubles (the reference's SumAll).
+    // The preconditioner wants its argument replicated, so v_k is all-gathered before each ApplyInverse.
+    const int P = comm_.active() ? comm_.size() : 1;
+    const int64_t chunk = (n + P - 1) / P;
+    const int64_t r0 = std::min<int64_t>(n, (int64_t)(comm_.active() ? comm_.rank() : 0) * chunk);
+    const int64_t r1 = std::min<int64_t>(n, r0 + chunk);
+    const int64_t nloc = r1 - r0;
+    DevBuf<double> gath;  // P*chunk: all-gather target (padded)
+    DevBuf<double> wloc;  // chunk: local rows scratch
+    if (P > 1) {
+      gath.alloc((size_t)P * chunk);
+      wloc.alloc((size_t)chunk);
+      HY_CUDA(cudaMemsetAsync(wloc.p, 0, (size_t)chunk * sizeof(double), s));
+    }
+    kV_.alloc((size_t)(m + 1) * chunk);
+    HY_CUDA(cudaMemsetAsync(kV_.p, 0, (size_t)(m + 1) * chunk * sizeof(double), s));
     std::vector<double> H((size_t)(m + 1) * m, 0.0), cs(m), sn(m), g(m + 1), hbuf(2 * m + 8);
     double* dH1 = kH_.p;              // first Gram-Schmidt pass  (m+1)
     double* dH2 = kH_.p + (m + 1);    // second pass              (m+1)
     double* dNrm = kH_.p + 2 * m + 2; // ||w||^2
-    // initial residual
+    // full (replicated) vector from local rows
+    auto gatherFull = [&](const double* loc) -> const double* {
+      if (P == 1) return loc;
+      comm_.allGather(loc, gath.p, (size_t)chunk, s);
+      return gath.p;
+    };
+    auto localRowsOfA = [&](const double* full, double* outLoc) {  // outLoc = (A full)[r0:r1]
+      spmv(L0.rowptr.p + r0, L0.colidx.p, L0.val.p, full, outLoc, nloc, 0.0, nullptr, nullptr, 1.0, s, &launches_);
+    };
+    // initial residual (kX_, kB_ replicated; kR_ full)
     A(kX_.p, kR_.p);
     axpby(1.0, kB_.p, -1.0, kR_.p, n, s, &launches_);  // r = b - A x
     const double r0norm = std::sqrt(dot(kR_.p, kR_.p));
@@ -1104,29 +1129,40 @@ void Engine::solve(const double* b, double* x, int where, uint64_t seed, hymls_b
         converged = true;
         break;
       }
-      axpby(1.0 / beta, r, 0.0, kV_.p, n, s, &launches_);  // v0 = r / beta
+      axpby(1.0 / beta, r + r0, 0.0, kV_.p, nloc, s, &launches_);  // v0 = r / beta (local rows)
       std::fill(g.begin(), g.end(), 0.0);
       g[0] = beta;
       int kDone = 0;
       for (int k = 0; k < m && iters < maxIters; ++k) {
-        double* vk = kV_.p + (size_t)k * n;
-        double* w = kV_.p + (size_t)(k + 1) * n;
+        double* vk = kV_.p + (size_t)k * chunk;
+        double* w = kV_.p + (size_t)(k + 1) * chunk;
+        const double* vfull = gatherFull(vk);
         if (right) {
-          applyDevice(vk, kZ_.p);
-          A(kZ_.p, w);
+          applyDevice(vfull, kZ_.p);
+          localRowsOfA(kZ_.p, w);
         } else if (left) {
-          A(vk, kZ_.p);
-          applyDevice(kZ_.p, w);
+          if (P == 1) {
+            A(vfull, kZ_.p);
+          } else {
+            localRowsOfA(vfull, wloc.p);
+            comm_.allGather(wloc.p, gath.p, (size_t)chunk, s);
+            HY_CUDA(cudaMemcpyAsync(kZ_.p, gath.p, n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+          }
+          applyDevice(kZ_.p, kW_.p);
+          HY_CUDA(cudaMemcpyAsync(w, kW_.p + r0, nloc * sizeof(double), cudaMemcpyDeviceToDevice, s));
         } else {
-          A(vk, w);
+          localRowsOfA(vfull, w);
         }
         // two passes of classical Gram-Schmidt (Belos ICGS/DGKS), fused multi-dot + multi-axpy
-        multiDot(kV_.p, n, k + 1, w, n, kPartial_.p, dH1, 0, s, &launches_);
-        multiAxpy(kV_.p, n, k + 1, dH1, w, n, -1.0, s, &launches_);
-        multiDot(kV_.p, n, k + 1, w, n, kPartial_.p, dH2, 0, s, &launches_);
-        multiAxpy(kV_.p, n, k + 1, dH2, w, n, -1.0, s, &launches_);
-        multiDot(w, n, 1, w, n, kPartial_.p, dNrm, 0, s, &launches_);
-        scaleByInvNorm(w, dNrm, w, n, s, &launches_);
+        multiDot(kV_.p, chunk, k + 1, w, nloc, kPartial_.p, dH1, 0, s, &launches_);
+        comm_.allReduceSum(dH1, (size_t)(k + 1), s);
+        multiAxpy(kV_.p, chunk, k + 1, dH1, w, nloc, -1.0, s, &launches_);
+        multiDot(kV_.p, chunk, k + 1, w, nloc, kPartial_.p, dH2, 0, s, &launches_);
+        comm_.allReduceSum(dH2, (size_t)(k + 1), s);
+        multiAxpy(kV_.p, chunk, k + 1, dH2, w, nloc, -1.0, s, &launches_);
+        multiDot(w, chunk, 1, w, nloc, kPartial_.p, dNrm, 0, s, &launches_);
+        comm_.allReduceSum(dNrm, 1, s);
+        scaleByInvNorm(w, dNrm, w, nloc, s, &launches_);
         HY_CUDA(cudaMemcpyAsync(hbuf.data(), kH_.p, (2 * m + 3) * sizeof(double), cudaMemcpyDeviceToHost, s));
         HY_CUDA(cudaStreamSynchronize(s));
         for (int i = 0; i <= k; ++i) H[(size_t)i * m + k] = hbuf[i] + hbuf[m + 1 + i];
@@ -1159,14 +1195,20 @@ void Engine::solve(const double* b, double* x, int where, uint64_t seed, hymls_b
           y[i] = t / H[(size_t)i * m + i];
         }
         HY_CUDA(cudaMemcpyAsync(dH1, y.data(), kDone * sizeof(double), cudaMemcpyHostToDevice, s));
-        HY_CUDA(cudaMemsetAsync(kZ_.p, 0, n * sizeof(double), s));
-        multiAxpy(kV_.p, n, kDone, dH1, kZ_.p, n, 1.0, s, &launches_);
+        double* updLoc = (P == 1) ? kZ_.p : wloc.p;
+        HY_CUDA(cudaMemsetAsync(updLoc, 0, (size_t)(P == 1 ? n : chunk) * sizeof(double), s));
+        multiAxpy(kV_.p, chunk, kDone, dH1, updLoc, nloc, 1.0, s, &launches_);
         HY_CUDA(cudaStreamSynchronize(s));
+        const double* updFull = updLoc;
+        if (P > 1) {
+          comm_.allGather(wloc.p, gath.p, (size_t)chunk, s);
+          updFull = gath.p;
+        }
         if (right) {
-          applyDevice(kZ_.p, kW_.p);
+          applyDevice(updFull, kW_.p);
           axpby(1.0, kW_.p, 1.0, kX_.p, n, s, &launches_);
         } else {
-          axpby(1.0, kZ_.p, 1.0, kX_.p, n, s, &launches_);
+          axpby(1.0, updFull, 1.0, kX_.p, n, s, &launches_);
         }
       }
       A(kX_.p, kR_.p);

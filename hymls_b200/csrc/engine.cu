@@ -145,7 +145,7 @@ void Engine::setTestVector(const double* tv) {
 // ---------------------------------------------------------------------------------------------
 void BatchedInverse::setup(const std::vector<int>& n_, const std::vector<int>& np_,
                            const std::vector<int64_t>& matOff_, const std::vector<int64_t>& vecOff_,
-                           cudaStream_t s) {
+                           cudaStream_t s, const std::vector<char>* applyMask) {
   hN = n_;
   hNp = np_;
   hMatOff = matOff_;
@@ -156,6 +156,7 @@ void BatchedInverse::setup(const std::vector<int>& n_, const std::vector<int>& n
   const int rows = gemvRowsPerItem();
   for (int m = 0; m < count; ++m) {
     npMax = std::max(npMax, np_[m]);
+    if (applyMask && !(*applyMask)[m]) continue;
     for (int r0 = 0; r0 < n_[m]; r0 += rows) {
       im.push_back(m);
       ir.push_back(r0);
@@ -196,6 +197,7 @@ void Engine::initialize() {
   for (int l = 0; l < nlev; ++l) {
     if (l > 0) levels_.emplace_back(new Level());
     Level& L = *levels_[l];
+    L.sym = LevelSym();  // a re-Initialize starts from scratch
     LevelSym& S = L.sym;
     S.level = l;
     L.exact = (maxLevel_ == 0);
@@ -466,7 +468,15 @@ void Engine::uploadLevel(Level& L) {
   L.redCol.upload(S.redCol, s);
   // separator blocks
   std::vector<int64_t> blkVecOff(S.blkRowPtr.begin(), S.blkRowPtr.end() - 1);
-  L.blk.setup(S.blkN, S.blkNp, S.blkOff, blkVecOff, s);
+  if (L.sharded) {
+    // every rank holds (and inverts) all separator blocks, but applies only the ones whose owner
+    // subdomain it owns; the block results are summed over the ranks in ApplyInverse
+    std::vector<char> mask(S.nblk, 0);
+    for (int b = 0; b < S.nblk; ++b) mask[b] = isOwn[S.blkOwnerSd[b]];
+    L.blk.setup(S.blkN, S.blkNp, S.blkOff, blkVecOff, s, &mask);
+  } else {
+    L.blk.setup(S.blkN, S.blkNp, S.blkOff, blkVecOff, s);
+  }
   L.blkRows.upload(S.blkRows, s);
   // work vectors
   L.x1.alloc(S.nI);
@@ -787,10 +797,30 @@ void Engine::computeCoarse(const int64_t* ptr, const int* col, double* val, int 
 // ---------------------------------------------------------------------------------------------
 // ApplyInverse
 // ---------------------------------------------------------------------------------------------
+struct ApplyTimer {
+  cudaStream_t s;
+  bool on;
+  int level;
+  std::chrono::steady_clock::time_point t0;
+  ApplyTimer(cudaStream_t st, int lvl, bool enable) : s(st), on(enable), level(lvl) {
+    if (on) { cudaStreamSynchronize(s); t0 = std::chrono::steady_clock::now(); }
+  }
+  void lap(const char* what) {
+    if (!on) return;
+    cudaStreamSynchronize(s);
+    auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[hymls_b200 apply] level %d %-34s %8.3f ms\n", level, what,
+            std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+};
+
 void Engine::applyLevel(int l, const double* B, double* X) {
   Level& L = *levels_[l];
   const LevelSym& S = L.sym;
   cudaStream_t s = stream_;
+  static const bool verboseApply = getenv("HYMLS_B200_VERBOSE_APPLY") != nullptr;
+  ApplyTimer at(s, l, verboseApply && comm_.rank() == 0 && (stats_.num_apply_inverse % 16) == 5);
   // x1 = A11 \ b1   (b1 gathered from B on the fly)
   GemvArgs g = L.a11.args();
   g.xin = B;
@@ -809,6 +839,7 @@ void Engine::applyLevel(int l, const double* B, double* X) {
     a11Ms_ += ms;
     a11Launches_++;
   }
+  at.lap("A11 gemv 1");
   // schurRhs = b2 - A21 x1
   if (!L.sharded) {
     spmv(L.p21.p, L.c21.p, L.v21.p, L.x1.p, L.rhsS.p, S.nS, 1.0, B, L.sepRow.p, -1.0, s, &launches_);
@@ -819,6 +850,7 @@ void Engine::applyLevel(int l, const double* B, double* X) {
     comm_.allReduceSum(L.Z.p, (size_t)S.nS, s);
     gatherAdd(B, L.sepRow.p, L.Z.p, L.rhsS.p, S.nS, s, &launches_);
   }
+  at.lap("A21 spmv (+allreduce)");
   double* x2 = L.Y.p;
   if (L.exact) {
     // direct solve with the dense Schur complement (CoarseSolver::ApplyInverse :268-323)
@@ -841,7 +873,10 @@ void Engine::applyLevel(int l, const double* B, double* X) {
     b.out = L.Y.p;
     b.scatter = L.blkRows.p;
     b.mode = 0;
+    if (L.sharded) HY_CUDA(cudaMemsetAsync(L.Y.p, 0, (size_t)S.nS * sizeof(double), s));
     batchedGemv(b, L.blk.numItems, L.blk.npMax, s, &launches_);
+    if (L.sharded) comm_.allReduceSum(L.Y.p, (size_t)S.nS, s);  // owned block rows from every rank
+    at.lap("householder + separator blocks");
     // V-sums: next level or coarse solver
     if (l + 1 < (int)levels_.size()) {
       applyLevel(l + 1, L.vsRhs.p, L.vsSol.p);
@@ -853,20 +888,16 @@ void Engine::applyLevel(int l, const double* B, double* X) {
       c.out = L.vsSol.p;
       c.mode = 0;
       batchedGemv(c, coarse_.numItems, coarse_.npMax, s, &launches_);
+      // the coarse solve is replicated; rank 0's copy becomes the common one so that every rank
+      // continues with bit-identical data (replicas may differ in the last bit, which a Krylov method
+      // mixing per-rank partial results would amplify)
+      if (L.sharded) comm_.broadcast(L.vsSol.p, (size_t)S.nuniq, 0, s);
     }
+    at.lap("next level / coarse");
     // x2 = H [Y(non-V-sum); vsumSol], exported to X
-    if (!L.sharded) {
-      householder(L.uniqStart.p, S.nuniq, L.what.p, L.Y.p, L.Y.p, nullptr, L.vsSol.p, X, L.sepRow.p, s, &launches_);
-    } else {
-      // The separator part is computed redundantly on every rank; the replicas may differ in the last
-      // bit (atomic accumulation order in Compute), which a Krylov method that mixes per-rank partial
-      // results would amplify.  Rank 0's copy is made the common one.
-      householder(L.uniqStart.p, S.nuniq, L.what.p, L.Y.p, L.Y.p, nullptr, L.vsSol.p, nullptr, nullptr, s,
-                  &launches_);
-      comm_.broadcast(L.Y.p, (size_t)S.nS, 0, s);
-      scatterVec(L.Y.p, L.sepRow.p, X, S.nS, s, &launches_);
-    }
+    householder(L.uniqStart.p, S.nuniq, L.what.p, L.Y.p, L.Y.p, nullptr, L.vsSol.p, X, L.sepRow.p, s, &launches_);
   }
+  at.lap("householder back (+bcast)");
   // y1 = A12 x2 ;  X[interior] = x1 - A11 \ y1
   spmv(L.p12.p, L.c12.p, L.v12.p, x2, L.y1.p, S.nI, 0.0, nullptr, nullptr, 1.0, s, &launches_);
   g.xin = L.y1.p;
@@ -890,10 +921,12 @@ void Engine::applyLevel(int l, const double* B, double* X) {
     a11Ms_ += ms;
     a11Launches_++;
   }
+  at.lap("A12 spmv + A11 gemv 2");
   if (L.sharded) {
     comm_.allReduceSum(L.xI.p, (size_t)S.nI, s);
     scatterVec(L.xI.p, L.intRow.p, X, S.nI, s, &launches_);
   }
+  at.lap("interior allreduce + export");
 }
 
 void Engine::applyDevice(const double* dB, double* dX) {

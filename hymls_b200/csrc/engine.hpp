@@ -18,8 +18,9 @@ struct BatchedInverse {  // a set of dense inverses + the GEMV work list over th
   std::vector<int> hN, hNp;
   std::vector<int64_t> hMatOff, hVecOff;
   int count = 0, numItems = 0, npMax = 0;
+  // `applyMask` (optional, one flag per matrix): GEMV work items are created for flagged matrices only
   void setup(const std::vector<int>& n_, const std::vector<int>& np_, const std::vector<int64_t>& matOff_,
-             const std::vector<int64_t>& vecOff_, cudaStream_t s);
+             const std::vector<int64_t>& vecOff_, cudaStream_t s, const std::vector<char>* applyMask = nullptr);
   GemvArgs args() const;
 };
 

@@ -187,6 +187,7 @@ void buildLevelSym(LevelSym& L, const CartesianPartitioner& part, const std::vec
           }
         }
         L.blkN.push_back(rows);
+        L.blkOwnerSd.push_back(sd);
         L.blkNp.push_back(roundUp8(rows));
         L.blkOff.push_back(L.blkOff.back() + (int64_t)roundUp8(rows) * roundUp8(rows));
         L.blkRowPtr.push_back((int64_t)L.blkRows.size());

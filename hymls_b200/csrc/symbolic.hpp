@@ -53,7 +53,7 @@ struct LevelSym {
   // unique groups (separator ordering): start/len via H.uniqPtr; block assignment
   std::vector<int> uniqBlk, uniqBlkOff;
   // blocks (one per owner subdomain and local linked set)
-  std::vector<int> blkN, blkNp;
+  std::vector<int> blkN, blkNp, blkOwnerSd;
   std::vector<int64_t> blkOff;       // nblk+1, in doubles
   std::vector<int64_t> blkRowPtr;    // nblk+1
   std::vector<int> blkRows;          // separator positions of the block rows

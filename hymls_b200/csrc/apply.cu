@@ -64,7 +64,8 @@ k_batched_gemv(GemvArgs a) {
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (lane == 0) {
       const double v = (a.mode == 0) ? acc : a.xprev[v0 + r] - acc;
-      a.out[a.scatter ? a.scatter[v0 + r] : v0 + r] = v;
+      const int64_t o = (a.outOff ? a.outOff[mat] : v0) + r;
+      a.out[a.scatter ? a.scatter[o] : o] = v;
     }
   }
 }
@@ -306,6 +307,16 @@ __global__ void k_scatter_vec(const double* __restrict__ x, const int* __restric
                               int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) y[idx[i]] = x[i];
+}
+__global__ void k_scatter_vec_masked(const double* __restrict__ x, const int* __restrict__ idx,
+                                     double* __restrict__ y, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && idx[i] >= 0) y[idx[i]] = x[i];
+}
+void scatterVecMasked(const double* x, const int* idx, double* y, int64_t n, cudaStream_t s, int64_t* launches) {
+  if (n == 0) return;
+  k_scatter_vec_masked<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, idx, y, n);
+  ++*launches;
 }
 void scatterVec(const double* x, const int* idx, double* y, int64_t n, cudaStream_t s, int64_t* launches) {
   if (n == 0) return;

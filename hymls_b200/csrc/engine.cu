@@ -239,8 +239,11 @@ void Engine::initialize() {
       CartesianPartitioner pidPart(pp, l, comm_.size(), comm_.rank());
       pidPart.partition();
       const std::vector<int>& pm = pidPart.pidMap();
-      for (int sd = 0; sd < S.nsd; ++sd)
-        if (pm[part.globalSubdomain(sd)] == comm_.rank()) L.ownSd.push_back(sd);
+      L.sdRank.assign(S.nsd, 0);
+      for (int sd = 0; sd < S.nsd; ++sd) {
+        L.sdRank[sd] = pm[part.globalSubdomain(sd)];
+        if (L.sdRank[sd] == comm_.rank()) L.ownSd.push_back(sd);
+      }
     } else {
       for (int sd = 0; sd < S.nsd; ++sd) L.ownSd.push_back(sd);
     }
@@ -335,7 +338,24 @@ void Engine::uploadLevel(Level& L) {
     L.c21.upload(col, s);
     L.src21.upload(src, s);
     L.v21.alloc(col.size());
-    L.xI.alloc(S.nI);
+    // interior results: every rank packs its owned segments, the packs are all-gathered
+    const int P = comm_.size();
+    std::vector<int64_t> cnt(P, 0);
+    for (int sd = 0; sd < S.nsd; ++sd) cnt[L.sdRank[sd]] += S.sdN[sd];
+    L.maxOwnI = *std::max_element(cnt.begin(), cnt.end());
+    std::vector<int> packedRow((size_t)P * L.maxOwnI, -1);
+    std::vector<int64_t> fill(P, 0), outOff(nown);
+    int k = 0;
+    for (int sd = 0; sd < S.nsd; ++sd) {
+      const int q = L.sdRank[sd];
+      const int64_t base = (int64_t)q * L.maxOwnI + fill[q];
+      for (int i = 0; i < S.sdN[sd]; ++i) packedRow[base + i] = S.intRow[S.H.intPtr[sd] + i];
+      if (q == comm_.rank()) outOff[k++] = base;
+      fill[q] += S.sdN[sd];
+    }
+    L.packedRow.upload(packedRow, s);
+    L.gatherOutOff.upload(outOff, s);
+    L.xI.alloc((size_t)P * L.maxOwnI);
   }
   if (L.exact) {
     L.p22.upload(S.A22.ptr, s);
@@ -906,9 +926,9 @@ void Engine::applyLevel(int l, const double* B, double* X) {
   g.out = X;
   g.scatter = L.intRow.p;
   g.mode = 1;
-  if (L.sharded) {  // owned interiors into a packed zeroed vector, summed over the ranks, then exported
-    HY_CUDA(cudaMemsetAsync(L.xI.p, 0, (size_t)S.nI * sizeof(double), s));
+  if (L.sharded) {  // owned interiors packed per rank, all-gathered, then exported
     g.out = L.xI.p;
+    g.outOff = L.gatherOutOff.p;
     g.scatter = nullptr;
   }
   if (timeIt) HY_CUDA(cudaEventRecord(evA_, s));
@@ -923,8 +943,8 @@ void Engine::applyLevel(int l, const double* B, double* X) {
   }
   at.lap("A12 spmv + A11 gemv 2");
   if (L.sharded) {
-    comm_.allReduceSum(L.xI.p, (size_t)S.nI, s);
-    scatterVec(L.xI.p, L.intRow.p, X, S.nI, s, &launches_);
+    comm_.allGather(L.xI.p + (int64_t)comm_.rank() * L.maxOwnI, L.xI.p, (size_t)L.maxOwnI, s);
+    scatterVecMasked(L.xI.p, L.packedRow.p, X, (int64_t)comm_.size() * L.maxOwnI, s, &launches_);
   }
   at.lap("interior allreduce + export");
 }

@@ -36,6 +36,7 @@ struct Level {
   // A11: inverses of the subdomains this rank owns (all of them on one GPU), compact storage
   BatchedInverse a11;
   std::vector<int> ownSd;           // owned subdomains, ascending
+  std::vector<int> sdRank;          // owner rank of every subdomain (sharded levels)
   std::vector<int64_t> ownOff;      // compact offsets (doubles) of the owned matrices, ownSd.size()+1
   DevBuf<int> sdNG, sdNpG;          // per (global) subdomain: n, np
   DevBuf<int64_t> a11OffG;          // per (global) subdomain: compact offset (undefined if not owned)
@@ -45,7 +46,10 @@ struct Level {
   DevBuf<int> ownSdList;            // device copies of the owned lists for the pass-2 Schur kernels
   DevBuf<int64_t> ownRowList, ownLinkList;
   std::vector<int64_t> chunkOwnSd, chunkOwnRow, chunkOwnLink;  // per chunk: ranges in the lists (nchunks+1)
-  DevBuf<double> xI;                // packed interior result (sharded apply: all-reduced)
+  DevBuf<double> xI;                // per-rank packed interior results, all-gathered (nranks * maxOwnI)
+  DevBuf<int64_t> gatherOutOff;     // per owned matrix: position of its segment in xI
+  DevBuf<int> packedRow;            // matrix row of every xI entry (-1: padding)
+  int64_t maxOwnI = 0;
   // off-diagonal blocks
   DevBuf<int64_t> p12, p21, src12, src21, p22, src22;
   DevBuf<int> c12, c21, c22;

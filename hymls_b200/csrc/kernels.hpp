@@ -66,6 +66,7 @@ struct GemvArgs {
   const int *n, *np;
   const int64_t* matOff;   // offset of each matrix in A
   const int64_t* vecOff;   // offset of each matrix' segment in the packed vectors
+  const int64_t* outOff;   // optional: offset of each matrix' segment in `out` (default: vecOff)
   const double* A;
   const double* xin;
   const int* gather;
@@ -97,5 +98,7 @@ void putDirichlet(double* D, int n, int np, int fix, cudaStream_t s, int64_t* la
 void gatherAdd(const double* b, const int* idx, const double* t, double* y, int64_t n, cudaStream_t s,
                int64_t* launches);
 void scatterVec(const double* x, const int* idx, double* y, int64_t n, cudaStream_t s, int64_t* launches);
+// y[idx[i]] = x[i] for idx[i] >= 0
+void scatterVecMasked(const double* x, const int* idx, double* y, int64_t n, cudaStream_t s, int64_t* launches);
 
 }  // namespace hymls

@@ -1,5 +1,6 @@
 // C ABI (include/hymls_b200.h) -> Engine.  No exception crosses the boundary.
 #include <cstring>
+#include <memory>
 #include <string>
 
 #include "../../include/hymls_b200.h"
@@ -221,9 +222,9 @@ int64_t hymls_b200_get_map(hymls_b200_t* h, int level, int which, int64_t* gids,
 int hymls_b200_pid_map(const char* xml, int nprocs, int32_t* pid, int cap) {
   HY_TRY
   ParameterList p = ParameterList::fromXml(xml);
-  CartesianPartitioner part(p, 0, nprocs, 0);
-  part.partition();
-  const std::vector<int>& m = part.pidMap();
+  std::unique_ptr<CartesianPartitioner> part(makePartitioner(p, 0, nprocs, 0));
+  part->partition();
+  const std::vector<int>& m = part->pidMap();
   if (pid && cap >= (int)m.size()) std::memcpy(pid, m.data(), m.size() * sizeof(int));
   return (int)m.size();
   HY_CATCH

@@ -48,8 +48,8 @@ Engine::Engine(const std::string& xml) {
   validatePreconditionerList(prec);
   maxLevel_ = prec.get("Number of Levels", 1);
   std::string method = prec.get("Partitioner", "Cartesian");
-  if (method != "Cartesian")
-    throw Error(HYMLS_B200_ERR_UNSUPPORTED, "Partitioner '" + method + "': only 'Cartesian' is implemented");
+  if (method != "Cartesian" && method != "Skew Cartesian")
+    throw Error(HYMLS_B200_ERR_ARG, "Partitioner '" + method + "': Up to now we only support Cartesian partitioning");
   std::string variant = prec.get("Preconditioner Variant", "Block Diagonal");
   bool dropping = prec.get("Apply Dropping", true);
   bool ot = prec.get("Apply Orthogonal Transformation", dropping);
@@ -201,7 +201,8 @@ void Engine::initialize() {
     LevelSym& S = L.sym;
     S.level = l;
     L.exact = (maxLevel_ == 0);
-    CartesianPartitioner part(levelParams, l);
+    std::unique_ptr<CartesianPartitioner> partPtr(makePartitioner(levelParams, l));
+    CartesianPartitioner& part = *partPtr;
     if (l == 0) {
       // write the defaults back like the reference does (Fix GID 1, ...) so later queries see them
       params_.sublist("Preconditioner") = levelParams.sublist("Preconditioner").deepCopy();
@@ -236,7 +237,8 @@ void Engine::initialize() {
     if (L.sharded) {
       if (maxLevel_ == 0) throw Error(HYMLS_B200_ERR_UNSUPPORTED, "Number of Levels = 0 is single-GPU only");
       ParameterList pp = levelParams.deepCopy();
-      CartesianPartitioner pidPart(pp, l, comm_.size(), comm_.rank());
+      std::unique_ptr<CartesianPartitioner> pidPartPtr(makePartitioner(pp, l, comm_.size(), comm_.rank()));
+      CartesianPartitioner& pidPart = *pidPartPtr;
       pidPart.partition();
       const std::vector<int>& pm = pidPart.pidMap();
       L.sdRank.assign(S.nsd, 0);

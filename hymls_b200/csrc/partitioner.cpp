@@ -179,11 +179,12 @@ void CartesianPartitioner::setNextLevelParameters(ParameterList& params) const {
 }
 
 // src/HYMLS_CartesianPartitioner.cpp:80-121
-void CartesianPartitioner::subdomainPosition(int sd, int sx, int sy, int sz, int& x, int& y, int& z) const {
+int CartesianPartitioner::subdomainPosition(int sd, int sx, int sy, int sz, int& x, int& y, int& z) const {
   int npx = (nx_ - 1) / sx + 1, npy = (ny_ - 1) / sy + 1, npz = (nz_ - 1) / sz + 1;
   x = (sd % npx) * sx;
   y = ((sd / npx) % npy) * sy;
   z = ((sd / npx / npy) % npz) * sz;
+  return 0;
 }
 int CartesianPartitioner::subdomainId(int sx, int sy, int sz, int x, int y, int z) const {
   int npx = (nx_ - 1) / sx + 1, npy = (ny_ - 1) / sy + 1;
@@ -502,6 +503,367 @@ void buildHierarchicalMap(const CartesianPartitioner& part, const std::vector<ch
     }
     H.sdGrpPtr.push_back((int64_t)H.grpType.size());
   }
+}
+
+}  // namespace hymls
+
+// =============================================================================================
+// Skew Cartesian partitioner (src/HYMLS_SkewCartesianPartitioner.cpp)
+// =============================================================================================
+namespace hymls {
+
+CartesianPartitioner* makePartitioner(ParameterList& params, int level, int nprocs, int mypid) {
+  std::string method = params.sublist("Preconditioner").get("Partitioner", "Cartesian");
+  if (method == "Cartesian") return new CartesianPartitioner(params, level, nprocs, mypid);
+  if (method == "Skew Cartesian") return new SkewCartesianPartitioner(params, level, nprocs, mypid);
+  throw Error(HYMLS_B200_ERR_ARG, "Up to now we only support Cartesian partitioning");
+}
+
+// :128-160
+int SkewCartesianPartitioner::subdomainPosition(int sd, int sx, int sy, int sz, int& x, int& y, int& z) const {
+  (void)sz;
+  const int npx = nx_ / sx, npy = ny_ / sy;
+  const int perLayer = 2 * npx * npy + npx + npy;
+  const int perRow = 2 * npx + 1;
+  const int Z = perLayer > 0 ? sd / perLayer : 0;
+  int Y = ((sd - Z * perLayer) / perRow) * 2 - 1;
+  int X = ((sd - Z * perLayer) % perRow) * 2;
+  if (X >= npx * 2) {
+    X -= npx * 2 + 1;
+    Y += 1;
+  }
+  x = (X * sx) / 2;
+  y = (Y * sx) / 2 + sx / 2;
+  z = Z * sx;
+  if (x == nx_ - sx / 2 && (perio_ & X_PERIO)) return 1;
+  if (y == ny_ && (perio_ & Y_PERIO)) return 1;
+  if (z == nz_ && (perio_ & Z_PERIO)) return 1;
+  return 0;
+}
+
+// :162-207
+int SkewCartesianPartitioner::subdomainId(int sx, int sy, int sz, int x, int y, int z) const {
+  const int npx = nx_ / sx, npy = ny_ / sy, npz = nz_ / sz;
+  const int dir1 = npx + 1, dir2 = npx, dir3 = 2 * npx * npy + npx + npy;
+  const int xc = x / sx, yc = y / sx, zc = z / sx;
+  int sd = zc * dir3 + yc * (dir2 + dir1) + xc;
+  x -= xc * sx - 1;
+  y -= yc * sx;
+  z -= zc * sx;
+  const bool front = y < sx - x;
+  const bool right = y < x;
+  bool below = z <= y - x;
+  if (right) below = z <= sx + y - x;
+  if (!front) sd += dir1;
+  if (!right) sd += dir2;
+  if (!below) sd += dir3;
+  if (!front && right && (perio_ & X_PERIO) && xc == npx - 1) sd -= dir2;
+  if (!front && !right && (perio_ & Y_PERIO) && yc == npy - 1) sd -= dir3 - dir2;
+  if (!below && (perio_ & Z_PERIO) && zc == npz - 1) sd -= npz * dir3;
+  return sd;
+}
+
+// :219-238
+int SkewCartesianPartitioner::numGlobalParts(int sx, int sy, int sz) const {
+  const int npx = nx_ / sx, npy = ny_ / sy, npz = nz_ / sz;
+  const int perLayer = 2 * npx * npy + npx + npy;
+  int n = perLayer;
+  if (nz_ > 1) n += perLayer * npz;
+  return std::max(n, 1);
+}
+
+// :240-368
+void SkewCartesianPartitioner::partition() {
+  if (sx_ != sy_ || (nz_ > 1 && sx_ != sz_)) throw argError("sx, sy and sz should be the same");
+  if ((sx_ / 2) * 2 != sx_) throw argError("sx should be even");
+  if (nx_ % sx_ || ny_ % sy_ || nz_ % sz_)
+    throw argError("You are trying to partition a domain whose size is not a multiple of the subdomain size");
+  createPidMap();
+  sdMap_.clear();
+  const int nparts = numGlobalParts(sx_, sy_, sz_);
+  for (int sd = 0; sd < nparts; ++sd) {
+    int i, j, k;
+    if (subdomainPosition(sd, sx_, sy_, sz_, i, j, k) == 1) continue;
+    i = (i % nx_ + nx_) % nx_;
+    j = (j % ny_ + ny_) % ny_;
+    k = (k % nz_ + nz_) % nz_;
+    if (pidMap_[subdomainId(sx_, sy_, sz_, i, j, k)] == mypid_) sdMap_.push_back(sd);
+  }
+  buildTemplate();
+  solveGroups();
+}
+
+namespace {
+struct Plane45 {
+  std::vector<long long> ptr, plane;
+};
+// :27-78: a diamond of nodes in the xy-plane, row by row
+Plane45 buildPlane45(long long first, int length, long long dirX, long long dirY, int type) {
+  long long left = first, right = first;
+  int height = 2 * length;
+  bool extra = false;
+  const long long dir1 = dirY + dirX, dir2 = dirY - dirX;
+  if (type == 0) {
+    left -= dirX;
+    height++;
+    extra = true;
+  } else if (type == 3) {
+    height++;
+    extra = true;
+  }
+  Plane45 P;
+  P.ptr.push_back(0);
+  for (int i = 0; i < height - 1; ++i) {
+    for (long long j = left; j <= right; j += dirX) P.plane.push_back(j);
+    P.ptr.push_back((long long)P.plane.size());
+    if (i < length - 1) {
+      left += dir2;
+      right += dir1;
+    } else if (extra && i == length - 1) {
+      left += dirY;
+      right += dirY;
+    } else {
+      left += dir1;
+      right += dir2;
+    }
+  }
+  return P;
+}
+}  // namespace
+
+// getTemplate :372-565
+void SkewCartesianPartitioner::buildTemplate() {
+  const int sx = sx_, dof = dof_;
+  const long long nx = sx * 4;
+  const long long dirX = dof, dirY = dof * nx, dirZ = dof * nx * nx;
+  const long long first[4] = {dof * sx / 2 + dirY + dirZ * sx, dof * sx / 2 + dirZ * sx,
+                              dof * sx / 2 + dirY + dirZ * sx, dof * sx / 2 + dirY + dirZ * sx};
+  const int baseLen[4] = {sx / 2, sx / 2 + 1, sx / 2 + 1, sx / 2};
+  const int typeArr[4] = {VT_U, VT_V, VT_W, VT_PRESSURE};
+  std::vector<std::vector<std::vector<long long>>> nodes(4);
+  for (int type = 0; type < 4; ++type) {
+    auto& layers = nodes[type];
+    layers.assign(2 * sx + 1, std::vector<long long>());
+    Plane45 P = buildPlane45(first[type], baseLen[type], dirX, dirY, type);
+    layers[sx] = P.plane;
+    if (nz_ <= 1) continue;
+    std::vector<long long> bottom, top = P.plane, rowLen;
+    for (size_t i = 0; i + 1 < P.ptr.size(); ++i) rowLen.push_back(P.ptr[i + 1] - P.ptr[i] - 1);
+    std::vector<long long> active, offset;
+    for (int i = 0; i < baseLen[type]; ++i) active.push_back(i);
+    for (long long a : active) offset.push_back(rowLen[a]);
+    for (int i = 0; i < sx; ++i) {
+      for (size_t j = 0; j < active.size(); ++j) {
+        const long long val = P.plane[P.ptr[active[j]] + offset[j]];
+        bottom.push_back(val);
+        top.erase(std::remove(top.begin(), top.end(), val), top.end());
+      }
+      if (typeArr[type] == VT_W) {
+        if (i % 2 == 1) {
+          for (long long j : top) layers[sx + i].push_back(j + i * dirZ - dirY);
+          for (long long j : top) layers[sx + 1 + i].push_back(j + (i + 1) * dirZ);
+        } else {
+          for (long long j : bottom) layers[i].push_back(j - (sx - i) * dirZ);
+          if (i > 0) {
+            for (long long j : bottom) layers[i - 1].push_back(j - (sx - i + 1) * dirZ - dirY);
+          } else {
+            for (long long j : P.plane) layers[sx - 1].push_back(j - dirZ - dirY);
+          }
+        }
+      } else {
+        const int isP = typeArr[type] == VT_PRESSURE ? 1 : 0;
+        if (i < sx - isP)
+          for (long long j : bottom) layers[i + isP].push_back(j - (sx - i - isP) * dirZ);
+        for (long long j : top) layers[sx + 1 + i].push_back(j + (i + 1) * dirZ);
+      }
+      if (i < sx - 1) {
+        for (auto& d : offset) d--;
+        if (typeArr[type] == VT_PRESSURE) {
+          if (offset[0] < 0) {
+            active.push_back(active.back() + 1);
+            active.erase(active.begin());
+            offset.push_back(rowLen[active.back()]);
+            offset.erase(offset.begin());
+          }
+        } else {
+          if (offset[0] < 0) {
+            active.erase(active.begin());
+            offset.erase(offset.begin());
+          } else if (offset[0] == 0) {
+            active.push_back(active.back() + 1);
+            offset.push_back(rowLen[active.back()]);
+          }
+        }
+      }
+    }
+  }
+  nodes[0].pop_back();
+  nodes[0].erase(nodes[0].begin());
+  nodes[1].pop_back();
+  nodes[1].erase(nodes[1].begin());
+  nodes[2].pop_back();
+  nodes[3].pop_back();
+  nodes[3].erase(nodes[3].begin());
+  template_.clear();
+  template_.emplace_back();
+  for (int i = 0; i < dof; ++i)
+    if (variableType_[i] == VT_W) {
+      for (long long v : nodes[2].front()) template_.back().push_back(v + i);
+      nodes[2].erase(nodes[2].begin());
+      break;
+    }
+  for (int j = 0; j < 2 * sx - 1; ++j) {
+    template_.emplace_back();
+    for (int i = 0; i < dof; ++i)
+      for (int type = 0; type < 4; ++type)
+        if (variableType_[i] == typeArr[type])
+          for (long long v : nodes[type][j]) template_.back().push_back(v + i);
+    std::sort(template_.back().begin(), template_.back().end());
+  }
+}
+
+// solveGroups :567-654: classify every template node by the set of neighbouring domains it lies in
+void SkewCartesianPartitioner::solveGroups() {
+  const long long nx = sx_ * 4;
+  const long long dirX = (long long)dof_ * sx_, dirY = (long long)dof_ * nx * sx_, dirZ = (long long)dof_ * nx * nx * sx_;
+  const long long first = dirX + dirY + dirZ;
+  const long long d1 = (dirY + dirX) / 2, d2 = (dirY - dirX) / 2 + dirZ, d3 = dirZ;
+  const long long pos[27] = {0, -d3, d3, -d2, -d2 - d3, -d2 + d3, d2, d2 - d3, d2 + d3,
+                             -d1, -d1 - d3, -d1 + d3, -d1 - d2, -d1 - d2 - d3, -d1 - d2 + d3, -d1 + d2,
+                             -d1 + d2 - d3, -d1 + d2 + d3, d1, d1 - d3, d1 + d3, d1 - d2,
+                             d1 - d2 - d3, d1 - d2 + d3, d1 + d2, d1 + d2 - d3, d1 + d2 + d3};
+  std::vector<long long> temp;
+  for (auto& layer : template_)
+    for (long long v : layer) temp.push_back(v + first);
+  std::vector<long long> sorted(temp);
+  std::sort(sorted.begin(), sorted.end());
+  std::vector<std::vector<long long>> groups(1);
+  std::vector<unsigned long> domains(1, 1ul);
+  for (long long node : temp) {
+    unsigned long bits = 0;
+    for (int i = 0; i < 27; ++i)
+      if (std::binary_search(sorted.begin(), sorted.end(), node - pos[i])) bits += 1ul << i;
+    bool found = false;
+    for (size_t g = 0; g < groups.size(); ++g)
+      if (domains[g] == bits) {
+        groups[g].push_back(node);
+        found = true;
+        break;
+      }
+    if (!found) {
+      groups.emplace_back(1, node);
+      domains.push_back(bits);
+    }
+  }
+  groupsT_.clear();
+  groupsT_.emplace_back(1, groups[0]);
+  for (size_t g = 1; g < groups.size(); ++g) {
+    groupsT_.emplace_back(dof_);
+    for (long long node : groups[g]) groupsT_.back()[((node % dof_) + dof_) % dof_].push_back(node);
+  }
+}
+
+// GetGroups :656-812
+void SkewCartesianPartitioner::getGroups(int localSd, std::vector<gidx>& interior,
+                                         std::vector<SepGroup>& out) const {
+  interior.clear();
+  out.clear();
+  const int gsd = sdMap_[localSd];
+  int sdx, sdy, sdz;
+  subdomainPosition(gsd, sx_, sy_, sz_, sdx, sdy, sdz);
+  const long long nx = 4 * sx_;
+  std::vector<std::vector<std::vector<gidx>>> groups;
+  for (auto const& cat : groupsT_) {
+    groups.emplace_back();
+    for (auto const& group : cat) {
+      groups.back().emplace_back();
+      for (long long node : group) {
+        const int var = (int)(node % dof_);
+        int x = (int)((node / dof_) % nx) + sdx - 1 - sx_;
+        int y = (int)((node / dof_ / nx) % nx) + sdy - 1 - 3 * sx_ / 2;
+        int z = (int)(node / dof_ / nx / nx) + sdz - 2 * sx_;
+        if (perio_ & X_PERIO) x = (x + nx_) % nx_;
+        if (perio_ & Y_PERIO) y = (y + ny_) % ny_;
+        if (perio_ & Z_PERIO) z = (z + nz_) % nz_;
+        if (x >= 0 && x < nx_ && y >= 0 && y < ny_ && z >= 0 && z < nz_)
+          groups.back().back().push_back((gidx)x * dof_ + (gidx)nx_ * y * dof_ + (gidx)nx_ * ny_ * z * dof_ + var);
+      }
+    }
+  }
+  // first pressure nodes of the interior become retained (singleton) groups.  The reference erases from
+  // the vector it iterates over, so the element sliding into the erased slot is skipped: same here.
+  {
+    int retained = 0;
+    std::vector<gidx>& in0 = groups[0][0];
+    for (size_t it = 0; it < in0.size(); ++it) {
+      const gidx node = in0[it];
+      if (variableType_[(int)(((node % dof_) + dof_) % dof_)] == VT_PRESSURE) {
+        groups.emplace_back();
+        groups.back().emplace_back(1, node);
+        std::vector<gidx>& in = groups[0][0];  // (emplace_back may have moved the outer vector)
+        in.erase(in.begin() + it);
+        if (++retained >= retainPressures_) break;
+      }
+    }
+  }
+  interior = groups[0][0];
+  auto cellOwner = [&](gidx node) {
+    gidx cell = node / dof_;
+    return subdomainId(sx_, sy_, sz_, (int)(cell % nx_), (int)((cell / nx_) % ny_), (int)(cell / ((gidx)nx_ * ny_)));
+  };
+  int type = 1;
+  for (size_t i = 1; i < groups.size(); ++i) {
+    type++;
+    for (auto const& group : groups[i]) {
+      std::vector<std::pair<int, SepGroup>> parts;  // keyed by owner subdomain, kept sorted (std::map order)
+      for (gidx node : group) {
+        const int owner = cellOwner(node);
+        auto it = std::lower_bound(parts.begin(), parts.end(), owner,
+                                   [](const std::pair<int, SepGroup>& a, int b) { return a.first < b; });
+        if (it != parts.end() && it->first == owner) {
+          it->second.nodes.push_back(node);
+        } else {
+          SepGroup g;
+          g.type = linkVelocities_ ? type : -1;
+          g.nodes.push_back(node);
+          parts.insert(it, std::make_pair(owner, g));
+        }
+      }
+      for (auto& pr : parts) {
+        if (rx_ > 1) {
+          if (!linkVelocities_) type++;
+          const int len = (int)pr.second.nodes.size();
+          const int newLen = std::max((len + rx_ - 1) / rx_, 1);
+          const int numParts = (len - 1) / newLen + 1;
+          for (int j = 0; j < numParts; ++j) {
+            SepGroup g2;
+            g2.type = (linkVelocities_ || linkRetained_) ? type : -1;
+            for (int q = j * newLen; q < (j + 1) * newLen && q < len; ++q) g2.nodes.push_back(pr.second.nodes[q]);
+            out.push_back(g2);
+          }
+        } else {
+          out.push_back(pr.second);
+        }
+      }
+    }
+  }
+  // velocity nodes on the far (non-periodic) boundaries are Dirichlet rows, not separators
+  for (auto& g : out) {
+    std::vector<gidx> copy = g.nodes;
+    for (gidx node : copy) {
+      const int x = (int)((node / dof_) % nx_), y = (int)((node / dof_ / nx_) % ny_);
+      const int z = (int)(node / dof_ / nx_ / ny_);
+      const int vt = variableType_[(int)(node % dof_)];
+      const bool hit = (dof_ > 1 && x == nx_ - 1 && vt == VT_U && !(perio_ & X_PERIO)) ||
+                       (dof_ > 1 && y == ny_ - 1 && vt == VT_V && !(perio_ & Y_PERIO)) ||
+                       (nz_ > 1 && dof_ > 1 && z == nz_ - 1 && vt == VT_W && !(perio_ & Z_PERIO));
+      if (hit) {
+        if (subdomainId(sx_, sy_, sz_, x, y, z) == gsd) interior.push_back(node);
+        g.nodes.erase(std::remove(g.nodes.begin(), g.nodes.end(), node), g.nodes.end());
+      }
+    }
+  }
+  std::sort(interior.begin(), interior.end());
 }
 
 }  // namespace hymls

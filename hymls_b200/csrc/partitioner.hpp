@@ -25,8 +25,9 @@ struct SepGroup {
 class CartesianPartitioner {
  public:
   CartesianPartitioner(ParameterList& params, int level, int nprocs = 1, int mypid = 0);
+  virtual ~CartesianPartitioner() {}
 
-  void partition();  // CreatePIDMap + CreateSubdomainMap
+  virtual void partition();  // CreatePIDMap + CreateSubdomainMap
   int numLocalParts() const { return (int)sdMap_.size(); }
   int numGlobalParts() const { return numGlobalParts(sx_, sy_, sz_); }
   int globalSubdomain(int localSd) const { return sdMap_[localSd]; }
@@ -34,11 +35,11 @@ class CartesianPartitioner {
   int numActiveProcs() const { return nprocs_; }
 
   // interior nodes and separator groups in the reference's emission order (not yet sorted)
-  void getGroups(int localSd, std::vector<gidx>& interior, std::vector<SepGroup>& groups) const;
+  virtual void getGroups(int localSd, std::vector<gidx>& interior, std::vector<SepGroup>& groups) const;
   void setNextLevelParameters(ParameterList& params) const;
 
-  int subdomainId(int sx, int sy, int sz, int x, int y, int z) const;
-  void subdomainPosition(int sd, int sx, int sy, int sz, int& x, int& y, int& z) const;
+  virtual int subdomainId(int sx, int sy, int sz, int x, int y, int z) const;
+  virtual int subdomainPosition(int sd, int sx, int sy, int sz, int& x, int& y, int& z) const;
   int pid(gidx gid) const;
 
   int nx() const { return nx_; }
@@ -49,9 +50,9 @@ class CartesianPartitioner {
   int pvar() const { return pvar_; }
   gidx numGlobalNodes() const { return (gidx)nx_ * ny_ * nz_ * dof_; }
 
- private:
+ protected:
   void setParameters(ParameterList& params);
-  int numGlobalParts(int sx, int sy, int sz) const;
+  virtual int numGlobalParts(int sx, int sy, int sz) const;
   void createPidMap();
 
   int level_, nprocsComm_, mypid_;
@@ -64,6 +65,30 @@ class CartesianPartitioner {
   std::vector<int> sdMap_;
   int nprocs_ = 1;
 };
+
+// src/HYMLS_SkewCartesianPartitioner.cpp: 45-degree rotated (octahedral) subdomains built from a
+// template domain and its 26 neighbours.  Same BasePartitioner machinery (parameters, CreatePIDMap).
+class SkewCartesianPartitioner : public CartesianPartitioner {
+ public:
+  SkewCartesianPartitioner(ParameterList& params, int level, int nprocs = 1, int mypid = 0)
+      : CartesianPartitioner(params, level, nprocs, mypid) {}
+  void partition() override;
+  void getGroups(int localSd, std::vector<gidx>& interior, std::vector<SepGroup>& groups) const override;
+  int subdomainId(int sx, int sy, int sz, int x, int y, int z) const override;
+  int subdomainPosition(int sd, int sx, int sy, int sz, int& x, int& y, int& z) const override;
+
+ protected:
+  int numGlobalParts(int sx, int sy, int sz) const override;
+
+ private:
+  void buildTemplate();
+  void solveGroups();
+  std::vector<std::vector<long long>> template_;                // layers of the template domain
+  std::vector<std::vector<std::vector<long long>>> groupsT_;    // [category][variable][node]
+};
+
+// factory: "Cartesian" | "Skew Cartesian" (OverlappingPartitioner::Partition, :96-119)
+CartesianPartitioner* makePartitioner(ParameterList& params, int level, int nprocs = 1, int mypid = 0);
 
 // One level of the hierarchy after FillComplete, flattened.
 struct HierarchicalMap {

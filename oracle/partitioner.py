@@ -557,9 +557,13 @@ class OverlappingPartitioner(HierarchicalMap):
         self.params = params
         self.level = level
         method = params.sublist("Preconditioner").get("Partitioner", "Cartesian")
-        if method != "Cartesian":
-            raise NotImplementedError("oracle implements the Cartesian partitioner only")
-        part = CartesianPartitioner(params, level, nprocs, mypid).partition()
+        if method == "Cartesian":
+            part = CartesianPartitioner(params, level, nprocs, mypid).partition()
+        elif method == "Skew Cartesian":
+            from .skew import SkewCartesianPartitioner
+            part = SkewCartesianPartitioner(params, level, nprocs, mypid).partition()
+        else:
+            raise NotImplementedError("Up to now we only support Cartesian partitioning")
         self.partitioner = part
         self.next_level_params = params.copy()
         part.set_next_level_parameters(self.next_level_params)

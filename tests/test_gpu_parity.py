@@ -59,6 +59,11 @@ CASES = [
     ("Stokes-C", 3, 8, 4, 1, None, {"Eliminate_Tube_Pressures_With_Velocities": True}, TOL_STOKES),
     ("Stokes-C", 3, 16, 4, 2, 2, {"Eliminate_Tube_Pressures_With_Velocities": True}, TOL_STOKES),
     ("Stokes-C", 3, 16, 8, 1, None, {"Eliminate_Tube_Pressures_With_Velocities": True}, TOL_STOKES),
+    # skew Cartesian partitioner (the reference's partitioner for Stokes)
+    ("Stokes-C", 2, 32, 4, 2, 2, {"Partitioner": "Skew Cartesian"}, TOL_STOKES),
+    ("Stokes-C", 3, 8, 4, 1, None, {"Partitioner": "Skew Cartesian"}, TOL_STOKES),
+    ("Stokes-C", 3, 16, 4, 2, 2, {"Partitioner": "Skew Cartesian"}, TOL_STOKES),
+    ("Stokes-C", 3, 16, 8, 0, None, {"Partitioner": "Skew Cartesian"}, TOL_STOKES),
 ]
 
 
@@ -116,6 +121,29 @@ def test_exact_path_on_reference_fixture():
     pv = np.zeros(A.shape[0]); pv[2::3] = 1; pv /= np.linalg.norm(pv)
     err -= pv * (pv @ err)
     assert np.linalg.norm(err) / np.linalg.norm(b) <= 1e-10
+
+
+def test_reference_3d_targets_with_skew_partitioner():
+    """integration_tests/stokes1_3D.xml on the shipped 16^3 fixture: Skew sx=8, 1 level, tol 1e-8,
+    target <= 130 iterations and res/err <= 1.5e-5; the GPU must agree with the oracle within +-1."""
+    A, b, sol = load_fixture("cavity3d_16_Re0")
+    solver = {"Krylov Method": "GMRES", "Initial Vector": "Zero", "Left or Right Preconditioning": "Right",
+              "Iterative Solver": {"Maximum Iterations": 160, "Maximum Restarts": 1, "Convergence Tolerance": 1e-8,
+                                   "Explicit Residual Test": True, "Implicit Residual Scaling": "Norm of RHS",
+                                   "Explicit Residual Scaling": "Norm of RHS"}}
+    A, P, O = build("Stokes-C", 3, 16, 8, 1, A=A, solver=solver, Partitioner="Skew Cartesian")
+    S = hb.Solver(P)
+    x = S.ApplyInverse(b)
+    n = A.shape[0]
+    xo, its, conv, h = ok.gmres(lambda v: A @ v, b, np.zeros(n), O.apply_inverse, side="Right", tol=1e-8,
+                                max_iters=160, max_restarts=1, explicit_test=True, imp_scaling="Norm of RHS",
+                                exp_scaling="Norm of RHS")
+    assert S.info["converged"] and S.num_iter <= 130 and abs(S.num_iter - its) <= 1
+    assert np.linalg.norm(A @ x - b) / np.linalg.norm(b) <= 1.5e-5
+    err = x - sol
+    pv = np.zeros(n); pv[3::4] = 1; pv /= np.linalg.norm(pv)
+    err -= pv * (pv @ err)
+    assert np.linalg.norm(err) / np.linalg.norm(b) <= 1.5e-5
 
 
 def test_high_reynolds_fixture_two_levels():

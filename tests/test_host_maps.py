@@ -106,3 +106,53 @@ def test_pid_map_matches_oracle(nx, sx, nprocs):
     got = hb.pid_map(_dictify(p), nprocs)
     ref = CartesianPartitioner(p.copy(), 0, nprocs, 0).partition().pid_map
     assert np.array_equal(got, np.asarray(ref, dtype=np.int32))
+
+
+SKEW_CASES = [
+    ("Stokes-C", 2, 16, 4, 1, None),
+    ("Stokes-C", 2, 32, 4, 3, 2),
+    ("Stokes-C", 3, 8, 4, 1, None),
+    ("Stokes-C", 3, 16, 4, 2, 2),
+    ("Stokes-C", 3, 16, 8, 1, None),
+    ("Laplace", 2, 16, 4, 2, 2),
+]
+
+
+@pytest.mark.parametrize("eqn,dim,nx,sx,levels,cx", SKEW_CASES)
+def test_skew_maps_match_oracle_on_every_level(eqn, dim, nx, sx, levels, cx):
+    """Skew Cartesian partitioner: C++ host code vs the oracle that
+    tests/test_oracle_skew.py pins to the reference's goldens."""
+    import scipy.sparse as sps
+    p = make_params(eqn, dim, nx, sx, levels, cx, Partitioner="Skew Cartesian")
+    A = hb.galeri.create_matrix(eqn, dim, nx)
+    tv = hb.galeri.create_testvector(A)
+    P = hb.Preconditioner(A, _dictify(p), tv, pattern_only=True)
+    P.Initialize()
+    lvl = ohymls.Preconditioner(A, p.copy(), tv)
+    lvl.initialize()
+    for l in range(P.NumLevels()):
+        hid = lvl.hid
+        assert P.NumMySubdomains(l) == hid.num_subdomains()
+        for sd in range(hid.num_subdomains()):
+            assert np.array_equal(P.GetInteriorGroup(sd, l), np.asarray(hid.interior[sd], dtype=np.int64))
+            got = P.GetSeparatorGroups(sd, l)
+            assert len(got) == len(hid.groups[sd])
+            for (t, g), (to, go) in zip(got, hid.groups[sd]):
+                assert t == to and np.array_equal(g, np.asarray(go, dtype=np.int64))
+        assert np.array_equal(P.GetMap(api.MAP_SEPARATOR, l), hid.separator_map())
+        assert np.array_equal(P.GetMap(api.MAP_VSUM, l), lvl.schur_prec.vsum_gids)
+        if l + 1 < P.NumLevels():
+            sp_ = lvl.schur_prec
+            nv = len(sp_.vsum_gids)
+            lvl = ohymls.Preconditioner(sps.identity(nv, format="csr"), p.copy(), np.ones(nv), l + 1,
+                                        sp_.next_hid, gids=sp_.vsum_gids)
+            lvl.initialize()
+
+
+@pytest.mark.parametrize("nx,sx,nprocs", [(8, 4, 4), (16, 4, 8), (32, 8, 8), (16, 4, 3)])
+def test_skew_pid_map_matches_oracle(nx, sx, nprocs):
+    from oracle.skew import SkewCartesianPartitioner
+    p = make_params("Stokes-C", 3, nx, sx, 1, Partitioner="Skew Cartesian")
+    got = hb.pid_map(_dictify(p), nprocs)
+    ref = SkewCartesianPartitioner(p.copy(), 0, nprocs, 0).partition().pid_map
+    assert np.array_equal(got, np.asarray(ref, dtype=np.int32))

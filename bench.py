@@ -36,17 +36,26 @@ def parse():
     ap.add_argument("--nx", type=int, default=int(os.environ.get("HYMLS_BENCH_NX", 128)))
     ap.add_argument("--sx", type=int, default=int(os.environ.get("HYMLS_BENCH_SX", 8)))
     ap.add_argument("--levels", type=int, default=2)
-    ap.add_argument("--cx", type=int, default=8, help="coarsening factor between levels")
+    ap.add_argument("--cx", type=int, default=4, help="coarsening factor between levels")
+    ap.add_argument("--partitioner", default="Skew Cartesian", choices=["Skew Cartesian", "Cartesian"],
+                    help="'Skew Cartesian' is what the reference uses for 3D Stokes; 'Cartesian' needs the "
+                         "documented tube-pressure extension (DESIGN.md, Deviations)")
     ap.add_argument("--no-solve", action="store_true", help="skip the GMRES solve")
     ap.add_argument("--cpu-sample-nx", type=int, default=16)
     return ap.parse_args()
 
 
+PARTITIONER = "Skew Cartesian"
+
+
 def make_params(nx, sx, levels, cx):
+    prec = {"Partitioner": PARTITIONER, "Separator Length": sx, "Number of Levels": levels,
+            "Coarsening Factor": cx}
+    if PARTITIONER == "Cartesian":
+        prec["Eliminate Tube Pressures With Velocities"] = True
     return {
         "Problem": {"Equations": "Stokes-C", "Dimension": 3, "nx": nx, "ny": nx, "nz": nx},
-        "Preconditioner": {"Partitioner": "Cartesian", "Separator Length": sx, "Number of Levels": levels,
-                           "Coarsening Factor": cx, "Eliminate Tube Pressures With Velocities": True},
+        "Preconditioner": prec,
         "Solver": {"Krylov Method": "GMRES", "Initial Vector": "Random", "Left or Right Preconditioning": "Right",
                    "Iterative Solver": {"Maximum Iterations": 600, "Num Blocks": 600, "Maximum Restarts": 0,
                                         "Convergence Tolerance": 1e-8}},
@@ -178,15 +187,18 @@ def cpu_reference_all_cores(nx_sample, sx, levels, cx, secs, max_procs=64):
 
 
 def main():
+    global PARTITIONER
     args = parse()
+    PARTITIONER = args.partitioner
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     nx, sx = args.nx, args.sx
     cx = args.cx
-    nsd_full = (nx // sx) ** 3
-    workload = "synthetic 3D lid-driven cavity (Stokes-C, GaleriExt::Stokes3D a=nx^2 b=1) %d^3, dof 4, sx=%d, %d levels, cx=%d" % (
-        nx, sx, args.levels, cx)
+    npx = nx // sx
+    nsd_full = npx ** 3 if PARTITIONER == "Cartesian" else (2 * npx * npx + 2 * npx) * (npx + 1)
+    workload = ("synthetic 3D lid-driven cavity (Stokes-C, GaleriExt::Stokes3D a=nx^2 b=1) %d^3, dof 4, %s partitioner, "
+                "sx=%d, %d levels, cx=%d" % (nx, PARTITIONER, sx, args.levels, cx))
 
     if args.impl == "reference":
         # the reference's own CPU path, restated (the real binary needs Trilinos+MPI: not buildable here)

@@ -16,15 +16,15 @@ n = A.shape[0]
 xex = np.random.default_rng(42).uniform(-1, 1, n)
 b = A @ xex
 for desc, prec in [
-    ("sx8 L2 cx4", {"Separator Length": 8, "Number of Levels": 2, "Coarsening Factor": 4}),
-    ("sx8 L1", {"Separator Length": 8, "Number of Levels": 1}),
-    ("sx8 L2 cx4 retain2", {"Separator Length": 8, "Number of Levels": 2, "Coarsening Factor": 4, "Retain Nodes": 2}),
-    ("sx8 L1 retain2", {"Separator Length": 8, "Number of Levels": 1, "Retain Nodes": 2}),
-    ("sx4 L2 cx4", {"Separator Length": 4, "Number of Levels": 2, "Coarsening Factor": 4}),
-    ("sx4 L3 cx2", {"Separator Length": 4, "Number of Levels": 3, "Coarsening Factor": 2}),
+    ("cart sx8 L1 +tube", {"Separator Length": 8, "Number of Levels": 1, "Eliminate Tube Pressures With Velocities": True}),
+    ("cart sx8 L2 cx4 +tube", {"Separator Length": 8, "Number of Levels": 2, "Coarsening Factor": 4, "Eliminate Tube Pressures With Velocities": True}),
+    ("skew sx8 L1", {"Partitioner": "Skew Cartesian", "Separator Length": 8, "Number of Levels": 1}),
+    ("skew sx8 L2 cx2", {"Partitioner": "Skew Cartesian", "Separator Length": 8, "Number of Levels": 2, "Coarsening Factor": 2}),
+    ("skew sx8 L2 cx4", {"Partitioner": "Skew Cartesian", "Separator Length": 8, "Number of Levels": 2, "Coarsening Factor": 4}),
+    ("skew sx4 L2 cx2", {"Partitioner": "Skew Cartesian", "Separator Length": 4, "Number of Levels": 2, "Coarsening Factor": 2}),
+    ("skew sx4 L3 cx2", {"Partitioner": "Skew Cartesian", "Separator Length": 4, "Number of Levels": 3, "Coarsening Factor": 2}),
 ]:
     prec = dict(prec)
-    prec["Eliminate Tube Pressures With Velocities"] = True
     params = {"Problem": {"Equations": "Stokes-C", "Dimension": 3, "nx": nx, "ny": nx, "nz": nx},
               "Preconditioner": prec,
               "Solver": {"Krylov Method": "GMRES", "Initial Vector": "Random",
@@ -38,9 +38,9 @@ for desc, prec in [
         S = hb.Solver(P)
         S.ApplyInverse(b, seed=43)
         st = P.Stats()
-        print("%-22s its %4d conv %d res %.1e solve %.2fs setup %.1fs vsums %d apply_bytes %.2f GB" % (
+        print("%-22s its %4d conv %d res %.1e solve %.2fs setup %.1fs vsums %d nsd %d apply_bytes %.2f GB" % (
             desc, S.num_iter, S.info["converged"], S.info["explicit_rel_residual"], S.info["solve_seconds"], tc,
-            st["num_vsum"], st["bytes_apply"] / 1e9), flush=True)
+            st["num_vsum"], st["num_subdomains"], st["bytes_apply"] / 1e9), flush=True)
         del S, P
     except Exception as e:
         print(desc, "FAILED", str(e)[:200], flush=True)

@@ -69,6 +69,8 @@ def load_library():
     lib.hymls_b200_initialize.argtypes = [vp]
     lib.hymls_b200_compute.argtypes = [vp]
     lib.hymls_b200_apply_inverse.argtypes = [vp, vp, i64, vp, i64, C.c_int, C.c_int]
+    lib.hymls_b200_local_rows.argtypes = [vp, P(i64), P(i64)]
+    lib.hymls_b200_apply_inverse_dist.argtypes = [vp, vp, vp, C.c_int]
     lib.hymls_b200_set_border.argtypes = [vp, vp, vp, vp, C.c_int]
     lib.hymls_b200_apply_inverse_bordered.argtypes = [vp, vp, i64, vp, vp, i64, vp, C.c_int, C.c_int]
     lib.hymls_b200_apply_matrix.argtypes = [vp, vp, vp, C.c_int]
@@ -232,6 +234,18 @@ class Preconditioner:
         _check(self._lib, self._lib.hymls_b200_apply_inverse(self._h, B.data_ptr(), self.n, X.data_ptr(), self.n,
                                                               nvec, DEVICE))
         return X
+
+    def LocalRows(self):
+        a, b = C.c_int64(), C.c_int64()
+        _check(self._lib, self._lib.hymls_b200_local_rows(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def ApplyInverseDist(self, b_local):
+        """distributed-vector ApplyInverse: this rank's rows in, this rank's rows out (numpy, host)"""
+        bl = np.ascontiguousarray(b_local, dtype=np.float64)
+        xl = np.zeros_like(bl)
+        _check(self._lib, self._lib.hymls_b200_apply_inverse_dist(self._h, bl.ctypes.data, xl.ctypes.data, HOST))
+        return xl
 
     def Apply(self, X, Y):  # Preconditioner::Apply returns -1 (:122-123)
         return -1

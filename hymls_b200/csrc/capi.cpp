@@ -135,6 +135,21 @@ int hymls_b200_apply_inverse(hymls_b200_t* h, const double* B, int64_t ldb, doub
   HY_CATCH
 }
 
+int hymls_b200_local_rows(hymls_b200_t* h, int64_t* r0, int64_t* r1) {
+  HY_TRY
+  if (!r0 || !r1) throw Error(HYMLS_B200_ERR_ARG, "null argument");
+  h->eng->localRows(r0, r1);
+  return 0;
+  HY_CATCH
+}
+
+int hymls_b200_apply_inverse_dist(hymls_b200_t* h, const double* Bl, double* Xl, int where) {
+  HY_TRY
+  h->eng->applyInverseDist(Bl, Xl, where);
+  return 0;
+  HY_CATCH
+}
+
 int hymls_b200_set_border(hymls_b200_t*, const double*, const double*, const double*, int) {
   g_lastError = "bordered preconditioner (SetBorder) is not implemented yet";
   return HYMLS_B200_ERR_UNSUPPORTED;

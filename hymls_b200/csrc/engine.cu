@@ -976,6 +976,33 @@ void Engine::applyInverse(const double* B, int64_t ldb, double* X, int64_t ldx, 
   }
 }
 
+void Engine::localRows(int64_t* r0, int64_t* r1) const {
+  const int P = comm_.size();
+  const int64_t chunk = (n_ + P - 1) / P;
+  *r0 = std::min<int64_t>(n_, (int64_t)comm_.rank() * chunk);
+  *r1 = std::min<int64_t>(n_, *r0 + chunk);
+}
+
+void Engine::applyInverseDist(const double* Bloc, double* Xloc, int where) {
+  needDevice();
+  if (!computed_) throw Error(HYMLS_B200_ERR_STATE, "The preconditioner has not yet been computed.");
+  const int P = comm_.size();
+  const int64_t chunk = (n_ + P - 1) / P;
+  int64_t r0, r1;
+  localRows(&r0, &r1);
+  const int64_t nloc = r1 - r0;
+  bufG_.alloc((size_t)P * chunk);
+  bufX_.alloc(n_);
+  double* mine = bufG_.p + (int64_t)comm_.rank() * chunk;
+  HY_CUDA(cudaMemcpyAsync(mine, Bloc, nloc * sizeof(double),
+                          where == HYMLS_B200_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, stream_));
+  if (comm_.active()) comm_.allGather(mine, bufG_.p, (size_t)chunk, stream_);
+  applyDevice(bufG_.p, bufX_.p);
+  HY_CUDA(cudaMemcpyAsync(Xloc, bufX_.p + r0, nloc * sizeof(double),
+                          where == HYMLS_B200_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, stream_));
+  if (where == HYMLS_B200_HOST) HY_CUDA(cudaStreamSynchronize(stream_));
+}
+
 void Engine::applyMatrix(const double* x, double* y, int where) {
   needDevice();
   if (!haveMatrix_) throw Error(HYMLS_B200_ERR_STATE, "no matrix set");

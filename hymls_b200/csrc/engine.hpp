@@ -92,6 +92,8 @@ class Engine {
   void compute();
   void applyInverse(const double* B, int64_t ldb, double* X, int64_t ldx, int nvec, int where);
   void applyMatrix(const double* x, double* y, int where);
+  void localRows(int64_t* r0, int64_t* r1) const;
+  void applyInverseDist(const double* Bloc, double* Xloc, int where);
   void solve(const double* b, double* x, int where, uint64_t seed, hymls_b200_solve_info* info, double* hist,
              int histCap);
   void timeApply(int reps, double* msApply, double* msA11);
@@ -131,6 +133,7 @@ class Engine {
   DevBuf<int> piv_, perm_, info_;
   DevBuf<double> wsC_, wsSV_, wsSLL_, diagScratch_;
   DevBuf<double> bufB_, bufX_;  // staging for host vectors
+  DevBuf<double> bufG_;          // all-gather target of the distributed-vector entry point
   // Krylov workspace
   DevBuf<double> kV_, kW_, kZ_, kH_, kPartial_, kX_, kB_, kR_;
   int kCap_ = 0;

@@ -97,6 +97,15 @@ int hymls_b200_apply_inverse(hymls_b200_t* h, const double* B, int64_t ldb, doub
                              int nvec, int where);
 
 /*
+ * Distributed-vector variant for multi-GPU use (the reference's vectors are distributed Epetra_MultiVectors):
+ * rank r passes / receives only rows [r0, r1) of B and X (hymls_b200_local_rows; contiguous row blocks of
+ * ceil(n / nranks) rows).  The library all-gathers B over NVLink, so each rank moves n/nranks values over
+ * PCIe instead of n.  With one rank it is the same as hymls_b200_apply_inverse.
+ */
+int hymls_b200_local_rows(hymls_b200_t* h, int64_t* r0, int64_t* r1);
+int hymls_b200_apply_inverse_dist(hymls_b200_t* h, const double* B_local, double* X_local, int where);
+
+/*
  * BorderedOperator interface (src/HYMLS_Preconditioner.cpp:844-918): V, W are n x m (column major,
  * host), C is m x m; W == NULL means W = V, C == NULL means 0.  V == NULL removes the border.
  * Compute() must be called afterwards.

@@ -254,11 +254,29 @@ class Preconditioner:
         return -1
 
     def SetBorder(self, V, W=None, Cm=None):
-        V = np.asfortranarray(V, dtype=np.float64)
-        m = V.shape[1] if V.ndim > 1 else 1
+        """BorderedOperator::SetBorder(V, W, C) (src/HYMLS_Preconditioner.cpp:844-918); V=None removes it.
+        Compute() has to be called afterwards."""
+        if V is None:
+            return _check(self._lib, self._lib.hymls_b200_set_border(self._h, None, None, None, 0))
+        Vc = np.asfortranarray(np.asarray(V, dtype=np.float64).reshape(self.n, -1))
+        m = Vc.shape[1]
+        Wc = None if W is None else np.asfortranarray(np.asarray(W, dtype=np.float64).reshape(self.n, -1))
+        Cc = None if Cm is None else np.asfortranarray(np.asarray(Cm, dtype=np.float64).reshape(m, m))
         return _check(self._lib, self._lib.hymls_b200_set_border(
-            self._h, V.ctypes.data, None if W is None else np.asfortranarray(W).ctypes.data,
-            None if Cm is None else np.asfortranarray(Cm).ctypes.data, m))
+            self._h, Vc.ctypes.data, None if Wc is None else Wc.ctypes.data,
+            None if Cc is None else Cc.ctypes.data, m))
+
+    def ApplyInverseBordered(self, B, T):
+        """[X; S] = [K V; W' C]^-1 [B; T] approximately (BorderedOperator::ApplyInverse of the preconditioner,
+        src/HYMLS_Preconditioner.cpp:930-1070).  numpy, host: B is n (x nvec), T is m (x nvec)."""
+        Bc = np.asfortranarray(np.asarray(B, dtype=np.float64).reshape(self.n, -1))
+        nvec = Bc.shape[1]
+        Tc = np.asfortranarray(np.asarray(T, dtype=np.float64).reshape(-1, nvec))
+        Xc = np.zeros_like(Bc, order="F")
+        Sc = np.zeros_like(Tc, order="F")
+        _check(self._lib, self._lib.hymls_b200_apply_inverse_bordered(
+            self._h, Bc.ctypes.data, self.n, Tc.ctypes.data, Xc.ctypes.data, self.n, Sc.ctypes.data, nvec, HOST))
+        return Xc, Sc
 
     def ApplyMatrix(self, x):
         if isinstance(x, np.ndarray):

@@ -324,4 +324,126 @@ void scatterVec(const double* x, const int* idx, double* y, int64_t n, cudaStrea
   ++*launches;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Kernels of the bordered variant (Preconditioner::ComputeBorder src/HYMLS_Preconditioner.cpp:519-588,
+// SchurPreconditioner::ComputeBorder src/HYMLS_SchurPreconditioner.cpp:631-664, CoarseSolver's
+// AugmentedMatrix src/HYMLS_CoarseSolver.cpp:200-224).  Borders have m <= a few columns and these run
+// once per Compute, so they are plain coalesced kernels.
+// ---------------------------------------------------------------------------------------------
+// y_sd = Ainv_sd^T x_sd (the transposed subdomain solve of ComputeBorder :564-566): thread per column,
+// rows streamed (coalesced across the columns of the row-major inverse)
+__global__ void __launch_bounds__(256)
+k_batched_gemv_t(GemvArgs a, int tilesPerMat) {
+  const int mat = blockIdx.x / tilesPerMat;
+  const int j = (blockIdx.x % tilesPerMat) * 256 + threadIdx.x;
+  const int n = a.n[mat], np = a.np[mat];
+  if ((blockIdx.x % tilesPerMat) * 256 >= n) return;
+  const int64_t v0 = a.vecOff[mat];
+  const double* __restrict__ A = a.A + a.matOff[mat];
+  __shared__ double sx[256];
+  double acc = 0.0;
+  for (int i0 = 0; i0 < n; i0 += 256) {
+    const int i = i0 + threadIdx.x;
+    __syncthreads();
+    sx[threadIdx.x] = i < n ? (a.gather ? a.xin[a.gather[v0 + i]] : a.xin[v0 + i]) : 0.0;
+    __syncthreads();
+    const int lim = min(256, n - i0);
+    if (j < n)
+      for (int q = 0; q < lim; ++q) acc += sx[q] * A[(int64_t)(i0 + q) * np + j];
+  }
+  if (j < n) a.out[v0 + j] = acc;
+}
+void batchedGemvT(const GemvArgs& a, int count, int npMax, cudaStream_t s, int64_t* launches) {
+  if (count == 0 || npMax == 0) return;
+  const int tiles = (npMax + 255) / 256;
+  k_batched_gemv_t<<<(unsigned)(count * tiles), 256, 0, s>>>(a, tiles);
+  ++*launches;
+}
+// y[col[e]] += alpha * val[e] * x[r]   (y = alpha A^T x, y zeroed by the caller)
+__global__ void k_spmv_t(const int64_t* __restrict__ ptr, const int* __restrict__ col, const double* __restrict__ val,
+                         const double* __restrict__ x, double* __restrict__ y, int64_t n, double alpha) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const double xr = alpha * x[r];
+  if (xr == 0.0) return;
+  for (int64_t e = ptr[r]; e < ptr[r + 1]; ++e) atomicAdd(y + col[e], val[e] * xr);
+}
+void spmvT(const int64_t* ptr, const int* col, const double* val, const double* x, double* y, int64_t n, double alpha,
+           cudaStream_t s, int64_t* launches) {
+  if (n == 0) return;
+  k_spmv_t<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ptr, col, val, x, y, n, alpha);
+  ++*launches;
+}
+__global__ void k_gather_vec(const double* __restrict__ x, const int* __restrict__ idx, double* __restrict__ y,
+                             int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = x[idx[i]];
+}
+void gatherVec(const double* x, const int* idx, double* y, int64_t n, cudaStream_t s, int64_t* launches) {
+  if (n == 0) return;
+  k_gather_vec<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, idx, y, n);
+  ++*launches;
+}
+__global__ void k_zero_at(double* __restrict__ x, const int* __restrict__ idx, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[idx[i]] = 0.0;
+}
+void zeroAt(double* x, const int* idx, int64_t n, cudaStream_t s, int64_t* launches) {
+  if (n == 0) return;
+  k_zero_at<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, idx, n);
+  ++*launches;
+}
+// X[idx[p]] -= sum_j Q[j*ld + p] * S[j]    (x1 -= Q1 S of the bordered ApplyInverse, Preconditioner.cpp:1036-1041)
+__global__ void k_border_correct(double* __restrict__ X, const int* __restrict__ idx, const double* __restrict__ Q,
+                                 int64_t ld, int m, const double* __restrict__ S, int64_t n) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  double t = 0.0;
+  for (int j = 0; j < m; ++j) t += Q[(int64_t)j * ld + p] * S[j];
+  X[idx[p]] -= t;
+}
+void borderCorrect(double* X, const int* idx, const double* Q, int64_t ld, int m, const double* S, int64_t n,
+                   cudaStream_t s, int64_t* launches) {
+  if (n == 0 || m == 0) return;
+  k_border_correct<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(X, idx, Q, ld, m, S, n);
+  ++*launches;
+}
+// augmented dense matrix [D V; W' C]: D is n x n inside an np x np row-major array, V, W are n x m
+// (column major, leading dimension ld), C is m x m column major
+__global__ void k_dense_border(double* __restrict__ D, int n, int np, const double* __restrict__ V,
+                               const double* __restrict__ W, int64_t ld, const double* __restrict__ C, int m) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n) {
+    for (int j = 0; j < m; ++j) {
+      D[(int64_t)r * np + n + j] = V[(int64_t)j * ld + r];
+      D[(int64_t)(n + j) * np + r] = W[(int64_t)j * ld + r];
+    }
+  } else if (r < n + m) {
+    const int i = r - n;
+    for (int j = 0; j < m; ++j) D[(int64_t)(n + i) * np + n + j] = C[i + (int64_t)j * m];
+  }
+}
+void denseBorder(double* D, int n, int np, const double* V, const double* W, int64_t ld, const double* C, int m,
+                 cudaStream_t s, int64_t* launches) {
+  if (m == 0) return;
+  k_dense_border<<<(n + m + 255) / 256, 256, 0, s>>>(D, n, np, V, W, ld, C, m);
+  ++*launches;
+}
+
+// out[i - i0] = dots[i] + sum_j C[i + j*m] sv[j]  (border rows of BorderedOperator::Apply)
+__global__ void k_border_rows(const double* __restrict__ dots, const double* __restrict__ C,
+                              const double* __restrict__ sv, int m, int i0, int i1, double* __restrict__ out) {
+  const int i = i0 + threadIdx.x;
+  if (i >= i1) return;
+  double t = dots[i];
+  for (int j = 0; j < m; ++j) t += C[i + (int64_t)j * m] * sv[j];
+  out[i - i0] = t;
+}
+void borderRows(const double* dots, const double* C, const double* sv, int m, int i0, int i1, double* out,
+                cudaStream_t s, int64_t* launches) {
+  if (i1 <= i0) return;
+  k_border_rows<<<1, 32 * ((i1 - i0 + 31) / 32), 0, s>>>(dots, C, sv, m, i0, i1, out);
+  ++*launches;
+}
+
 }  // namespace hymls

@@ -150,14 +150,18 @@ int hymls_b200_apply_inverse_dist(hymls_b200_t* h, const double* Bl, double* Xl,
   HY_CATCH
 }
 
-int hymls_b200_set_border(hymls_b200_t*, const double*, const double*, const double*, int) {
-  g_lastError = "bordered preconditioner (SetBorder) is not implemented yet";
-  return HYMLS_B200_ERR_UNSUPPORTED;
+int hymls_b200_set_border(hymls_b200_t* h, const double* V, const double* W, const double* C, int m) {
+  HY_TRY
+  h->eng->setBorder(V, W, C, m);
+  return 0;
+  HY_CATCH
 }
-int hymls_b200_apply_inverse_bordered(hymls_b200_t*, const double*, int64_t, const double*, double*, int64_t, double*,
-                                      int, int) {
-  g_lastError = "bordered preconditioner (ApplyInverse with border) is not implemented yet";
-  return HYMLS_B200_ERR_UNSUPPORTED;
+int hymls_b200_apply_inverse_bordered(hymls_b200_t* h, const double* B, int64_t ldb, const double* T, double* X,
+                                      int64_t ldx, double* S, int nvec, int where) {
+  HY_TRY
+  h->eng->applyInverseBordered(B, ldb, T, X, ldx, S, nvec, where);
+  return 0;
+  HY_CATCH
 }
 
 int hymls_b200_apply_matrix(hymls_b200_t* h, const double* x, double* y, int where) {

@@ -508,6 +508,10 @@ void Engine::uploadLevel(Level& L) {
   L.Y.alloc(S.nS);
   L.vsRhs.alloc(S.nuniq);
   L.vsSol.alloc(S.nuniq);
+  // x1 keeps zeros outside the owned subdomains and Y finite values in the V-sum rows: the border dot
+  // products of the bordered ApplyInverse run over the whole vectors
+  if (L.x1.n) HY_CUDA(cudaMemsetAsync(L.x1.p, 0, L.x1.bytes(), s));
+  if (L.Y.n) HY_CUDA(cudaMemsetAsync(L.Y.p, 0, L.Y.bytes(), s));
   HY_CUDA(cudaStreamSynchronize(s));
 }
 
@@ -621,6 +625,10 @@ void Engine::computeLevel(int l) {
     checkInfo(info_, s, "subdomain solver (A11) of level " + std::to_string(l));
   }
   pt.lap("A11 fill + inversion");
+  if (borderM_ > 0) {
+    computeBorder(l);
+    pt.lap("border");
+  }
   // (3) Schur complement
   SchurArgs a{};
   a.rowSd = L.rowSd.p;
@@ -669,10 +677,8 @@ void Engine::computeLevel(int l) {
     // Number of Levels = 0: S = A22 - sum_sd A21 A11^-1 A12, dense, solved directly
     // (Preconditioner::Compute :485-500 -> CoarseSolver)
     const int nS = (int)S.nS;
-    const int np = (nS + 7) & ~7;
-    std::vector<int> cn(1, nS), cnp(1, np);
-    std::vector<int64_t> off{0, (int64_t)np * np}, voff(1, 0);
-    coarse_.setup(cn, cnp, off, voff, s);
+    const int bm = borderM_;
+    const int np = (nS + bm + 7) & ~7;
     work_.alloc((size_t)np * np);
     HY_CUDA(cudaMemsetAsync(work_.p, 0, (size_t)np * np * sizeof(double), s));
     // A22 part: gather the values of the A22 block into a temporary and densify
@@ -692,12 +698,9 @@ void Engine::computeLevel(int l) {
       coarseFix_.push_back(row);
       putDirichlet(work_.p, nS, np, row, s, &launches_);
     }
-    DevBuf<int64_t> relOff;
-    invertRange(coarse_, 0, 1, work_.p, piv_, perm_, relOff, info_.p, s, &launches_);
-    checkInfo(info_, s, "exact Schur complement");
-    stats_.flops_compute += 2.0 * std::pow((double)nS, 3);
-    coarseN_ = nS;
-    coarseRhs_.alloc(nS);
+    // with a border the Schur complement's border (sV, sW, sC of ComputeBorder) augments the dense matrix
+    augmentAndInvertCoarse(nS, np, bm ? L.sV.p : nullptr, bm ? L.sW.p : nullptr, bm ? &L.hC : nullptr,
+                           "exact Schur complement");
     v22.release();
     return;
   }
@@ -777,7 +780,8 @@ void Engine::computeLevel(int l) {
   if (!next) {
     std::vector<gidx> rowGid(S.nuniq);
     for (int u = 0; u < S.nuniq; ++u) rowGid[u] = S.H.sepGid[S.H.uniqPtr[u]];
-    computeCoarse(L.redPtr.p, L.redCol.p, redVal, S.nuniq, rowGid);
+    if (borderM_ > 0) computeCoarse(L.redPtr.p, L.redCol.p, redVal, S.nuniq, rowGid, L.cV.p, L.cW.p, &L.hC);
+    else computeCoarse(L.redPtr.p, L.redCol.p, redVal, S.nuniq, rowGid);
   }
   pt.lap("drop + coarse solver");
   HY_CUDA(cudaStreamSynchronize(s));
@@ -785,15 +789,18 @@ void Engine::computeLevel(int l) {
 
 // CoarseSolver::Compute (src/HYMLS_CoarseSolver.cpp:131-248): drop (RelFullDiag), Dirichlet rows for the
 // "Fix GID k" entries, dense inverse.
-void Engine::computeCoarse(const int64_t* ptr, const int* col, double* val, int n, const std::vector<gidx>& rowGid) {
+void Engine::computeCoarse(const int64_t* ptr, const int* col, double* val, int n, const std::vector<gidx>& rowGid,
+                           const double* bV, const double* bW, const std::vector<double>* bC) {
   cudaStream_t s = stream_;
-  const int np = (n + 7) & ~7;
-  std::vector<int> cn(1, n), cnp(1, np);
-  std::vector<int64_t> off{0, (int64_t)np * np}, voff(1, 0);
-  coarse_.setup(cn, cnp, off, voff, s);
-  coarseN_ = n;
-  coarseRhs_.alloc(n);
-  if (n == 0) return;
+  const int bm = bV ? borderM_ : 0;
+  const int np = (n + bm + 7) & ~7;
+  if (n == 0) {
+    std::vector<int> z(1, 0);
+    std::vector<int64_t> off{0, 0}, voff(1, 0);
+    coarse_.setup(z, z, off, voff, s);
+    coarseN_ = coarseM_ = 0;
+    return;
+  }
   diagScratch_.alloc(n);
   dropByValue(val, ptr, col, diagScratch_.p, n, SMALL_ENTRY, s, &launches_);
   work_.alloc((size_t)np * np);
@@ -810,10 +817,145 @@ void Engine::computeCoarse(const int64_t* ptr, const int* col, double* val, int 
     coarseFix_.push_back(row);
     putDirichlet(work_.p, n, np, row, s, &launches_);
   }
+  augmentAndInvertCoarse(n, np, bV, bW, bC, "coarse solver");
+}
+
+// work_ holds the n x n coarse matrix (leading dimension np >= n + m): append the border
+// (AugmentedMatrix [S V; W' C], src/HYMLS_CoarseSolver.cpp:200-224) and invert
+void Engine::augmentAndInvertCoarse(int n, int np, const double* bV, const double* bW, const std::vector<double>* bC,
+                                    const char* what) {
+  cudaStream_t s = stream_;
+  const int bm = bV ? borderM_ : 0;
+  if (bm) {
+    bC_.upload(*bC, s);
+    denseBorder(work_.p, n, np, bV, bW, n, bC_.p, bm, s, &launches_);
+  }
+  std::vector<int> cn(1, n + bm), cnp(1, np);
+  std::vector<int64_t> off{0, (int64_t)np * np}, voff(1, 0);
+  coarse_.setup(cn, cnp, off, voff, s);
+  coarseN_ = n;
+  coarseM_ = bm;
+  coarseRhs_.alloc(n + bm);
+  coarseSol_.alloc(n + bm);
   DevBuf<int64_t> relOff;
   invertRange(coarse_, 0, 1, work_.p, piv_, perm_, relOff, info_.p, s, &launches_);
-  checkInfo(info_, s, "coarse solver");
-  stats_.flops_compute += 2.0 * std::pow((double)n, 3);
+  checkInfo(info_, s, what);
+  stats_.flops_compute += 2.0 * std::pow((double)(n + bm), 3);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Border (Preconditioner::SetBorder / ComputeBorder, src/HYMLS_Preconditioner.cpp:844-918, 519-588;
+// SchurPreconditioner::ComputeBorder, src/HYMLS_SchurPreconditioner.cpp:631-664)
+// ---------------------------------------------------------------------------------------------
+void Engine::setBorder(const double* V, const double* W, const double* C, int m) {
+  if (!haveMatrix_) throw Error(HYMLS_B200_ERR_STATE, "set the matrix before the border");
+  if (!V || m <= 0) {  // removes the border
+    borderM_ = 0;
+    hV_.clear();
+    hW_.clear();
+    hC_.clear();
+  } else {
+    borderM_ = m;
+    hV_.assign(V, V + (size_t)n_ * m);
+    if (W) hW_.assign(W, W + (size_t)n_ * m); else hW_ = hV_;
+    if (C) hC_.assign(C, C + (size_t)m * m); else hC_.assign((size_t)m * m, 0.0);
+  }
+  computed_ = false;  // "Compute() needs to be called after SetBorder" (:874-875)
+}
+
+void Engine::computeBorder(int l) {
+  Level& L = *levels_[l];
+  const LevelSym& S = L.sym;
+  cudaStream_t s = stream_;
+  const int bm = borderM_;
+  const int64_t n = S.n, nI = S.nI, nS = S.nS;
+  if (l == 0) {
+    L.bV.upload(hV_, s);
+    L.bW.upload(hW_, s);
+    bC0_.upload(hC_, s);
+    L.hC = hC_;
+  }
+  L.Q1.alloc((size_t)nI * bm);
+  L.W1.alloc((size_t)nI * bm);
+  L.sV.alloc((size_t)nS * bm);
+  L.sW.alloc((size_t)nS * bm);
+  L.bQ.alloc(bm);
+  L.bT.alloc(bm);
+  bS_.alloc(bm);
+  bTin_.alloc(bm);
+  bPartial_.alloc((size_t)(bm + 2) * multiDotBlocks());
+  bDots_.alloc((size_t)bm * bm + bm);
+  if (L.Q1.n) HY_CUDA(cudaMemsetAsync(L.Q1.p, 0, L.Q1.bytes(), s));
+  DevBuf<double> w1tmp;
+  w1tmp.alloc((size_t)nI);
+  for (int j = 0; j < bm; ++j) {
+    const double* Vj = L.bV.p + (int64_t)j * n;
+    const double* Wj = L.bW.p + (int64_t)j * n;
+    double* Q1j = L.Q1.p + (int64_t)j * nI;
+    double* sVj = L.sV.p + (int64_t)j * nS;
+    double* sWj = L.sW.p + (int64_t)j * nS;
+    // Q1 = A11 \ V1  (owned subdomains; the other ranks' parts are added below)
+    GemvArgs g = L.a11.args();
+    g.xin = Vj;
+    g.gather = L.intRow.p;
+    g.out = Q1j;
+    g.mode = 0;
+    batchedGemv(g, L.a11.numItems, L.a11.npMax, s, &launches_);
+    // sV = V2 - A21 Q1
+    if (!L.sharded) {
+      spmv(L.p21.p, L.c21.p, L.v21.p, Q1j, sVj, nS, 1.0, Vj, L.sepRow.p, -1.0, s, &launches_);
+    } else {
+      spmv(L.p21.p, L.c21.p, L.v21.p, Q1j, L.Z.p, nS, 0.0, nullptr, nullptr, -1.0, s, &launches_);
+      comm_.allReduceSum(L.Z.p, (size_t)nS, s);
+      gatherAdd(Vj, L.sepRow.p, L.Z.p, sVj, nS, s, &launches_);
+    }
+    // w1tmp = A11' \ W1 (transposed subdomain solves, :564-566) ;  sW = W2 - A12' w1tmp
+    if (nI) HY_CUDA(cudaMemsetAsync(w1tmp.p, 0, w1tmp.bytes(), s));
+    GemvArgs gt = L.a11.args();
+    gt.xin = Wj;
+    gt.gather = L.intRow.p;
+    gt.out = w1tmp.p;
+    batchedGemvT(gt, L.a11.count, L.a11.npMax, s, &launches_);
+    if (nS) HY_CUDA(cudaMemsetAsync(L.Z.p, 0, (size_t)nS * sizeof(double), s));
+    spmvT(L.p12.p, L.c12.p, L.v12.p, w1tmp.p, L.Z.p, nI, -1.0, s, &launches_);
+    if (L.sharded) comm_.allReduceSum(L.Z.p, (size_t)nS, s);
+    gatherAdd(Wj, L.sepRow.p, L.Z.p, sWj, nS, s, &launches_);
+    gatherVec(Wj, L.intRow.p, L.W1.p + (int64_t)j * nI, nI, s, &launches_);
+  }
+  // sC = C - W1' Q1 (Q1 still holds the owned subdomains only: partial sums over the ranks)
+  for (int j = 0; j < bm; ++j)
+    multiDot(L.W1.p, nI, bm, L.Q1.p + (int64_t)j * nI, nI, bPartial_.p, bDots_.p + (size_t)j * bm, 0, s, &launches_);
+  if (nI == 0) HY_CUDA(cudaMemsetAsync(bDots_.p, 0, bDots_.bytes(), s));
+  if (L.sharded) {
+    comm_.allReduceSum(bDots_.p, (size_t)bm * bm, s);
+    comm_.allReduceSum(L.Q1.p, L.Q1.n, s);
+  }
+  std::vector<double> dots((size_t)bm * bm), sC(L.hC);
+  HY_CUDA(cudaMemcpyAsync(dots.data(), bDots_.p, dots.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+  HY_CUDA(cudaStreamSynchronize(s));
+  for (int j = 0; j < bm; ++j)
+    for (int i = 0; i < bm; ++i) sC[i + (size_t)j * bm] -= dots[(size_t)j * bm + i];
+  if (L.exact) {  // the dense Schur complement takes (sV, sW, sC) as they are
+    L.hC = sC;
+    return;
+  }
+  // borders of the transformed Schur complement: H sV, H sW; their V-sum rows are the next level's border
+  Level* next = (l + 1 < (int)levels_.size()) ? levels_[l + 1].get() : nullptr;
+  DevBuf<double>& nV = next ? next->bV : L.cV;
+  DevBuf<double>& nW = next ? next->bW : L.cW;
+  nV.alloc((size_t)S.nuniq * bm);
+  nW.alloc((size_t)S.nuniq * bm);
+  for (int j = 0; j < bm; ++j) {
+    double* sVj = L.sV.p + (int64_t)j * nS;
+    double* sWj = L.sW.p + (int64_t)j * nS;
+    householder(L.uniqStart.p, S.nuniq, L.what.p, sVj, sVj, nV.p + (int64_t)j * S.nuniq, nullptr, nullptr, nullptr, s,
+                &launches_);
+    householder(L.uniqStart.p, S.nuniq, L.what.p, sWj, sWj, nW.p + (int64_t)j * S.nuniq, nullptr, nullptr, nullptr, s,
+                &launches_);
+    zeroAt(sWj, L.uniqStart.p, S.nuniq, s, &launches_);  // "note zeros in X2" (SchurPreconditioner.cpp:1585)
+  }
+  if (next) next->hC = sC; else L.hC = sC;  // last level: hC is what the coarse solver gets
+  HY_CUDA(cudaStreamSynchronize(s));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -837,7 +979,23 @@ struct ApplyTimer {
   }
 };
 
-void Engine::applyLevel(int l, const double* B, double* X) {
+// [sol; S] = coarse^-1 [rhs; T]  (CoarseSolver::ApplyInverse with a border, src/HYMLS_CoarseSolver.cpp:454-564:
+// no zeroing of the fixed rows in the augmented solve); S goes to bS_
+void Engine::coarseSolveBordered(const double* rhs, const double* T, double* sol, int n) {
+  cudaStream_t s = stream_;
+  const int bm = coarseM_;
+  HY_CUDA(cudaMemcpyAsync(coarseRhs_.p, rhs, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  HY_CUDA(cudaMemcpyAsync(coarseRhs_.p + n, T, (size_t)bm * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  GemvArgs c = coarse_.args();
+  c.xin = coarseRhs_.p;
+  c.out = coarseSol_.p;
+  c.mode = 0;
+  batchedGemv(c, coarse_.numItems, coarse_.npMax, s, &launches_);
+  HY_CUDA(cudaMemcpyAsync(sol, coarseSol_.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  HY_CUDA(cudaMemcpyAsync(bS_.p, coarseSol_.p + n, (size_t)bm * sizeof(double), cudaMemcpyDeviceToDevice, s));
+}
+
+void Engine::applyLevel(int l, const double* B, double* X, const double* T) {
   Level& L = *levels_[l];
   const LevelSym& S = L.sym;
   cudaStream_t s = stream_;
@@ -862,6 +1020,14 @@ void Engine::applyLevel(int l, const double* B, double* X) {
     a11Launches_++;
   }
   at.lap("A11 gemv 1");
+  const int bm = borderM_;
+  if (bm) {
+    // q = T - W1' x1 (Preconditioner.cpp:1006-1013); x1 is zero outside the owned subdomains
+    multiDot(L.W1.p, S.nI, bm, L.x1.p, S.nI, bPartial_.p, L.bQ.p, 0, s, &launches_);
+    if (S.nI == 0) HY_CUDA(cudaMemsetAsync(L.bQ.p, 0, bm * sizeof(double), s));
+    if (L.sharded) comm_.allReduceSum(L.bQ.p, (size_t)bm, s);
+    axpby(T ? 1.0 : 0.0, T ? T : L.bQ.p, -1.0, L.bQ.p, bm, s, &launches_);
+  }
   // schurRhs = b2 - A21 x1
   if (!L.sharded) {
     spmv(L.p21.p, L.c21.p, L.v21.p, L.x1.p, L.rhsS.p, S.nS, 1.0, B, L.sepRow.p, -1.0, s, &launches_);
@@ -876,13 +1042,17 @@ void Engine::applyLevel(int l, const double* B, double* X) {
   double* x2 = L.Y.p;
   if (L.exact) {
     // direct solve with the dense Schur complement (CoarseSolver::ApplyInverse :268-323)
-    for (int row : coarseFix_)
-      if (row > 0) setValue(L.rhsS.p, row, 0.0, s, &launches_);  // sic: 'lid > 0'
-    GemvArgs c = coarse_.args();
-    c.xin = L.rhsS.p;
-    c.out = x2;
-    c.mode = 0;
-    batchedGemv(c, coarse_.numItems, coarse_.npMax, s, &launches_);
+    if (bm) {
+      coarseSolveBordered(L.rhsS.p, L.bQ.p, x2, (int)S.nS);
+    } else {
+      for (int row : coarseFix_)
+        if (row > 0) setValue(L.rhsS.p, row, 0.0, s, &launches_);  // sic: 'lid > 0'
+      GemvArgs c = coarse_.args();
+      c.xin = L.rhsS.p;
+      c.out = x2;
+      c.mode = 0;
+      batchedGemv(c, coarse_.numItems, coarse_.npMax, s, &launches_);
+    }
     scatterVec(x2, L.sepRow.p, X, S.nS, s, &launches_);
   } else {
     // B' = H rhs ; V-sum part goes to the next level (ApplyOT + UpdateVsumRhs)
@@ -899,9 +1069,20 @@ void Engine::applyLevel(int l, const double* B, double* X) {
     batchedGemv(b, L.blk.numItems, L.blk.npMax, s, &launches_);
     if (L.sharded) comm_.allReduceSum(L.Y.p, (size_t)S.nS, s);  // owned block rows from every rank
     at.lap("householder + separator blocks");
+    if (bm) {
+      // Tc = q - bW' Y with zeros in the V-sum rows (SchurPreconditioner.cpp:1585-1590)
+      multiDot(L.sW.p, S.nS, bm, L.Y.p, S.nS, bPartial_.p, L.bT.p, 0, s, &launches_);
+      axpby(1.0, L.bQ.p, -1.0, L.bT.p, bm, s, &launches_);
+    }
     // V-sums: next level or coarse solver
     if (l + 1 < (int)levels_.size()) {
-      applyLevel(l + 1, L.vsRhs.p, L.vsSol.p);
+      applyLevel(l + 1, L.vsRhs.p, L.vsSol.p, bm ? L.bT.p : nullptr);
+    } else if (bm) {
+      coarseSolveBordered(L.vsRhs.p, L.bT.p, L.vsSol.p, S.nuniq);
+      if (L.sharded) {
+        comm_.broadcast(L.vsSol.p, (size_t)S.nuniq, 0, s);
+        comm_.broadcast(bS_.p, (size_t)bm, 0, s);
+      }
     } else {
       for (int row : coarseFix_)
         if (row > 0) setValue(L.vsRhs.p, row, 0.0, s, &launches_);
@@ -948,12 +1129,46 @@ void Engine::applyLevel(int l, const double* B, double* X) {
     comm_.allGather(L.xI.p + (int64_t)comm_.rank() * L.maxOwnI, L.xI.p, (size_t)L.maxOwnI, s);
     scatterVecMasked(L.xI.p, L.packedRow.p, X, (int64_t)comm_.size() * L.maxOwnI, s, &launches_);
   }
+  // x1 -= Q1 S (Preconditioner.cpp:1036-1041), on the exported interior rows
+  if (bm) borderCorrect(X, L.intRow.p, L.Q1.p, S.nI, bm, bS_.p, S.nI, s, &launches_);
   at.lap("interior allreduce + export");
 }
 
-void Engine::applyDevice(const double* dB, double* dX) {
-  applyLevel(0, dB, dX);
+void Engine::applyDevice(const double* dB, double* dX, const double* dT, double* dS) {
+  applyLevel(0, dB, dX, dT);
+  if (dS && borderM_)
+    HY_CUDA(cudaMemcpyAsync(dS, bS_.p, borderM_ * sizeof(double), cudaMemcpyDeviceToDevice, stream_));
   stats_.num_apply_inverse++;
+}
+
+// BorderedOperator::ApplyInverse(X, T, Y, S) of the preconditioner (src/HYMLS_Preconditioner.cpp:930-1070)
+void Engine::applyInverseBordered(const double* B, int64_t ldb, const double* T, double* X, int64_t ldx, double* Sout,
+                                  int nvec, int where) {
+  needDevice();
+  if (!computed_) throw Error(HYMLS_B200_ERR_STATE, "The preconditioner has not yet been computed.");
+  if (!B || !X || nvec < 0 || ldb < n_ || ldx < n_) throw Error(HYMLS_B200_ERR_ARG, "apply_inverse: bad arguments");
+  const int bm = borderM_;
+  if (bm == 0) {  // no border: S = 0 (:985-995 falls through to the plain path)
+    applyInverse(B, ldb, X, ldx, nvec, where);
+    return;
+  }
+  if (!T || !Sout) throw Error(HYMLS_B200_ERR_ARG, "apply_inverse_bordered: T and S are required");
+  for (int k = 0; k < nvec; ++k) {
+    const double* b = B + k * ldb;
+    double* x = X + k * ldx;
+    if (where == HYMLS_B200_DEVICE) {
+      applyDevice(b, x, T + (size_t)k * bm, Sout + (size_t)k * bm);
+    } else {
+      bufB_.alloc(n_);
+      bufX_.alloc(n_);
+      HY_CUDA(cudaMemcpyAsync(bufB_.p, b, n_ * sizeof(double), cudaMemcpyHostToDevice, stream_));
+      HY_CUDA(cudaMemcpyAsync(bTin_.p, T + (size_t)k * bm, bm * sizeof(double), cudaMemcpyHostToDevice, stream_));
+      applyDevice(bufB_.p, bufX_.p, bTin_.p, nullptr);
+      HY_CUDA(cudaMemcpyAsync(x, bufX_.p, n_ * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+      HY_CUDA(cudaMemcpyAsync(Sout + (size_t)k * bm, bS_.p, bm * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+      HY_CUDA(cudaStreamSynchronize(stream_));
+    }
+  }
 }
 
 void Engine::applyInverse(const double* B, int64_t ldb, double* X, int64_t ldx, int nvec, int where) {
@@ -1057,6 +1272,22 @@ static double hostScalar(const double* d, cudaStream_t s) {
   return v;
 }
 
+void Engine::operatorRows(const double* full, double* out, int64_t r0, int64_t r1) {
+  Level& L0 = *levels_[0];
+  cudaStream_t s = stream_;
+  const int64_t a0 = std::min(r0, n_), a1 = std::min(r1, n_);
+  spmv(L0.rowptr.p + a0, L0.colidx.p, L0.val.p, full, out, a1 - a0, 0.0, nullptr, nullptr, 1.0, s, &launches_);
+  const int bm = borderM_;
+  if (!bm) return;
+  // BorderedOperator::Apply (src/HYMLS_BorderedOperator.cpp:99-140): Y = K X + V S ; T = W' X + C S
+  multiAxpy(L0.bV.p + a0, n_, bm, full + n_, out, a1 - a0, 1.0, s, &launches_);
+  if (r1 > n_) {
+    multiDot(L0.bW.p, n_, bm, full, n_, bPartial_.p, bDots_.p, 0, s, &launches_);
+    const int i0 = (int)(std::max(r0, n_) - n_), i1 = (int)(r1 - n_);
+    borderRows(bDots_.p, bC0_.p, full + n_, bm, i0, i1, out + (n_ + i0 - r0), s, &launches_);
+  }
+}
+
 void Engine::solve(const double* b, double* x, int where, uint64_t seed, hymls_b200_solve_info* info, double* hist,
                    int histCap) {
   needDevice();
@@ -1073,11 +1304,16 @@ void Engine::solve(const double* b, double* x, int where, uint64_t seed, hymls_b
   const bool explicitTest = it.get("Explicit Residual Test", false);
   const std::string impScaling = it.get("Implicit Residual Scaling", "Norm of Preconditioned Initial Residual");
   const std::string expScaling = it.get("Explicit Residual Scaling", "Norm of Initial Residual");
-  if (sol.get("Use Bordering", false) || sol.get("Use Deflation", false))
-    throw Error(HYMLS_B200_ERR_UNSUPPORTED, "bordered / deflated solvers are not implemented yet");
-  const int64_t n = n_;
+  if (sol.get("Use Deflation", false))
+    throw Error(HYMLS_B200_ERR_UNSUPPORTED, "deflated solvers are not implemented");
+  // With a border set the bordered system [K V; W' C] [x; s] = [b; 0] is solved on vectors of length n + m
+  // (HYMLS::BorderedSolver::ApplyInverse, src/HYMLS_BorderedSolver.cpp:159-219), preconditioned by the
+  // bordered ApplyInverse.  ("Use Bordering" = true without a border is the plain solve with a warning there.)
+  const int bm = borderM_;
+  const int64_t nK = n_;
+  const int64_t n = n_ + bm;
   cudaStream_t s = stream_;
-  Level& L0 = *levels_[0];
+  if (bm && method == "CG") throw Error(HYMLS_B200_ERR_UNSUPPORTED, "bordered solves use GMRES");
   numBlocks = std::max(1, std::min(numBlocks, maxIters));
   const int m = numBlocks;
 
@@ -1089,7 +1325,8 @@ void Engine::solve(const double* b, double* x, int where, uint64_t seed, hymls_b
   kH_.alloc(2 * m + 8);
   kPartial_.alloc((size_t)(m + 2) * multiDotBlocks());
   const auto kind = where == HYMLS_B200_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-  HY_CUDA(cudaMemcpyAsync(kB_.p, b, n * sizeof(double), kind, s));
+  HY_CUDA(cudaMemcpyAsync(kB_.p, b, nK * sizeof(double), kind, s));
+  if (bm) HY_CUDA(cudaMemsetAsync(kB_.p + nK, 0, bm * sizeof(double), s));
   if (startVec == "Random") {
     // MatrixUtils::Random (src/HYMLS_MatrixUtils.cpp:961-1007): uniform in (-1,1); the reference's
     // Epetra_Util LCG stream is replaced by a documented 64-bit Mersenne Twister with `seed`.
@@ -1101,11 +1338,13 @@ void Engine::solve(const double* b, double* x, int where, uint64_t seed, hymls_b
   } else if (startVec == "Zero") {
     HY_CUDA(cudaMemsetAsync(kX_.p, 0, n * sizeof(double), s));
   } else {
-    HY_CUDA(cudaMemcpyAsync(kX_.p, x, n * sizeof(double), kind, s));
+    HY_CUDA(cudaMemcpyAsync(kX_.p, x, nK * sizeof(double), kind, s));
+    if (bm) HY_CUDA(cudaMemsetAsync(kX_.p + nK, 0, bm * sizeof(double), s));
   }
   HY_CUDA(cudaEventRecord(ev0_, s));
-  auto A = [&](const double* in, double* out) {
-    spmv(L0.rowptr.p, L0.colidx.p, L0.val.p, in, out, n, 0.0, nullptr, nullptr, 1.0, s, &launches_);
+  auto A = [&](const double* in, double* out) { operatorRows(in, out, 0, n); };
+  auto M = [&](const double* in, double* out) {
+    applyDevice(in, out, bm ? in + nK : nullptr, bm ? out + nK : nullptr);
   };
   auto dot = [&](const double* u, const double* v) {
     multiDot(u, n, 1, v, n, kPartial_.p, kH_.p + 2 * m + 4, 0, s, &launches_);
@@ -1130,7 +1369,7 @@ void Engine::solve(const double* b, double* x, int where, uint64_t seed, hymls_b
     if (r0 == 0) {
       converged = true;
     } else {
-      applyDevice(kR_.p, kZ_.p);
+      M(kR_.p, kZ_.p);
       axpby(1.0, kZ_.p, 0.0, P.p, n, s, &launches_);
       double rz = dot(kR_.p, kZ_.p);
       while (iters < maxIters) {
@@ -1145,7 +1384,7 @@ void Engine::solve(const double* b, double* x, int where, uint64_t seed, hymls_b
           converged = true;
           break;
         }
-        applyDevice(kR_.p, kZ_.p);
+        M(kR_.p, kZ_.p);
         const double rzNew = dot(kR_.p, kZ_.p);
         axpby(1.0, kZ_.p, rzNew / rz, P.p, n, s, &launches_);
         rz = rzNew;
@@ -1180,7 +1419,7 @@ void Engine::solve(const double* b, double* x, int where, uint64_t seed, hymls_b
       return gath.p;
     };
     auto localRowsOfA = [&](const double* full, double* outLoc) {  // outLoc = (A full)[r0:r1]
-      spmv(L0.rowptr.p + r0, L0.colidx.p, L0.val.p, full, outLoc, nloc, 0.0, nullptr, nullptr, 1.0, s, &launches_);
+      operatorRows(full, outLoc, r0, r1);
     };
     // initial residual (kX_, kB_ replicated; kR_ full)
     A(kX_.p, kR_.p);
@@ -1188,7 +1427,7 @@ void Engine::solve(const double* b, double* x, int where, uint64_t seed, hymls_b
     const double r0norm = std::sqrt(dot(kR_.p, kR_.p));
     double* r = kR_.p;
     if (left) {
-      applyDevice(kR_.p, kZ_.p);
+      M(kR_.p, kZ_.p);
       r = kZ_.p;
     }
     const double pr0norm = left ? std::sqrt(dot(r, r)) : r0norm;
@@ -1220,7 +1459,7 @@ void Engine::solve(const double* b, double* x, int where, uint64_t seed, hymls_b
         double* w = kV_.p + (size_t)(k + 1) * chunk;
         const double* vfull = gatherFull(vk);
         if (right) {
-          applyDevice(vfull, kZ_.p);
+          M(vfull, kZ_.p);
           localRowsOfA(kZ_.p, w);
         } else if (left) {
           if (P == 1) {
@@ -1230,7 +1469,7 @@ void Engine::solve(const double* b, double* x, int where, uint64_t seed, hymls_b
             comm_.allGather(wloc.p, gath.p, (size_t)chunk, s);
             HY_CUDA(cudaMemcpyAsync(kZ_.p, gath.p, n * sizeof(double), cudaMemcpyDeviceToDevice, s));
           }
-          applyDevice(kZ_.p, kW_.p);
+          M(kZ_.p, kW_.p);
           HY_CUDA(cudaMemcpyAsync(w, kW_.p + r0, nloc * sizeof(double), cudaMemcpyDeviceToDevice, s));
         } else {
           localRowsOfA(vfull, w);
@@ -1287,7 +1526,7 @@ void Engine::solve(const double* b, double* x, int where, uint64_t seed, hymls_b
           updFull = gath.p;
         }
         if (right) {
-          applyDevice(updFull, kW_.p);
+          M(updFull, kW_.p);
           axpby(1.0, kW_.p, 1.0, kX_.p, n, s, &launches_);
         } else {
           axpby(1.0, updFull, 1.0, kX_.p, n, s, &launches_);
@@ -1299,7 +1538,7 @@ void Engine::solve(const double* b, double* x, int where, uint64_t seed, hymls_b
       r = kR_.p;
       beta = trueRes;
       if (left) {
-        applyDevice(kR_.p, kZ_.p);
+        M(kR_.p, kZ_.p);
         r = kZ_.p;
         beta = std::sqrt(dot(r, r));
       }
@@ -1323,7 +1562,7 @@ void Engine::solve(const double* b, double* x, int where, uint64_t seed, hymls_b
   axpby(1.0, kB_.p, -1.0, kR_.p, n, s, &launches_);
   const double res = std::sqrt(dot(kR_.p, kR_.p));
   const auto back = where == HYMLS_B200_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
-  HY_CUDA(cudaMemcpyAsync(x, kX_.p, n * sizeof(double), back, s));
+  HY_CUDA(cudaMemcpyAsync(x, kX_.p, nK * sizeof(double), back, s));
   HY_CUDA(cudaStreamSynchronize(s));
   if (info) {
     info->iterations = iters;

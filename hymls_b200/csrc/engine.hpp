@@ -76,6 +76,11 @@ struct Level {
   // work vectors
   DevBuf<double> x1, y1, rhsS, Z, Y, vsRhs, vsSol;
   DevBuf<double> redValLast;  // reduced Schur values when this is the last level (kept for inspection)
+  // bordered variant (BorderedOperator): V, W of this level in its row numbering (n_l x m), Q1 = A11^-1 V1,
+  // W1, the transformed separator border sW (V-sum positions zeroed), the border handed to the coarse
+  // solver (cV, cW) and the border right-hand sides q (after the interior elimination) / Tc (next level's T)
+  DevBuf<double> bV, bW, Q1, W1, sV, sW, cV, cW, bQ, bT;
+  std::vector<double> hC;     // C of this level (m x m, column major)
 };
 
 class Engine {
@@ -91,6 +96,10 @@ class Engine {
   void initialize();
   void compute();
   void applyInverse(const double* B, int64_t ldb, double* X, int64_t ldx, int nvec, int where);
+  void setBorder(const double* V, const double* W, const double* C, int m);
+  void applyInverseBordered(const double* B, int64_t ldb, const double* T, double* X, int64_t ldx, double* S, int nvec,
+                            int where);
+  int borderSize() const { return borderM_; }
   void applyMatrix(const double* x, double* y, int where);
   void localRows(int64_t* r0, int64_t* r1) const;
   void applyInverseDist(const double* Bloc, double* Xloc, int where);
@@ -106,11 +115,18 @@ class Engine {
   bool initialized() const { return initialized_; }
 
  private:
-  void applyLevel(int l, const double* B, double* X);  // device pointers
+  void applyLevel(int l, const double* B, double* X, const double* T = nullptr);  // device pointers
   void computeLevel(int l);
-  void computeCoarse(const int64_t* ptr, const int* col, double* val, int n, const std::vector<gidx>& rowGid);
+  void computeBorder(int l);
+  void computeCoarse(const int64_t* ptr, const int* col, double* val, int n, const std::vector<gidx>& rowGid,
+                     const double* bV = nullptr, const double* bW = nullptr, const std::vector<double>* bC = nullptr);
+  void augmentAndInvertCoarse(int n, int np, const double* bV, const double* bW, const std::vector<double>* bC,
+                              const char* what);
+  void coarseSolveBordered(const double* rhs, const double* T, double* sol, int n);
   void uploadLevel(Level& L);
-  void applyDevice(const double* dB, double* dX);
+  void applyDevice(const double* dB, double* dX, const double* dT = nullptr, double* dS = nullptr);
+  // rows [r0, r1) of the (bordered) operator [K V; W' C] applied to the replicated vector `full`
+  void operatorRows(const double* full, double* out, int64_t r0, int64_t r1);
 
   ParameterList params_;
   Comm comm_;
@@ -126,8 +142,12 @@ class Engine {
   // coarse solver (dense inverse)
   BatchedInverse coarse_;
   std::vector<int> coarseFix_;  // rows with a Dirichlet condition
-  int coarseN_ = 0;
-  DevBuf<double> coarseRhs_;
+  int coarseN_ = 0, coarseM_ = 0;
+  DevBuf<double> coarseRhs_, coarseSol_;
+  // border (SetBorder): host copies of V, W (n x m, column major) and C (m x m)
+  int borderM_ = 0;
+  std::vector<double> hV_, hW_, hC_;
+  DevBuf<double> bS_, bTin_, bPartial_, bDots_, bC_, bC0_;
   // scratch
   DevBuf<double> work_;      // inversion workspace
   DevBuf<int> piv_, perm_, info_;

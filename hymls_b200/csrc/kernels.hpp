@@ -101,4 +101,18 @@ void scatterVec(const double* x, const int* idx, double* y, int64_t n, cudaStrea
 // y[idx[i]] = x[i] for idx[i] >= 0
 void scatterVecMasked(const double* x, const int* idx, double* y, int64_t n, cudaStream_t s, int64_t* launches);
 
+// ---- bordered variant (apply.cu) ----
+void batchedGemvT(const GemvArgs& a, int count, int npMax, cudaStream_t s, int64_t* launches);  // out = Ainv^T x
+void spmvT(const int64_t* ptr, const int* col, const double* val, const double* x, double* y, int64_t n, double alpha,
+           cudaStream_t s, int64_t* launches);                                                   // y += alpha A^T x
+void gatherVec(const double* x, const int* idx, double* y, int64_t n, cudaStream_t s, int64_t* launches);
+void zeroAt(double* x, const int* idx, int64_t n, cudaStream_t s, int64_t* launches);
+void borderCorrect(double* X, const int* idx, const double* Q, int64_t ld, int m, const double* S, int64_t n,
+                   cudaStream_t s, int64_t* launches);
+void denseBorder(double* D, int n, int np, const double* V, const double* W, int64_t ld, const double* C, int m,
+                 cudaStream_t s, int64_t* launches);
+
+void borderRows(const double* dots, const double* C, const double* sv, int m, int i0, int i1, double* out,
+                cudaStream_t s, int64_t* launches);
+
 }  // namespace hymls

@@ -1,0 +1,63 @@
+"""The driver flow of `hymls_main <params.xml>` (src/main.cpp:48-535) on the shipped configurations:
+configs/*.xml are BASELINE.json's five configurations with the reference's parameter names."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import hymls_b200 as hb
+from hymls_b200 import driver
+from tests.conftest import ROOT
+
+CONFIGS = sorted(glob.glob(os.path.join(ROOT, "configs", "*.xml")))
+
+
+def test_configs_parse_and_validate_on_cpu():
+    assert len(CONFIGS) == 5
+    for f in CONFIGS:
+        xml = open(f).read()
+        p = driver.parse_parameter_list(xml)
+        assert {"Problem", "Solver", "Preconditioner"} <= set(p)
+        hb.Preconditioner(None, xml)          # C-side XML parser + parameter validation (no device needed)
+
+
+def test_stale_reference_parameter_is_rejected_like_validate_parameters():
+    xml = open(os.path.join(ROOT, "configs", "cavity.xml")).read().replace(
+        '<Parameter name="Partitioner"', '<Parameter name="Classifier" type="string" value="Stokes"/>\n'
+        '<Parameter name="Partitioner"')
+    with pytest.raises(hb.HymlsError) as e:   # src/HYMLS_Preconditioner.cpp:126-130
+        hb.Preconditioner(None, xml)
+    assert "Classifier" in str(e.value)
+
+
+def test_nullspace_generators():
+    prob = {"Equations": "Stokes-C", "Dimension": 2, "nx": 4, "ny": 4}
+    V = driver.create_nullspace(48, "Constant P", prob)
+    assert V.shape == (48, 1) and np.allclose(np.linalg.norm(V, axis=0), 1)
+    assert np.all(V[2::3, 0] > 0) and np.all(V[0::3, 0] == 0) and np.all(V[1::3, 0] == 0)
+    C = driver.create_nullspace(48, "Checkerboard", prob)
+    assert C.shape == (48, 2) and abs(C[:, 0] @ C[:, 1]) < 1e-15
+    assert np.allclose(C[2::3].sum(axis=1), C[2, :].sum())
+    K = driver.create_nullspace(48, "Constant", prob)
+    assert K.shape == (48, 3) and np.allclose(K.T @ K, np.eye(3))
+
+
+GPU_RUNS = [
+    ("laplace.xml", {"Problem/nx": 64, "Problem/ny": 64}, 35, 1e-9),
+    ("stokes2D.xml", {"Problem/nx": 64, "Problem/ny": 64}, 200, 1e-9),
+    ("cavity.xml", {}, 250, 1e-10),
+    ("cavity3D.xml", {"Problem/nx": 16, "Problem/ny": 16, "Problem/nz": 16, "Preconditioner/Separator Length": 4,
+                      "Preconditioner/Coarsening Factor": 2}, 200, 1e-7),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,over,max_its,tol", GPU_RUNS, ids=[r[0] for r in GPU_RUNS])
+def test_configs_run_on_gpu(name, over, max_its, tol):
+    out = driver.run(open(os.path.join(ROOT, "configs", name)).read(), over, verbose=False)
+    assert out["converged"] and out["iterations"] <= max_its
+    assert out["residual"] <= tol
+    if name == "cavity.xml":   # fixture solution available: error with the constant pressure projected out
+        assert out["border"] == 1 and out["levels"] == 3
+        assert out["error"] <= 1e-8

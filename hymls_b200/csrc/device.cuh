@@ -24,7 +24,8 @@ namespace hymls {
 template <typename T>
 struct DevBuf {
   T* p = nullptr;
-  size_t n = 0;
+  size_t n = 0;    // elements in use
+  size_t cap = 0;  // elements allocated (grow-only: cudaMalloc/cudaFree of GB-sized buffers stall for 100s of ms)
   DevBuf() {}
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
@@ -33,11 +34,15 @@ struct DevBuf {
     if (p) cudaFree(p);
     p = nullptr;
     n = 0;
+    cap = 0;
   }
   void alloc(size_t count) {
-    if (count == n && p) return;
+    if (p && count <= cap) {
+      n = count;
+      return;
+    }
     release();
-    n = count;
+    n = cap = count;
     if (count) HY_CUDA(cudaMalloc((void**)&p, count * sizeof(T)));
   }
   void upload(const std::vector<T>& h, cudaStream_t s) {

@@ -543,13 +543,8 @@ void Engine::compute() {
   HY_CUDA(cudaEventElapsedTime(&ms, ev0_, ev1_));
   stats_.time_compute += ms * 1e-3;
   stats_.num_compute++;
-  // scratch of Compute is not needed by ApplyInverse
-  work_.release();
-  wsC_.release();
-  wsSV_.release();
-  wsSLL_.release();
-  piv_.release();
-  perm_.release();
+  // the scratch of Compute (about 6 GB at the 128^3 workload) is kept for the next Compute: NOX recomputes the
+  // preconditioner every Newton step, and cudaFree / cudaMalloc of buffers this size stall for 100s of ms
   computed_ = true;
 }
 
@@ -566,10 +561,10 @@ static void invertRange(BatchedInverse& B, int m0, int m1, double* W, DevBuf<int
   }
   if (npMax == 0) return;
   relOff.upload(rel, s);
-  piv.alloc((size_t)cnt * npMax);
+  piv.alloc((size_t)cnt * (npMax + 128));  // pivots + the composed interchange lists (2 x 64 per matrix)
   perm.alloc((size_t)cnt * npMax);
-  invertBatched(W, B.F.p + B.hMatOff[m0], relOff.p, B.n.p + m0, B.np.p + m0, cnt, npMax, piv.p, perm.p, info, s,
-                launches);
+  invertBatched(W, B.F.p + B.hMatOff[m0], relOff.p, B.n.p + m0, B.np.p + m0, cnt, npMax, piv.p, perm.p,
+                piv.p + (size_t)cnt * npMax, info, s, launches);
   HY_CUDA(cudaStreamSynchronize(s));  // relOff is reused by the next chunk
 }
 
@@ -603,7 +598,7 @@ void Engine::computeLevel(int l) {
   {
     const int nown = (int)L.ownSd.size();
     const int64_t budget = (int64_t)1 << 29;  // doubles (4 GB) of inversion workspace
-    DevBuf<int64_t> relOff;
+    DevBuf<int64_t>& relOff = relOff_;
     int k0 = 0;
     while (k0 < nown) {
       int k1 = k0;
@@ -618,7 +613,9 @@ void Engine::computeLevel(int l) {
       HY_CUDA(cudaMemsetAsync(work_.p, 0, used * sizeof(double), s));
       const int64_t e0 = L.a11ListPtr[k0], e1 = L.a11ListPtr[k1];
       scatterValues(L.val.p, L.a11Src.p + e0, L.a11Dst.p + e0, L.ownOff[k0], work_.p, e1 - e0, s, &launches_);
+      pt.lap("  chunk fill");
       invertRange(L.a11, k0, k1, work_.p, piv_, perm_, relOff, info_.p, s, &launches_);
+      pt.lap("  chunk inversion");
       for (int k = k0; k < k1; ++k) stats_.flops_compute += 2.0 * std::pow((double)L.a11.hN[k], 3);
       k0 = k1;
     }
@@ -715,7 +712,7 @@ void Engine::computeLevel(int l) {
     redVal = L.redValLast.p;
   }
   HY_CUDA(cudaMemsetAsync(redVal, 0, S.redCol.size() * sizeof(double), s));
-  DevBuf<double> blkW;
+  DevBuf<double>& blkW = blkW_;
   blkW.alloc((size_t)S.blkOff[S.nblk]);
   HY_CUDA(cudaMemsetAsync(blkW.p, 0, blkW.bytes(), s));
   wsC_.alloc((size_t)L.wsCLen);
@@ -735,7 +732,7 @@ void Engine::computeLevel(int l) {
     // owned subdomains into zeroed buffers that are summed over the ranks (FECrsMatrix::GlobalAssemble)
     for (const Level::Chunk& c : L.chunks)
       schurAssemble(a, c.sd0, c.sd1, c.R0, c.R1, c.lk0, c.lk1, 1, L.rowSmem, L.blkSmem, s, &launches_);
-    DevBuf<double> red2, blk2;
+    DevBuf<double>&red2 = red2_, &blk2 = blk2_;
     red2.alloc(S.redCol.size());
     blk2.alloc((size_t)S.blkOff[S.nblk]);
     HY_CUDA(cudaMemsetAsync(red2.p, 0, red2.bytes(), s));
@@ -763,7 +760,7 @@ void Engine::computeLevel(int l) {
   }
   // separator blocks (SchurPreconditioner::Compute :284-291)
   {
-    DevBuf<int64_t> relOff;
+    DevBuf<int64_t>& relOff = relOff_;
     int b0 = 0;
     while (b0 < S.nblk) {
       int b1 = std::min(S.nblk, b0 + 16384);
@@ -837,7 +834,7 @@ void Engine::augmentAndInvertCoarse(int n, int np, const double* bV, const doubl
   coarseM_ = bm;
   coarseRhs_.alloc(n + bm);
   coarseSol_.alloc(n + bm);
-  DevBuf<int64_t> relOff;
+  DevBuf<int64_t>& relOff = relOff_;
   invertRange(coarse_, 0, 1, work_.p, piv_, perm_, relOff, info_.p, s, &launches_);
   checkInfo(info_, s, what);
   stats_.flops_compute += 2.0 * std::pow((double)(n + bm), 3);

@@ -151,7 +151,8 @@ class Engine {
   // scratch
   DevBuf<double> work_;      // inversion workspace
   DevBuf<int> piv_, perm_, info_;
-  DevBuf<double> wsC_, wsSV_, wsSLL_, diagScratch_;
+  DevBuf<double> wsC_, wsSV_, wsSLL_, diagScratch_, blkW_, red2_, blk2_;
+  DevBuf<int64_t> relOff_;
   DevBuf<double> bufB_, bufX_;  // staging for host vectors
   DevBuf<double> bufG_;          // all-gather target of the distributed-vector entry point
   // Krylov workspace

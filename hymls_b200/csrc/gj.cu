@@ -184,11 +184,12 @@ static constexpr int GJ_SMEM_ROWS = 3072;  // 8 * 3072 * 8 B = 192 KB
 
 __global__ void __launch_bounds__(GJ_PANEL_T)
 k_gj_panel_smem(double* __restrict__ W, const int64_t* __restrict__ off, const int* __restrict__ npArr,
-                int* __restrict__ pivAll, int npMax, int k0, int* __restrict__ info, int rowsCap) {
+                int* __restrict__ pivAll, int npMax, int k0, int* __restrict__ info, int rowsCap, int rowsMin) {
   const int mat = blockIdx.x;
   const int np = npArr[mat];
   if (k0 >= np) return;
-  if (np - k0 > rowsCap) return;  // handled by the generic kernel
+  if (np - k0 > rowsCap) return;   // handled by the generic kernel
+  if (np - k0 <= rowsMin) return;  // handled by the whole-panel kernel
   const int nb = min(GJ_NB, np - k0);
   double* M = W + off[mat];
   int* piv = pivAll + (int64_t)mat * npMax;
@@ -376,6 +377,265 @@ k_gj_panel_smem(double* __restrict__ W, const int64_t* __restrict__ off, const i
 }
 
 // ---------------------------------------------------------------------------------------------
+// panel kernel, whole-panel version: when the active part of the 32-column panel (R = np - k0 rows) fits in
+// shared memory ([32][R] column major, R <= GJ_FULL_ROWS) the complete step runs out of it: pivot search,
+// row swaps, the 8-column sub-panels with their rank-8 updates of the rest of the panel, the inverses of
+// the triangular factors of the K x K block and the transform block G' of the active rows; global memory
+// sees one coalesced read and one coalesced write of the panel.  The rows above the panel
+// (G'[r] = -M[r,K] inv(M[K,K]), r < k0) stream through the same shared memory in tiles.
+// ---------------------------------------------------------------------------------------------
+static constexpr int GJ_FULL_ROWS = 824;   // 32 * 825 * 8 B = 206 KB dynamic + 20 KB static <= 227 KB
+static constexpr int GJ_FULL_MINROWS = 256; // tile height of the rows above the panel is at least this
+static constexpr int GJ_XS = GJ_NB + 4;    // row stride of the 32 x 32 factor inverses (16-byte aligned rows)
+
+// rows [0, rows) of the tile sT ([nb][rsT] column major): row <- -(row * X), X = sX (nb x nb, stride GJ_XS)
+__device__ __forceinline__ void gjTransformRows(double* __restrict__ sT, int rsT, int rFirst, int rows, int nb,
+                                                const double* __restrict__ sX, int tid) {
+  for (int r = rFirst + tid; r < rows; r += GJ_PANEL_T) {
+    double a[GJ_NB];
+#pragma unroll
+    for (int k = 0; k < GJ_NB; ++k) a[k] = k < nb ? sT[k * rsT + r] : 0.0;
+    for (int q = 0; q < nb; q += 4) {
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+      for (int k = 0; k < GJ_NB; ++k) {
+        if (k < nb) {
+          const double2 x01 = *reinterpret_cast<const double2*>(sX + k * GJ_XS + q);
+          const double2 x23 = *reinterpret_cast<const double2*>(sX + k * GJ_XS + q + 2);
+          s0 += a[k] * x01.x;
+          s1 += a[k] * x01.y;
+          s2 += a[k] * x23.x;
+          s3 += a[k] * x23.y;
+        }
+      }
+      sT[q * rsT + r] = -s0;
+      sT[(q + 1) * rsT + r] = -s1;
+      sT[(q + 2) * rsT + r] = -s2;
+      sT[(q + 3) * rsT + r] = -s3;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(GJ_PANEL_T)
+k_gj_panel_full(double* __restrict__ W, const int64_t* __restrict__ off, const int* __restrict__ npArr,
+                int* __restrict__ pivAll, int npMax, int k0, int* __restrict__ info, int rowsCap, int tileRows) {
+  const int mat = blockIdx.x;
+  const int np = npArr[mat];
+  if (k0 >= np) return;
+  const int R = np - k0;
+  if (R > rowsCap) return;  // handled by the sub-panel kernels
+  const int nb = min(GJ_NB, R);  // np is a multiple of 8, so nb is a multiple of 4
+  double* M = W + off[mat];
+  int* piv = pivAll + (int64_t)mat * npMax;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  constexpr int NW = GJ_PANEL_T / 32;
+
+  extern __shared__ double sP[];  // [nb][rs] active panel / [nb][rsT] tiles of the rows above
+  __shared__ __align__(16) double sLinv[GJ_NB * GJ_XS];
+  __shared__ __align__(16) double sDinv[GJ_NB * GJ_XS];
+  __shared__ double sU[GJ_SW];
+  __shared__ double sUn[GJ_SW][GJ_NB];
+  __shared__ double sRedV[NW];
+  __shared__ int sRedI[NW];
+  __shared__ int sPiv;
+  __shared__ double sPivVal;
+  const int rs = R | 1;
+
+  for (int e = tid; e < R * nb; e += GJ_PANEL_T) {
+    const int r = e / nb, q = e - r * nb;
+    sP[q * rs + r] = M[(int64_t)(k0 + r) * np + k0 + q];
+  }
+  __syncthreads();
+  for (int c0 = 0; c0 < nb; c0 += GJ_SW) {
+    const int w = min(GJ_SW, nb - c0);
+    for (int jj = 0; jj < w; ++jj) {
+      const int j = c0 + jj;  // local column = local row of the pivot position
+      double bestV = -1.0;
+      int bestR = 0x7fffffff;
+      for (int r = j + tid; r < R; r += GJ_PANEL_T) {
+        const double v = fabs(sP[j * rs + r]);
+        if (v > bestV) {
+          bestV = v;
+          bestR = r;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_down_sync(0xffffffffu, bestV, o);
+        const int orow = __shfl_down_sync(0xffffffffu, bestR, o);
+        if (ov > bestV || (ov == bestV && orow < bestR)) {
+          bestV = ov;
+          bestR = orow;
+        }
+      }
+      if (lane == 0) {
+        sRedV[wid] = bestV;
+        sRedI[wid] = bestR;
+      }
+      __syncthreads();
+      if (wid == 0) {
+        bestV = lane < NW ? sRedV[lane] : -1.0;
+        bestR = lane < NW ? sRedI[lane] : 0x7fffffff;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const double ov = __shfl_down_sync(0xffffffffu, bestV, o);
+          const int orow = __shfl_down_sync(0xffffffffu, bestR, o);
+          if (ov > bestV || (ov == bestV && orow < bestR)) {
+            bestV = ov;
+            bestR = orow;
+          }
+        }
+        if (lane == 0) {
+          if (bestR == 0x7fffffff) bestR = j;
+          sPiv = bestR;
+          piv[k0 + j] = k0 + bestR;
+          if (!(bestV > 0.0)) atomicExch(info, mat + 1);
+        }
+      }
+      __syncthreads();
+      const int p = sPiv;
+      if (tid < nb) {  // swap the two rows over the whole panel
+        const double a = sP[tid * rs + j];
+        const double b = sP[tid * rs + p];
+        sP[tid * rs + j] = b;
+        sP[tid * rs + p] = a;
+        if (tid >= c0 && tid < c0 + w) sU[tid - c0] = b;
+        if (tid == j) sPivVal = b;
+      }
+      __syncthreads();
+      const double rp = 1.0 / sPivVal;
+      for (int r = j + 1 + tid; r < R; r += GJ_PANEL_T) {
+        const double l = sP[j * rs + r] * rp;
+        sP[j * rs + r] = l;
+        for (int q = jj + 1; q < w; ++q) sP[(c0 + q) * rs + r] -= l * sU[q];
+      }
+      __syncthreads();
+    }
+    const int nRight = nb - (c0 + w);
+    if (nRight > 0) {
+      if (tid < nRight) {
+        const int col = c0 + w + tid;
+        double u[GJ_SW];
+#pragma unroll
+        for (int i = 0; i < GJ_SW; ++i) {
+          if (i < w) {
+            double x = sP[col * rs + c0 + i];
+            for (int t = 0; t < i; ++t) x -= sP[(c0 + t) * rs + c0 + i] * u[t];
+            u[i] = x;
+            sP[col * rs + c0 + i] = x;
+            sUn[i][tid] = x;
+          }
+        }
+      }
+      __syncthreads();
+      for (int r = c0 + w + tid; r < R; r += GJ_PANEL_T) {
+        double l[GJ_SW];
+#pragma unroll
+        for (int t = 0; t < GJ_SW; ++t) l[t] = t < w ? sP[(c0 + t) * rs + r] : 0.0;
+        for (int q = 0; q < nRight; ++q) {
+          double x = sP[(c0 + w + q) * rs + r];
+#pragma unroll
+          for (int t = 0; t < GJ_SW; ++t) x -= l[t] * sUn[t][q];
+          sP[(c0 + w + q) * rs + r] = x;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  // Linv = inv(L_KK) (unit lower), Dinv = inv(U_KK) * Linv; the K x K block is the first nb rows of the panel
+  if (tid < nb) {
+    const int t = tid;
+    for (int i = 0; i < nb; ++i) {
+      double x = (i == t) ? 1.0 : 0.0;
+      for (int k = t; k < i; ++k) x -= sP[k * rs + i] * sLinv[k * GJ_XS + t];
+      sLinv[i * GJ_XS + t] = (i < t) ? 0.0 : x;
+    }
+    for (int i = nb - 1; i >= 0; --i) {
+      double x = sLinv[i * GJ_XS + t];
+      for (int k = i + 1; k < nb; ++k) x -= sP[k * rs + i] * sDinv[k * GJ_XS + t];
+      sDinv[i * GJ_XS + t] = x / sP[i * rs + i];
+    }
+  }
+  __syncthreads();
+  // G' of the active rows, in place: rows below the block -L Linv, the block itself Dinv
+  gjTransformRows(sP, rs, nb, R, nb, sLinv, tid);
+  for (int e = tid; e < nb * nb; e += GJ_PANEL_T) {
+    const int r = e / nb, q = e - r * nb;
+    sP[q * rs + r] = sDinv[r * GJ_XS + q];
+  }
+  __syncthreads();
+  for (int e = tid; e < R * nb; e += GJ_PANEL_T) {
+    const int r = e / nb, q = e - r * nb;
+    M[(int64_t)(k0 + r) * np + k0 + q] = sP[q * rs + r];
+  }
+  // rows above the panel, tile by tile
+  const int rsT = tileRows | 1;
+  for (int t0 = 0; t0 < k0; t0 += tileRows) {
+    const int rows = min(tileRows, k0 - t0);
+    __syncthreads();
+    for (int e = tid; e < rows * nb; e += GJ_PANEL_T) {
+      const int r = e / nb, q = e - r * nb;
+      sP[q * rsT + r] = M[(int64_t)(t0 + r) * np + k0 + q];
+    }
+    __syncthreads();
+    gjTransformRows(sP, rsT, 0, rows, nb, sDinv, tid);
+    __syncthreads();
+    for (int e = tid; e < rows * nb; e += GJ_PANEL_T) {
+      const int r = e / nb, q = e - r * nb;
+      M[(int64_t)(t0 + r) * np + k0 + q] = sP[q * rsT + r];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// The 32 row interchanges of a panel composed into one gather list per matrix (one warp each):
+// rowsT[i] = a row whose content changes (-1: unused), origT[i] = the row its new content comes from.
+// Entries 0..31 are the panel rows k0..k0+31 themselves, 32..63 the pivot rows outside the panel.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_gj_swaplist(const int* __restrict__ npArr, const int* __restrict__ pivAll, int npMax, int k0,
+                              int count, int* __restrict__ rowsT, int* __restrict__ origT) {
+  const int mat = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (mat >= count) return;
+  const int np = npArr[mat];
+  if (k0 >= np) return;
+  const int lane = threadIdx.x & 31;
+  const int nb = min(GJ_NB, np - k0);
+  const int* piv = pivAll + (int64_t)mat * npMax;
+  int origK = k0 + lane, outRow = -1, origOut = -1, nOut = 0;
+  for (int j = 0; j < nb; ++j) {
+    const int p = piv[k0 + j];
+    if (p == k0 + j) continue;
+    const int a = __shfl_sync(0xffffffffu, origK, j);
+    if (p < k0 + nb) {
+      const int b = __shfl_sync(0xffffffffu, origK, p - k0);
+      if (lane == j) origK = b;
+      if (lane == p - k0) origK = a;
+    } else {
+      const unsigned m = __ballot_sync(0xffffffffu, outRow == p);
+      int slot;
+      if (m) {
+        slot = __ffs(m) - 1;
+      } else {
+        slot = nOut++;
+        if (lane == slot) {
+          outRow = p;
+          origOut = p;
+        }
+      }
+      const int b = __shfl_sync(0xffffffffu, origOut, slot);
+      if (lane == j) origK = b;
+      if (lane == slot) origOut = a;
+    }
+  }
+  int* rT = rowsT + (int64_t)mat * 64;
+  int* oT = origT + (int64_t)mat * 64;
+  rT[lane] = lane < nb ? k0 + lane : -1;
+  oT[lane] = origK;
+  rT[32 + lane] = lane < nOut ? outRow : -1;
+  oT[32 + lane] = origOut;
+}
+
+// ---------------------------------------------------------------------------------------------
 // DMMA m8n8k4 (FP64 tensor core): D(8x8) += A(8x4, row) * B(4x8, col)
 //   a : A[lane/4][lane%4]        b : B[lane%4][lane/4]        c0,c1 : C[lane/4][2*(lane%4) + {0,1}]
 // ---------------------------------------------------------------------------------------------
@@ -386,9 +646,9 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 }
 
 // update kernel: grid (column strips, matrices)
-__global__ void __launch_bounds__(GJ_UPD_T, 3)
+__global__ void __launch_bounds__(GJ_UPD_T, 2)
 k_gj_update(double* __restrict__ W, const int64_t* __restrict__ off, const int* __restrict__ npArr,
-            const int* __restrict__ pivAll, int npMax, int k0) {
+            const int* __restrict__ rowsT, const int* __restrict__ origT, int k0) {
   const int mat = blockIdx.y;
   const int np = npArr[mat];
   if (k0 >= np) return;
@@ -396,7 +656,6 @@ k_gj_update(double* __restrict__ W, const int64_t* __restrict__ off, const int* 
   if (j0 >= np) return;
   const int nb = min(GJ_NB, np - k0);
   double* M = W + off[mat];
-  const int* piv = pivAll + (int64_t)mat * npMax;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int jw = min(GJ_TJ, np - j0);  // np is a multiple of 8, so jw is too
 
@@ -406,40 +665,48 @@ k_gj_update(double* __restrict__ W, const int64_t* __restrict__ off, const int* 
   double* sB = gjSmem;                // GJ_NB x SB
   double* sA = gjSmem + GJ_NB * SB;   // GJ_TM x SA
 
-  // (1) row swaps of this strip (each thread owns one column, so the sequence needs no barrier)
-  if (tid < jw) {
-    const int col = j0 + tid;
-    if (col < k0 || col >= k0 + nb) {
-      for (int j = 0; j < nb; ++j) {
-        const int c = k0 + j, p = piv[c];
-        if (p != c) {
-          double a = M[(int64_t)c * np + col];
-          double b = M[(int64_t)p * np + col];
-          M[(int64_t)c * np + col] = b;
-          M[(int64_t)p * np + col] = a;
-        }
-      }
-    }
+  // (1) row interchanges of this strip from the composed gather list: every touched row is fetched from the
+  //     row its new content comes from (coalesced, independent loads), staged in shared memory and written
+  //     back; the first nb staged rows are B = M[K, strip] after the interchanges.
+  __shared__ int sRow[64], sOrig[64];
+  if (tid < 64) {
+    sRow[tid] = rowsT[(int64_t)mat * 64 + tid];
+    sOrig[tid] = origT[(int64_t)mat * 64 + tid];
   }
   __syncthreads();
-  // (2) B = old M[K, strip]  (zero-padded to GJ_NB x GJ_TJ)
-  for (int e = tid; e < GJ_NB * GJ_TJ; e += GJ_UPD_T) {
-    const int k = e / GJ_TJ, c = e % GJ_TJ;
-    sB[k * SB + c] = (k < nb && c < jw) ? M[(int64_t)(k0 + k) * np + j0 + c] : 0.0;
+  for (int e = tid; e < 64 * GJ_TJ; e += GJ_UPD_T) {
+    const int i = e / GJ_TJ, c = e % GJ_TJ;
+    const int row = sRow[i];
+    gjSmem[i * SB + c] = (row >= 0 && c < jw) ? M[(int64_t)sOrig[i] * np + j0 + c] : 0.0;
   }
   __syncthreads();
-  // warp layout: 2 x 4 warps, each 4 x 4 tiles of 8 x 8 -> CTA tile 64 x 128
+  for (int e = tid; e < 64 * GJ_TJ; e += GJ_UPD_T) {
+    const int i = e / GJ_TJ, c = e % GJ_TJ;
+    const int row = sRow[i], col = j0 + c;
+    // the panel's own columns were interchanged by the panel kernel
+    if (row >= 0 && sOrig[i] != row && c < jw && (col < k0 || col >= k0 + nb))
+      M[(int64_t)row * np + col] = gjSmem[i * SB + c];
+  }
+  __syncthreads();
+  // warp layout: 2 x 4 warps, each 4 x 2 tiles of 8 x 8 -> CTA tile 64 x 64
   const int wr = wid >> 2, wc = wid & 3;
   const int fr = lane >> 2, fk = lane & 3;
 
-  for (int r0 = 0; r0 < np; r0 += GJ_TM) {
-    // (3a) stage G'[r0 : r0+64, K] in shared memory
-    for (int e = tid; e < GJ_TM * GJ_NB; e += GJ_UPD_T) {
-      const int r = e / GJ_NB, k = e % GJ_NB;
-      sA[r * SA + k] = (r0 + r < np && k < nb) ? M[(int64_t)(r0 + r) * np + k0 + k] : 0.0;
+  // software pipeline over the row tiles: while tile i is multiplied, the G' rows of tile i+1 arrive in the
+  // other shared-memory buffer (cp.async) and its accumulator values in registers
+  auto stageA = [&](int r0, int buf) {
+    double* dst = sA + buf * (GJ_TM * SA);
+    for (int e = tid; e < GJ_TM * (GJ_NB / 2); e += GJ_UPD_T) {
+      const int r = e / (GJ_NB / 2), k = (e % (GJ_NB / 2)) * 2;
+      const bool ok = (r0 + r < np) && (k < nb);
+      const double* src = ok ? M + (int64_t)(r0 + r) * np + k0 + k : M;
+      const unsigned saddr = (unsigned)__cvta_generic_to_shared(dst + r * SA + k);
+      const int bytes = ok ? 16 : 0;  // src-size 0: zero fill
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(saddr), "l"(src), "r"(bytes));
     }
-    __syncthreads();
-    double acc[4][GJ_CS][2];
+    asm volatile("cp.async.commit_group;\n" ::);
+  };
+  auto loadAcc = [&](int r0, double (&acc)[4][GJ_CS][2]) {
 #pragma unroll
     for (int ti = 0; ti < 4; ++ti) {
       const int row = r0 + (wr * 4 + ti) * 8 + fr;
@@ -448,15 +715,37 @@ k_gj_update(double* __restrict__ W, const int64_t* __restrict__ off, const int* 
       for (int tj = 0; tj < GJ_CS; ++tj) {
         const int col = j0 + (wc * GJ_CS + tj) * 8 + 2 * fk;
         const bool ok = row < np && col < j0 + jw && !inK;
-        acc[ti][tj][0] = ok ? M[(int64_t)row * np + col] : 0.0;
-        acc[ti][tj][1] = ok ? M[(int64_t)row * np + col + 1] : 0.0;
+        double2 v = make_double2(0.0, 0.0);
+        if (ok) v = *reinterpret_cast<const double2*>(M + (int64_t)row * np + col);
+        acc[ti][tj][0] = v.x;
+        acc[ti][tj][1] = v.y;
       }
     }
+  };
+  double accN[4][GJ_CS][2];
+  stageA(0, 0);
+  loadAcc(0, accN);
+  int buf = 0;
+  for (int r0 = 0; r0 < np; r0 += GJ_TM, buf ^= 1) {
+    const bool more = r0 + GJ_TM < np;
+    if (more) stageA(r0 + GJ_TM, buf ^ 1);
+    if (more) asm volatile("cp.async.wait_group 1;\n" ::); else asm volatile("cp.async.wait_group 0;\n" ::);
+    __syncthreads();
+    double acc[4][GJ_CS][2];
+#pragma unroll
+    for (int ti = 0; ti < 4; ++ti)
+#pragma unroll
+      for (int tj = 0; tj < GJ_CS; ++tj) {
+        acc[ti][tj][0] = accN[ti][tj][0];
+        acc[ti][tj][1] = accN[ti][tj][1];
+      }
+    if (more) loadAcc(r0 + GJ_TM, accN);
+    const double* cA = sA + buf * (GJ_TM * SA);
 #pragma unroll
     for (int kk = 0; kk < GJ_NB / 4; ++kk) {
       double a[4], b[GJ_CS];
 #pragma unroll
-      for (int ti = 0; ti < 4; ++ti) a[ti] = sA[((wr * 4 + ti) * 8 + fr) * SA + kk * 4 + fk];
+      for (int ti = 0; ti < 4; ++ti) a[ti] = cA[((wr * 4 + ti) * 8 + fr) * SA + kk * 4 + fk];
 #pragma unroll
       for (int tj = 0; tj < GJ_CS; ++tj) b[tj] = sB[(kk * 4 + fk) * SB + (wc * GJ_CS + tj) * 8 + fr];
 #pragma unroll
@@ -471,13 +760,11 @@ k_gj_update(double* __restrict__ W, const int64_t* __restrict__ off, const int* 
       for (int tj = 0; tj < GJ_CS; ++tj) {
         const int col = j0 + (wc * GJ_CS + tj) * 8 + 2 * fk;
         // the panel's own columns hold G' and are left alone
-        if (row < np && col < j0 + jw && (col < k0 || col >= k0 + nb)) {
-          M[(int64_t)row * np + col] = acc[ti][tj][0];
-          M[(int64_t)row * np + col + 1] = acc[ti][tj][1];
-        }
+        if (row < np && col < j0 + jw && (col < k0 || col >= k0 + nb))
+          *reinterpret_cast<double2*>(M + (int64_t)row * np + col) = make_double2(acc[ti][tj][0], acc[ti][tj][1]);
       }
     }
-    __syncthreads();
+    __syncthreads();  // all warps are done with this buffer before the next prefetch overwrites it
   }
 }
 
@@ -523,33 +810,48 @@ __global__ void k_gj_gather(const double* __restrict__ W, double* __restrict__ F
   }
 }
 
-static constexpr size_t GJ_UPD_SMEM = (size_t)(GJ_NB * (GJ_TJ + 4) + GJ_TM * (GJ_NB + 4)) * sizeof(double);
+static constexpr size_t GJ_UPD_SMEM = (size_t)(GJ_NB * (GJ_TJ + 4) + 2 * GJ_TM * (GJ_NB + 4)) * sizeof(double);
 
 void invertBatched(double* W, double* F, const int64_t* dOff, const int* dN, const int* dNp, int count, int npMax,
-                   int* dPiv, int* dPerm, int* dInfo, cudaStream_t s, int64_t* launches) {
+                   int* dPiv, int* dPerm, int* dSwap, int* dInfo, cudaStream_t s, int64_t* launches) {
   if (count == 0 || npMax == 0) return;
   static bool attrSet = false, permAttrSet = false;
   if (!attrSet) {
     HY_CUDA(cudaFuncSetAttribute(k_gj_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GJ_UPD_SMEM));
     HY_CUDA(cudaFuncSetAttribute(k_gj_panel_smem, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)((size_t)GJ_SW * (GJ_SMEM_ROWS | 1) * sizeof(double))));
+    HY_CUDA(cudaFuncSetAttribute(k_gj_panel_full, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)((size_t)GJ_NB * (GJ_FULL_ROWS | 1) * sizeof(double))));
     attrSet = true;
   }
   if ((size_t)npMax * sizeof(int) > 200 * 1024)
     throw Error(HYMLS_B200_ERR_UNSUPPORTED, "dense block larger than 51200 rows");
+  int* rowsT = dSwap;                       // count x 64
+  int* origT = dSwap + (size_t)count * 64;  // count x 64
   k_pad_identity<<<count, 64, 0, s>>>(W, dOff, dN, dNp, count);
   ++*launches;
   for (int k0 = 0; k0 < npMax; k0 += GJ_NB) {
     const int activeMax = npMax - k0;
-    const int rowsCap = GJ_SMEM_ROWS;
-    const size_t psm = (size_t)GJ_SW * ((std::min(activeMax, rowsCap)) | 1) * sizeof(double);
-    k_gj_panel_smem<<<count, GJ_PANEL_T, psm, s>>>(W, dOff, dNp, dPiv, npMax, k0, dInfo, rowsCap);
-    if (activeMax > rowsCap) {
-      k_gj_panel<<<count, GJ_PANEL_T, 0, s>>>(W, dOff, dNp, dPiv, npMax, k0, dInfo, rowsCap);
+    // panel: matrices whose active part fits in shared memory as a whole, then the two fallbacks
+    {
+      const int tileRows = std::max(std::min(activeMax, GJ_FULL_ROWS), GJ_FULL_MINROWS);
+      const size_t fsm = (size_t)GJ_NB * (tileRows | 1) * sizeof(double);
+      k_gj_panel_full<<<count, GJ_PANEL_T, fsm, s>>>(W, dOff, dNp, dPiv, npMax, k0, dInfo, GJ_FULL_ROWS, tileRows);
       ++*launches;
     }
+    if (activeMax > GJ_FULL_ROWS) {
+      const size_t psm = (size_t)GJ_SW * ((std::min(activeMax, GJ_SMEM_ROWS)) | 1) * sizeof(double);
+      k_gj_panel_smem<<<count, GJ_PANEL_T, psm, s>>>(W, dOff, dNp, dPiv, npMax, k0, dInfo, GJ_SMEM_ROWS,
+                                                     GJ_FULL_ROWS);
+      ++*launches;
+    }
+    if (activeMax > GJ_SMEM_ROWS) {
+      k_gj_panel<<<count, GJ_PANEL_T, 0, s>>>(W, dOff, dNp, dPiv, npMax, k0, dInfo, GJ_SMEM_ROWS);
+      ++*launches;
+    }
+    k_gj_swaplist<<<(count + 3) / 4, 128, 0, s>>>(dNp, dPiv, npMax, k0, count, rowsT, origT);
     dim3 g((npMax + GJ_TJ - 1) / GJ_TJ, count);
-    k_gj_update<<<g, GJ_UPD_T, GJ_UPD_SMEM, s>>>(W, dOff, dNp, dPiv, npMax, k0);
+    k_gj_update<<<g, GJ_UPD_T, GJ_UPD_SMEM, s>>>(W, dOff, dNp, rowsT, origT, k0);
     *launches += 2;
   }
   if ((size_t)npMax * sizeof(int) > 48 * 1024 && !permAttrSet) {

@@ -8,7 +8,7 @@ namespace hymls {
 
 // ---- gj.cu: batched dense inversion, W (workspace, destroyed) -> F (inverse), same offsets ----
 void invertBatched(double* W, double* F, const int64_t* dOff, const int* dN, const int* dNp, int count, int npMax,
-                   int* dPiv, int* dPerm, int* dInfo, cudaStream_t s, int64_t* launches);
+                   int* dPiv, int* dPerm, int* dSwap, int* dInfo, cudaStream_t s, int64_t* launches);
 
 // ---- schur.cu ----
 struct SchurArgs {

@@ -15,7 +15,8 @@ namespace hymls {
 // The dominant kernel of ApplyInverse: streams 8 n_sd^2 bytes per subdomain exactly once.
 // Work item = (matrix, slab of GEMV_ROWS rows); one warp per row, lanes stride the row with 16-byte
 // loads, x_sd staged in shared memory.
-//   x_sd[q] = xin[gather ? gather[p] : p],  p = vecOff[mat] + q
+//   x_sd[q] = xin[gather ? gather[p] : p] (- xsub[p]),  p = vecOff[mat] + q
+//   rows [0, nrows[mat]) only when nrows is given (the first solve of ApplyInverse needs a leading block)
 //   mode 0:  out[scatter ? scatter[p] : p] = acc
 //   mode 1:  out[scatter ? scatter[p] : p] = xprev[p] - acc   (second A11 solve of ApplyInverse: fused update + export)
 // ---------------------------------------------------------------------------------------------
@@ -28,20 +29,24 @@ k_batched_gemv(GemvArgs a) {
   const int mat = a.itemMat[item];
   const int r0 = a.itemRow0[item];
   const int n = a.n[mat], np = a.np[mat];
+  const int nr = a.nrows ? a.nrows[mat] : n;
   const int64_t v0 = a.vecOff[mat];  // offset of this matrix' segment in the packed vectors
   const double* __restrict__ A = a.A + a.matOff[mat];
   extern __shared__ double sx[];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   for (int q = tid; q < np; q += GEMV_T) {
     double v = 0.0;
-    if (q < n) v = a.gather ? a.xin[a.gather[v0 + q]] : a.xin[v0 + q];
+    if (q < n) {
+      v = a.gather ? a.xin[a.gather[v0 + q]] : a.xin[v0 + q];
+      if (a.xsub) v -= a.xsub[v0 + q];
+    }
     sx[q] = v;
   }
   __syncthreads();
 #pragma unroll
   for (int rr = 0; rr < GEMV_ROWS / (GEMV_T / 32); ++rr) {
     const int r = r0 + wid * (GEMV_ROWS / (GEMV_T / 32)) + rr;
-    if (r >= n) break;
+    if (r >= nr) break;
     const double2* __restrict__ row = reinterpret_cast<const double2*>(A + (int64_t)r * np);
     const double2* __restrict__ x2 = reinterpret_cast<const double2*>(sx);
     double acc0 = 0.0, acc1 = 0.0;
@@ -172,14 +177,18 @@ void householder(const int* uniqStart, int nuniq, const double* w, const double*
 // partial[i * nblk + b] = sum over rows of block b of V_i[r] * w[r],  i = 0..k-1   (one pass over w)
 __global__ void __launch_bounds__(256)
 k_multi_dot(const double* __restrict__ V, int64_t ldv, int k, const double* __restrict__ w, int64_t n,
-            double* __restrict__ partial) {
+            double* __restrict__ partial, const int* __restrict__ widx) {
   __shared__ double red[8];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int i = 0; i < k; ++i) {
     const double* v = V + (int64_t)i * ldv;
     double s = 0.0;
-    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + tid; r < n; r += stride) s += v[r] * w[r];
+    if (widx) {
+      for (int64_t r = (int64_t)blockIdx.x * blockDim.x + tid; r < n; r += stride) s += v[r] * w[widx[r]];
+    } else {
+      for (int64_t r = (int64_t)blockIdx.x * blockDim.x + tid; r < n; r += stride) s += v[r] * w[r];
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0) red[wid] = s;
@@ -215,9 +224,9 @@ __global__ void k_reduce_partials(const double* __restrict__ partial, int nblk, 
 }
 static const int DOT_BLOCKS = 592;  // 4 x 148 SMs
 void multiDot(const double* V, int64_t ldv, int k, const double* w, int64_t n, double* partial, double* h,
-              int accumulate, cudaStream_t s, int64_t* launches) {
+              int accumulate, cudaStream_t s, int64_t* launches, const int* widx) {
   if (k == 0) return;
-  k_multi_dot<<<DOT_BLOCKS, 256, 0, s>>>(V, ldv, k, w, n, partial);
+  k_multi_dot<<<DOT_BLOCKS, 256, 0, s>>>(V, ldv, k, w, n, partial, widx);
   k_reduce_partials<<<k, 256, 0, s>>>(partial, DOT_BLOCKS, k, h, accumulate);
   *launches += 2;
 }

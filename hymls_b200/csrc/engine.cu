@@ -145,7 +145,7 @@ void Engine::setTestVector(const double* tv) {
 // ---------------------------------------------------------------------------------------------
 void BatchedInverse::setup(const std::vector<int>& n_, const std::vector<int>& np_,
                            const std::vector<int64_t>& matOff_, const std::vector<int64_t>& vecOff_,
-                           cudaStream_t s, const std::vector<char>* applyMask) {
+                           cudaStream_t s, const std::vector<char>* applyMask, const std::vector<int>* leadRows) {
   hN = n_;
   hNp = np_;
   hMatOff = matOff_;
@@ -163,6 +163,19 @@ void BatchedInverse::setup(const std::vector<int>& n_, const std::vector<int>& n
     }
   }
   numItems = (int)im.size();
+  numItemsLead = 0;
+  if (leadRows) {
+    std::vector<int> lm, lr;
+    for (int m = 0; m < count; ++m)
+      for (int r0 = 0; r0 < (*leadRows)[m]; r0 += rows) {
+        lm.push_back(m);
+        lr.push_back(r0);
+      }
+    numItemsLead = (int)lm.size();
+    rowLimit.upload(*leadRows, s);
+    itemMatLead.upload(lm, s);
+    itemRow0Lead.upload(lr, s);
+  }
   n.upload(hN, s);
   np.upload(hNp, s);
   matOff.upload(hMatOff, s);
@@ -278,7 +291,7 @@ void Engine::uploadLevel(Level& L) {
   // A11: compact storage of the owned subdomains
   const int nown = (int)L.ownSd.size();
   std::vector<char> isOwn(S.nsd, 0);
-  std::vector<int> on(nown), onp(nown);
+  std::vector<int> on(nown), onp(nown), onb(nown);
   std::vector<int64_t> ovec(nown), a11OffG(S.nsd, -1);
   L.ownOff.assign(nown + 1, 0);
   for (int k = 0; k < nown; ++k) {
@@ -286,11 +299,12 @@ void Engine::uploadLevel(Level& L) {
     isOwn[sd] = 1;
     on[k] = S.sdN[sd];
     onp[k] = S.sdNp[sd];
+    onb[k] = S.sdNb[sd];
     ovec[k] = S.H.intPtr[sd];
     a11OffG[sd] = L.ownOff[k];
     L.ownOff[k + 1] = L.ownOff[k] + (int64_t)onp[k] * onp[k];
   }
-  L.a11.setup(on, onp, L.ownOff, ovec, s);
+  L.a11.setup(on, onp, L.ownOff, ovec, s, nullptr, &onb);
   L.sdNG.upload(S.sdN, s);
   L.sdNpG.upload(S.sdNp, s);
   L.a11OffG.upload(a11OffG, s);
@@ -873,7 +887,7 @@ void Engine::computeBorder(int l) {
     L.hC = hC_;
   }
   L.Q1.alloc((size_t)nI * bm);
-  L.W1.alloc((size_t)nI * bm);
+  L.W1t.alloc((size_t)nI * bm);
   L.sV.alloc((size_t)nS * bm);
   L.sW.alloc((size_t)nS * bm);
   L.bQ.alloc(bm);
@@ -883,8 +897,6 @@ void Engine::computeBorder(int l) {
   bPartial_.alloc((size_t)(bm + 2) * multiDotBlocks());
   bDots_.alloc((size_t)bm * bm + bm);
   if (L.Q1.n) HY_CUDA(cudaMemsetAsync(L.Q1.p, 0, L.Q1.bytes(), s));
-  DevBuf<double> w1tmp;
-  w1tmp.alloc((size_t)nI);
   for (int j = 0; j < bm; ++j) {
     const double* Vj = L.bV.p + (int64_t)j * n;
     const double* Wj = L.bW.p + (int64_t)j * n;
@@ -906,22 +918,25 @@ void Engine::computeBorder(int l) {
       comm_.allReduceSum(L.Z.p, (size_t)nS, s);
       gatherAdd(Vj, L.sepRow.p, L.Z.p, sVj, nS, s, &launches_);
     }
-    // w1tmp = A11' \ W1 (transposed subdomain solves, :564-566) ;  sW = W2 - A12' w1tmp
-    if (nI) HY_CUDA(cudaMemsetAsync(w1tmp.p, 0, w1tmp.bytes(), s));
+    // W1t = A11' \ W1 (transposed subdomain solves, :564-566) ;  sW = W2 - A12' W1t
+    double* w1t = L.W1t.p + (int64_t)j * nI;
+    if (nI) HY_CUDA(cudaMemsetAsync(w1t, 0, (size_t)nI * sizeof(double), s));
     GemvArgs gt = L.a11.args();
     gt.xin = Wj;
     gt.gather = L.intRow.p;
-    gt.out = w1tmp.p;
+    gt.out = w1t;
     batchedGemvT(gt, L.a11.count, L.a11.npMax, s, &launches_);
     if (nS) HY_CUDA(cudaMemsetAsync(L.Z.p, 0, (size_t)nS * sizeof(double), s));
-    spmvT(L.p12.p, L.c12.p, L.v12.p, w1tmp.p, L.Z.p, nI, -1.0, s, &launches_);
+    spmvT(L.p12.p, L.c12.p, L.v12.p, w1t, L.Z.p, nI, -1.0, s, &launches_);
     if (L.sharded) comm_.allReduceSum(L.Z.p, (size_t)nS, s);
     gatherAdd(Wj, L.sepRow.p, L.Z.p, sWj, nS, s, &launches_);
-    gatherVec(Wj, L.intRow.p, L.W1.p + (int64_t)j * nI, nI, s, &launches_);
   }
-  // sC = C - W1' Q1 (Q1 still holds the owned subdomains only: partial sums over the ranks)
+  // sC = C - W1' Q1 (Q1 still holds the owned subdomains only: partial sums over the ranks); entry (i, j) is
+  // W_i[interior] . Q1_j, with W gathered on the fly
   for (int j = 0; j < bm; ++j)
-    multiDot(L.W1.p, nI, bm, L.Q1.p + (int64_t)j * nI, nI, bPartial_.p, bDots_.p + (size_t)j * bm, 0, s, &launches_);
+    for (int i = 0; i < bm; ++i)
+      multiDot(L.Q1.p + (int64_t)j * nI, nI, 1, L.bW.p + (int64_t)i * n, nI, bPartial_.p,
+               bDots_.p + (size_t)j * bm + i, 0, s, &launches_, L.intRow.p);
   if (nI == 0) HY_CUDA(cudaMemsetAsync(bDots_.p, 0, bDots_.bytes(), s));
   if (L.sharded) {
     comm_.allReduceSum(bDots_.p, (size_t)bm * bm, s);
@@ -998,29 +1013,34 @@ void Engine::applyLevel(int l, const double* B, double* X, const double* T) {
   cudaStream_t s = stream_;
   static const bool verboseApply = getenv("HYMLS_B200_VERBOSE_APPLY") != nullptr;
   ApplyTimer at(s, l, verboseApply && comm_.rank() == 0 && (stats_.num_apply_inverse % 16) == 5);
-  // x1 = A11 \ b1   (b1 gathered from B on the fly)
+  // x1 = A11 \ b1 (b1 gathered from B on the fly).  x1 is only used in A21 x1, so only the leading rows of every
+  // A11^-1 -- the interior nodes that separator rows couple to (LevelSym::sdNb) -- are computed and streamed;
+  // the interior part of the result comes from ONE full solve at the end, x1 = A11 \ (b1 - A12 x2).
   GemvArgs g = L.a11.args();
   g.xin = B;
   g.gather = L.intRow.p;
   g.out = L.x1.p;
   g.scatter = nullptr;
   g.mode = 0;
+  g.itemMat = L.a11.itemMatLead.p;
+  g.itemRow0 = L.a11.itemRow0Lead.p;
+  g.nrows = L.a11.rowLimit.p;
   const bool timeIt = timeA11_ && l == 0;
   if (timeIt) HY_CUDA(cudaEventRecord(evA_, s));
-  batchedGemv(g, L.a11.numItems, L.a11.npMax, s, &launches_);
+  batchedGemv(g, L.a11.numItemsLead, L.a11.npMax, s, &launches_);
   if (timeIt) {
     HY_CUDA(cudaEventRecord(evB_, s));
     HY_CUDA(cudaEventSynchronize(evB_));
     float ms = 0;
     HY_CUDA(cudaEventElapsedTime(&ms, evA_, evB_));
-    a11Ms_ += ms;
-    a11Launches_++;
+    a11LeadMs_ += ms;
   }
-  at.lap("A11 gemv 1");
+  at.lap("A11 gemv 1 (leading rows)");
   const int bm = borderM_;
   if (bm) {
-    // q = T - W1' x1 (Preconditioner.cpp:1006-1013); x1 is zero outside the owned subdomains
-    multiDot(L.W1.p, S.nI, bm, L.x1.p, S.nI, bPartial_.p, L.bQ.p, 0, s, &launches_);
+    // q = T - W1' (A11 \ b1) = T - (A11' \ W1)' b1 (Preconditioner.cpp:1006-1013); W1t is zero outside the
+    // owned subdomains
+    multiDot(L.W1t.p, S.nI, bm, B, S.nI, bPartial_.p, L.bQ.p, 0, s, &launches_, L.intRow.p);
     if (S.nI == 0) HY_CUDA(cudaMemsetAsync(L.bQ.p, 0, bm * sizeof(double), s));
     if (L.sharded) comm_.allReduceSum(L.bQ.p, (size_t)bm, s);
     axpby(T ? 1.0 : 0.0, T ? T : L.bQ.p, -1.0, L.bQ.p, bm, s, &launches_);
@@ -1098,14 +1118,15 @@ void Engine::applyLevel(int l, const double* B, double* X, const double* T) {
     householder(L.uniqStart.p, S.nuniq, L.what.p, L.Y.p, L.Y.p, nullptr, L.vsSol.p, X, L.sepRow.p, s, &launches_);
   }
   at.lap("householder back (+bcast)");
-  // y1 = A12 x2 ;  X[interior] = x1 - A11 \ y1
+  // y1 = A12 x2 ;  X[interior] = A11 \ (b1 - y1)
   spmv(L.p12.p, L.c12.p, L.v12.p, x2, L.y1.p, S.nI, 0.0, nullptr, nullptr, 1.0, s, &launches_);
-  g.xin = L.y1.p;
-  g.gather = nullptr;
-  g.xprev = L.x1.p;
+  g = L.a11.args();
+  g.xin = B;
+  g.gather = L.intRow.p;
+  g.xsub = L.y1.p;
   g.out = X;
   g.scatter = L.intRow.p;
-  g.mode = 1;
+  g.mode = 0;
   if (L.sharded) {  // owned interiors packed per rank, all-gathered, then exported
     g.out = L.xI.p;
     g.outOff = L.gatherOutOff.p;
@@ -1252,11 +1273,13 @@ void Engine::timeApply(int reps, double* msApply, double* msA11) {
   // second loop with per-launch events around the A11 kernel (serialises the stream: not used for msApply)
   timeA11_ = true;
   a11Ms_ = 0;
+  a11LeadMs_ = 0;
   a11Launches_ = 0;
   for (int i = 0; i < reps; ++i) applyDevice(bufB_.p, bufX_.p);
   HY_CUDA(cudaStreamSynchronize(stream_));
   timeA11_ = false;
   if (msA11) *msA11 = a11Launches_ ? a11Ms_ / a11Launches_ : 0.0;
+  stats_.ms_a11_lead = a11Launches_ ? a11LeadMs_ / a11Launches_ : 0.0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1620,20 +1643,25 @@ void Engine::getStats(hymls_b200_stats* st) {
     st->num_subdomains = S.nsd;
     st->num_blocks = S.nblk;
     st->sum_nsd_sq = S.sumNsq;
+    st->sum_nsd_nb = S.sumNNb;
     {
-      double own = 0;
-      for (int v : levels_[0]->a11.hN) own += (double)v * v;
-      if (levels_[0]->a11.hN.empty()) for (int sd : levels_[0]->ownSd) own += (double)S.sdN[sd] * S.sdN[sd];
-      st->bytes_a11_level0 = 16.0 * own;  // this rank's share when sharded
+      double own = 0, ownLead = 0;
+      for (int sd : levels_[0]->ownSd) {
+        own += (double)S.sdN[sd] * S.sdN[sd];
+        ownLead += (double)S.sdN[sd] * S.sdNb[sd];
+      }
+      st->bytes_a11_full_pass = 8.0 * own;             // this rank's share when sharded
+      st->bytes_a11_level0 = 8.0 * (own + ownLead);
     }
-    // algorithmic bytes of one ApplyInverse, summed over the levels
+    // algorithmic bytes of one ApplyInverse, summed over the levels; the A11 term is
+    // 8 (sum n^2 + sum n nb) since the first solve needs only the leading nb rows of every inverse
     double bytes = 0;
     for (auto& lp : levels_) {
       const LevelSym& T = lp->sym;
       double sb = 0;
       for (int b = 0; b < T.nblk; ++b) sb += 8.0 * (double)T.blkN[b] * T.blkN[b];
-      bytes += 16.0 * T.sumNsq + 12.0 * (double)(T.A12.nnz() + T.A21.nnz()) + 4.0 * (double)(T.nI + T.nS + 2) + sb +
-               2.0 * 12.0 * (double)T.nS * 2.0 + 8.0 * (10.0 * T.nI + 14.0 * T.nS);
+      bytes += 8.0 * (T.sumNsq + T.sumNNb) + 12.0 * (double)(T.A12.nnz() + T.A21.nnz()) +
+               4.0 * (double)(T.nI + T.nS + 2) + sb + 2.0 * 12.0 * (double)T.nS * 2.0 + 8.0 * (10.0 * T.nI + 14.0 * T.nS);
     }
     bytes += 8.0 * (double)coarseN_ * coarseN_;
     st->bytes_apply = bytes;

@@ -18,9 +18,13 @@ struct BatchedInverse {  // a set of dense inverses + the GEMV work list over th
   std::vector<int> hN, hNp;
   std::vector<int64_t> hMatOff, hVecOff;
   int count = 0, numItems = 0, npMax = 0;
+  // second work list over the leading `leadRows[m]` rows of every matrix (first solve of ApplyInverse)
+  DevBuf<int> rowLimit, itemMatLead, itemRow0Lead;
+  int numItemsLead = 0;
   // `applyMask` (optional, one flag per matrix): GEMV work items are created for flagged matrices only
   void setup(const std::vector<int>& n_, const std::vector<int>& np_, const std::vector<int64_t>& matOff_,
-             const std::vector<int64_t>& vecOff_, cudaStream_t s, const std::vector<char>* applyMask = nullptr);
+             const std::vector<int64_t>& vecOff_, cudaStream_t s, const std::vector<char>* applyMask = nullptr,
+             const std::vector<int>* leadRows = nullptr);
   GemvArgs args() const;
 };
 
@@ -77,9 +81,9 @@ struct Level {
   DevBuf<double> x1, y1, rhsS, Z, Y, vsRhs, vsSol;
   DevBuf<double> redValLast;  // reduced Schur values when this is the last level (kept for inspection)
   // bordered variant (BorderedOperator): V, W of this level in its row numbering (n_l x m), Q1 = A11^-1 V1,
-  // W1, the transformed separator border sW (V-sum positions zeroed), the border handed to the coarse
+  // W1t = A11^-T W1, the transformed separator border sW (V-sum positions zeroed), the border handed to the coarse
   // solver (cV, cW) and the border right-hand sides q (after the interior elimination) / Tc (next level's T)
-  DevBuf<double> bV, bW, Q1, W1, sV, sW, cV, cW, bQ, bT;
+  DevBuf<double> bV, bW, Q1, W1t, sV, sW, cV, cW, bQ, bT;
   std::vector<double> hC;     // C of this level (m x m, column major)
 };
 
@@ -163,7 +167,7 @@ class Engine {
   int64_t launches_ = 0;
   cudaEvent_t ev0_ = nullptr, ev1_ = nullptr, evA_ = nullptr, evB_ = nullptr;
   bool timeA11_ = false;
-  double a11Ms_ = 0;
+  double a11Ms_ = 0, a11LeadMs_ = 0;
   int a11Launches_ = 0;
 };
 

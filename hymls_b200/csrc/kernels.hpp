@@ -67,9 +67,11 @@ struct GemvArgs {
   const int64_t* matOff;   // offset of each matrix in A
   const int64_t* vecOff;   // offset of each matrix' segment in the packed vectors
   const int64_t* outOff;   // optional: offset of each matrix' segment in `out` (default: vecOff)
+  const int* nrows;        // optional: only rows [0, nrows[mat]) are computed (default: all n)
   const double* A;
   const double* xin;
   const int* gather;
+  const double* xsub;      // optional: x_sd[q] = xin[...] - xsub[p]
   const double* xprev;
   double* out;
   const int* scatter;
@@ -85,7 +87,7 @@ void scatterValues(const double* src, const int64_t* srcIdx, const int64_t* dstI
 void householder(const int* uniqStart, int nuniq, const double* w, const double* in, double* out, double* vsumOut,
                  const double* vsumIn, double* X, const int* sepRow, cudaStream_t s, int64_t* launches);
 void multiDot(const double* V, int64_t ldv, int k, const double* w, int64_t n, double* partial, double* h,
-              int accumulate, cudaStream_t s, int64_t* launches);
+              int accumulate, cudaStream_t s, int64_t* launches, const int* widx = nullptr);  // widx: w[widx[r]]
 int multiDotBlocks();
 void multiAxpy(const double* V, int64_t ldv, int k, const double* h, double* w, int64_t n, double sign,
                cudaStream_t s, int64_t* launches);

@@ -32,11 +32,38 @@ void buildLevelSym(LevelSym& L, const CartesianPartitioner& part, const std::vec
   L.intRow.resize(L.nI);
   L.sepRow.resize(L.nS);
   L.rowPos.assign(L.n, INT32_MIN);
-  for (int64_t p = 0; p < L.nI; ++p) {
-    int r = gid2row[H.intGid[p]];
-    if (r < 0 || L.rowPos[r] != INT32_MIN) throw Error(HYMLS_B200_ERR_ARG, "interior node not in map / listed twice");
-    L.intRow[p] = r;
-    L.rowPos[r] = (int)p;
+  // Interior ordering inside a subdomain: the nodes that separator rows couple to (the columns of A21) come
+  // first, in GID order, then the rest.  The first subdomain solve of ApplyInverse only feeds A21 x1, so it
+  // needs just this leading block of rows of A11^-1 (engine.cu:applyLevel).
+  {
+    std::vector<char> isInt(L.n, 0), hit(L.n, 0);
+    for (int64_t p = 0; p < L.nI; ++p) {
+      int r = gid2row[H.intGid[p]];
+      if (r < 0 || isInt[r]) throw Error(HYMLS_B200_ERR_ARG, "interior node not in map / listed twice");
+      isInt[r] = 1;
+    }
+    for (int64_t p = 0; p < L.nS; ++p) {
+      int r = gid2row[H.sepGid[p]];
+      if (r < 0) throw Error(HYMLS_B200_ERR_ARG, "separator node not in map / listed twice");
+      for (int64_t e = L.rowptr[r]; e < L.rowptr[r + 1]; ++e)
+        if (isInt[L.colidx[e]]) hit[L.colidx[e]] = 1;
+    }
+    L.sdNb.assign(H.nsd, 0);
+    L.sumNNb = 0;
+    for (int sd = 0; sd < H.nsd; ++sd) {
+      int64_t q = H.intPtr[sd];
+      for (int pass = 0; pass < 2; ++pass)
+        for (int64_t p = H.intPtr[sd]; p < H.intPtr[sd + 1]; ++p) {
+          int r = gid2row[H.intGid[p]];
+          if ((hit[r] != 0) == (pass == 0)) {
+            L.intRow[q] = r;
+            L.rowPos[r] = (int)q;
+            ++q;
+          }
+        }
+      for (int64_t p = H.intPtr[sd]; p < H.intPtr[sd + 1]; ++p) L.sdNb[sd] += hit[L.intRow[p]] ? 1 : 0;
+      L.sumNNb += (double)L.sdNb[sd] * (double)(H.intPtr[sd + 1] - H.intPtr[sd]);
+    }
   }
   for (int64_t p = 0; p < L.nS; ++p) {
     int r = gid2row[H.sepGid[p]];

@@ -33,6 +33,8 @@ struct LevelSym {
 
   // A11: one padded (np = roundup8(n)) row-major block per subdomain
   std::vector<int> sdN, sdNp;
+  std::vector<int> sdNb;        // leading interior nodes of sd that separator rows couple to (columns of A21)
+  double sumNNb = 0;            // sum n_sd * nb_sd
   std::vector<int64_t> a11Off;  // nsd+1, in doubles
   std::vector<int64_t> a11Src, a11Dst;
   int64_t ignoredInteriorCouplings = 0;  // entries between interiors of different subdomains

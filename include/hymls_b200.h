@@ -163,15 +163,21 @@ typedef struct {
   double sum_nsd_sq;            /* sum over subdomains of n_sd^2 (level 0), the roofline figure of SURVEY 8(d) */
   double bytes_apply;           /* algorithmic bytes of one ApplyInverse (all levels), SURVEY 8(d) formula */
   double flops_compute;         /* algorithmic flops of Compute (inversions: 2 n^3) */
-  double bytes_a11_level0;      /* 8 * sum n_sd^2 * 2 : the two A11 passes of one ApplyInverse */
+  double bytes_a11_level0;      /* this rank's level-0 A11^-1 bytes streamed by one ApplyInverse:
+                                   8 * sum (n_sd^2 + n_sd * nb_sd), full second solve + leading rows of the first */
   int64_t kernel_launches;      /* launches issued by this handle so far */
   double device_bytes;          /* device memory held */
+  double sum_nsd_nb;            /* sum n_sd * nb_sd (level 0): nb_sd = interior nodes that separator rows couple to;
+                                   the first subdomain solve of ApplyInverse needs only these rows of A11^-1 */
+  double bytes_a11_full_pass;   /* this rank's 8 * sum n_sd^2: one full pass over its level-0 inverses */
+  double ms_a11_lead;           /* set by hymls_b200_time_apply: CUDA-event time of the leading-rows pass */
 } hymls_b200_stats;
 int hymls_b200_get_stats(hymls_b200_t* h, hymls_b200_stats* st);
 
 /* Timed loop helpers used by bench.py: run ApplyInverse `reps` times on device-resident vectors and
    return the average CUDA-event time per call of (a) the whole call, (b) the dominant kernel
-   (batched A11^-1 apply, both passes). */
+   (batched A11^-1 apply, the full pass of the second subdomain solve; the shorter leading-rows pass of the
+   first solve is reported in hymls_b200_stats.ms_a11_lead). */
 int hymls_b200_time_apply(hymls_b200_t* h, int reps, double* ms_per_apply, double* ms_a11_kernel_per_launch);
 
 /* Test hook: copies a named device array of a level ("a11inv", "blkinv", "coarseinv", "redval", "v12",

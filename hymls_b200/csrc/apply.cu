@@ -174,30 +174,50 @@ void householder(const int* uniqStart, int nuniq, const double* w, const double*
 // ---------------------------------------------------------------------------------------------
 // small vector kernels of the Krylov loop
 // ---------------------------------------------------------------------------------------------
-// partial[i * nblk + b] = sum over rows of block b of V_i[r] * w[r],  i = 0..k-1   (one pass over w)
+// partial[i * nblk + b] = sum over rows of block b of V_i[r] * w[r],  i = 0..k-1.
+// The basis vectors are taken DOT_G at a time: one read of w[r] feeds DOT_G products with independent loads
+// in flight, and the block reduction is paid once per group instead of once per vector.
+static constexpr int DOT_G = 8;
 __global__ void __launch_bounds__(256)
 k_multi_dot(const double* __restrict__ V, int64_t ldv, int k, const double* __restrict__ w, int64_t n,
             double* __restrict__ partial, const int* __restrict__ widx) {
-  __shared__ double red[8];
+  __shared__ double red[DOT_G][8];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int i = 0; i < k; ++i) {
-    const double* v = V + (int64_t)i * ldv;
-    double s = 0.0;
-    if (widx) {
-      for (int64_t r = (int64_t)blockIdx.x * blockDim.x + tid; r < n; r += stride) s += v[r] * w[widx[r]];
+  for (int i0 = 0; i0 < k; i0 += DOT_G) {
+    const int ng = min(DOT_G, k - i0);
+    const double* __restrict__ v0 = V + (int64_t)i0 * ldv;
+    double acc[DOT_G];
+#pragma unroll
+    for (int g = 0; g < DOT_G; ++g) acc[g] = 0.0;
+    if (ng == DOT_G) {
+      for (int64_t r = (int64_t)blockIdx.x * blockDim.x + tid; r < n; r += stride) {
+        const double wv = widx ? w[widx[r]] : w[r];
+#pragma unroll
+        for (int g = 0; g < DOT_G; ++g) acc[g] += v0[(int64_t)g * ldv + r] * wv;
+      }
     } else {
-      for (int64_t r = (int64_t)blockIdx.x * blockDim.x + tid; r < n; r += stride) s += v[r] * w[r];
+      for (int64_t r = (int64_t)blockIdx.x * blockDim.x + tid; r < n; r += stride) {
+        const double wv = widx ? w[widx[r]] : w[r];
+#pragma unroll
+        for (int g = 0; g < DOT_G; ++g)
+          if (g < ng) acc[g] += v0[(int64_t)g * ldv + r] * wv;
+      }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) red[wid] = s;
-    __syncthreads();
-    if (wid == 0) {
-      s = lane < 8 ? red[lane] : 0.0;
+    for (int g = 0; g < DOT_G; ++g) {
+      double s = acc[g];
 #pragma unroll
-      for (int o = 4; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (lane == 0) partial[(int64_t)i * gridDim.x + blockIdx.x] = s;
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) red[g][wid] = s;
+    }
+    __syncthreads();
+    if (tid < DOT_G * 8) {
+      const int g = tid >> 3, j = tid & 7;
+      double s = red[g][j];
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o, 8);
+      if (j == 0 && g < ng) partial[(int64_t)(i0 + g) * gridDim.x + blockIdx.x] = s;
     }
     __syncthreads();
   }
@@ -232,20 +252,37 @@ void multiDot(const double* V, int64_t ldv, int k, const double* w, int64_t n, d
 }
 int multiDotBlocks() { return DOT_BLOCKS; }
 
-// w -= sum_i h[i] V_i
-__global__ void k_multi_axpy(const double* __restrict__ V, int64_t ldv, int k, const double* __restrict__ h,
-                             double* __restrict__ w, int64_t n, double sign) {
+// w += sign * sum_i h[i] V_i : coefficients in shared memory, four independent partial sums per row
+__global__ void __launch_bounds__(256)
+k_multi_axpy(const double* __restrict__ V, int64_t ldv, int k, const double* __restrict__ h,
+             double* __restrict__ w, int64_t n, double sign) {
+  extern __shared__ double sh[];
+  for (int i = threadIdx.x; i < k; i += blockDim.x) sh[i] = h[i];
+  __syncthreads();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) {
-    double s = 0.0;
-    for (int i = 0; i < k; ++i) s += h[i] * V[(int64_t)i * ldv + r];
-    w[r] += sign * s;
+    const double* __restrict__ v = V + r;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int i = 0;
+    for (; i + 8 <= k; i += 8) {
+      const double a0 = v[(int64_t)i * ldv], a1 = v[(int64_t)(i + 1) * ldv], a2 = v[(int64_t)(i + 2) * ldv],
+                   a3 = v[(int64_t)(i + 3) * ldv], a4 = v[(int64_t)(i + 4) * ldv], a5 = v[(int64_t)(i + 5) * ldv],
+                   a6 = v[(int64_t)(i + 6) * ldv], a7 = v[(int64_t)(i + 7) * ldv];
+      s0 += sh[i] * a0 + sh[i + 4] * a4;
+      s1 += sh[i + 1] * a1 + sh[i + 5] * a5;
+      s2 += sh[i + 2] * a2 + sh[i + 6] * a6;
+      s3 += sh[i + 3] * a3 + sh[i + 7] * a7;
+    }
+    for (; i < k; ++i) s0 += sh[i] * v[(int64_t)i * ldv];
+    w[r] += sign * ((s0 + s1) + (s2 + s3));
   }
 }
 void multiAxpy(const double* V, int64_t ldv, int k, const double* h, double* w, int64_t n, double sign,
                cudaStream_t s, int64_t* launches) {
   if (k == 0 || n == 0) return;
-  k_multi_axpy<<<DOT_BLOCKS, 256, 0, s>>>(V, ldv, k, h, w, n, sign);
+  if ((size_t)k * sizeof(double) > 48 * 1024)
+    throw Error(HYMLS_B200_ERR_UNSUPPORTED, "more than 6144 Krylov vectors in one orthogonalisation");
+  k_multi_axpy<<<DOT_BLOCKS, 256, (size_t)k * sizeof(double), s>>>(V, ldv, k, h, w, n, sign);
   ++*launches;
 }
 // y = a*x + b*y   (b == 0 : y = a*x, no read of y)

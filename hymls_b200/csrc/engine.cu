@@ -532,13 +532,26 @@ void Engine::uploadLevel(Level& L) {
 // ---------------------------------------------------------------------------------------------
 // Compute
 // ---------------------------------------------------------------------------------------------
-static void checkInfo(DevBuf<int>& info, cudaStream_t s, const std::string& what) {
+// Collective when sharded: every rank learns whether ANY rank met a zero pivot, so that all of them leave
+// Compute with the same error instead of one rank throwing while the others wait in the next collective.
+void Engine::checkInfo(const std::string& what) {
+  cudaStream_t s = stream_;
   int h = 0;
-  HY_CUDA(cudaMemcpyAsync(&h, info.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+  HY_CUDA(cudaMemcpyAsync(&h, info_.p, sizeof(int), cudaMemcpyDeviceToHost, s));
   HY_CUDA(cudaStreamSynchronize(s));
-  if (h != 0)
+  bool elsewhere = false;
+  if (comm_.active()) {
+    flag_.alloc(1);
+    double f = h != 0 ? 1.0 : 0.0;
+    HY_CUDA(cudaMemcpyAsync(flag_.p, &f, sizeof(double), cudaMemcpyHostToDevice, s));
+    comm_.allReduceSum(flag_.p, 1, s);
+    HY_CUDA(cudaMemcpyAsync(&f, flag_.p, sizeof(double), cudaMemcpyDeviceToHost, s));
+    HY_CUDA(cudaStreamSynchronize(s));
+    elsewhere = (f != 0.0 && h == 0);
+  }
+  if (h != 0 || elsewhere)
     throw Error(HYMLS_B200_ERR_NUMERIC,
-                what + ": zero pivot (matrix " + std::to_string(h - 1) +
+                what + ": zero pivot (" + (elsewhere ? std::string("on another rank") : "matrix " + std::to_string(h - 1)) +
                     " is exactly singular). For 3D Stokes-C on the Cartesian partitioner the reference's pressure "
                     "'tube' blocks are identically zero; see 'Eliminate Tube Pressures With Velocities' in DESIGN.md");
 }
@@ -580,6 +593,33 @@ static void invertRange(BatchedInverse& B, int m0, int m1, double* W, DevBuf<int
   invertBatched(W, B.F.p + B.hMatOff[m0], relOff.p, B.n.p + m0, B.np.p + m0, cnt, npMax, piv.p, perm.p,
                 piv.p + (size_t)cnt * npMax, info, s, launches);
   HY_CUDA(cudaStreamSynchronize(s));  // relOff is reused by the next chunk
+}
+
+// the same for an arbitrary subset `list` of the matrices of `B` (absolute offsets; W and F share the layout)
+static void invertSubset(BatchedInverse& B, const std::vector<int>& list, size_t lo, size_t hi, double* Wbase,
+                         DevBuf<int>& piv, DevBuf<int>& perm, DevBuf<int64_t>& offBuf, DevBuf<int>& nBuf,
+                         DevBuf<int>& npBuf, int* info, cudaStream_t s, int64_t* launches) {
+  const int cnt = (int)(hi - lo);
+  if (cnt <= 0) return;
+  int npMax = 0;
+  std::vector<int64_t> off(cnt);
+  std::vector<int> n(cnt), np(cnt);
+  for (int k = 0; k < cnt; ++k) {
+    const int m = list[lo + k];
+    off[k] = B.hMatOff[m];
+    n[k] = B.hN[m];
+    np[k] = B.hNp[m];
+    npMax = std::max(npMax, np[k]);
+  }
+  if (npMax == 0) return;
+  offBuf.upload(off, s);
+  nBuf.upload(n, s);
+  npBuf.upload(np, s);
+  piv.alloc((size_t)cnt * (npMax + 128));
+  perm.alloc((size_t)cnt * npMax);
+  invertBatched(Wbase, B.F.p, offBuf.p, nBuf.p, npBuf.p, cnt, npMax, piv.p, perm.p, piv.p + (size_t)cnt * npMax, info,
+                s, launches);
+  HY_CUDA(cudaStreamSynchronize(s));  // the host vectors and offBuf are reused by the next chunk
 }
 
 struct PhaseTimer {
@@ -633,7 +673,7 @@ void Engine::computeLevel(int l) {
       for (int k = k0; k < k1; ++k) stats_.flops_compute += 2.0 * std::pow((double)L.a11.hN[k], 3);
       k0 = k1;
     }
-    checkInfo(info_, s, "subdomain solver (A11) of level " + std::to_string(l));
+    checkInfo("subdomain solver (A11) of level " + std::to_string(l));
   }
   pt.lap("A11 fill + inversion");
   if (borderM_ > 0) {
@@ -775,14 +815,24 @@ void Engine::computeLevel(int l) {
   // separator blocks (SchurPreconditioner::Compute :284-291)
   {
     DevBuf<int64_t>& relOff = relOff_;
-    int b0 = 0;
-    while (b0 < S.nblk) {
-      int b1 = std::min(S.nblk, b0 + 16384);
-      invertRange(L.blk, b0, b1, blkW.p + S.blkOff[b0], piv_, perm_, relOff, info_.p, s, &launches_);
-      b0 = b1;
+    if (!L.sharded) {
+      int b0 = 0;
+      while (b0 < S.nblk) {
+        int b1 = std::min(S.nblk, b0 + 16384);
+        invertRange(L.blk, b0, b1, blkW.p + S.blkOff[b0], piv_, perm_, relOff, info_.p, s, &launches_);
+        b0 = b1;
+      }
+    } else {
+      // a rank applies only the blocks whose owner subdomain it owns (uploadLevel): it inverts only those
+      std::vector<int> mine;
+      for (int b = 0; b < S.nblk; ++b)
+        if (L.sdRank[S.blkOwnerSd[b]] == comm_.rank()) mine.push_back(b);
+      for (size_t lo = 0; lo < mine.size(); lo += 16384)
+        invertSubset(L.blk, mine, lo, std::min(mine.size(), lo + 16384), blkW.p, piv_, perm_, relOff, subsetN_,
+                     subsetNp_, info_.p, s, &launches_);
     }
     for (int b = 0; b < S.nblk; ++b) stats_.flops_compute += 2.0 * std::pow((double)S.blkN[b], 3);
-    checkInfo(info_, s, "separator block of level " + std::to_string(l));
+    checkInfo("separator block of level " + std::to_string(l));
   }
   pt.lap("separator block inversion");
   // reduced Schur complement: drop (RelDropDiag, ComputeNextLevel :548), then next level or coarse solver
@@ -850,7 +900,7 @@ void Engine::augmentAndInvertCoarse(int n, int np, const double* bV, const doubl
   coarseSol_.alloc(n + bm);
   DevBuf<int64_t>& relOff = relOff_;
   invertRange(coarse_, 0, 1, work_.p, piv_, perm_, relOff, info_.p, s, &launches_);
-  checkInfo(info_, s, what);
+  checkInfo(what);
   stats_.flops_compute += 2.0 * std::pow((double)(n + bm), 3);
 }
 

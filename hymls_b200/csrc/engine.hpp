@@ -122,6 +122,7 @@ class Engine {
   void applyLevel(int l, const double* B, double* X, const double* T = nullptr);  // device pointers
   void computeLevel(int l);
   void computeBorder(int l);
+  void checkInfo(const std::string& what);
   void computeCoarse(const int64_t* ptr, const int* col, double* val, int n, const std::vector<gidx>& rowGid,
                      const double* bV = nullptr, const double* bW = nullptr, const std::vector<double>* bC = nullptr);
   void augmentAndInvertCoarse(int n, int np, const double* bV, const double* bW, const std::vector<double>* bC,
@@ -154,9 +155,10 @@ class Engine {
   DevBuf<double> bS_, bTin_, bPartial_, bDots_, bC_, bC0_;
   // scratch
   DevBuf<double> work_;      // inversion workspace
-  DevBuf<int> piv_, perm_, info_;
+  DevBuf<int> piv_, perm_, info_, subsetN_, subsetNp_;
   DevBuf<double> wsC_, wsSV_, wsSLL_, diagScratch_, blkW_, red2_, blk2_;
   DevBuf<int64_t> relOff_;
+  DevBuf<double> flag_;
   DevBuf<double> bufB_, bufX_;  // staging for host vectors
   DevBuf<double> bufG_;          // all-gather target of the distributed-vector entry point
   // Krylov workspace

@@ -179,9 +179,11 @@ k_gj_panel(double* __restrict__ W, const int64_t* __restrict__ off, const int* _
 // rank-1 update runs; each finished sub-panel updates the rest of the panel in global memory (L2) once.
 // Falls back to k_gj_panel when the active part of a matrix does not fit (rows > GJ_SMEM_ROWS).
 // ---------------------------------------------------------------------------------------------
-static constexpr int GJ_SW = 8;            // sub-panel width
-static constexpr int GJ_SMEM_ROWS = 3072;  // 8 * 3072 * 8 B = 192 KB
+static constexpr int GJ_SW = 8;             // sub-panel width
+static constexpr int GJ_SMEM_ROWS = 3072;   // 8 * 3072 * 8 B = 192 KB
+static constexpr int GJ_SMEM_ROWS4 = 6144;  // 4-column sub-panels for taller panels (single large matrices)
 
+template <int SW>
 __global__ void __launch_bounds__(GJ_PANEL_T)
 k_gj_panel_smem(double* __restrict__ W, const int64_t* __restrict__ off, const int* __restrict__ npArr,
                 int* __restrict__ pivAll, int npMax, int k0, int* __restrict__ info, int rowsCap, int rowsMin) {
@@ -196,9 +198,9 @@ k_gj_panel_smem(double* __restrict__ W, const int64_t* __restrict__ off, const i
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   constexpr int NW = GJ_PANEL_T / 32;
 
-  extern __shared__ double sS[];  // [GJ_SW][rs] sub-panel, column major
-  __shared__ double sU[GJ_SW];
-  __shared__ double sUn[GJ_SW][GJ_NB];  // freshly solved U rows of the columns right of the sub-panel
+  extern __shared__ double sS[];  // [SW][rs] sub-panel, column major
+  __shared__ double sU[SW];
+  __shared__ double sUn[SW][GJ_NB];  // freshly solved U rows of the columns right of the sub-panel
   __shared__ double sKK[GJ_NB][GJ_NB + 1];
   __shared__ double sLinv[GJ_NB][GJ_NB + 1];
   __shared__ double sDinv[GJ_NB][GJ_NB + 1];
@@ -208,8 +210,8 @@ k_gj_panel_smem(double* __restrict__ W, const int64_t* __restrict__ off, const i
   __shared__ double sPivVal;
   const int rs = (np - k0) | 1;  // odd stride: column-wise and row-wise accesses both conflict-light
 
-  for (int c0 = k0; c0 < k0 + nb; c0 += GJ_SW) {
-    const int w = min(GJ_SW, k0 + nb - c0);
+  for (int c0 = k0; c0 < k0 + nb; c0 += SW) {
+    const int w = min(SW, k0 + nb - c0);
     const int R = np - c0;  // active rows of this sub-panel (local row r <-> global row c0 + r)
     // load
     for (int e = tid; e < R * w; e += GJ_PANEL_T) {
@@ -306,9 +308,9 @@ k_gj_panel_smem(double* __restrict__ W, const int64_t* __restrict__ off, const i
     if (nRight > 0) {
       if (tid < nRight) {
         const int col = c0 + w + tid;
-        double u[GJ_SW];
+        double u[SW];
 #pragma unroll
-        for (int i = 0; i < GJ_SW; ++i) {
+        for (int i = 0; i < SW; ++i) {
           if (i < w) {
             double x = M[(int64_t)(c0 + i) * np + col];
             for (int t = 0; t < i; ++t) x -= sS[t * rs + i] * u[t];
@@ -320,14 +322,14 @@ k_gj_panel_smem(double* __restrict__ W, const int64_t* __restrict__ off, const i
       }
       __syncthreads();
       for (int r = w + tid; r < R; r += GJ_PANEL_T) {
-        double l[GJ_SW];
+        double l[SW];
 #pragma unroll
-        for (int t = 0; t < GJ_SW; ++t) l[t] = t < w ? sS[t * rs + r] : 0.0;
+        for (int t = 0; t < SW; ++t) l[t] = t < w ? sS[t * rs + r] : 0.0;
         double* row = M + (int64_t)(c0 + r) * np + c0 + w;
         for (int q = 0; q < nRight; ++q) {
           double x = row[q];
 #pragma unroll
-          for (int t = 0; t < GJ_SW; ++t) x -= l[t] * sUn[t][q];
+          for (int t = 0; t < SW; ++t) x -= l[t] * sUn[t][q];
           row[q] = x;
         }
       }
@@ -818,8 +820,10 @@ void invertBatched(double* W, double* F, const int64_t* dOff, const int* dN, con
   static bool attrSet = false, permAttrSet = false;
   if (!attrSet) {
     HY_CUDA(cudaFuncSetAttribute(k_gj_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GJ_UPD_SMEM));
-    HY_CUDA(cudaFuncSetAttribute(k_gj_panel_smem, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)((size_t)GJ_SW * (GJ_SMEM_ROWS | 1) * sizeof(double))));
+    HY_CUDA(cudaFuncSetAttribute(k_gj_panel_smem<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)((size_t)8 * (GJ_SMEM_ROWS | 1) * sizeof(double))));
+    HY_CUDA(cudaFuncSetAttribute(k_gj_panel_smem<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)((size_t)4 * (GJ_SMEM_ROWS4 | 1) * sizeof(double))));
     HY_CUDA(cudaFuncSetAttribute(k_gj_panel_full, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)((size_t)GJ_NB * (GJ_FULL_ROWS | 1) * sizeof(double))));
     attrSet = true;
@@ -840,13 +844,19 @@ void invertBatched(double* W, double* F, const int64_t* dOff, const int* dN, con
       ++*launches;
     }
     if (activeMax > GJ_FULL_ROWS) {
-      const size_t psm = (size_t)GJ_SW * ((std::min(activeMax, GJ_SMEM_ROWS)) | 1) * sizeof(double);
-      k_gj_panel_smem<<<count, GJ_PANEL_T, psm, s>>>(W, dOff, dNp, dPiv, npMax, k0, dInfo, GJ_SMEM_ROWS,
-                                                     GJ_FULL_ROWS);
+      const size_t psm = (size_t)8 * ((std::min(activeMax, GJ_SMEM_ROWS)) | 1) * sizeof(double);
+      k_gj_panel_smem<8><<<count, GJ_PANEL_T, psm, s>>>(W, dOff, dNp, dPiv, npMax, k0, dInfo, GJ_SMEM_ROWS,
+                                                        GJ_FULL_ROWS);
       ++*launches;
     }
     if (activeMax > GJ_SMEM_ROWS) {
-      k_gj_panel<<<count, GJ_PANEL_T, 0, s>>>(W, dOff, dNp, dPiv, npMax, k0, dInfo, GJ_SMEM_ROWS);
+      const size_t psm = (size_t)4 * ((std::min(activeMax, GJ_SMEM_ROWS4)) | 1) * sizeof(double);
+      k_gj_panel_smem<4><<<count, GJ_PANEL_T, psm, s>>>(W, dOff, dNp, dPiv, npMax, k0, dInfo, GJ_SMEM_ROWS4,
+                                                        GJ_SMEM_ROWS);
+      ++*launches;
+    }
+    if (activeMax > GJ_SMEM_ROWS4) {
+      k_gj_panel<<<count, GJ_PANEL_T, 0, s>>>(W, dOff, dNp, dPiv, npMax, k0, dInfo, GJ_SMEM_ROWS4);
       ++*launches;
     }
     k_gj_swaplist<<<(count + 3) / 4, 128, 0, s>>>(dNp, dPiv, npMax, k0, count, rowsT, origT);

@@ -241,8 +241,14 @@ void Engine::initialize() {
       std::fill(gid2row.begin(), gid2row.end(), -1);
     }
     for (int64_t r = 0; r < S.n; ++r) gid2row[S.rowGid[r]] = (int)r;
+    auto tp0 = std::chrono::steady_clock::now();
     part.partition();
+    auto tp1 = std::chrono::steady_clock::now();
     buildLevelSym(S, part, gid2row);
+    if (getenv("HYMLS_B200_VERBOSE"))
+      fprintf(stderr, "[hymls_b200] level %d initialize: partition %.3f s, symbolic %.3f s\n", l,
+              std::chrono::duration<double>(tp1 - tp0).count(),
+              std::chrono::duration<double>(std::chrono::steady_clock::now() - tp1).count());
     // ownership: every level is sharded by the reference's subdomain -> rank map of that level
     // (BasePartitioner::CreatePIDMap); with fewer subdomains than ranks some ranks own nothing there
     L.ownSd.clear();
@@ -1694,6 +1700,8 @@ void Engine::getStats(hymls_b200_stats* st) {
     st->num_blocks = S.nblk;
     st->sum_nsd_sq = S.sumNsq;
     st->sum_nsd_nb = S.sumNNb;
+    st->interior_couplings = 0;
+    for (auto& lp : levels_) st->interior_couplings += lp->sym.ignoredInteriorCouplings;
     {
       double own = 0, ownLead = 0;
       for (int sd : levels_[0]->ownSd) {

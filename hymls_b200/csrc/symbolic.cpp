@@ -1,3 +1,6 @@
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include "symbolic.hpp"
 
 #include <algorithm>
@@ -12,7 +15,18 @@ static const double SMALL_ENTRY = 1e-14;  // HYMLS_SMALL_ENTRY, src/HYMLS_Macros
 static inline int roundUp8(int n) { return (n + 7) & ~7; }
 static inline double hsign(double x) { return (x < 0) ? -1.0 : (x > 0 ? 1.0 : 0.0); }  // Householder.cpp:15-18
 
+struct SymTimer {
+  bool on = getenv("HYMLS_B200_VERBOSE_SYM") != nullptr;
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  void lap(const char* what) {
+    if (!on) return;
+    auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[hymls_b200 sym] %-40s %.3f s\n", what, std::chrono::duration<double>(t1 - t0).count());
+    t0 = t1;
+  }
+};
 void buildLevelSym(LevelSym& L, const CartesianPartitioner& part, const std::vector<int>& gid2row) {
+  SymTimer st;
   std::vector<char> present;
   if (L.level > 0) {
     present.assign(gid2row.size(), 0);
@@ -28,6 +42,7 @@ void buildLevelSym(LevelSym& L, const CartesianPartitioner& part, const std::vec
     throw Error(HYMLS_B200_ERR_ARG, "partition does not cover the row map of level " + std::to_string(L.level) +
                                         " (interior " + std::to_string(L.nI) + " + separators " +
                                         std::to_string(L.nS) + " != " + std::to_string(L.n) + ")");
+  st.lap("before: orderings");
   // ---- orderings ----
   L.intRow.resize(L.nI);
   L.sepRow.resize(L.nS);
@@ -71,6 +86,7 @@ void buildLevelSym(LevelSym& L, const CartesianPartitioner& part, const std::vec
     L.sepRow[p] = r;
     L.rowPos[r] = -(int)p - 1;
   }
+  st.lap("before: A11 blocks");
   // ---- A11 blocks ----
   L.sdN.resize(L.nsd);
   L.sdNp.resize(L.nsd);
@@ -85,6 +101,7 @@ void buildLevelSym(LevelSym& L, const CartesianPartitioner& part, const std::vec
     L.sumNsq += (double)n * n;
     for (int64_t p = H.intPtr[sd]; p < H.intPtr[sd + 1]; ++p) sdOfInt[p] = sd;
   }
+  st.lap("before: split the matrix into A11");
   // ---- split the matrix into A11 (dense scatter list), A12, A21, A22 ----
   L.A12.ptr.assign(L.nI + 1, 0);
   L.A21.ptr.assign(L.nS + 1, 0);
@@ -156,6 +173,7 @@ void buildLevelSym(LevelSym& L, const CartesianPartitioner& part, const std::vec
       }
     }
   }
+  st.lap("before: group instances, per-subdomain separator lists");
   // ---- group instances, per-subdomain separator lists ----
   L.sdM.resize(L.nsd);
   L.sdRowPtr.assign(L.nsd + 1, 0);
@@ -185,6 +203,7 @@ void buildLevelSym(LevelSym& L, const CartesianPartitioner& part, const std::vec
     L.sdRowPtr[sd + 1] = L.sdRowPtr[sd] + m;
     L.sdInstPtr[sd + 1] = (int64_t)L.instLoc.size();
   }
+  st.lap("before: blocks: per owner subdomain");
   // ---- blocks: per owner subdomain, linked sets among the groups it owns (InitializeBlocks :301-340) ----
   L.uniqBlk.assign(L.nuniq, -1);
   L.uniqBlkOff.assign(L.nuniq, 0);
@@ -223,6 +242,7 @@ void buildLevelSym(LevelSym& L, const CartesianPartitioner& part, const std::vec
     }
   }
   L.nblk = (int)L.blkN.size();
+  st.lap("before: per-subdomain local sparse pieces");
   // ---- per-subdomain local sparse pieces (Construct11 / Construct22 index work) ----
   {
     const int64_t totalRows = L.sdRowPtr[L.nsd];
@@ -297,6 +317,7 @@ void buildLevelSym(LevelSym& L, const CartesianPartitioner& part, const std::vec
       }
     }
   }
+  st.lap("before: reduced Schur pattern on the V-sums");
   // ---- reduced Schur pattern on the V-sums: union of per-subdomain cliques (:737-787) ----
   {
     std::vector<std::vector<int>> rows(L.nuniq);
@@ -317,6 +338,7 @@ void buildLevelSym(LevelSym& L, const CartesianPartitioner& part, const std::vec
     L.redCol.resize(L.redPtr[L.nuniq]);
     for (int u = 0; u < L.nuniq; ++u) std::copy(rows[u].begin(), rows[u].end(), L.redCol.begin() + L.redPtr[u]);
   }
+  st.lap("before: Householder reflectors from the test vector");
   // ---- Householder reflectors from the test vector (InitializeOT :384-467, Householder::Construct) ----
   if ((int64_t)L.testVector.size() != L.n) L.testVector.assign(L.n, 1.0);
   L.what.assign(L.nS, 0.0);
@@ -357,6 +379,7 @@ void buildLevelSym(LevelSym& L, const CartesianPartitioner& part, const std::vec
     // next level test vector = V-sum part of H*tv with H = 2ww'-I (ComputeNextLevel :569-573)
     L.nextTestVector[u] = 2.0 * L.what[a] * dotv - L.testVector[L.sepRow[a]];
   }
+  st.lap("reflectors");
 }
 
 }  // namespace hymls

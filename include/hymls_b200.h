@@ -171,6 +171,9 @@ typedef struct {
                                    the first subdomain solve of ApplyInverse needs only these rows of A11^-1 */
   double bytes_a11_full_pass;   /* this rank's 8 * sum n_sd^2: one full pass over its level-0 inverses */
   double ms_a11_lead;           /* set by hymls_b200_time_apply: CUDA-event time of the leading-rows pass */
+  int64_t interior_couplings;   /* matrix entries between interiors of DIFFERENT subdomains, all levels: must be 0
+                                   for a correct domain decomposition (Tester::isDDcorrect, src/HYMLS_Tester.cpp:253-455);
+                                   such entries would be ignored by the subdomain solvers */
 } hymls_b200_stats;
 int hymls_b200_get_stats(hymls_b200_t* h, hymls_b200_stats* st);
 

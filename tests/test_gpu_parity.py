@@ -190,23 +190,36 @@ def test_recompute_with_new_values_same_pattern():
     assert rel(P.ApplyInverse(v), O2.apply_inverse(v)) < TOL_STOKES
 
 
-def test_large_problem_properties():
-    """32^3 Stokes (131k rows, 512 subdomains): residual reduction of the preconditioned solve and
-    agreement of device-resident and host-buffer ApplyInverse."""
+@pytest.mark.parametrize("nx,sx,cx,extra", [
+    (32, 4, 2, {"Eliminate_Tube_Pressures_With_Velocities": True}),
+    (64, 8, 4, {"Partitioner": "Skew Cartesian"}),        # the bench workload at 1/8 of its size (1296 subdomains)
+])
+def test_large_problem_properties(nx, sx, cx, extra):
+    """Sizes the oracle cannot reach in seconds: size-independent properties -- linearity, agreement of the
+    device-resident and host-buffer ApplyInverse, residual reduction of the preconditioned solve, a clean
+    domain decomposition and repeatability of Compute."""
     import torch
-    p = dictify(make_params("Stokes-C", 3, 32, 4, 2, 2, Eliminate_Tube_Pressures_With_Velocities=True))
+    p = dictify(make_params("Stokes-C", 3, nx, sx, 2, cx, **extra))
     p["Solver"] = {"Krylov Method": "GMRES", "Initial Vector": "Zero",
                    "Iterative Solver": {"Maximum Iterations": 300, "Convergence Tolerance": 1e-8}}
-    A = -hb.galeri.create_matrix("Stokes-C", 3, 32)
+    A = -hb.galeri.create_matrix("Stokes-C", 3, nx)
     P = hb.Preconditioner(A, p, hb.galeri.create_testvector(A))
     P.Initialize(); P.Compute()
+    assert P.Stats()["interior_couplings"] == 0
     n = A.shape[0]
-    xex = np.random.default_rng(0).uniform(-1, 1, n)
+    rng = np.random.default_rng(0)
+    xex = rng.uniform(-1, 1, n)
     b = A @ xex
     xh = P.ApplyInverse(b)
     xd = P.ApplyInverse(torch.from_numpy(b).cuda()).cpu().numpy()
     assert np.array_equal(xh, xd)          # same kernels, same order: bitwise identical
+    c = rng.uniform(-1, 1, n)
+    assert rel(P.ApplyInverse(2.0 * b - 3.0 * c), 2.0 * xh - 3.0 * P.ApplyInverse(c)) < 1e-11   # linearity
+    # the preconditioner inverts the matrix approximately: one application reduces the error
+    assert np.linalg.norm(xh - xex) < np.linalg.norm(xex)
     S = hb.Solver(P)
     x = S.ApplyInverse(b)
     assert S.info["converged"]
     assert np.linalg.norm(A @ x - b) / np.linalg.norm(b) < 2e-8
+    P.Compute()                             # recompute: the same factors, bit for bit
+    assert np.array_equal(P.ApplyInverse(b), xh)

@@ -5,6 +5,9 @@
 #include <cmath>
 #include <cstring>
 #include <random>
+#include <thread>
+
+#include "hostpar.hpp"
 
 namespace hymls {
 
@@ -205,6 +208,11 @@ void Engine::initialize() {
   auto t0 = std::chrono::steady_clock::now();
   ParameterList levelParams = params_.deepCopy();
   levels_.resize(1);
+  // the symbolic phase is threaded on the host; ranks of one node share its cores
+  if (!getenv("HYMLS_B200_HOST_THREADS")) {
+    const unsigned hw = std::thread::hardware_concurrency();
+    setHostThreads((int)std::max(1u, std::min(16u, (hw ? hw : 1u) / (unsigned)std::max(1, comm_.size()))));
+  }
   const int nlev = std::max(maxLevel_, 1);
   std::vector<int> gid2row;
   for (int l = 0; l < nlev; ++l) {

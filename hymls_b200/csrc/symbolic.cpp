@@ -2,6 +2,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include "symbolic.hpp"
+#include "hostpar.hpp"
 
 #include <algorithm>
 #include <cmath>
@@ -9,6 +10,15 @@
 #include "../../include/hymls_b200.h"
 
 namespace hymls {
+
+static int g_hostThreads = 0;
+int hostThreads() {
+  if (g_hostThreads > 0) return g_hostThreads;
+  if (const char* e = getenv("HYMLS_B200_HOST_THREADS")) return std::max(1, atoi(e));
+  const unsigned hw = std::thread::hardware_concurrency();
+  return (int)std::max(1u, std::min(16u, hw ? hw : 1u));
+}
+void setHostThreads(int n) { g_hostThreads = n > 0 ? n : 0; }
 
 static const double SMALL_ENTRY = 1e-14;  // HYMLS_SMALL_ENTRY, src/HYMLS_Macros.hpp:29
 
@@ -107,71 +117,92 @@ void buildLevelSym(LevelSym& L, const CartesianPartitioner& part, const std::vec
   L.A21.ptr.assign(L.nS + 1, 0);
   L.A22.ptr.assign(L.nS + 1, 0);
   L.ignoredInteriorCouplings = 0;
-  for (int pass = 0; pass < 2; ++pass) {
-    if (pass == 1) {
-      for (int64_t p = 0; p < L.nI; ++p) L.A12.ptr[p + 1] += L.A12.ptr[p];
-      for (int64_t p = 0; p < L.nS; ++p) L.A21.ptr[p + 1] += L.A21.ptr[p];
-      for (int64_t p = 0; p < L.nS; ++p) L.A22.ptr[p + 1] += L.A22.ptr[p];
-      L.A12.col.resize(L.A12.ptr[L.nI]);
-      L.A12.src.resize(L.A12.ptr[L.nI]);
-      L.A21.col.resize(L.A21.ptr[L.nS]);
-      L.A21.src.resize(L.A21.ptr[L.nS]);
-      L.A22.col.resize(L.A22.ptr[L.nS]);
-      L.A22.src.resize(L.A22.ptr[L.nS]);
-    }
-    std::vector<int64_t> f12, f21, f22;
-    if (pass == 1) {
-      f12.assign(L.A12.ptr.begin(), L.A12.ptr.end() - 1);
-      f21.assign(L.A21.ptr.begin(), L.A21.ptr.end() - 1);
-      f22.assign(L.A22.ptr.begin(), L.A22.ptr.end() - 1);
-    }
-    for (int64_t p = 0; p < L.nI; ++p) {
-      int r = L.intRow[p];
-      int sd = sdOfInt[p];
-      for (int64_t e = L.rowptr[r]; e < L.rowptr[r + 1]; ++e) {
-        int cp = L.rowPos[L.colidx[e]];
-        if (cp >= 0) {
-          if (sdOfInt[cp] == sd) {
-            if (pass == 1) {
-              int64_t li = p - H.intPtr[sd], lj = cp - H.intPtr[sd];
-              L.a11Src.push_back(e);
-              L.a11Dst.push_back(L.a11Off[sd] + li * L.sdNp[sd] + lj);
-            }
-          } else if (pass == 0) {
-            L.ignoredInteriorCouplings++;
-          }
-        } else {
-          int ps = -cp - 1;
-          if (pass == 0) {
-            L.A12.ptr[p + 1]++;
+  {
+    // counting pass (parallel over rows), prefix sums, fill pass (every row writes its own slots, so the
+    // arrays are identical to a sequential sweep whatever the thread count)
+    std::vector<int64_t> a11Ptr(L.nI + 1, 0);
+    std::vector<int64_t> ignoredPerThread(64, 0);
+    parallelFor(L.nI, [&](int64_t p0, int64_t p1, int t) {
+      int64_t ignored = 0;
+      for (int64_t p = p0; p < p1; ++p) {
+        const int r = L.intRow[p], sd = sdOfInt[p];
+        int64_t c11 = 0, c12 = 0;
+        for (int64_t e = L.rowptr[r]; e < L.rowptr[r + 1]; ++e) {
+          const int cp = L.rowPos[L.colidx[e]];
+          if (cp >= 0) {
+            if (sdOfInt[cp] == sd) ++c11; else ++ignored;
           } else {
-            L.A12.col[f12[p]] = ps;
-            L.A12.src[f12[p]++] = e;
+            ++c12;
           }
         }
+        a11Ptr[p + 1] = c11;
+        L.A12.ptr[p + 1] = c12;
       }
+      ignoredPerThread[t & 63] += ignored;
+    });
+    for (int64_t v : ignoredPerThread) L.ignoredInteriorCouplings += v;
+    parallelFor(L.nS, [&](int64_t p0, int64_t p1, int) {
+      for (int64_t p = p0; p < p1; ++p) {
+        const int r = L.sepRow[p];
+        int64_t c21 = 0, c22 = 0;
+        for (int64_t e = L.rowptr[r]; e < L.rowptr[r + 1]; ++e) {
+          if (L.rowPos[L.colidx[e]] >= 0) ++c21; else ++c22;
+        }
+        L.A21.ptr[p + 1] = c21;
+        L.A22.ptr[p + 1] = c22;
+      }
+    });
+    for (int64_t p = 0; p < L.nI; ++p) {
+      L.A12.ptr[p + 1] += L.A12.ptr[p];
+      a11Ptr[p + 1] += a11Ptr[p];
     }
     for (int64_t p = 0; p < L.nS; ++p) {
-      int r = L.sepRow[p];
-      for (int64_t e = L.rowptr[r]; e < L.rowptr[r + 1]; ++e) {
-        int cp = L.rowPos[L.colidx[e]];
-        if (cp >= 0) {
-          if (pass == 0) {
-            L.A21.ptr[p + 1]++;
+      L.A21.ptr[p + 1] += L.A21.ptr[p];
+      L.A22.ptr[p + 1] += L.A22.ptr[p];
+    }
+    L.A12.col.resize(L.A12.ptr[L.nI]);
+    L.A12.src.resize(L.A12.ptr[L.nI]);
+    L.A21.col.resize(L.A21.ptr[L.nS]);
+    L.A21.src.resize(L.A21.ptr[L.nS]);
+    L.A22.col.resize(L.A22.ptr[L.nS]);
+    L.A22.src.resize(L.A22.ptr[L.nS]);
+    L.a11Src.resize(a11Ptr[L.nI]);
+    L.a11Dst.resize(a11Ptr[L.nI]);
+    parallelFor(L.nI, [&](int64_t p0, int64_t p1, int) {
+      for (int64_t p = p0; p < p1; ++p) {
+        const int r = L.intRow[p], sd = sdOfInt[p];
+        int64_t f11 = a11Ptr[p], f12 = L.A12.ptr[p];
+        for (int64_t e = L.rowptr[r]; e < L.rowptr[r + 1]; ++e) {
+          const int cp = L.rowPos[L.colidx[e]];
+          if (cp >= 0) {
+            if (sdOfInt[cp] == sd) {
+              const int64_t li = p - H.intPtr[sd], lj = cp - H.intPtr[sd];
+              L.a11Src[f11] = e;
+              L.a11Dst[f11++] = L.a11Off[sd] + li * L.sdNp[sd] + lj;
+            }
           } else {
-            L.A21.col[f21[p]] = cp;
-            L.A21.src[f21[p]++] = e;
-          }
-        } else {
-          if (pass == 0) {
-            L.A22.ptr[p + 1]++;
-          } else {
-            L.A22.col[f22[p]] = -cp - 1;
-            L.A22.src[f22[p]++] = e;
+            L.A12.col[f12] = -cp - 1;
+            L.A12.src[f12++] = e;
           }
         }
       }
-    }
+    });
+    parallelFor(L.nS, [&](int64_t p0, int64_t p1, int) {
+      for (int64_t p = p0; p < p1; ++p) {
+        const int r = L.sepRow[p];
+        int64_t f21 = L.A21.ptr[p], f22 = L.A22.ptr[p];
+        for (int64_t e = L.rowptr[r]; e < L.rowptr[r + 1]; ++e) {
+          const int cp = L.rowPos[L.colidx[e]];
+          if (cp >= 0) {
+            L.A21.col[f21] = cp;
+            L.A21.src[f21++] = e;
+          } else {
+            L.A22.col[f22] = -cp - 1;
+            L.A22.src[f22++] = e;
+          }
+        }
+      }
+    });
   }
   st.lap("before: group instances, per-subdomain separator lists");
   // ---- group instances, per-subdomain separator lists ----
@@ -249,8 +280,7 @@ void buildLevelSym(LevelSym& L, const CartesianPartitioner& part, const std::vec
     L.s21Ptr.assign(totalRows + 1, 0);
     L.s22Ptr.assign(totalRows + 1, 0);
     L.s12Ptr.assign(totalRows + 1, 0);
-    std::vector<int> loc(L.nS, -1);
-    // counting pass then fill pass
+    // counting pass then fill pass, both parallel over the subdomains (disjoint row ranges)
     for (int pass = 0; pass < 2; ++pass) {
       if (pass == 1) {
         for (int64_t i = 0; i < totalRows; ++i) {
@@ -265,78 +295,93 @@ void buildLevelSym(LevelSym& L, const CartesianPartitioner& part, const std::vec
         L.s12Row.resize(L.s12Ptr[totalRows]);
         L.s12Src.resize(L.s12Ptr[totalRows]);
       }
-      std::vector<int64_t> f21, f22, f12;
-      if (pass == 1) {
-        f21.assign(L.s21Ptr.begin(), L.s21Ptr.end() - 1);
-        f22.assign(L.s22Ptr.begin(), L.s22Ptr.end() - 1);
-        f12.assign(L.s12Ptr.begin(), L.s12Ptr.end() - 1);
-      }
-      for (int sd = 0; sd < L.nsd; ++sd) {
-        const int64_t base = L.sdRowPtr[sd];
-        const int m = L.sdM[sd];
-        const int64_t i0 = H.intPtr[sd], i1 = H.intPtr[sd + 1];
-        for (int i = 0; i < m; ++i) loc[L.sdSep[base + i]] = i;
-        for (int i = 0; i < m; ++i) {
-          int ps = L.sdSep[base + i];
-          for (int64_t e = L.A21.ptr[ps]; e < L.A21.ptr[ps + 1]; ++e) {
-            int c = L.A21.col[e];
-            if (c >= i0 && c < i1) {
-              if (pass == 0) {
-                L.s21Ptr[base + i + 1]++;
-              } else {
-                L.s21Col[f21[base + i]] = (int)(c - i0);
-                L.s21Src[f21[base + i]++] = L.A21.src[e];
+      parallelFor(L.nsd, [&](int64_t sd0, int64_t sd1, int) {
+        std::vector<int> loc(L.nS, -1);
+        std::vector<int64_t> f21, f22, f12;
+        for (int64_t sd = sd0; sd < sd1; ++sd) {
+          const int64_t base = L.sdRowPtr[sd];
+          const int m = L.sdM[sd];
+          const int64_t i0 = H.intPtr[sd], i1 = H.intPtr[sd + 1];
+          if (pass == 1) {
+            f21.assign(L.s21Ptr.begin() + base, L.s21Ptr.begin() + base + m);
+            f22.assign(L.s22Ptr.begin() + base, L.s22Ptr.begin() + base + m);
+            f12.assign(L.s12Ptr.begin() + base, L.s12Ptr.begin() + base + m);
+          }
+          for (int i = 0; i < m; ++i) loc[L.sdSep[base + i]] = i;
+          for (int i = 0; i < m; ++i) {
+            int ps = L.sdSep[base + i];
+            for (int64_t e = L.A21.ptr[ps]; e < L.A21.ptr[ps + 1]; ++e) {
+              int c = L.A21.col[e];
+              if (c >= i0 && c < i1) {
+                if (pass == 0) {
+                  L.s21Ptr[base + i + 1]++;
+                } else {
+                  L.s21Col[f21[i]] = (int)(c - i0);
+                  L.s21Src[f21[i]++] = L.A21.src[e];
+                }
+              }
+            }
+            for (int64_t e = L.A22.ptr[ps]; e < L.A22.ptr[ps + 1]; ++e) {
+              int j = loc[L.A22.col[e]];
+              if (j >= 0) {
+                if (pass == 0) {
+                  L.s22Ptr[base + i + 1]++;
+                } else {
+                  L.s22Col[f22[i]] = j;
+                  L.s22Src[f22[i]++] = L.A22.src[e];
+                }
               }
             }
           }
-          for (int64_t e = L.A22.ptr[ps]; e < L.A22.ptr[ps + 1]; ++e) {
-            int j = loc[L.A22.col[e]];
-            if (j >= 0) {
+          for (int64_t p = i0; p < i1; ++p) {
+            for (int64_t e = L.A12.ptr[p]; e < L.A12.ptr[p + 1]; ++e) {
+              int j = loc[L.A12.col[e]];
+              if (j < 0) continue;  // coupling to a separator that does not surround this subdomain
               if (pass == 0) {
-                L.s22Ptr[base + i + 1]++;
+                L.s12Ptr[base + j + 1]++;
               } else {
-                L.s22Col[f22[base + i]] = j;
-                L.s22Src[f22[base + i]++] = L.A22.src[e];
+                L.s12Row[f12[j]] = (int)(p - i0);
+                L.s12Src[f12[j]++] = L.A12.src[e];
               }
             }
           }
+          for (int i = 0; i < m; ++i) loc[L.sdSep[base + i]] = -1;
         }
-        for (int64_t p = i0; p < i1; ++p) {
-          for (int64_t e = L.A12.ptr[p]; e < L.A12.ptr[p + 1]; ++e) {
-            int j = loc[L.A12.col[e]];
-            if (j < 0) continue;  // coupling to a separator that does not surround this subdomain
-            if (pass == 0) {
-              L.s12Ptr[base + j + 1]++;
-            } else {
-              L.s12Row[f12[base + j]] = (int)(p - i0);
-              L.s12Src[f12[base + j]++] = L.A12.src[e];
-            }
-          }
-        }
-        for (int i = 0; i < m; ++i) loc[L.sdSep[base + i]] = -1;
-      }
+      }, 8);
     }
   }
   st.lap("before: reduced Schur pattern on the V-sums");
   // ---- reduced Schur pattern on the V-sums: union of per-subdomain cliques (:737-787) ----
   {
+    // inverse index unique group -> the subdomains that see it, then one sorted union per group (parallel)
+    std::vector<int64_t> occPtr(L.nuniq + 1, 0);
+    for (int sd = 0; sd < L.nsd; ++sd)
+      for (int64_t g = L.sdInstPtr[sd]; g < L.sdInstPtr[sd + 1]; ++g) occPtr[L.instUniq[g] + 1]++;
+    for (int u = 0; u < L.nuniq; ++u) occPtr[u + 1] += occPtr[u];
+    std::vector<int> occSd(occPtr[L.nuniq]);
+    {
+      std::vector<int64_t> f(occPtr.begin(), occPtr.end() - 1);
+      for (int sd = 0; sd < L.nsd; ++sd)
+        for (int64_t g = L.sdInstPtr[sd]; g < L.sdInstPtr[sd + 1]; ++g) occSd[f[L.instUniq[g]]++] = sd;
+    }
     std::vector<std::vector<int>> rows(L.nuniq);
-    for (int sd = 0; sd < L.nsd; ++sd) {
-      int64_t a = L.sdInstPtr[sd], z = L.sdInstPtr[sd + 1];
-      for (int64_t g = a; g < z; ++g) {
-        std::vector<int>& r = rows[L.instUniq[g]];
-        for (int64_t h = a; h < z; ++h) r.push_back(L.instUniq[h]);
+    parallelFor(L.nuniq, [&](int64_t u0, int64_t u1, int) {
+      for (int64_t u = u0; u < u1; ++u) {
+        std::vector<int>& r = rows[u];
+        for (int64_t o = occPtr[u]; o < occPtr[u + 1]; ++o) {
+          const int sd = occSd[o];
+          for (int64_t h = L.sdInstPtr[sd]; h < L.sdInstPtr[sd + 1]; ++h) r.push_back(L.instUniq[h]);
+        }
+        std::sort(r.begin(), r.end());
+        r.erase(std::unique(r.begin(), r.end()), r.end());
       }
-    }
+    }, 256);
     L.redPtr.assign(L.nuniq + 1, 0);
-    for (int u = 0; u < L.nuniq; ++u) {
-      std::vector<int>& r = rows[u];
-      std::sort(r.begin(), r.end());
-      r.erase(std::unique(r.begin(), r.end()), r.end());
-      L.redPtr[u + 1] = L.redPtr[u] + (int64_t)r.size();
-    }
+    for (int u = 0; u < L.nuniq; ++u) L.redPtr[u + 1] = L.redPtr[u] + (int64_t)rows[u].size();
     L.redCol.resize(L.redPtr[L.nuniq]);
-    for (int u = 0; u < L.nuniq; ++u) std::copy(rows[u].begin(), rows[u].end(), L.redCol.begin() + L.redPtr[u]);
+    parallelFor(L.nuniq, [&](int64_t u0, int64_t u1, int) {
+      for (int64_t u = u0; u < u1; ++u) std::copy(rows[u].begin(), rows[u].end(), L.redCol.begin() + L.redPtr[u]);
+    }, 256);
   }
   st.lap("before: Householder reflectors from the test vector");
   // ---- Householder reflectors from the test vector (InitializeOT :384-467, Householder::Construct) ----

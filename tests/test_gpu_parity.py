@@ -219,5 +219,5 @@ def test_large_problem_properties(nx, sx, cx, extra):
     x = S.ApplyInverse(b)
     assert S.info["converged"]
     assert np.linalg.norm(A @ x - b) / np.linalg.norm(b) < 2e-8
-    P.Compute()                             # recompute: the same factors, bit for bit
-    assert np.array_equal(P.ApplyInverse(b), xh)
+    P.Compute()                             # recompute: the same factors up to the summation order of the
+    assert rel(P.ApplyInverse(b), xh) < 1e-11   # atomically assembled Schur contributions (rounding level)

@@ -24,8 +24,8 @@ static constexpr int GJ_NB = 32;       // panel width
 static constexpr int GJ_PANEL_T = 512; // threads of the panel kernel
 static constexpr int GJ_TJ = 64;       // column strip of the update kernel
 static constexpr int GJ_CS = GJ_TJ / 32; // 8x8 tiles per warp along the strip (4 warps across)
-static constexpr int GJ_TM = 64;       // row tile of the update kernel
-static constexpr int GJ_UPD_T = 256;   // 8 warps: 2 (rows) x 4 (cols), each 4x4 DMMA tiles of 8x8
+static constexpr int GJ_TM = 32;       // row tile of the update kernel
+static constexpr int GJ_UPD_T = 128;   // 4 warps side by side, each 4 x 2 DMMA tiles of 8x8; 4 CTAs per SM
 
 // ---------------------------------------------------------------------------------------------
 // identity in the padding rows/cols n..np-1 so the padded matrix stays invertible
@@ -648,7 +648,7 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 }
 
 // update kernel: grid (column strips, matrices)
-__global__ void __launch_bounds__(GJ_UPD_T, 2)
+__global__ void __launch_bounds__(GJ_UPD_T, 4)
 k_gj_update(double* __restrict__ W, const int64_t* __restrict__ off, const int* __restrict__ npArr,
             const int* __restrict__ rowsT, const int* __restrict__ origT, int k0) {
   const int mat = blockIdx.y;
@@ -690,7 +690,7 @@ k_gj_update(double* __restrict__ W, const int64_t* __restrict__ off, const int* 
       M[(int64_t)row * np + col] = gjSmem[i * SB + c];
   }
   __syncthreads();
-  // warp layout: 2 x 4 warps, each 4 x 2 tiles of 8 x 8 -> CTA tile 64 x 64
+  // warp layout: 1 x 4 warps, each 4 x 2 tiles of 8 x 8 -> CTA tile 32 x 64
   const int wr = wid >> 2, wc = wid & 3;
   const int fr = lane >> 2, fk = lane & 3;
 
@@ -812,7 +812,9 @@ __global__ void k_gj_gather(const double* __restrict__ W, double* __restrict__ F
   }
 }
 
-static constexpr size_t GJ_UPD_SMEM = (size_t)(GJ_NB * (GJ_TJ + 4) + 2 * GJ_TM * (GJ_NB + 4)) * sizeof(double);
+static constexpr size_t GJ_UPD_SMEM =
+    (size_t)(GJ_NB * (GJ_TJ + 4) + (2 * GJ_TM * (GJ_NB + 4) > 32 * (GJ_TJ + 4) ? 2 * GJ_TM * (GJ_NB + 4) : 32 * (GJ_TJ + 4))) *
+    sizeof(double);  // B tile + max(two G' buffers, rows 32..63 of the interchange staging)
 
 void invertBatched(double* W, double* F, const int64_t* dOff, const int* dN, const int* dNp, int count, int npMax,
                    int* dPiv, int* dPerm, int* dSwap, int* dInfo, cudaStream_t s, int64_t* launches) {

@@ -220,4 +220,4 @@ def test_large_problem_properties(nx, sx, cx, extra):
     assert S.info["converged"]
     assert np.linalg.norm(A @ x - b) / np.linalg.norm(b) < 2e-8
     P.Compute()                             # recompute: the same factors up to the summation order of the
-    assert rel(P.ApplyInverse(b), xh) < 1e-11   # atomically assembled Schur contributions (rounding level)
+    assert rel(P.ApplyInverse(b), xh) < 1e-9    # atomically assembled Schur contributions (rounding x conditioning)

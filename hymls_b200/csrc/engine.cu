@@ -280,7 +280,10 @@ void Engine::initialize() {
     part.setNextLevelParameters(levelParams);
     if (deviceOk_) uploadLevel(L);
   }
-  if (deviceOk_) HY_CUDA(cudaStreamSynchronize(stream_));
+  if (deviceOk_) {
+    reserveComputeScratch();
+    HY_CUDA(cudaStreamSynchronize(stream_));
+  }
   initialized_ = true;
   computed_ = false;
   stats_.num_initialize++;
@@ -654,6 +657,72 @@ struct PhaseTimer {
   }
 };
 
+// chunks [k0, k1) of owned subdomains whose dense input fits the inversion workspace (4 GB)
+std::vector<std::pair<int, int>> Engine::a11Chunks(const Level& L) const {
+  std::vector<std::pair<int, int>> out;
+  const int nown = (int)L.ownSd.size();
+  const int64_t budget = (int64_t)1 << 29;  // doubles
+  int k0 = 0;
+  while (k0 < nown) {
+    int k1 = k0;
+    int64_t used = 0;
+    while (k1 < nown && k1 - k0 < 16384) {
+      const int64_t need = L.ownOff[k1 + 1] - L.ownOff[k1];
+      if (k1 > k0 && used + need > budget) break;
+      used += need;
+      ++k1;
+    }
+    out.emplace_back(k0, k1);
+    k0 = k1;
+  }
+  return out;
+}
+
+// Allocates the scratch of Compute once, at the end of Initialize, so that the first Compute does not pay
+// for cudaMalloc of multi-GB buffers (the buffers only grow afterwards)
+void Engine::reserveComputeScratch() {
+  size_t work = 0, piv = 0, perm = 0, blkW = 0, wsC = 0, wsSLL = 0, red = 0;
+  auto batch = [&](int cnt, int npMax) {
+    piv = std::max(piv, (size_t)cnt * (npMax + 128));
+    perm = std::max(perm, (size_t)cnt * npMax);
+  };
+  for (auto& lp : levels_) {
+    const Level& L = *lp;
+    const LevelSym& S = L.sym;
+    for (const auto& ch : a11Chunks(L)) {
+      work = std::max(work, (size_t)(L.ownOff[ch.second] - L.ownOff[ch.first]));
+      int npMax = 0;
+      for (int k = ch.first; k < ch.second; ++k) npMax = std::max(npMax, L.a11.hNp[k]);
+      batch(ch.second - ch.first, npMax);
+    }
+    if (!L.exact) {
+      blkW = std::max(blkW, (size_t)S.blkOff[S.nblk]);
+      red = std::max(red, S.redCol.size());
+      wsC = std::max(wsC, (size_t)L.wsCLen);
+      wsSLL = std::max(wsSLL, (size_t)L.wsSLLLen);
+      int npMax = 0;
+      for (int b = 0; b < S.nblk; ++b) npMax = std::max(npMax, S.blkNp[b]);
+      batch(std::min(S.nblk, 16384), npMax);
+    }
+  }
+  // coarse solver: V-sums of the last level (or all separators when Number of Levels = 0), room for a border
+  const LevelSym& T = levels_.back()->sym;
+  const int64_t nc = ((levels_.back()->exact ? T.nS : (int64_t)T.nuniq) + 8 + 7) & ~(int64_t)7;
+  work = std::max(work, (size_t)(nc * nc));
+  batch(1, (int)nc);
+  work_.alloc(work);
+  piv_.alloc(piv);
+  perm_.alloc(perm);
+  blkW_.alloc(blkW);
+  wsC_.alloc(wsC);
+  wsSV_.alloc(wsC);
+  wsSLL_.alloc(wsSLL);
+  if (comm_.size() > 1) {
+    red2_.alloc(red);
+    blk2_.alloc(blkW);
+  }
+}
+
 void Engine::computeLevel(int l) {
   Level& L = *levels_[l];
   LevelSym& S = L.sym;
@@ -664,20 +733,11 @@ void Engine::computeLevel(int l) {
   gatherValues(L.val.p, L.src21.p, L.v21.p, (int64_t)L.v21.n, s, &launches_);
   // (2) A11 blocks: dense fill + batched inversion, in chunks of (owned) subdomains (ComputeSubdomainSolvers)
   {
-    const int nown = (int)L.ownSd.size();
-    const int64_t budget = (int64_t)1 << 29;  // doubles (4 GB) of inversion workspace
     DevBuf<int64_t>& relOff = relOff_;
-    int k0 = 0;
-    while (k0 < nown) {
-      int k1 = k0;
-      int64_t used = 0;
-      while (k1 < nown && k1 - k0 < 16384) {
-        int64_t need = L.ownOff[k1 + 1] - L.ownOff[k1];
-        if (k1 > k0 && used + need > budget) break;
-        used += need;
-        ++k1;
-      }
-      if (work_.n < (size_t)used) work_.alloc((size_t)std::max<int64_t>(used, std::min<int64_t>(budget, L.ownOff[nown])));
+    for (const auto& ch : a11Chunks(L)) {
+      const int k0 = ch.first, k1 = ch.second;
+      const int64_t used = L.ownOff[k1] - L.ownOff[k0];
+      work_.alloc((size_t)used);
       HY_CUDA(cudaMemsetAsync(work_.p, 0, used * sizeof(double), s));
       const int64_t e0 = L.a11ListPtr[k0], e1 = L.a11ListPtr[k1];
       scatterValues(L.val.p, L.a11Src.p + e0, L.a11Dst.p + e0, L.ownOff[k0], work_.p, e1 - e0, s, &launches_);
@@ -685,7 +745,6 @@ void Engine::computeLevel(int l) {
       invertRange(L.a11, k0, k1, work_.p, piv_, perm_, relOff, info_.p, s, &launches_);
       pt.lap("  chunk inversion");
       for (int k = k0; k < k1; ++k) stats_.flops_compute += 2.0 * std::pow((double)L.a11.hN[k], 3);
-      k0 = k1;
     }
     checkInfo("subdomain solver (A11) of level " + std::to_string(l));
   }

@@ -122,6 +122,8 @@ class Engine {
   void applyLevel(int l, const double* B, double* X, const double* T = nullptr);  // device pointers
   void computeLevel(int l);
   void computeBorder(int l);
+  std::vector<std::pair<int, int>> a11Chunks(const Level& L) const;
+  void reserveComputeScratch();
   void checkInfo(const std::string& what);
   void computeCoarse(const int64_t* ptr, const int* col, double* val, int n, const std::vector<gidx>& rowGid,
                      const double* bV = nullptr, const double* bW = nullptr, const std::vector<double>* bC = nullptr);

@@ -219,5 +219,10 @@ def test_large_problem_properties(nx, sx, cx, extra):
     x = S.ApplyInverse(b)
     assert S.info["converged"]
     assert np.linalg.norm(A @ x - b) / np.linalg.norm(b) < 2e-8
-    P.Compute()                             # recompute: the same factors up to the summation order of the
-    assert rel(P.ApplyInverse(b), xh) < 1e-9    # atomically assembled Schur contributions (rounding x conditioning)
+    # recompute: the same factors up to the summation order of the atomically assembled Schur contributions;
+    # the nearly singular pressure mode (entries of 1e7 in x) amplifies that rounding, hence norm-wise 1e-6
+    its = S.num_iter
+    P.Compute()
+    assert rel(P.ApplyInverse(b), xh) < 1e-6
+    S.ApplyInverse(b)
+    assert abs(S.num_iter - its) <= 1

@@ -22,7 +22,8 @@
 
 namespace hymls {
 
-// one CTA per local separator row of a subdomain
+// one CTA (128 threads) per local separator row of a subdomain
+static constexpr int SCHUR_QPT = 9;  // register-resident entries of d per thread: subdomains up to 1152 unknowns
 __global__ void __launch_bounds__(128)
 k_schur_rows(SchurArgs a, int64_t R0, int pass, double* __restrict__ denseS, int64_t ldS,
              const int64_t* __restrict__ rowList) {
@@ -37,13 +38,47 @@ k_schur_rows(SchurArgs a, int64_t R0, int pass, double* __restrict__ denseS, int
   double* sk = sm + a.dLen;  // m   : row i of Sk
 
   if (pass == 2) {
-    for (int q = tid; q < n; q += T) d[q] = 0.0;
-    __syncthreads();
+    // d = sum_e A21[i, col_e] * Ainv[col_e, :]: every thread keeps its entries of d in registers while the
+    // (few at level 0, ~100 at the coarser levels) rows of A11^-1 stream by, two rows in flight
     const double* Ainv = a.Ainv + a.a11Off[sd];
-    for (int64_t e = a.s21Ptr[R]; e < a.s21Ptr[R + 1]; ++e) {
-      const double v = a.val[a.s21Src[e]];
-      const double* row = Ainv + (int64_t)a.s21Col[e] * np;
-      for (int q = tid; q < n; q += T) d[q] += v * row[q];
+    const int64_t e0 = a.s21Ptr[R], e1 = a.s21Ptr[R + 1];
+    if (n <= SCHUR_QPT * 128) {
+      double acc[SCHUR_QPT];
+#pragma unroll
+      for (int j = 0; j < SCHUR_QPT; ++j) acc[j] = 0.0;
+      int64_t e = e0;
+      for (; e + 1 < e1; e += 2) {
+        const double v0 = a.val[a.s21Src[e]], v1 = a.val[a.s21Src[e + 1]];
+        const double* r0p = Ainv + (int64_t)a.s21Col[e] * np;
+        const double* r1p = Ainv + (int64_t)a.s21Col[e + 1] * np;
+#pragma unroll
+        for (int j = 0; j < SCHUR_QPT; ++j) {
+          const int q = tid + j * 128;
+          if (q < n) acc[j] += v0 * r0p[q] + v1 * r1p[q];
+        }
+      }
+      if (e < e1) {
+        const double v0 = a.val[a.s21Src[e]];
+        const double* r0p = Ainv + (int64_t)a.s21Col[e] * np;
+#pragma unroll
+        for (int j = 0; j < SCHUR_QPT; ++j) {
+          const int q = tid + j * 128;
+          if (q < n) acc[j] += v0 * r0p[q];
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < SCHUR_QPT; ++j) {
+        const int q = tid + j * 128;
+        if (q < n) d[q] = acc[j];
+      }
+    } else {
+      for (int q = tid; q < n; q += T) d[q] = 0.0;
+      __syncthreads();
+      for (int64_t e = e0; e < e1; ++e) {
+        const double v = a.val[a.s21Src[e]];
+        const double* row = Ainv + (int64_t)a.s21Col[e] * np;
+        for (int q = tid; q < n; q += T) d[q] += v * row[q];
+      }
     }
     __syncthreads();
     for (int j = tid; j < m; j += T) {

@@ -5,6 +5,8 @@
 // Krylov loop (Belos inside src/HYMLS_BaseSolver.cpp:347-356).  All of them are HBM-bandwidth bound.
 #include <cuda_runtime.h>
 
+#include <cstdint>
+
 #include "device.cuh"
 #include "kernels.hpp"
 
@@ -252,7 +254,9 @@ void multiDot(const double* V, int64_t ldv, int k, const double* w, int64_t n, d
 }
 int multiDotBlocks() { return DOT_BLOCKS; }
 
-// w += sign * sum_i h[i] V_i : coefficients in shared memory, four independent partial sums per row
+// w += sign * sum_i h[i] V_i : coefficients in shared memory; a thread owns two adjacent rows (16-byte loads,
+// eight of them in flight) when the basis is 16-byte aligned, one row otherwise
+template <bool PAIR>
 __global__ void __launch_bounds__(256)
 k_multi_axpy(const double* __restrict__ V, int64_t ldv, int k, const double* __restrict__ h,
              double* __restrict__ w, int64_t n, double sign) {
@@ -260,21 +264,60 @@ k_multi_axpy(const double* __restrict__ V, int64_t ldv, int k, const double* __r
   for (int i = threadIdx.x; i < k; i += blockDim.x) sh[i] = h[i];
   __syncthreads();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) {
-    const double* __restrict__ v = V + r;
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    int i = 0;
-    for (; i + 8 <= k; i += 8) {
-      const double a0 = v[(int64_t)i * ldv], a1 = v[(int64_t)(i + 1) * ldv], a2 = v[(int64_t)(i + 2) * ldv],
-                   a3 = v[(int64_t)(i + 3) * ldv], a4 = v[(int64_t)(i + 4) * ldv], a5 = v[(int64_t)(i + 5) * ldv],
-                   a6 = v[(int64_t)(i + 6) * ldv], a7 = v[(int64_t)(i + 7) * ldv];
-      s0 += sh[i] * a0 + sh[i + 4] * a4;
-      s1 += sh[i + 1] * a1 + sh[i + 5] * a5;
-      s2 += sh[i + 2] * a2 + sh[i + 6] * a6;
-      s3 += sh[i + 3] * a3 + sh[i + 7] * a7;
+  if (PAIR) {
+    const int64_t n2 = n >> 1;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n2; r += stride) {
+      const double2* __restrict__ v = reinterpret_cast<const double2*>(V) + r;
+      const int64_t ld2 = ldv >> 1;
+      double2 s0 = make_double2(0.0, 0.0), s1 = s0, s2 = s0, s3 = s0;
+      int i = 0;
+      for (; i + 8 <= k; i += 8) {
+        const double2 a0 = v[(int64_t)i * ld2], a1 = v[(int64_t)(i + 1) * ld2], a2 = v[(int64_t)(i + 2) * ld2],
+                      a3 = v[(int64_t)(i + 3) * ld2], a4 = v[(int64_t)(i + 4) * ld2], a5 = v[(int64_t)(i + 5) * ld2],
+                      a6 = v[(int64_t)(i + 6) * ld2], a7 = v[(int64_t)(i + 7) * ld2];
+        s0.x += sh[i] * a0.x + sh[i + 4] * a4.x;
+        s0.y += sh[i] * a0.y + sh[i + 4] * a4.y;
+        s1.x += sh[i + 1] * a1.x + sh[i + 5] * a5.x;
+        s1.y += sh[i + 1] * a1.y + sh[i + 5] * a5.y;
+        s2.x += sh[i + 2] * a2.x + sh[i + 6] * a6.x;
+        s2.y += sh[i + 2] * a2.y + sh[i + 6] * a6.y;
+        s3.x += sh[i + 3] * a3.x + sh[i + 7] * a7.x;
+        s3.y += sh[i + 3] * a3.y + sh[i + 7] * a7.y;
+      }
+      for (; i < k; ++i) {
+        const double2 a0 = v[(int64_t)i * ld2];
+        s0.x += sh[i] * a0.x;
+        s0.y += sh[i] * a0.y;
+      }
+      double2* wp = reinterpret_cast<double2*>(w) + r;
+      double2 wv = *wp;
+      wv.x += sign * ((s0.x + s1.x) + (s2.x + s3.x));
+      wv.y += sign * ((s0.y + s1.y) + (s2.y + s3.y));
+      *wp = wv;
     }
-    for (; i < k; ++i) s0 += sh[i] * v[(int64_t)i * ldv];
-    w[r] += sign * ((s0 + s1) + (s2 + s3));
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {  // odd tail row
+      const int64_t r = n - 1;
+      double s = 0.0;
+      for (int i = 0; i < k; ++i) s += sh[i] * V[(int64_t)i * ldv + r];
+      w[r] += sign * s;
+    }
+  } else {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) {
+      const double* __restrict__ v = V + r;
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      int i = 0;
+      for (; i + 8 <= k; i += 8) {
+        const double a0 = v[(int64_t)i * ldv], a1 = v[(int64_t)(i + 1) * ldv], a2 = v[(int64_t)(i + 2) * ldv],
+                     a3 = v[(int64_t)(i + 3) * ldv], a4 = v[(int64_t)(i + 4) * ldv], a5 = v[(int64_t)(i + 5) * ldv],
+                     a6 = v[(int64_t)(i + 6) * ldv], a7 = v[(int64_t)(i + 7) * ldv];
+        s0 += sh[i] * a0 + sh[i + 4] * a4;
+        s1 += sh[i + 1] * a1 + sh[i + 5] * a5;
+        s2 += sh[i + 2] * a2 + sh[i + 6] * a6;
+        s3 += sh[i + 3] * a3 + sh[i + 7] * a7;
+      }
+      for (; i < k; ++i) s0 += sh[i] * v[(int64_t)i * ldv];
+      w[r] += sign * ((s0 + s1) + (s2 + s3));
+    }
   }
 }
 void multiAxpy(const double* V, int64_t ldv, int k, const double* h, double* w, int64_t n, double sign,
@@ -282,7 +325,9 @@ void multiAxpy(const double* V, int64_t ldv, int k, const double* h, double* w, 
   if (k == 0 || n == 0) return;
   if ((size_t)k * sizeof(double) > 48 * 1024)
     throw Error(HYMLS_B200_ERR_UNSUPPORTED, "more than 6144 Krylov vectors in one orthogonalisation");
-  k_multi_axpy<<<DOT_BLOCKS, 256, (size_t)k * sizeof(double), s>>>(V, ldv, k, h, w, n, sign);
+  const bool pair = !(ldv & 1) && !(reinterpret_cast<uintptr_t>(V) & 15) && !(reinterpret_cast<uintptr_t>(w) & 15);
+  if (pair) k_multi_axpy<true><<<DOT_BLOCKS, 256, (size_t)k * sizeof(double), s>>>(V, ldv, k, h, w, n, sign);
+  else k_multi_axpy<false><<<DOT_BLOCKS, 256, (size_t)k * sizeof(double), s>>>(V, ldv, k, h, w, n, sign);
   ++*launches;
 }
 // y = a*x + b*y   (b == 0 : y = a*x, no read of y)

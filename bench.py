@@ -251,6 +251,8 @@ def main():
     P.Initialize()
     t_init = time.time() - t0
     torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()  # ranks leave the (host-side) Initialize at different times: do not bill that to Compute
     t0 = time.time()
     P.Compute()
     torch.cuda.synchronize()

@@ -71,6 +71,21 @@ void Engine::commInit(const void* id128, int rank, int nranks) {
   needDevice();
   if (nranks < 1 || rank < 0 || rank >= nranks) throw Error(HYMLS_B200_ERR_ARG, "comm_init: bad rank");
   if (nranks > 1) comm_.init(id128, rank, nranks); else comm_.setRankOnly(0, 1);
+  if (comm_.active()) {
+    // NCCL connects its channels lazily, per protocol, at the first collective that needs them (hundreds of ms
+    // on 8 ranks): do that here, as part of communicator setup, with one tiny and one large call of every
+    // collective the library uses, instead of inside the first Compute / ApplyInverse
+    DevBuf<double> warm;
+    const size_t big = (size_t)1 << 20;
+    warm.alloc(big * (size_t)nranks);
+    HY_CUDA(cudaMemsetAsync(warm.p, 0, warm.bytes(), stream_));
+    for (size_t cnt : {(size_t)1, big}) {
+      comm_.allReduceSum(warm.p, cnt, stream_);
+      comm_.broadcast(warm.p, cnt, 0, stream_);
+      comm_.allGather(warm.p + (size_t)rank * cnt, warm.p, cnt, stream_);
+    }
+    HY_CUDA(cudaStreamSynchronize(stream_));
+  }
   initialized_ = false;
   computed_ = false;
 }

@@ -76,6 +76,9 @@ def load_library():
     lib.hymls_b200_apply_inverse_bordered.argtypes = [vp, vp, i64, vp, vp, i64, vp, C.c_int, C.c_int]
     lib.hymls_b200_apply_matrix.argtypes = [vp, vp, vp, C.c_int]
     lib.hymls_b200_solve.argtypes = [vp, vp, vp, C.c_int, C.c_uint64, P(_SolveInfo), vp, C.c_int]
+    lib.hymls_b200_set_tolerance.argtypes = [vp, C.c_double]
+    lib.hymls_b200_get_parameters_xml.argtypes = [vp, C.c_char_p, i64]
+    lib.hymls_b200_get_parameters_xml.restype = i64
     lib.hymls_b200_num_levels.argtypes = [vp]
     lib.hymls_b200_num_subdomains.argtypes = [vp, C.c_int]
     lib.hymls_b200_get_interior.argtypes = [vp, C.c_int, C.c_int, vp, i64]
@@ -290,6 +293,14 @@ class Preconditioner:
         _check(self._lib, self._lib.hymls_b200_apply_matrix(self._h, x.data_ptr(), y.data_ptr(), DEVICE))
         return y
 
+    def GetParametersXml(self):
+        """The list with the defaults written back (the reference's 'Store Final Parameter List')."""
+        n = int(self._lib.hymls_b200_get_parameters_xml(self._h, None, 0))
+        _check(self._lib, n)
+        buf = C.create_string_buffer(n + 1)
+        self._lib.hymls_b200_get_parameters_xml(self._h, buf, n + 1)
+        return buf.value.decode()
+
     # -- index maps --------------------------------------------------------------------------------
     def NumLevels(self):
         return self._lib.hymls_b200_num_levels(self._h)
@@ -373,3 +384,7 @@ class Solver:
 
     def getNumIter(self):
         return self.num_iter
+
+    def SetTolerance(self, tol):
+        """BaseSolver::SetTolerance: overrides "Convergence Tolerance" for the following solves (NOX does this)."""
+        return _check(self.prec._lib, self.prec._lib.hymls_b200_set_tolerance(self.prec._h, float(tol)))

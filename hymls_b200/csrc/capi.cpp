@@ -179,6 +179,22 @@ int hymls_b200_solve(hymls_b200_t* h, const double* b, double* x, int where, uin
   HY_CATCH
 }
 
+int hymls_b200_set_tolerance(hymls_b200_t* h, double tol) {
+  HY_TRY
+  if (!(tol > 0)) throw Error(HYMLS_B200_ERR_ARG, "set_tolerance: tolerance must be positive");
+  h->eng->params().sublist("Solver").sublist("Iterative Solver").set("Convergence Tolerance", tol);
+  return 0;
+  HY_CATCH
+}
+
+int64_t hymls_b200_get_parameters_xml(hymls_b200_t* h, char* buf, int64_t cap) {
+  HY_TRY
+  const std::string xml = h->eng->params().toXml("Trilinos HYMLS");
+  if (buf && cap > (int64_t)xml.size()) std::memcpy(buf, xml.c_str(), xml.size() + 1);
+  return (int64_t)xml.size();
+  HY_CATCH
+}
+
 int hymls_b200_num_levels(hymls_b200_t* h) { return h->eng->initialized() ? h->eng->numLevels() : 0; }
 
 int hymls_b200_num_subdomains(hymls_b200_t* h, int level) {

@@ -1,5 +1,7 @@
 #include "params.hpp"
 
+#include <cstdio>
+
 #include <cstdlib>
 #include <cstring>
 
@@ -202,6 +204,45 @@ ParameterList ParameterList::fromXml(const std::string& xml) {
   ParameterList root;
   if (!sc) ps.parseList(root);
   return root;
+}
+
+static std::string xmlEscape(const std::string& t) {
+  std::string o;
+  for (char c : t) {
+    switch (c) {
+      case '&': o += "&amp;"; break;
+      case '<': o += "&lt;"; break;
+      case '>': o += "&gt;"; break;
+      case '"': o += "&quot;"; break;
+      default: o += c;
+    }
+  }
+  return o;
+}
+
+std::string ParameterList::toXml(const std::string& name, int indent) const {
+  const std::string pad((size_t)indent, ' ');
+  std::string o = pad + "<ParameterList name=\"" + xmlEscape(name) + "\">\n";
+  for (const std::string& n : order_) {
+    auto v = vals_.find(n);
+    if (v != vals_.end()) {
+      const Value& x = v->second;
+      char buf[64];
+      std::string type, val;
+      switch (x.kind) {
+        case BOOL: type = "bool"; val = x.b ? "true" : "false"; break;
+        case INT: type = "int"; val = std::to_string(x.i); break;
+        case DOUBLE: type = "double"; snprintf(buf, sizeof buf, "%.17g", x.d); val = buf; break;
+        default: type = "string"; val = xmlEscape(x.s);
+      }
+      o += pad + "  <Parameter name=\"" + xmlEscape(n) + "\" type=\"" + type + "\" value=\"" + val + "\"/>\n";
+      continue;
+    }
+    auto sub = subs_.find(n);
+    if (sub != subs_.end()) o += sub->second->toXml(n, indent + 2);
+  }
+  o += pad + "</ParameterList>\n";
+  return o;
 }
 
 }  // namespace hymls

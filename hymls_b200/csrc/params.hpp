@@ -58,6 +58,8 @@ class ParameterList {
   std::vector<std::string> sublistNames() const;
 
   static ParameterList fromXml(const std::string& xml);
+  // Teuchos XML of the list (writeParameterListToXmlOStream): entries in insertion order, sublists nested
+  std::string toXml(const std::string& name = "HYMLS", int indent = 0) const;
 
  private:
   Value& slot(const std::string& n) {

@@ -138,6 +138,15 @@ typedef struct {
 int hymls_b200_solve(hymls_b200_t* h, const double* b, double* x, int where, uint64_t random_seed,
                      hymls_b200_solve_info* info, double* resid_history, int history_cap);
 
+/* BaseSolver::SetTolerance (src/HYMLS_BaseSolver.cpp, used by NOX_Epetra_LinearSystem_Hymls.cpp:330-334 to
+   override "Convergence Tolerance" per solve). */
+int hymls_b200_set_tolerance(hymls_b200_t* h, double tol);
+
+/* The parameter list as it stands -- with the defaults the partitioner / preconditioner / solver wrote back
+   (e.g. "Fix GID 1", "Degrees of Freedom"), like the reference's "Store Final Parameter List" (src/main.cpp:492-509) --
+   as Teuchos XML.  Returns the length (without the terminating 0); writes only if cap > length. */
+int64_t hymls_b200_get_parameters_xml(hymls_b200_t* h, char* buf, int64_t cap);
+
 /* ---- index maps, for bit-exact comparison with the reference (HierarchicalMap) ---- */
 int hymls_b200_num_levels(hymls_b200_t* h);
 int hymls_b200_num_subdomains(hymls_b200_t* h, int level);

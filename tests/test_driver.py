@@ -61,3 +61,29 @@ def test_configs_run_on_gpu(name, over, max_its, tol):
     if name == "cavity.xml":   # fixture solution available: error with the constant pressure projected out
         assert out["border"] == 1 and out["levels"] == 3
         assert out["error"] <= 1e-8
+
+
+def test_final_parameter_list_round_trip():
+    """'Store Final Parameter List' (src/main.cpp:492-509): the list with the defaults the partitioner wrote
+    back (SetParameters, src/HYMLS_BasePartitioner.cpp:31-319) comes out as Teuchos XML and reproduces the run."""
+    import scipy.sparse as sp
+    from tests.conftest import load_fixture
+    A, _, _ = load_fixture("cavity2d_32_Re1000")
+    xml = open(os.path.join(ROOT, "configs", "cavity.xml")).read()
+    P = hb.Preconditioner(sp.csr_matrix(A), xml, pattern_only=True)
+    P.Initialize()
+    final = driver.parse_parameter_list(P.GetParametersXml())
+    assert final["Problem"]["Degrees of Freedom"] == 3 and final["Problem"]["Pressure Variable"] == 2
+    assert final["Problem"]["Variable 2"]["Variable Type"] == "Pressure"
+    assert final["Preconditioner"]["Eliminate Velocities Together"] is True
+    assert final["Preconditioner"]["Number of Levels"] == 3 and final["Driver"]["Null Space Type"] == "Constant P"
+    hb.Solver(P).SetTolerance(1e-6)               # BaseSolver::SetTolerance, what NOX calls before every solve
+    assert driver.parse_parameter_list(P.GetParametersXml())["Solver"]["Iterative Solver"][
+        "Convergence Tolerance"] == 1e-6
+    with pytest.raises(hb.HymlsError):
+        hb.Solver(P).SetTolerance(-1.0)
+    Q = hb.Preconditioner(sp.csr_matrix(A), P.GetParametersXml(), pattern_only=True)
+    Q.Initialize()
+    assert Q.NumLevels() == P.NumLevels()
+    for lev in range(P.NumLevels()):
+        assert np.array_equal(P.GetMap(hb.api.MAP_SEPARATOR, lev), Q.GetMap(hb.api.MAP_SEPARATOR, lev))

@@ -49,6 +49,7 @@ k_schur_rows(SchurArgs a, int64_t R0, int pass, double* __restrict__ denseS, int
       int64_t e = e0;
       for (; e + 1 < e1; e += 2) {
         const double v0 = a.val[a.s21Src[e]], v1 = a.val[a.s21Src[e + 1]];
+        if (v0 == 0.0 && v1 == 0.0) continue;  // stored zeros (dropped entries keep their slot): nothing to stream
         const double* r0p = Ainv + (int64_t)a.s21Col[e] * np;
         const double* r1p = Ainv + (int64_t)a.s21Col[e + 1] * np;
 #pragma unroll

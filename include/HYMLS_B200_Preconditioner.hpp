@@ -130,6 +130,14 @@ class B200Preconditioner : public Ifpack_Preconditioner, public BorderedOperator
   double Condest() const { return -1.0; }
   std::ostream& Print(std::ostream& os) const { return os << Label() << " (" << hymls_b200_version() << ")\n"; }
 
+  // HYMLS::Solver-side helpers when hymls_b200_solve replaces the Belos loop
+  int SetTolerance(double tol) { return hymls_b200_set_tolerance(h_, tol); }  // BaseSolver::SetTolerance
+  std::string FinalParameterListXml() const {                                  // "Store Final Parameter List"
+    std::string s((size_t)hymls_b200_get_parameters_xml(h_, nullptr, 0) + 1, '\0');
+    hymls_b200_get_parameters_xml(h_, &s[0], (int64_t)s.size());
+    s.resize(s.size() - 1);
+    return s;
+  }
   hymls_b200_t* Handle() const { return h_; }
 
  private:

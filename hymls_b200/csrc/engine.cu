@@ -1750,13 +1750,16 @@ int64_t Engine::debugCopy(int level, const std::string& name, double* out, int64
   else if (name == "v12") { p = L.v12.p; n = (int64_t)L.v12.n; }
   else if (name == "v21") { p = L.v21.p; n = (int64_t)L.v21.n; }
   else if (name == "what") { p = L.what.p; n = (int64_t)L.what.n; }
-  else if (name == "redptr" || name == "redcol" || name == "a11off" || name == "blkoff" || name == "blkrows") {
+  else if (name == "redptr" || name == "redcol" || name == "a11off" || name == "blkoff" || name == "blkrows" ||
+           name == "introw" || name == "seprow") {
     const LevelSym& S = L.sym;
     std::vector<double> v;
     if (name == "redptr") v.assign(S.redPtr.begin(), S.redPtr.end());
     else if (name == "redcol") v.assign(S.redCol.begin(), S.redCol.end());
     else if (name == "a11off") v.assign(S.a11Off.begin(), S.a11Off.end());
     else if (name == "blkoff") v.assign(S.blkOff.begin(), S.blkOff.end());
+    else if (name == "introw") v.assign(S.intRow.begin(), S.intRow.end());
+    else if (name == "seprow") v.assign(S.sepRow.begin(), S.sepRow.end());
     else v.assign(S.blkRows.begin(), S.blkRows.end());
     if (out && cap >= (int64_t)v.size()) std::copy(v.begin(), v.end(), out);
     return (int64_t)v.size();

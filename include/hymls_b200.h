@@ -193,7 +193,9 @@ int hymls_b200_get_stats(hymls_b200_t* h, hymls_b200_stats* st);
 int hymls_b200_time_apply(hymls_b200_t* h, int reps, double* ms_per_apply, double* ms_a11_kernel_per_launch);
 
 /* Test hook: copies a named device array of a level ("a11inv", "blkinv", "coarseinv", "redval", "v12",
-   "v21", "what") to the host; returns its length in doubles (call with out == NULL to query). */
+   "v21", "what") or host index array ("a11off", "blkoff", "blkrows", "redptr", "redcol", "introw", "seprow":
+   the matrix row of every interior / separator position) to the host as doubles; returns its length
+   (call with out == NULL to query). */
 int64_t hymls_b200_debug_copy(hymls_b200_t* h, int level, const char* name, double* out, int64_t cap);
 
 #ifdef __cplusplus

@@ -55,14 +55,19 @@ def stage(eqn, dim, nx, sx, levels, cx=None, detail=True, solve=True, **extra):
         # A11 inverses
         off = P.DebugArray("a11off").astype(np.int64)
         F = P.DebugArray("a11inv")
+        introw = P.DebugArray("introw").astype(np.int64)   # library interior ordering (boundary nodes first)
         worst = 0
+        pos = 0
         for sd in range(O.hid.num_subdomains()):
             idx = O.sd_int[sd]
             k = len(idx)
             if k == 0:
                 continue
+            where = {int(r): q for q, r in enumerate(O.int_rows[idx])}
+            perm = np.array([where[int(r)] for r in introw[pos:pos + k]])
+            pos += k
             npad = (k + 7) // 8 * 8
-            inv = np.linalg.inv(O.A11[idx[0]:idx[-1] + 1, idx[0]:idx[-1] + 1].toarray())
+            inv = np.linalg.inv(O.A11[idx[0]:idx[-1] + 1, idx[0]:idx[-1] + 1].toarray())[np.ix_(perm, perm)]
             G = F[off[sd]:off[sd] + npad * npad].reshape(npad, npad)[:k, :k]
             worst = max(worst, rel(G, inv))
         print("A11 inverse max rel diff: %.3e" % worst)

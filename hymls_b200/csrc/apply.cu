@@ -465,16 +465,6 @@ void spmvT(const int64_t* ptr, const int* col, const double* val, const double* 
   k_spmv_t<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ptr, col, val, x, y, n, alpha);
   ++*launches;
 }
-__global__ void k_gather_vec(const double* __restrict__ x, const int* __restrict__ idx, double* __restrict__ y,
-                             int64_t n) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) y[i] = x[idx[i]];
-}
-void gatherVec(const double* x, const int* idx, double* y, int64_t n, cudaStream_t s, int64_t* launches) {
-  if (n == 0) return;
-  k_gather_vec<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, idx, y, n);
-  ++*launches;
-}
 __global__ void k_zero_at(double* __restrict__ x, const int* __restrict__ idx, int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) x[idx[i]] = 0.0;

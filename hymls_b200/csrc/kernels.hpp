@@ -107,7 +107,6 @@ void scatterVecMasked(const double* x, const int* idx, double* y, int64_t n, cud
 void batchedGemvT(const GemvArgs& a, int count, int npMax, cudaStream_t s, int64_t* launches);  // out = Ainv^T x
 void spmvT(const int64_t* ptr, const int* col, const double* val, const double* x, double* y, int64_t n, double alpha,
            cudaStream_t s, int64_t* launches);                                                   // y += alpha A^T x
-void gatherVec(const double* x, const int* idx, double* y, int64_t n, cudaStream_t s, int64_t* launches);
 void zeroAt(double* x, const int* idx, int64_t n, cudaStream_t s, int64_t* launches);
 void borderCorrect(double* X, const int* idx, const double* Q, int64_t ld, int m, const double* S, int64_t n,
                    cudaStream_t s, int64_t* launches);

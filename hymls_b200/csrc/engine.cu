@@ -447,12 +447,13 @@ void Engine::uploadLevel(Level& L) {
   L.blkSmem = maxBlkSmem;
   // chunks of subdomains whose workspace (C, SV: m*G each; S_LL: sum lsz^2) fits the budget
   const int64_t budget = (int64_t)96 << 20;  // doubles per array (768 MB)
-  std::vector<int64_t> wsOffC(S.nsd, 0), lnkOff(lnkSd.size(), 0);
+  std::vector<int64_t> wsOffC(S.nsd, 0), wsOffD(S.nsd, 0), lnkOff(lnkSd.size(), 0);
   L.chunks.clear();
-  L.wsCLen = L.wsSLLLen = 0;
+  L.chunkDLen.clear();
+  L.wsCLen = L.wsSLLLen = L.wsDLen = 0;
   {
     int sd0 = 0;
-    int64_t cUsed = 0, lUsed = 0;
+    int64_t cUsed = 0, lUsed = 0, dUsed = 0;
     for (int sd = 0; sd < S.nsd; ++sd) {
       const int64_t G = S.sdInstPtr[sd + 1] - S.sdInstPtr[sd];
       const int64_t needC = (int64_t)S.sdM[sd] * G;
@@ -460,10 +461,14 @@ void Engine::uploadLevel(Level& L) {
       for (int64_t lk = sdLinkPtr[sd]; lk < sdLinkPtr[sd + 1]; ++lk) needL += (int64_t)lnkSize[lk] * lnkSize[lk];
       if (sd > sd0 && (cUsed + needC > budget || lUsed + needL > budget)) {
         L.chunks.push_back({sd0, sd, S.sdRowPtr[sd0], S.sdRowPtr[sd], sdLinkPtr[sd0], sdLinkPtr[sd]});
+        L.chunkDLen.push_back(dUsed);
         sd0 = sd;
-        cUsed = lUsed = 0;
+        cUsed = lUsed = dUsed = 0;
       }
       wsOffC[sd] = cUsed;
+      wsOffD[sd] = dUsed;  // m x np arrays of the dense Schur path (A21d, D)
+      dUsed += (int64_t)S.sdM[sd] * S.sdNp[sd];
+      L.wsDLen = std::max(L.wsDLen, dUsed);
       cUsed += needC;
       for (int64_t lk = sdLinkPtr[sd]; lk < sdLinkPtr[sd + 1]; ++lk) {
         lnkOff[lk] = lUsed;
@@ -472,8 +477,24 @@ void Engine::uploadLevel(Level& L) {
       L.wsCLen = std::max(L.wsCLen, cUsed);
       L.wsSLLLen = std::max(L.wsSLLLen, lUsed);
     }
-    if (S.nsd > sd0)
+    if (S.nsd > sd0) {
       L.chunks.push_back({sd0, S.nsd, S.sdRowPtr[sd0], S.sdRowPtr[S.nsd], sdLinkPtr[sd0], sdLinkPtr[S.nsd]});
+      L.chunkDLen.push_back(dUsed);
+    }
+  }
+  // Dense path for the rows of A21 A11^-1 (schurGemm): on the coarser levels a separator row couples to ~100
+  // interior nodes, and streaming that many rows of A11^-1 per separator row costs more than one DMMA GEMM
+  // per subdomain.  Level 0 (a few entries per row) keeps the sparse accumulation.
+  {
+    const double avgNnz = totalRows ? (double)S.s21Col.size() / (double)totalRows : 0.0;
+    // Measured at 128^3 (level 1: 200 subdomains, n ~ 700, m ~ 830): 123 ms with the GEMM against 113 ms without --
+    // the sparse product with A12 that follows dominates, so the path stays opt-in (HYMLS_B200_SCHUR_GEMM=1)
+    // until that product is a GEMM too.
+    (void)avgNnz;
+    L.schurGemm = false;
+    if (const char* e = getenv("HYMLS_B200_SCHUR_GEMM")) L.schurGemm = atoi(e) != 0 && L.wsDLen <= ((int64_t)1 << 28);
+    L.maxM = maxM;
+    L.maxNp = maxN;
   }
   if (L.sharded) {
     std::vector<int64_t> rows, links;
@@ -522,6 +543,7 @@ void Engine::uploadLevel(Level& L) {
   L.lnkSize.upload(lnkSize, s);
   L.lnkOff.upload(lnkOff, s);
   L.wsOffC.upload(wsOffC, s);
+  L.wsOffD.upload(wsOffD, s);
   L.uniqStart.upload(toInt(S.H.uniqPtr), s);
   L.uniqBlk.upload(S.uniqBlk, s);
   L.uniqBlkOff.upload(S.uniqBlkOff, s);
@@ -865,10 +887,31 @@ void Engine::computeLevel(int l) {
   a.wsC = wsC_.p;
   a.wsSV = wsSV_.p;
   a.wsSLL = wsSLL_.p;
+  a.wsOffD = L.wsOffD.p;
+  a.A21d = nullptr;
+  a.D = nullptr;
+  if (L.schurGemm) {
+    a21d_.alloc((size_t)L.wsDLen);
+    dmat_.alloc((size_t)L.wsDLen);
+  }
+  auto denseRows = [&](SchurArgs& aa, size_t c, bool owned) {  // D = A21 A11^-1 of one chunk, before its pass 2
+    if (!L.schurGemm) return;
+    aa.A21d = a21d_.p;
+    aa.D = dmat_.p;
+    const Level::Chunk& ch = L.chunks[c];
+    if (!owned)
+      schurGemm(aa, ch.sd0, ch.sd1, ch.R0, ch.R1, L.chunkDLen[c], L.maxM, L.maxNp, s, &launches_);
+    else
+      schurGemm(aa, (int)L.chunkOwnSd[c], (int)L.chunkOwnSd[c + 1], L.chunkOwnRow[c], L.chunkOwnRow[c + 1],
+                L.chunkDLen[c], L.maxM, L.maxNp, s, &launches_, L.ownSdList.p, L.ownRowList.p);
+  };
   if (!L.sharded) {
     for (int pass = 1; pass <= 2; ++pass)
-      for (const Level::Chunk& c : L.chunks)
+      for (size_t ci = 0; ci < L.chunks.size(); ++ci) {
+        const Level::Chunk& c = L.chunks[ci];
+        if (pass == 2) denseRows(a, ci, false);
         schurAssemble(a, c.sd0, c.sd1, c.R0, c.R1, c.lk0, c.lk1, pass, L.rowSmem, L.blkSmem, s, &launches_);
+      }
   } else {
     // pass 1 (A22 part, no A11 needed) for every subdomain on every rank; pass 2 (-A21 A11^-1 A12) for the
     // owned subdomains into zeroed buffers that are summed over the ranks (FECrsMatrix::GlobalAssemble)
@@ -882,10 +925,12 @@ void Engine::computeLevel(int l) {
     SchurArgs a2 = a;
     a2.redVal = red2.p;
     a2.blkW = blk2.p;
-    for (size_t c = 0; c < L.chunks.size(); ++c)
+    for (size_t c = 0; c < L.chunks.size(); ++c) {
+      denseRows(a2, c, true);
       schurAssemble(a2, (int)L.chunkOwnSd[c], (int)L.chunkOwnSd[c + 1], L.chunkOwnRow[c], L.chunkOwnRow[c + 1],
                     L.chunkOwnLink[c], L.chunkOwnLink[c + 1], 2, L.rowSmem, L.blkSmem, s, &launches_,
                     L.ownSdList.p, L.ownRowList.p, L.ownLinkList.p);
+    }
     HY_CUDA(cudaStreamSynchronize(s));  // surface kernel faults here rather than inside NCCL
     comm_.allReduceSum(red2.p, red2.n, s);
     comm_.allReduceSum(blk2.p, blk2.n, s);

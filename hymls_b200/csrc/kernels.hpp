@@ -47,6 +47,10 @@ struct SchurArgs {
   double* blkW;
   // workspace (per chunk)
   const int64_t* wsOffC;     // per subdomain: offset of its m x G arrays C and SV
+  // dense path of the coarser levels (many entries per A21 row): D = A21(sd) A11(sd)^-1 by a DMMA GEMM
+  const int64_t* wsOffD;     // per subdomain: offset of its m x np arrays A21d and D (chunk relative)
+  double* A21d;              // densified A21(sd), m x np row major
+  double* D;                 // nullptr: rows of A21 A11^-1 are accumulated sparsely inside k_schur_rows
   double *wsC, *wsSV, *wsSLL;
   int dLen;                  // doubles reserved for the A21*Ainv row in shared memory
   int* info;
@@ -54,6 +58,10 @@ struct SchurArgs {
 void schurAssemble(const SchurArgs& a, int sd0, int sd1, int64_t R0, int64_t R1, int64_t lk0, int64_t lk1, int pass,
                    size_t rowSmem, size_t blkSmem, cudaStream_t s, int64_t* launches, const int* sdList = nullptr,
                    const int64_t* rowList = nullptr, const int64_t* lkList = nullptr);
+// D = A21(sd) * A11(sd)^-1 for the subdomains [sd0, sd1) (or sdList[sd0..sd1)) whose local rows are [R0, R1)
+// (or rowList[R0..R1)); dLen = doubles of the chunk's A21d / D arrays
+void schurGemm(const SchurArgs& a, int sd0, int sd1, int64_t R0, int64_t R1, int64_t dLen, int maxM, int maxNp,
+               cudaStream_t s, int64_t* launches, const int* sdList = nullptr, const int64_t* rowList = nullptr);
 void schurDense(const SchurArgs& a, int64_t R0, int64_t R1, double* denseS, int64_t ldS, size_t rowSmem,
                 cudaStream_t s, int64_t* launches);
 void dropByValue(double* val, const int64_t* ptr, const int* col, double* diagScratch, int n, double tol,

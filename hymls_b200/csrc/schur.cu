@@ -42,7 +42,10 @@ k_schur_rows(SchurArgs a, int64_t R0, int pass, double* __restrict__ denseS, int
     // (few at level 0, ~100 at the coarser levels) rows of A11^-1 stream by, two rows in flight
     const double* Ainv = a.Ainv + a.a11Off[sd];
     const int64_t e0 = a.s21Ptr[R], e1 = a.s21Ptr[R + 1];
-    if (n <= SCHUR_QPT * 128) {
+    if (a.D != nullptr) {  // row i of A21 A11^-1 was computed by the dense GEMM (schurGemm)
+      const double* Drow = a.D + a.wsOffD[sd] + (int64_t)i * np;
+      for (int q = tid; q < n; q += T) d[q] = Drow[q];
+    } else if (n <= SCHUR_QPT * 128) {
       double acc[SCHUR_QPT];
 #pragma unroll
       for (int j = 0; j < SCHUR_QPT; ++j) acc[j] = 0.0;
@@ -232,6 +235,121 @@ k_schur_blocks(SchurArgs a, int64_t lk0, int pass, const int64_t* __restrict__ l
     double* dst = a.blkW + a.blkOff[b] + (int64_t)(a.uniqBlkOff[ui] + qi - 1) * npb + (a.uniqBlkOff[uj] + qj - 1);
     if (pass == 1) *dst = v; else atomicAdd(dst, v);
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Dense path for the coarser levels, where a separator row couples to ~100 interior nodes: instead of
+// streaming that many rows of A11^-1 per separator row, A21(sd) is densified and D = A21(sd) A11(sd)^-1 is one
+// FP64 tensor-core GEMM per subdomain (mma.sync.m8n8k4, cp.async double-buffered 32 x 32 / 32 x 64 tiles).
+// ---------------------------------------------------------------------------------------------
+__global__ void k_schur_densify(SchurArgs a, int64_t R0, int64_t R1, const int64_t* __restrict__ rowList) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= R1 - R0) return;
+  const int64_t R = rowList ? rowList[R0 + t] : R0 + t;
+  const int sd = a.rowSd[R];
+  const int i = (int)(R - a.sdRowPtr[sd]);
+  double* row = a.A21d + a.wsOffD[sd] + (int64_t)i * a.sdNp[sd];
+  for (int64_t e = a.s21Ptr[R]; e < a.s21Ptr[R + 1]; ++e) row[a.s21Col[e]] = a.val[a.s21Src[e]];
+}
+
+__device__ __forceinline__ void dmma884s(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+static constexpr int SG_TM = 32, SG_TN = 64, SG_TK = 32, SG_T = 128;
+static constexpr int SG_SA = SG_TK + 4, SG_SB = SG_TN + 4;  // strides = 4 mod 16 doubles: conflict-free fragments
+__global__ void __launch_bounds__(SG_T, 4)
+k_schur_gemm(SchurArgs a, int sd0, const int* __restrict__ sdList, int tilesN) {
+  const int sd = sdList ? sdList[sd0 + blockIdx.y] : sd0 + blockIdx.y;
+  const int m = a.sdM[sd], n = a.sdN[sd], np = a.sdNp[sd];
+  if (n == 0) return;
+  const int i0 = (blockIdx.x / tilesN) * SG_TM, j0 = (blockIdx.x % tilesN) * SG_TN;
+  if (i0 >= m || j0 >= np) return;
+  const double* __restrict__ A = a.A21d + a.wsOffD[sd];  // m x np
+  const double* __restrict__ B = a.Ainv + a.a11Off[sd];  // np x np
+  double* __restrict__ Dm = a.D + a.wsOffD[sd];
+  extern __shared__ __align__(16) double sgSm[];
+  constexpr int SZA = SG_TM * SG_SA, SZB = SG_TK * SG_SB;  // sA[buf] = sgSm + buf*SZA, sB[buf] = sgSm + 2*SZA + buf*SZB
+  const int tid = threadIdx.x, lane = tid & 31, wc = tid >> 5;
+  const int fr = lane >> 2, fk = lane & 3;
+  auto stage = [&](int k0, int buf) {
+    for (int e = tid; e < SG_TM * (SG_TK / 2); e += SG_T) {
+      const int r = e / (SG_TK / 2), c = (e % (SG_TK / 2)) * 2;
+      const bool ok = (i0 + r < m) && (k0 + c < np);
+      const double* src = ok ? A + (int64_t)(i0 + r) * np + k0 + c : A;
+      const unsigned saddr = (unsigned)__cvta_generic_to_shared(sgSm + buf * SZA + r * SG_SA + c);
+      const int bytes = ok ? 16 : 0;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(saddr), "l"(src), "r"(bytes));
+    }
+    for (int e = tid; e < SG_TK * (SG_TN / 2); e += SG_T) {
+      const int r = e / (SG_TN / 2), c = (e % (SG_TN / 2)) * 2;
+      const bool ok = (k0 + r < np) && (j0 + c < np);
+      const double* src = ok ? B + (int64_t)(k0 + r) * np + j0 + c : B;
+      const unsigned saddr = (unsigned)__cvta_generic_to_shared(sgSm + 2 * SZA + buf * SZB + r * SG_SB + c);
+      const int bytes = ok ? 16 : 0;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(saddr), "l"(src), "r"(bytes));
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+  };
+  double acc[4][2][2];
+#pragma unroll
+  for (int ti = 0; ti < 4; ++ti)
+#pragma unroll
+    for (int tj = 0; tj < 2; ++tj) acc[ti][tj][0] = acc[ti][tj][1] = 0.0;
+  const int nk = (np + SG_TK - 1) / SG_TK;
+  stage(0, 0);
+  for (int kt = 0; kt < nk; ++kt) {
+    const int buf = kt & 1;
+    const bool more = kt + 1 < nk;
+    if (more) stage((kt + 1) * SG_TK, buf ^ 1);
+    if (more) asm volatile("cp.async.wait_group 1;\n" ::); else asm volatile("cp.async.wait_group 0;\n" ::);
+    __syncthreads();
+    const double* cA = sgSm + buf * SZA;
+    const double* cB = sgSm + 2 * SZA + buf * SZB;
+#pragma unroll
+    for (int kk = 0; kk < SG_TK / 4; ++kk) {
+      double av[4], bv[2];
+#pragma unroll
+      for (int ti = 0; ti < 4; ++ti) av[ti] = cA[(ti * 8 + fr) * SG_SA + kk * 4 + fk];
+#pragma unroll
+      for (int tj = 0; tj < 2; ++tj) bv[tj] = cB[(kk * 4 + fk) * SG_SB + (wc * 2 + tj) * 8 + fr];
+#pragma unroll
+      for (int ti = 0; ti < 4; ++ti)
+#pragma unroll
+        for (int tj = 0; tj < 2; ++tj) dmma884s(acc[ti][tj][0], acc[ti][tj][1], av[ti], bv[tj]);
+    }
+    __syncthreads();  // the buffer is free for the prefetch after next
+  }
+#pragma unroll
+  for (int ti = 0; ti < 4; ++ti) {
+    const int row = i0 + ti * 8 + fr;
+#pragma unroll
+    for (int tj = 0; tj < 2; ++tj) {
+      const int col = j0 + (wc * 2 + tj) * 8 + 2 * fk;
+      if (row < m && col < np)
+        *reinterpret_cast<double2*>(Dm + (int64_t)row * np + col) = make_double2(acc[ti][tj][0], acc[ti][tj][1]);
+    }
+  }
+}
+
+void schurGemm(const SchurArgs& a, int sd0, int sd1, int64_t R0, int64_t R1, int64_t dLen, int maxM, int maxNp,
+               cudaStream_t s, int64_t* launches, const int* sdList, const int64_t* rowList) {
+  if (sd1 <= sd0 || R1 <= R0 || dLen <= 0) return;
+  HY_CUDA(cudaMemsetAsync(a.A21d, 0, (size_t)dLen * sizeof(double), s));
+  k_schur_densify<<<(unsigned)((R1 - R0 + 127) / 128), 128, 0, s>>>(a, R0, R1, rowList);
+  const int tilesM = (maxM + SG_TM - 1) / SG_TM, tilesN = (maxNp + SG_TN - 1) / SG_TN;
+  dim3 g((unsigned)(tilesM * tilesN), (unsigned)(sd1 - sd0));
+  constexpr size_t smem = (size_t)(2 * SG_TM * SG_SA + 2 * SG_TK * SG_SB) * sizeof(double);
+  static bool attrSet = false;
+  if (!attrSet) {
+    HY_CUDA(cudaFuncSetAttribute(k_schur_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attrSet = true;
+  }
+  k_schur_gemm<<<g, SG_T, smem, s>>>(a, sd0, sdList, tilesN);
+  *launches += 2;
+  HY_CUDA(cudaGetLastError());
 }
 
 // RelDropDiag / RelFullDiag value dropping (MatrixUtils::DropByValue :1010-1194) applied in place:

@@ -84,3 +84,28 @@ def test_compute_stages_match_oracle(eqn, dim, nx, sx, levels, cx, extra, tol):
         assert np.linalg.norm(G - inv) <= 100 * tol * np.linalg.norm(inv)
         nb += 1
     assert nb > 0
+
+
+@pytest.mark.parametrize("eqn,dim,nx,sx,levels,cx,extra,tol", [
+    ("Stokes-C", 2, 32, 4, 2, None, {}, 1e-9),
+    ("Stokes-C", 3, 16, 4, 2, 2, {"Partitioner": "Skew Cartesian"}, 1e-9),
+])
+def test_dense_schur_rows_path_matches_oracle(monkeypatch, eqn, dim, nx, sx, levels, cx, extra, tol):
+    """The coarser levels form the rows of A21 A11^-1 with a DMMA GEMM per subdomain instead of the sparse
+    accumulation (engine.cu: Level::schurGemm).  Forced on for every level here, so that the level-0 reduced
+    Schur complement and separator blocks -- which the oracle can be compared with entry by entry -- go
+    through it; ApplyInverse is compared as well."""
+    monkeypatch.setenv("HYMLS_B200_SCHUR_GEMM", "1")
+    test_compute_stages_match_oracle(eqn, dim, nx, sx, levels, cx, extra, tol)
+    p = make_params(eqn, dim, nx, sx, levels, cx, **extra)
+    A = sp.csr_matrix(-hb.galeri.create_matrix(eqn, dim, nx))
+    tv = hb.galeri.create_testvector(A)
+    O = oh.Preconditioner(A, p.copy(), tv)
+    O.initialize()
+    O.compute()
+    P = hb.Preconditioner(A, dictify(p), tv)
+    P.Initialize()
+    P.Compute()
+    b = np.random.default_rng(7).uniform(-1, 1, A.shape[0])
+    x, xo = P.ApplyInverse(b), O.apply_inverse(b)
+    assert np.linalg.norm(x - xo) <= 5e-10 * np.linalg.norm(xo)

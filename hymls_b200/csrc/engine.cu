@@ -447,13 +447,14 @@ void Engine::uploadLevel(Level& L) {
   L.blkSmem = maxBlkSmem;
   // chunks of subdomains whose workspace (C, SV: m*G each; S_LL: sum lsz^2) fits the budget
   const int64_t budget = (int64_t)96 << 20;  // doubles per array (768 MB)
-  std::vector<int64_t> wsOffC(S.nsd, 0), wsOffD(S.nsd, 0), lnkOff(lnkSd.size(), 0);
+  std::vector<int64_t> wsOffC(S.nsd, 0), wsOffD(S.nsd, 0), wsOffA(S.nsd, 0), wsOffS(S.nsd, 0), lnkOff(lnkSd.size(), 0);
   L.chunks.clear();
   L.chunkDLen.clear();
-  L.wsCLen = L.wsSLLLen = L.wsDLen = 0;
+  L.chunkALen.clear();
+  L.wsCLen = L.wsSLLLen = L.wsDLen = L.wsALen = L.wsSLen = 0;
   {
     int sd0 = 0;
-    int64_t cUsed = 0, lUsed = 0, dUsed = 0;
+    int64_t cUsed = 0, lUsed = 0, dUsed = 0, aUsed = 0, sUsed = 0;
     for (int sd = 0; sd < S.nsd; ++sd) {
       const int64_t G = S.sdInstPtr[sd + 1] - S.sdInstPtr[sd];
       const int64_t needC = (int64_t)S.sdM[sd] * G;
@@ -462,13 +463,23 @@ void Engine::uploadLevel(Level& L) {
       if (sd > sd0 && (cUsed + needC > budget || lUsed + needL > budget)) {
         L.chunks.push_back({sd0, sd, S.sdRowPtr[sd0], S.sdRowPtr[sd], sdLinkPtr[sd0], sdLinkPtr[sd]});
         L.chunkDLen.push_back(dUsed);
+        L.chunkALen.push_back(aUsed);
         sd0 = sd;
-        cUsed = lUsed = dUsed = 0;
+        cUsed = lUsed = dUsed = aUsed = sUsed = 0;
       }
       wsOffC[sd] = cUsed;
       wsOffD[sd] = dUsed;  // m x np arrays of the dense Schur path (A21d, D)
-      dUsed += (int64_t)S.sdM[sd] * S.sdNp[sd];
+      wsOffA[sd] = aUsed;  // np x mp (A12d)
+      wsOffS[sd] = sUsed;  // m x mp (SkD)
+      {
+        const int64_t mp = (S.sdM[sd] + 7) & ~7;
+        dUsed += (int64_t)S.sdM[sd] * S.sdNp[sd];
+        aUsed += (int64_t)S.sdNp[sd] * mp;
+        sUsed += (int64_t)S.sdM[sd] * mp;
+      }
       L.wsDLen = std::max(L.wsDLen, dUsed);
+      L.wsALen = std::max(L.wsALen, aUsed);
+      L.wsSLen = std::max(L.wsSLen, sUsed);
       cUsed += needC;
       for (int64_t lk = sdLinkPtr[sd]; lk < sdLinkPtr[sd + 1]; ++lk) {
         lnkOff[lk] = lUsed;
@@ -480,6 +491,7 @@ void Engine::uploadLevel(Level& L) {
     if (S.nsd > sd0) {
       L.chunks.push_back({sd0, S.nsd, S.sdRowPtr[sd0], S.sdRowPtr[S.nsd], sdLinkPtr[sd0], sdLinkPtr[S.nsd]});
       L.chunkDLen.push_back(dUsed);
+      L.chunkALen.push_back(aUsed);
     }
   }
   // Dense path for the rows of A21 A11^-1 (schurGemm): on the coarser levels a separator row couples to ~100
@@ -487,12 +499,12 @@ void Engine::uploadLevel(Level& L) {
   // per subdomain.  Level 0 (a few entries per row) keeps the sparse accumulation.
   {
     const double avgNnz = totalRows ? (double)S.s21Col.size() / (double)totalRows : 0.0;
-    // Measured at 128^3 (level 1: 200 subdomains, n ~ 700, m ~ 830): 123 ms with the GEMM against 113 ms without --
-    // the sparse product with A12 that follows dominates, so the path stays opt-in (HYMLS_B200_SCHUR_GEMM=1)
-    // until that product is a GEMM too.
-    (void)avgNnz;
-    L.schurGemm = false;
-    if (const char* e = getenv("HYMLS_B200_SCHUR_GEMM")) L.schurGemm = atoi(e) != 0 && L.wsDLen <= ((int64_t)1 << 28);
+    // Measured at 128^3 (level 1: 200 subdomains, n ~ 700, m ~ 830, ~100 entries per A21 row): sparse path 113 ms,
+    // dense D = A21 A11^-1 only 123 ms (the sparse product with A12 dominates), both products as GEMMs 25 ms.
+    // HYMLS_B200_SCHUR_GEMM overrides: 0 = sparse everywhere, 1 = dense on every level that fits, 2 = first GEMM only.
+    const bool fits = std::max(L.wsDLen, std::max(L.wsALen, L.wsSLen)) <= ((int64_t)1 << 28);
+    L.schurGemm = (S.level > 0 && avgNnz >= 16.0 && fits) ? 1 : 0;
+    if (const char* e = getenv("HYMLS_B200_SCHUR_GEMM")) L.schurGemm = fits ? atoi(e) : 0;
     L.maxM = maxM;
     L.maxNp = maxN;
   }
@@ -544,6 +556,8 @@ void Engine::uploadLevel(Level& L) {
   L.lnkOff.upload(lnkOff, s);
   L.wsOffC.upload(wsOffC, s);
   L.wsOffD.upload(wsOffD, s);
+  L.wsOffA.upload(wsOffA, s);
+  L.wsOffS.upload(wsOffS, s);
   L.uniqStart.upload(toInt(S.H.uniqPtr), s);
   L.uniqBlk.upload(S.uniqBlk, s);
   L.uniqBlkOff.upload(S.uniqBlkOff, s);
@@ -888,22 +902,31 @@ void Engine::computeLevel(int l) {
   a.wsSV = wsSV_.p;
   a.wsSLL = wsSLL_.p;
   a.wsOffD = L.wsOffD.p;
-  a.A21d = nullptr;
-  a.D = nullptr;
+  a.wsOffA = L.wsOffA.p;
+  a.wsOffS = L.wsOffS.p;
+  a.A21d = a.D = a.A12d = a.SkD = nullptr;
   if (L.schurGemm) {
     a21d_.alloc((size_t)L.wsDLen);
     dmat_.alloc((size_t)L.wsDLen);
+    if (L.schurGemm == 1) {
+      a12d_.alloc((size_t)L.wsALen);
+      skd_.alloc((size_t)L.wsSLen);
+    }
   }
   auto denseRows = [&](SchurArgs& aa, size_t c, bool owned) {  // D = A21 A11^-1 of one chunk, before its pass 2
     if (!L.schurGemm) return;
     aa.A21d = a21d_.p;
     aa.D = dmat_.p;
+    if (L.schurGemm == 1) {
+      aa.A12d = a12d_.p;
+      aa.SkD = skd_.p;
+    }
     const Level::Chunk& ch = L.chunks[c];
     if (!owned)
-      schurGemm(aa, ch.sd0, ch.sd1, ch.R0, ch.R1, L.chunkDLen[c], L.maxM, L.maxNp, s, &launches_);
+      schurGemm(aa, ch.sd0, ch.sd1, ch.R0, ch.R1, L.chunkDLen[c], L.chunkALen[c], L.maxM, L.maxNp, s, &launches_);
     else
       schurGemm(aa, (int)L.chunkOwnSd[c], (int)L.chunkOwnSd[c + 1], L.chunkOwnRow[c], L.chunkOwnRow[c + 1],
-                L.chunkDLen[c], L.maxM, L.maxNp, s, &launches_, L.ownSdList.p, L.ownRowList.p);
+                L.chunkDLen[c], L.chunkALen[c], L.maxM, L.maxNp, s, &launches_, L.ownSdList.p, L.ownRowList.p);
   };
   if (!L.sharded) {
     for (int pass = 1; pass <= 2; ++pass)

@@ -62,7 +62,7 @@ struct Level {
   DevBuf<int> rowSd, rowInst, rowLinkPos, sdSep, sdM;
   DevBuf<int64_t> sdRowPtr, s21Ptr, s12Ptr, s22Ptr, s21Src, s12Src, s22Src;
   DevBuf<int> s21Col, s12Row, s22Col;
-  DevBuf<int64_t> sdInstPtr, sdLinkPtr, lnkOff, wsOffC, wsOffD;
+  DevBuf<int64_t> sdInstPtr, sdLinkPtr, lnkOff, wsOffC, wsOffD, wsOffA, wsOffS;
   DevBuf<int> instLoc, instLen, instUniq, instLink, lnkSd, lnkSize;
   DevBuf<int> uniqStart, uniqBlk, uniqBlkOff;
   DevBuf<double> what, wd, usign;
@@ -71,9 +71,9 @@ struct Level {
   // chunking of the assembly workspace
   struct Chunk { int sd0, sd1; int64_t R0, R1, lk0, lk1; };
   std::vector<Chunk> chunks;
-  int64_t wsCLen = 0, wsSLLLen = 0, wsDLen = 0;
-  std::vector<int64_t> chunkDLen;   // per chunk: doubles of the m x np arrays of the dense Schur path
-  bool schurGemm = false;           // rows of A21 A11^-1 by a DMMA GEMM per subdomain (coarser levels)
+  int64_t wsCLen = 0, wsSLLLen = 0, wsDLen = 0, wsALen = 0, wsSLen = 0;
+  std::vector<int64_t> chunkDLen, chunkALen;   // per chunk: doubles of the m x np arrays of the dense Schur path
+  int schurGemm = 0;                // dense (DMMA GEMM) Schur rows: 0 off, 1 both products, 2 only A21 A11^-1
   int maxM = 0, maxNp = 0;
   size_t rowSmem = 0, blkSmem = 0;
   int dLen = 0;
@@ -161,7 +161,7 @@ class Engine {
   // scratch
   DevBuf<double> work_;      // inversion workspace
   DevBuf<int> piv_, perm_, info_, subsetN_, subsetNp_;
-  DevBuf<double> wsC_, wsSV_, wsSLL_, diagScratch_, blkW_, red2_, blk2_, a21d_, dmat_;
+  DevBuf<double> wsC_, wsSV_, wsSLL_, diagScratch_, blkW_, red2_, blk2_, a21d_, dmat_, a12d_, skd_;
   DevBuf<int64_t> relOff_;
   DevBuf<double> flag_;
   DevBuf<double> bufB_, bufX_;  // staging for host vectors

@@ -51,6 +51,9 @@ struct SchurArgs {
   const int64_t* wsOffD;     // per subdomain: offset of its m x np arrays A21d and D (chunk relative)
   double* A21d;              // densified A21(sd), m x np row major
   double* D;                 // nullptr: rows of A21 A11^-1 are accumulated sparsely inside k_schur_rows
+  const int64_t *wsOffA, *wsOffS;  // per subdomain: offsets of A12d (np x mp) and SkD (m x mp), mp = roundup8(m)
+  double* A12d;              // densified A12(sd)
+  double* SkD;               // -D A12d = the dense -A21 A11^-1 A12 of the subdomain (nullptr: sparse product)
   double *wsC, *wsSV, *wsSLL;
   int dLen;                  // doubles reserved for the A21*Ainv row in shared memory
   int* info;
@@ -60,8 +63,9 @@ void schurAssemble(const SchurArgs& a, int sd0, int sd1, int64_t R0, int64_t R1,
                    const int64_t* rowList = nullptr, const int64_t* lkList = nullptr);
 // D = A21(sd) * A11(sd)^-1 for the subdomains [sd0, sd1) (or sdList[sd0..sd1)) whose local rows are [R0, R1)
 // (or rowList[R0..R1)); dLen = doubles of the chunk's A21d / D arrays
-void schurGemm(const SchurArgs& a, int sd0, int sd1, int64_t R0, int64_t R1, int64_t dLen, int maxM, int maxNp,
-               cudaStream_t s, int64_t* launches, const int* sdList = nullptr, const int64_t* rowList = nullptr);
+void schurGemm(const SchurArgs& a, int sd0, int sd1, int64_t R0, int64_t R1, int64_t dLen, int64_t aLen, int maxM,
+               int maxNp, cudaStream_t s, int64_t* launches, const int* sdList = nullptr,
+               const int64_t* rowList = nullptr);
 void schurDense(const SchurArgs& a, int64_t R0, int64_t R1, double* denseS, int64_t ldS, size_t rowSmem,
                 cudaStream_t s, int64_t* launches);
 void dropByValue(double* val, const int64_t* ptr, const int* col, double* diagScratch, int n, double tol,

@@ -37,7 +37,12 @@ k_schur_rows(SchurArgs a, int64_t R0, int pass, double* __restrict__ denseS, int
   double* d = sm;            // n   : row i of A21(sd) * A11^-1
   double* sk = sm + a.dLen;  // m   : row i of Sk
 
-  if (pass == 2) {
+  if (pass == 2 && a.SkD != nullptr) {
+    // the whole row of -A21 A11^-1 A12 comes from the two dense GEMMs (schurGemm)
+    const int mp = (m + 7) & ~7;
+    const double* Srow = a.SkD + a.wsOffS[sd] + (int64_t)i * mp;
+    for (int j = tid; j < m; j += T) sk[j] = Srow[j];
+  } else if (pass == 2) {
     // d = sum_e A21[i, col_e] * Ainv[col_e, :]: every thread keeps its entries of d in registers while the
     // (few at level 0, ~100 at the coarser levels) rows of A11^-1 stream by, two rows in flight
     const double* Ainv = a.Ainv + a.a11Off[sd];
@@ -252,6 +257,18 @@ __global__ void k_schur_densify(SchurArgs a, int64_t R0, int64_t R1, const int64
   for (int64_t e = a.s21Ptr[R]; e < a.s21Ptr[R + 1]; ++e) row[a.s21Col[e]] = a.val[a.s21Src[e]];
 }
 
+// A12d[row, j] for the local separator column j = R - sdRowPtr[sd] (np x mp, row major)
+__global__ void k_schur_densify12(SchurArgs a, int64_t R0, int64_t R1, const int64_t* __restrict__ rowList) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= R1 - R0) return;
+  const int64_t R = rowList ? rowList[R0 + t] : R0 + t;
+  const int sd = a.rowSd[R];
+  const int j = (int)(R - a.sdRowPtr[sd]);
+  const int mp = (a.sdM[sd] + 7) & ~7;
+  double* col = a.A12d + a.wsOffA[sd] + j;
+  for (int64_t e = a.s12Ptr[R]; e < a.s12Ptr[R + 1]; ++e) col[(int64_t)a.s12Row[e] * mp] = a.val[a.s12Src[e]];
+}
+
 __device__ __forceinline__ void dmma884s(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                : "+d"(c0), "+d"(c1)
@@ -261,15 +278,19 @@ __device__ __forceinline__ void dmma884s(double& c0, double& c1, double a, doubl
 static constexpr int SG_TM = 32, SG_TN = 64, SG_TK = 32, SG_T = 128;
 static constexpr int SG_SA = SG_TK + 4, SG_SB = SG_TN + 4;  // strides = 4 mod 16 doubles: conflict-free fragments
 __global__ void __launch_bounds__(SG_T, 4)
-k_schur_gemm(SchurArgs a, int sd0, const int* __restrict__ sdList, int tilesN) {
+k_schur_gemm(SchurArgs a, int sd0, const int* __restrict__ sdList, int tilesN, int which) {
+  // which 0:  D (m x np)  =  A21d (m x np) * Ainv (np x np)
+  // which 1:  SkD (m x mp) = -D (m x np) * A12d (np x mp)
   const int sd = sdList ? sdList[sd0 + blockIdx.y] : sd0 + blockIdx.y;
   const int m = a.sdM[sd], n = a.sdN[sd], np = a.sdNp[sd];
   if (n == 0) return;
+  const int N = which ? ((m + 7) & ~7) : np;  // columns of B and C (= their leading dimension)
   const int i0 = (blockIdx.x / tilesN) * SG_TM, j0 = (blockIdx.x % tilesN) * SG_TN;
-  if (i0 >= m || j0 >= np) return;
-  const double* __restrict__ A = a.A21d + a.wsOffD[sd];  // m x np
-  const double* __restrict__ B = a.Ainv + a.a11Off[sd];  // np x np
-  double* __restrict__ Dm = a.D + a.wsOffD[sd];
+  if (i0 >= m || j0 >= N) return;
+  const double* __restrict__ A = (which ? a.D : a.A21d) + a.wsOffD[sd];                        // m x np
+  const double* __restrict__ B = which ? a.A12d + a.wsOffA[sd] : a.Ainv + a.a11Off[sd];        // np x N
+  double* __restrict__ Dm = which ? a.SkD + a.wsOffS[sd] : a.D + a.wsOffD[sd];                 // m x N
+  const double sgn = which ? -1.0 : 1.0;
   extern __shared__ __align__(16) double sgSm[];
   constexpr int SZA = SG_TM * SG_SA, SZB = SG_TK * SG_SB;  // sA[buf] = sgSm + buf*SZA, sB[buf] = sgSm + 2*SZA + buf*SZB
   const int tid = threadIdx.x, lane = tid & 31, wc = tid >> 5;
@@ -285,8 +306,8 @@ k_schur_gemm(SchurArgs a, int sd0, const int* __restrict__ sdList, int tilesN) {
     }
     for (int e = tid; e < SG_TK * (SG_TN / 2); e += SG_T) {
       const int r = e / (SG_TN / 2), c = (e % (SG_TN / 2)) * 2;
-      const bool ok = (k0 + r < np) && (j0 + c < np);
-      const double* src = ok ? B + (int64_t)(k0 + r) * np + j0 + c : B;
+      const bool ok = (k0 + r < np) && (j0 + c < N);
+      const double* src = ok ? B + (int64_t)(k0 + r) * N + j0 + c : B;
       const unsigned saddr = (unsigned)__cvta_generic_to_shared(sgSm + 2 * SZA + buf * SZB + r * SG_SB + c);
       const int bytes = ok ? 16 : 0;
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(saddr), "l"(src), "r"(bytes));
@@ -328,27 +349,41 @@ k_schur_gemm(SchurArgs a, int sd0, const int* __restrict__ sdList, int tilesN) {
 #pragma unroll
     for (int tj = 0; tj < 2; ++tj) {
       const int col = j0 + (wc * 2 + tj) * 8 + 2 * fk;
-      if (row < m && col < np)
-        *reinterpret_cast<double2*>(Dm + (int64_t)row * np + col) = make_double2(acc[ti][tj][0], acc[ti][tj][1]);
+      if (row < m && col < N)
+        *reinterpret_cast<double2*>(Dm + (int64_t)row * N + col) =
+            make_double2(sgn * acc[ti][tj][0], sgn * acc[ti][tj][1]);
     }
   }
 }
 
-void schurGemm(const SchurArgs& a, int sd0, int sd1, int64_t R0, int64_t R1, int64_t dLen, int maxM, int maxNp,
-               cudaStream_t s, int64_t* launches, const int* sdList, const int64_t* rowList) {
+void schurGemm(const SchurArgs& a, int sd0, int sd1, int64_t R0, int64_t R1, int64_t dLen, int64_t aLen, int maxM,
+               int maxNp, cudaStream_t s, int64_t* launches, const int* sdList, const int64_t* rowList) {
   if (sd1 <= sd0 || R1 <= R0 || dLen <= 0) return;
-  HY_CUDA(cudaMemsetAsync(a.A21d, 0, (size_t)dLen * sizeof(double), s));
-  k_schur_densify<<<(unsigned)((R1 - R0 + 127) / 128), 128, 0, s>>>(a, R0, R1, rowList);
-  const int tilesM = (maxM + SG_TM - 1) / SG_TM, tilesN = (maxNp + SG_TN - 1) / SG_TN;
-  dim3 g((unsigned)(tilesM * tilesN), (unsigned)(sd1 - sd0));
   constexpr size_t smem = (size_t)(2 * SG_TM * SG_SA + 2 * SG_TK * SG_SB) * sizeof(double);
   static bool attrSet = false;
   if (!attrSet) {
     HY_CUDA(cudaFuncSetAttribute(k_schur_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attrSet = true;
   }
-  k_schur_gemm<<<g, SG_T, smem, s>>>(a, sd0, sdList, tilesN);
+  const unsigned rowBlocks = (unsigned)((R1 - R0 + 127) / 128);
+  const int tilesM = (maxM + SG_TM - 1) / SG_TM;
+  HY_CUDA(cudaMemsetAsync(a.A21d, 0, (size_t)dLen * sizeof(double), s));
+  k_schur_densify<<<rowBlocks, 128, 0, s>>>(a, R0, R1, rowList);
+  {
+    const int tilesN = (maxNp + SG_TN - 1) / SG_TN;
+    dim3 g((unsigned)(tilesM * tilesN), (unsigned)(sd1 - sd0));
+    k_schur_gemm<<<g, SG_T, smem, s>>>(a, sd0, sdList, tilesN, 0);
+  }
   *launches += 2;
+  if (a.SkD != nullptr) {
+    HY_CUDA(cudaMemsetAsync(a.A12d, 0, (size_t)aLen * sizeof(double), s));
+    k_schur_densify12<<<rowBlocks, 128, 0, s>>>(a, R0, R1, rowList);
+    const int maxMp = (maxM + 7) & ~7;
+    const int tilesN = (maxMp + SG_TN - 1) / SG_TN;
+    dim3 g((unsigned)(tilesM * tilesN), (unsigned)(sd1 - sd0));
+    k_schur_gemm<<<g, SG_T, smem, s>>>(a, sd0, sdList, tilesN, 1);
+    *launches += 2;
+  }
   HY_CUDA(cudaGetLastError());
 }
 

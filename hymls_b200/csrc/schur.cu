@@ -283,7 +283,7 @@ k_schur_gemm(SchurArgs a, int sd0, const int* __restrict__ sdList, int tilesN, i
   // which 1:  SkD (m x mp) = -D (m x np) * A12d (np x mp)
   const int sd = sdList ? sdList[sd0 + blockIdx.y] : sd0 + blockIdx.y;
   const int m = a.sdM[sd], n = a.sdN[sd], np = a.sdNp[sd];
-  if (n == 0) return;
+  if (n == 0 && !which) return;  // no interior: D is m x 0; SkD (which = 1) still has to be written (zeros)
   const int N = which ? ((m + 7) & ~7) : np;  // columns of B and C (= their leading dimension)
   const int i0 = (blockIdx.x / tilesN) * SG_TM, j0 = (blockIdx.x % tilesN) * SG_TN;
   if (i0 >= m || j0 >= N) return;
@@ -320,7 +320,7 @@ k_schur_gemm(SchurArgs a, int sd0, const int* __restrict__ sdList, int tilesN, i
 #pragma unroll
     for (int tj = 0; tj < 2; ++tj) acc[ti][tj][0] = acc[ti][tj][1] = 0.0;
   const int nk = (np + SG_TK - 1) / SG_TK;
-  stage(0, 0);
+  if (nk > 0) stage(0, 0);
   for (int kt = 0; kt < nk; ++kt) {
     const int buf = kt & 1;
     const bool more = kt + 1 < nk;

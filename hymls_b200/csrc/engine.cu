@@ -503,7 +503,9 @@ void Engine::uploadLevel(Level& L) {
     // dense D = A21 A11^-1 only 123 ms (the sparse product with A12 dominates), both products as GEMMs 25 ms.
     // HYMLS_B200_SCHUR_GEMM overrides: 0 = sparse everywhere, 1 = dense on every level that fits, 2 = first GEMM only.
     const bool fits = std::max(L.wsDLen, std::max(L.wsALen, L.wsSLen)) <= ((int64_t)1 << 28);
-    L.schurGemm = (S.level > 0 && avgNnz >= 16.0 && fits) ? 1 : 0;
+    // (sharded runs keep the sparse path by default: the owned-list variant of the dense path has not been run
+    // on several GPUs yet; HYMLS_B200_SCHUR_GEMM=1 enables it there too)
+    L.schurGemm = (S.level > 0 && avgNnz >= 16.0 && fits && !L.sharded) ? 1 : 0;
     if (const char* e = getenv("HYMLS_B200_SCHUR_GEMM")) L.schurGemm = fits ? atoi(e) : 0;
     L.maxM = maxM;
     L.maxNp = maxN;

@@ -181,3 +181,64 @@ def test_domain_decomposition_decouples_interiors():
     P = hb.Preconditioner(A2, _dictify(make_params("Stokes-C", 2, 32, 4, 1)), pattern_only=True)
     P.Initialize()
     assert P.Stats()["interior_couplings"] > 0
+
+
+def _compare_all_levels(eqn, dim, nx, ny, nz, sx, levels, cx, part, extra):
+    import scipy.sparse as sps
+    p = make_params(eqn, dim, nx, sx, levels, cx, ny=ny, nz=nz, Partitioner=part, **extra)
+    A = hb.galeri.create_matrix(eqn, dim, nx, ny, nz)
+    tv = hb.galeri.create_testvector(A)
+    lvl = ohymls.Preconditioner(A, p.copy(), tv)
+    try:
+        lvl.initialize()
+        chain = [lvl]
+        for l in range(levels - 1):
+            s_ = chain[-1].schur_prec
+            nv = len(s_.vsum_gids)
+            nxt = ohymls.Preconditioner(sps.identity(nv, format="csr"), p.copy(), np.ones(nv), l + 1, s_.next_hid,
+                                        gids=s_.vsum_gids)
+            nxt.initialize()
+            chain.append(nxt)
+    except Exception:
+        chain = None                                   # the oracle rejects the configuration ...
+    P = hb.Preconditioner(A, _dictify(p), tv, pattern_only=True)
+    if chain is None:
+        with pytest.raises(hb.HymlsError):             # ... and so must the library (same message family)
+            P.Initialize()
+        return "rejected"
+    P.Initialize()
+    for l, lv in enumerate(chain):
+        hid = lv.hid
+        assert P.NumMySubdomains(l) == hid.num_subdomains()
+        for sd in range(hid.num_subdomains()):
+            assert np.array_equal(P.GetInteriorGroup(sd, l), np.asarray(hid.interior[sd], dtype=np.int64))
+            got = P.GetSeparatorGroups(sd, l)
+            assert len(got) == len(hid.groups[sd])
+            for (t, g), (to, go) in zip(got, hid.groups[sd]):
+                assert t == to and np.array_equal(g, np.asarray(go, dtype=np.int64))
+        assert np.array_equal(P.GetMap(api.MAP_SEPARATOR, l), hid.separator_map())
+        assert np.array_equal(P.GetMap(api.MAP_VSUM, l), lv.schur_prec.vsum_gids)
+    return "equal"
+
+
+def test_random_grids_and_partitioners_match_oracle():
+    """Seeded sweep over non-cubic and ragged grids, both partitioners, 1-2 levels: bit-exact maps on every level,
+    and configurations the reference refuses ('not a multiple of the subdomain size', 'subdomain of size 1')
+    are refused by both sides."""
+    rng = np.random.default_rng(2026)
+    outcomes = {"equal": 0, "rejected": 0}
+    for _ in range(24):
+        dim = int(rng.choice([2, 3]))
+        eqn = str(rng.choice(["Laplace", "Stokes-C"]))
+        part = str(rng.choice(["Cartesian", "Skew Cartesian"]))
+        sx = int(rng.choice([2, 4] if dim == 3 else [2, 4, 8]))
+        mult = lambda: int(rng.integers(2, 5 if dim == 3 else 7))   # noqa: E731
+        nx, ny = sx * mult(), sx * mult()
+        nz = sx * mult() if dim == 3 else 1
+        if part == "Cartesian" and rng.random() < 0.4:
+            nx += int(rng.integers(1, sx))                          # ragged last subdomain
+        levels = int(rng.choice([1, 2]))
+        extra = {"Eliminate_Tube_Pressures_With_Velocities": True} \
+            if (eqn == "Stokes-C" and dim == 3 and part == "Cartesian") else {}
+        outcomes[_compare_all_levels(eqn, dim, nx, ny, nz, sx, levels, 2 if levels > 1 else None, part, extra)] += 1
+    assert outcomes["equal"] >= 12 and outcomes["rejected"] >= 1, outcomes

@@ -242,3 +242,28 @@ def test_random_grids_and_partitioners_match_oracle():
             if (eqn == "Stokes-C" and dim == 3 and part == "Cartesian") else {}
         outcomes[_compare_all_levels(eqn, dim, nx, ny, nz, sx, levels, 2 if levels > 1 else None, part, extra)] += 1
     assert outcomes["equal"] >= 12 and outcomes["rejected"] >= 1, outcomes
+
+
+def test_random_pid_maps_match_oracle():
+    """BasePartitioner::CreatePIDMap (src/HYMLS_BasePartitioner.cpp:361-586) for random grid sizes, rank counts
+    (incl. counts that leave ranks idle) and both partitioners: the subdomain -> rank map is bit-exact."""
+    from oracle.skew import SkewCartesianPartitioner
+    rng = np.random.default_rng(5)
+    checked = 0
+    for _ in range(40):
+        dim = int(rng.choice([2, 3]))
+        sx = int(rng.choice([2, 4, 8] if dim == 2 else [2, 4]))
+        nx = sx * int(rng.integers(2, 9 if dim == 2 else 6))
+        nprocs = int(rng.choice([1, 2, 3, 4, 6, 8, 16]))
+        part = str(rng.choice(["Cartesian", "Skew Cartesian"]))
+        p = make_params("Stokes-C", dim, nx, sx, 1, Partitioner=part)
+        cls = CartesianPartitioner if part == "Cartesian" else SkewCartesianPartitioner
+        try:
+            ref = np.asarray(cls(p.copy(), 0, nprocs, 0).partition().pid_map, dtype=np.int32)
+        except Exception:
+            with pytest.raises(hb.HymlsError):
+                hb.pid_map(_dictify(p), nprocs)
+            continue
+        assert np.array_equal(hb.pid_map(_dictify(p), nprocs), ref), (dim, nx, sx, nprocs, part)
+        checked += 1
+    assert checked >= 30

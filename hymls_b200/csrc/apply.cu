@@ -79,13 +79,11 @@ k_batched_gemv(GemvArgs a) {
 
 void batchedGemv(const GemvArgs& a, int numItems, int npMax, cudaStream_t s, int64_t* launches) {
   if (numItems == 0) return;
-  static size_t smemSet = 48 * 1024;
+  static PerDeviceLimit limit;
   size_t smem = (size_t)npMax * sizeof(double);
-  if (smem > smemSet) {
-    if (smem > 227 * 1024) throw Error(HYMLS_B200_ERR_UNSUPPORTED, "dense block too large for the GEMV kernel");
+  if (smem > 227 * 1024) throw Error(HYMLS_B200_ERR_UNSUPPORTED, "dense block too large for the GEMV kernel");
+  if (limit.raise(smem))
     HY_CUDA(cudaFuncSetAttribute(k_batched_gemv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smemSet = smem;
-  }
   k_batched_gemv<<<numItems, GEMV_T, smem, s>>>(a);
   ++*launches;
 }
@@ -450,19 +448,21 @@ void batchedGemvT(const GemvArgs& a, int count, int npMax, cudaStream_t s, int64
   k_batched_gemv_t<<<(unsigned)(count * tiles), 256, 0, s>>>(a, tiles);
   ++*launches;
 }
-// y[col[e]] += alpha * val[e] * x[r]   (y = alpha A^T x, y zeroed by the caller)
-__global__ void k_spmv_t(const int64_t* __restrict__ ptr, const int* __restrict__ col, const double* __restrict__ val,
-                         const double* __restrict__ x, double* __restrict__ y, int64_t n, double alpha) {
+// y[r] = alpha * sum_e val[idx[e]] * x[col[e]]: SpMV with a transposed index (ptr/col/idx built on the host from
+// the CSR pattern) over the values of the untransposed matrix -- A12' w of ComputeBorder without atomics
+__global__ void k_spmv_indexed(const int64_t* __restrict__ ptr, const int* __restrict__ col,
+                               const int64_t* __restrict__ idx, const double* __restrict__ val,
+                               const double* __restrict__ x, double* __restrict__ y, int64_t n, double alpha) {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
-  const double xr = alpha * x[r];
-  if (xr == 0.0) return;
-  for (int64_t e = ptr[r]; e < ptr[r + 1]; ++e) atomicAdd(y + col[e], val[e] * xr);
+  double s = 0.0;
+  for (int64_t e = ptr[r]; e < ptr[r + 1]; ++e) s += val[idx[e]] * x[col[e]];
+  y[r] = alpha * s;
 }
-void spmvT(const int64_t* ptr, const int* col, const double* val, const double* x, double* y, int64_t n, double alpha,
-           cudaStream_t s, int64_t* launches) {
+void spmvIndexed(const int64_t* ptr, const int* col, const int64_t* idx, const double* val, const double* x, double* y,
+                 int64_t n, double alpha, cudaStream_t s, int64_t* launches) {
   if (n == 0) return;
-  k_spmv_t<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ptr, col, val, x, y, n, alpha);
+  k_spmv_indexed<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ptr, col, idx, val, x, y, n, alpha);
   ++*launches;
 }
 __global__ void k_zero_at(double* __restrict__ x, const int* __restrict__ idx, int64_t n) {

@@ -52,6 +52,21 @@ struct DevBuf {
   size_t bytes() const { return n * sizeof(T); }
 };
 
+// "largest opt-in dynamic shared memory size requested so far" of one kernel, tracked PER DEVICE: function
+// attributes belong to the device/context, so a process-wide flag is wrong once a process drives two devices
+struct PerDeviceLimit {
+  size_t v[64];
+  PerDeviceLimit() { for (size_t& x : v) x = 48 * 1024; }
+  bool raise(size_t want) {  // true: the attribute has to be (re)set on the current device
+    int d = 0;
+    cudaGetDevice(&d);
+    d &= 63;
+    if (want <= v[d]) return false;
+    v[d] = want;
+    return true;
+  }
+};
+
 extern thread_local double g_devBytes;  // running total for statistics
 
 }  // namespace hymls

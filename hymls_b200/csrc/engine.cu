@@ -120,7 +120,7 @@ void Engine::setMatrix(int64_t n, const int64_t* rowptr, const int32_t* colidx, 
   const int64_t nnz = rp[n];
   bool samePattern = haveMatrix_ && n == n_ && hRowptr_ == rp;
   std::vector<int> ci;
-  if (!samePattern || where == HYMLS_B200_HOST) {
+  {  // the column indices are compared on both paths: equal row lengths do not make an equal pattern
     ci.resize(nnz);
     if (where == HYMLS_B200_DEVICE) {
       HY_CUDA(cudaMemcpy(ci.data(), colidx, nnz * sizeof(int), cudaMemcpyDeviceToHost));
@@ -234,6 +234,7 @@ void Engine::initialize() {
     if (l > 0) levels_.emplace_back(new Level());
     Level& L = *levels_[l];
     L.sym = LevelSym();  // a re-Initialize starts from scratch
+    L.t12Ptr.release();
     LevelSym& S = L.sym;
     S.level = l;
     L.exact = (maxLevel_ == 0);
@@ -532,6 +533,50 @@ void Engine::uploadLevel(Level& L) {
     L.ownRowList.upload(rows, s);
     L.ownLinkList.upload(links, s);
   }
+  {
+    // Colouring of the subdomains for the pass-2 assembly: greedy, in subdomain order, on the conflict graph
+    // "share a separator group".  One colour is one launch, so contributions to an entry arrive in colour order.
+    std::vector<std::vector<int>> uniqSds(S.nuniq);
+    for (int sd = 0; sd < S.nsd; ++sd)
+      for (int64_t g = S.sdInstPtr[sd]; g < S.sdInstPtr[sd + 1]; ++g) uniqSds[S.instUniq[g]].push_back(sd);
+    std::vector<int> color(S.nsd, -1);
+    std::vector<char> used;
+    L.ncolors = 0;
+    for (int sd = 0; sd < S.nsd; ++sd) {
+      used.assign(L.ncolors + 1, 0);
+      for (int64_t g = S.sdInstPtr[sd]; g < S.sdInstPtr[sd + 1]; ++g)
+        for (int other : uniqSds[S.instUniq[g]])
+          if (color[other] >= 0) used[color[other]] = 1;
+      int c = 0;
+      while (used[c]) ++c;
+      color[sd] = c;
+      L.ncolors = std::max(L.ncolors, c + 1);
+    }
+    const size_t nch = L.chunks.size();
+    std::vector<char> isOwnSd(S.nsd, 0);
+    for (int sd : L.ownSd) isOwnSd[sd] = 1;
+    std::vector<int> colSd;
+    std::vector<int64_t> colLk, colRow;
+    L.colSdPtr.assign(1, 0);
+    L.colLkPtr.assign(1, 0);
+    L.colRowPtr.assign(1, 0);
+    for (size_t c = 0; c < nch; ++c)
+      for (int k = 0; k < L.ncolors; ++k) {
+        for (int sd = L.chunks[c].sd0; sd < L.chunks[c].sd1; ++sd) {
+          if (color[sd] != k || !isOwnSd[sd]) continue;
+          colSd.push_back(sd);
+          for (int64_t lk = sdLinkPtr[sd]; lk < sdLinkPtr[sd + 1]; ++lk) colLk.push_back(lk);
+          if (L.exact)
+            for (int64_t R = S.sdRowPtr[sd]; R < S.sdRowPtr[sd + 1]; ++R) colRow.push_back(R);
+        }
+        L.colSdPtr.push_back((int64_t)colSd.size());
+        L.colLkPtr.push_back((int64_t)colLk.size());
+        L.colRowPtr.push_back((int64_t)colRow.size());
+      }
+    L.colSd.upload(colSd, s);
+    L.colLk.upload(colLk, s);
+    L.colRow.upload(colRow, s);
+  }
   L.rowSd.upload(rowSd, s);
   L.rowInst.upload(rowInst, s);
   L.rowLinkPos.upload(rowLinkPos, s);
@@ -626,8 +671,17 @@ void Engine::checkInfo(const std::string& what) {
                     "'tube' blocks are identically zero; see 'Eliminate Tube Pressures With Velocities' in DESIGN.md");
 }
 
+void Engine::needComm() const {
+  if (comm_.size() > 1 && !comm_.active())
+    throw Error(HYMLS_B200_ERR_STATE,
+                "this handle was given a rank of a multi-rank run (hymls_b200_set_rank) but no communicator: "
+                "call hymls_b200_comm_init before Compute / ApplyInverse / solve");
+}
+
 void Engine::compute() {
   needDevice();
+  needComm();
+  computed_ = false;  // a Compute that throws must not leave half-updated factors marked usable
   if (!initialized_) initialize();  // "I'll do it for you", Preconditioner.cpp:403-409
   HY_CUDA(cudaEventRecord(ev0_, stream_));
   info_.alloc(1);
@@ -863,7 +917,8 @@ void Engine::computeLevel(int l) {
     v22.alloc(S.A22.col.size());
     gatherValues(L.val.p, L.src22.p, v22.p, (int64_t)S.A22.col.size(), s, &launches_);
     csrToDense(L.p22.p, L.c22.p, v22.p, work_.p, nS, np, s, &launches_);
-    schurDense(a, 0, S.sdRowPtr[S.nsd], work_.p, np, L.rowSmem, s, &launches_);
+    for (size_t q = 0; q + 1 < L.colRowPtr.size(); ++q)  // one colour of subdomains per launch: plain adds
+      schurDense(a, L.colRowPtr[q], L.colRowPtr[q + 1], work_.p, np, L.rowSmem, s, &launches_, L.colRow.p);
     coarseFix_.clear();
     ParameterList& prec = params_.sublist("Preconditioner");
     for (int pos = 1; prec.isParameter("Fix GID " + std::to_string(pos)); ++pos) {
@@ -930,18 +985,35 @@ void Engine::computeLevel(int l) {
       schurGemm(aa, (int)L.chunkOwnSd[c], (int)L.chunkOwnSd[c + 1], L.chunkOwnRow[c], L.chunkOwnRow[c + 1],
                 L.chunkDLen[c], L.chunkALen[c], L.maxM, L.maxNp, s, &launches_, L.ownSdList.p, L.ownRowList.p);
   };
+  // pass 2 of one chunk: rows of -A21 A11^-1 A12 for the (owned) subdomains into the per-subdomain workspaces,
+  // then the transformed entries colour by colour (plain adds, fixed order: bitwise reproducible)
+  auto pass2 = [&](SchurArgs& aa, size_t c) {
+    const Level::Chunk& ch = L.chunks[c];
+    if (!L.sharded) {
+      denseRows(aa, c, false);
+      schurRows(aa, ch.R0, ch.R1, 2, L.rowSmem, s, &launches_);
+    } else {
+      denseRows(aa, c, true);
+      schurRows(aa, L.chunkOwnRow[c], L.chunkOwnRow[c + 1], 2, L.rowSmem, s, &launches_, L.ownRowList.p);
+    }
+    for (int k = 0; k < L.ncolors; ++k) {
+      const size_t q = c * (size_t)L.ncolors + k;
+      schurScatter(aa, 2, (int)L.colSdPtr[q], (int)L.colSdPtr[q + 1], L.colLkPtr[q], L.colLkPtr[q + 1], L.blkSmem, s,
+                   &launches_, L.colSd.p, L.colLk.p);
+    }
+  };
+  auto pass1 = [&](SchurArgs& aa, size_t c) {  // A22 part: every subdomain sharing an entry stores the same value
+    const Level::Chunk& ch = L.chunks[c];
+    schurRows(aa, ch.R0, ch.R1, 1, L.rowSmem, s, &launches_);
+    schurScatter(aa, 1, ch.sd0, ch.sd1, ch.lk0, ch.lk1, L.blkSmem, s, &launches_);
+  };
   if (!L.sharded) {
-    for (int pass = 1; pass <= 2; ++pass)
-      for (size_t ci = 0; ci < L.chunks.size(); ++ci) {
-        const Level::Chunk& c = L.chunks[ci];
-        if (pass == 2) denseRows(a, ci, false);
-        schurAssemble(a, c.sd0, c.sd1, c.R0, c.R1, c.lk0, c.lk1, pass, L.rowSmem, L.blkSmem, s, &launches_);
-      }
+    for (size_t c = 0; c < L.chunks.size(); ++c) pass1(a, c);
+    for (size_t c = 0; c < L.chunks.size(); ++c) pass2(a, c);
   } else {
     // pass 1 (A22 part, no A11 needed) for every subdomain on every rank; pass 2 (-A21 A11^-1 A12) for the
     // owned subdomains into zeroed buffers that are summed over the ranks (FECrsMatrix::GlobalAssemble)
-    for (const Level::Chunk& c : L.chunks)
-      schurAssemble(a, c.sd0, c.sd1, c.R0, c.R1, c.lk0, c.lk1, 1, L.rowSmem, L.blkSmem, s, &launches_);
+    for (size_t c = 0; c < L.chunks.size(); ++c) pass1(a, c);
     DevBuf<double>&red2 = red2_, &blk2 = blk2_;
     red2.alloc(S.redCol.size());
     blk2.alloc((size_t)S.blkOff[S.nblk]);
@@ -950,12 +1022,7 @@ void Engine::computeLevel(int l) {
     SchurArgs a2 = a;
     a2.redVal = red2.p;
     a2.blkW = blk2.p;
-    for (size_t c = 0; c < L.chunks.size(); ++c) {
-      denseRows(a2, c, true);
-      schurAssemble(a2, (int)L.chunkOwnSd[c], (int)L.chunkOwnSd[c + 1], L.chunkOwnRow[c], L.chunkOwnRow[c + 1],
-                    L.chunkOwnLink[c], L.chunkOwnLink[c + 1], 2, L.rowSmem, L.blkSmem, s, &launches_,
-                    L.ownSdList.p, L.ownRowList.p, L.ownLinkList.p);
-    }
+    for (size_t c = 0; c < L.chunks.size(); ++c) pass2(a2, c);
     HY_CUDA(cudaStreamSynchronize(s));  // surface kernel faults here rather than inside NCCL
     comm_.allReduceSum(red2.p, red2.n, s);
     comm_.allReduceSum(blk2.p, blk2.n, s);
@@ -1105,6 +1172,23 @@ void Engine::computeBorder(int l) {
   bPartial_.alloc((size_t)(bm + 2) * multiDotBlocks());
   bDots_.alloc((size_t)bm * bm + bm);
   if (L.Q1.n) HY_CUDA(cudaMemsetAsync(L.Q1.p, 0, L.Q1.bytes(), s));
+  if (L.t12Ptr.n == 0) {  // transposed index of A12 (counting sort by column), once per pattern
+    std::vector<int64_t> tp(nS + 1, 0), ti(S.A12.col.size());
+    std::vector<int> tc(S.A12.col.size());
+    for (int c : S.A12.col) tp[c + 1]++;
+    for (int64_t p = 0; p < nS; ++p) tp[p + 1] += tp[p];
+    std::vector<int64_t> fill(tp.begin(), tp.end() - 1);
+    for (int64_t r = 0; r < nI; ++r)
+      for (int64_t e = S.A12.ptr[r]; e < S.A12.ptr[r + 1]; ++e) {
+        const int64_t q = fill[S.A12.col[e]]++;
+        tc[q] = (int)r;
+        ti[q] = e;
+      }
+    L.t12Ptr.upload(tp, s);
+    L.t12Col.upload(tc, s);
+    L.t12Idx.upload(ti, s);
+    HY_CUDA(cudaStreamSynchronize(s));
+  }
   for (int j = 0; j < bm; ++j) {
     const double* Vj = L.bV.p + (int64_t)j * n;
     const double* Wj = L.bW.p + (int64_t)j * n;
@@ -1134,8 +1218,7 @@ void Engine::computeBorder(int l) {
     gt.gather = L.intRow.p;
     gt.out = w1t;
     batchedGemvT(gt, L.a11.count, L.a11.npMax, s, &launches_);
-    if (nS) HY_CUDA(cudaMemsetAsync(L.Z.p, 0, (size_t)nS * sizeof(double), s));
-    spmvT(L.p12.p, L.c12.p, L.v12.p, w1t, L.Z.p, nI, -1.0, s, &launches_);
+    spmvIndexed(L.t12Ptr.p, L.t12Col.p, L.t12Idx.p, L.v12.p, w1t, L.Z.p, nS, -1.0, s, &launches_);
     if (L.sharded) comm_.allReduceSum(L.Z.p, (size_t)nS, s);
     gatherAdd(Wj, L.sepRow.p, L.Z.p, sWj, nS, s, &launches_);
   }
@@ -1371,6 +1454,7 @@ void Engine::applyDevice(const double* dB, double* dX, const double* dT, double*
 void Engine::applyInverseBordered(const double* B, int64_t ldb, const double* T, double* X, int64_t ldx, double* Sout,
                                   int nvec, int where) {
   needDevice();
+  needComm();
   if (!computed_) throw Error(HYMLS_B200_ERR_STATE, "The preconditioner has not yet been computed.");
   if (!B || !X || nvec < 0 || ldb < n_ || ldx < n_) throw Error(HYMLS_B200_ERR_ARG, "apply_inverse: bad arguments");
   const int bm = borderM_;
@@ -1399,6 +1483,7 @@ void Engine::applyInverseBordered(const double* B, int64_t ldb, const double* T,
 
 void Engine::applyInverse(const double* B, int64_t ldb, double* X, int64_t ldx, int nvec, int where) {
   needDevice();
+  needComm();
   if (!computed_) throw Error(HYMLS_B200_ERR_STATE, "The preconditioner has not yet been computed.");
   if (!B || !X || nvec < 0 || ldb < n_ || ldx < n_) throw Error(HYMLS_B200_ERR_ARG, "apply_inverse: bad arguments");
   for (int k = 0; k < nvec; ++k) {
@@ -1426,6 +1511,7 @@ void Engine::localRows(int64_t* r0, int64_t* r1) const {
 
 void Engine::applyInverseDist(const double* Bloc, double* Xloc, int where) {
   needDevice();
+  needComm();
   if (!computed_) throw Error(HYMLS_B200_ERR_STATE, "The preconditioner has not yet been computed.");
   const int P = comm_.size();
   const int64_t chunk = (n_ + P - 1) / P;
@@ -1462,6 +1548,7 @@ void Engine::applyMatrix(const double* x, double* y, int where) {
 
 void Engine::timeApply(int reps, double* msApply, double* msA11) {
   needDevice();
+  needComm();
   if (!computed_) throw Error(HYMLS_B200_ERR_STATE, "The preconditioner has not yet been computed.");
   bufB_.alloc(n_);
   bufX_.alloc(n_);
@@ -1519,6 +1606,7 @@ void Engine::operatorRows(const double* full, double* out, int64_t r0, int64_t r
 void Engine::solve(const double* b, double* x, int where, uint64_t seed, hymls_b200_solve_info* info, double* hist,
                    int histCap) {
   needDevice();
+  needComm();
   if (!computed_) throw Error(HYMLS_B200_ERR_STATE, "The preconditioner has not yet been computed.");
   ParameterList& sol = params_.sublist("Solver");
   ParameterList& it = sol.sublist("Iterative Solver");
@@ -1674,7 +1762,7 @@ void Engine::solve(const double* b, double* x, int where, uint64_t seed, hymls_b
     for (int restart = 0; restart <= maxRestarts; ++restart) {
       if (restart == 0) history.push_back(beta / impScale);
       lastRel = beta / impScale;
-      if (lastRel <= tol && !explicitTest) {
+      if (beta == 0.0 || (lastRel <= tol && !explicitTest)) {  // a zero residual cannot be normalised
         converged = true;
         break;
       }
@@ -1716,7 +1804,12 @@ void Engine::solve(const double* b, double* x, int where, uint64_t seed, hymls_b
         HY_CUDA(cudaStreamSynchronize(s));
         for (int i = 0; i <= k; ++i) H[(size_t)i * m + k] = hbuf[i] + hbuf[m + 1 + i];
         const double hn = std::sqrt(hbuf[2 * m + 2]);
-        H[(size_t)(k + 1) * m + k] = hn;
+        // happy breakdown: w is (numerically) in the span of the basis.  scaleByInvNorm has produced Inf/NaN in
+        // v_{k+1}, which is never used: the cycle ends after this column (Belos stops likewise)
+        double colNorm = 0.0;
+        for (int i = 0; i <= k; ++i) colNorm = std::hypot(colNorm, hbuf[i] + hbuf[m + 1 + i]);
+        const bool breakdown = !(hn > 1e-300) || hn <= 1e-15 * colNorm;
+        H[(size_t)(k + 1) * m + k] = breakdown ? 0.0 : hn;
         for (int i = 0; i < k; ++i) {
           const double t = cs[i] * H[(size_t)i * m + k] + sn[i] * H[(size_t)(i + 1) * m + k];
           H[(size_t)(i + 1) * m + k] = -sn[i] * H[(size_t)i * m + k] + cs[i] * H[(size_t)(i + 1) * m + k];
@@ -1733,7 +1826,7 @@ void Engine::solve(const double* b, double* x, int where, uint64_t seed, hymls_b
         kDone = k + 1;
         lastRel = std::fabs(g[k + 1]) / impScale;
         history.push_back(lastRel);
-        if (lastRel <= tol) break;
+        if (lastRel <= tol || breakdown) break;
       }
       if (kDone > 0) {
         // y = triu(H)^-1 g ; x += [M^-1] V y

@@ -50,6 +50,12 @@ struct Level {
   DevBuf<int> ownSdList;            // device copies of the owned lists for the pass-2 Schur kernels
   DevBuf<int64_t> ownRowList, ownLinkList;
   std::vector<int64_t> chunkOwnSd, chunkOwnRow, chunkOwnLink;  // per chunk: ranges in the lists (nchunks+1)
+  // Deterministic pass-2 assembly: (owned) subdomains coloured so that two subdomains of one colour share no
+  // separator group; per (chunk, colour) lists of subdomains / linked sets (/ local rows, exact path only)
+  int ncolors = 0;
+  DevBuf<int> colSd;
+  DevBuf<int64_t> colLk, colRow;
+  std::vector<int64_t> colSdPtr, colLkPtr, colRowPtr;  // nchunks * ncolors + 1
   DevBuf<double> xI;                // per-rank packed interior results, all-gathered (nranks * maxOwnI)
   DevBuf<int64_t> gatherOutOff;     // per owned matrix: position of its segment in xI
   DevBuf<int> packedRow;            // matrix row of every xI entry (-1: padding)
@@ -87,6 +93,8 @@ struct Level {
   // W1t = A11^-T W1, the transformed separator border sW (V-sum positions zeroed), the border handed to the coarse
   // solver (cV, cW) and the border right-hand sides q (after the interior elimination) / Tc (next level's T)
   DevBuf<double> bV, bW, Q1, W1t, sV, sW, cV, cW, bQ, bT;
+  DevBuf<int64_t> t12Ptr, t12Idx;  // transposed index of A12 (rows = separator positions), built at the first
+  DevBuf<int> t12Col;              // ComputeBorder: A12' w without atomics
   std::vector<double> hC;     // C of this level (m x m, column major)
 };
 
@@ -148,6 +156,7 @@ class Engine {
   std::vector<double> hTestVector_;
   bool haveMatrix_ = false, initialized_ = false, computed_ = false, deviceOk_ = false;
   void needDevice() const;
+  void needComm() const;
   std::vector<std::unique_ptr<Level>> levels_;
   // coarse solver (dense inverse)
   BatchedInverse coarse_;

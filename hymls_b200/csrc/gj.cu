@@ -819,8 +819,8 @@ static constexpr size_t GJ_UPD_SMEM =
 void invertBatched(double* W, double* F, const int64_t* dOff, const int* dN, const int* dNp, int count, int npMax,
                    int* dPiv, int* dPerm, int* dSwap, int* dInfo, cudaStream_t s, int64_t* launches) {
   if (count == 0 || npMax == 0) return;
-  static bool attrSet = false, permAttrSet = false;
-  if (!attrSet) {
+  static PerDeviceLimit attrLimit, permLimit;
+  if (attrLimit.raise(GJ_UPD_SMEM + 48 * 1024)) {  // once per device
     HY_CUDA(cudaFuncSetAttribute(k_gj_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GJ_UPD_SMEM));
     HY_CUDA(cudaFuncSetAttribute(k_gj_panel_smem<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)((size_t)8 * (GJ_SMEM_ROWS | 1) * sizeof(double))));
@@ -828,7 +828,6 @@ void invertBatched(double* W, double* F, const int64_t* dOff, const int* dN, con
                                  (int)((size_t)4 * (GJ_SMEM_ROWS4 | 1) * sizeof(double))));
     HY_CUDA(cudaFuncSetAttribute(k_gj_panel_full, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)((size_t)GJ_NB * (GJ_FULL_ROWS | 1) * sizeof(double))));
-    attrSet = true;
   }
   if ((size_t)npMax * sizeof(int) > 200 * 1024)
     throw Error(HYMLS_B200_ERR_UNSUPPORTED, "dense block larger than 51200 rows");
@@ -866,10 +865,8 @@ void invertBatched(double* W, double* F, const int64_t* dOff, const int* dN, con
     k_gj_update<<<g, GJ_UPD_T, GJ_UPD_SMEM, s>>>(W, dOff, dNp, rowsT, origT, k0);
     *launches += 2;
   }
-  if ((size_t)npMax * sizeof(int) > 48 * 1024 && !permAttrSet) {
+  if ((size_t)npMax * sizeof(int) > 48 * 1024 && permLimit.raise(200 * 1024))
     HY_CUDA(cudaFuncSetAttribute(k_gj_perm, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    permAttrSet = true;
-  }
   k_gj_perm<<<count, 256, npMax * sizeof(int), s>>>(dNp, dPiv, dPerm, npMax, count);
   dim3 g2((npMax + 7) / 8, count);
   k_gj_gather<<<g2, 256, 0, s>>>(W, F, dOff, dNp, dPerm, npMax);

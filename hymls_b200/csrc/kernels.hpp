@@ -58,16 +58,22 @@ struct SchurArgs {
   int dLen;                  // doubles reserved for the A21*Ainv row in shared memory
   int* info;
 };
-void schurAssemble(const SchurArgs& a, int sd0, int sd1, int64_t R0, int64_t R1, int64_t lk0, int64_t lk1, int pass,
-                   size_t rowSmem, size_t blkSmem, cudaStream_t s, int64_t* launches, const int* sdList = nullptr,
-                   const int64_t* rowList = nullptr, const int64_t* lkList = nullptr);
+// rows of Sk for the local separator rows [R0, R1) (or rowList[R0..R1)) into the per-subdomain workspaces
+void schurRows(const SchurArgs& a, int64_t R0, int64_t R1, int pass, size_t rowSmem, cudaStream_t s,
+               int64_t* launches, const int64_t* rowList = nullptr);
+// transformed V-sum x V-sum entries and separator-block entries of the subdomains [sd0, sd1) / linked sets
+// [lk0, lk1) (or of the lists).  pass 1 stores; pass 2 adds WITHOUT atomics: the caller launches one colour of
+// subdomains (no shared separator group) at a time, which fixes the order of every sum (reproducible Compute)
+void schurScatter(const SchurArgs& a, int pass, int sd0, int sd1, int64_t lk0, int64_t lk1, size_t blkSmem,
+                  cudaStream_t s, int64_t* launches, const int* sdList = nullptr, const int64_t* lkList = nullptr);
 // D = A21(sd) * A11(sd)^-1 for the subdomains [sd0, sd1) (or sdList[sd0..sd1)) whose local rows are [R0, R1)
 // (or rowList[R0..R1)); dLen = doubles of the chunk's A21d / D arrays
 void schurGemm(const SchurArgs& a, int sd0, int sd1, int64_t R0, int64_t R1, int64_t dLen, int64_t aLen, int maxM,
                int maxNp, cudaStream_t s, int64_t* launches, const int* sdList = nullptr,
                const int64_t* rowList = nullptr);
+// dense -A21 A11^-1 A12 added into denseS; the rows of one call belong to subdomains of one colour
 void schurDense(const SchurArgs& a, int64_t R0, int64_t R1, double* denseS, int64_t ldS, size_t rowSmem,
-                cudaStream_t s, int64_t* launches);
+                cudaStream_t s, int64_t* launches, const int64_t* rowList = nullptr);
 void dropByValue(double* val, const int64_t* ptr, const int* col, double* diagScratch, int n, double tol,
                  cudaStream_t s, int64_t* launches);
 
@@ -117,8 +123,9 @@ void scatterVecMasked(const double* x, const int* idx, double* y, int64_t n, cud
 
 // ---- bordered variant (apply.cu) ----
 void batchedGemvT(const GemvArgs& a, int count, int npMax, cudaStream_t s, int64_t* launches);  // out = Ainv^T x
-void spmvT(const int64_t* ptr, const int* col, const double* val, const double* x, double* y, int64_t n, double alpha,
-           cudaStream_t s, int64_t* launches);                                                   // y += alpha A^T x
+// y = alpha A^T x through a host-built transposed index into A's values (deterministic: no atomics)
+void spmvIndexed(const int64_t* ptr, const int* col, const int64_t* idx, const double* val, const double* x, double* y,
+                 int64_t n, double alpha, cudaStream_t s, int64_t* launches);
 void zeroAt(double* x, const int* idx, int64_t n, cudaStream_t s, int64_t* launches);
 void borderCorrect(double* X, const int* idx, const double* Q, int64_t ld, int m, const double* S, int64_t n,
                    cudaStream_t s, int64_t* launches);

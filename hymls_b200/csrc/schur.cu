@@ -103,9 +103,11 @@ k_schur_rows(SchurArgs a, int64_t R0, int pass, double* __restrict__ denseS, int
   __syncthreads();
 
   if (denseS != nullptr) {  // Number of Levels = 0: the full Schur complement, dense (Construct :88-129)
+    // plain adds: the rows of one launch belong to subdomains of one colour (no shared separator group),
+    // so no two CTAs touch the same entry and the order of the sum over subdomains is fixed by the launches
     const int64_t prow = a.sdSep[base + i];
     for (int j = tid; j < m; j += T)
-      if (sk[j] != 0.0) atomicAdd(&denseS[prow * ldS + a.sdSep[base + j]], sk[j]);
+      if (sk[j] != 0.0) denseS[prow * ldS + a.sdSep[base + j]] += sk[j];
     return;
   }
 
@@ -160,7 +162,9 @@ k_schur_vsum(SchurArgs a, int sd0, int pass, const int* __restrict__ sdList) {
                4.0 * w0g * w0h * Mgh;
     v *= a.usign[ug] * a.usign[uh];
     const int64_t pos = findCol(a.redCol, a.redPtr[ug], a.redPtr[ug + 1], uh);
-    if (pass == 1) a.redVal[pos] = v; else atomicAdd(&a.redVal[pos], v);
+    // pass 2 launches cover subdomains of ONE colour (no shared separator group): plain, race-free adds in a
+    // fixed order instead of FP64 atomics -> Compute is bitwise reproducible
+    if (pass == 1) a.redVal[pos] = v; else a.redVal[pos] += v;
   }
 }
 
@@ -238,7 +242,7 @@ k_schur_blocks(SchurArgs a, int64_t lk0, int pass, const int64_t* __restrict__ l
     v *= a.usign[ui] * a.usign[uj];
     const int npb = a.blkNp[b];
     double* dst = a.blkW + a.blkOff[b] + (int64_t)(a.uniqBlkOff[ui] + qi - 1) * npb + (a.uniqBlkOff[uj] + qj - 1);
-    if (pass == 1) *dst = v; else atomicAdd(dst, v);
+    if (pass == 1) *dst = v; else *dst += v;
   }
 }
 
@@ -360,11 +364,9 @@ void schurGemm(const SchurArgs& a, int sd0, int sd1, int64_t R0, int64_t R1, int
                int maxNp, cudaStream_t s, int64_t* launches, const int* sdList, const int64_t* rowList) {
   if (sd1 <= sd0 || R1 <= R0 || dLen <= 0) return;
   constexpr size_t smem = (size_t)(2 * SG_TM * SG_SA + 2 * SG_TK * SG_SB) * sizeof(double);
-  static bool attrSet = false;
-  if (!attrSet) {
+  static PerDeviceLimit gemmLimit;
+  if (gemmLimit.raise(smem))
     HY_CUDA(cudaFuncSetAttribute(k_schur_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attrSet = true;
-  }
   const unsigned rowBlocks = (unsigned)((R1 - R0 + 127) / 128);
   const int tilesM = (maxM + SG_TM - 1) / SG_TM;
   HY_CUDA(cudaMemsetAsync(a.A21d, 0, (size_t)dLen * sizeof(double), s));
@@ -419,40 +421,48 @@ void dropByValue(double* val, const int64_t* ptr, const int* col, double* diagSc
   *launches += 2;
 }
 
-// the opt-in dynamic shared memory limit of a kernel only ever grows (it caps launches, also below 48 KB)
-static size_t g_rowSmemSet = 48 * 1024, g_blkSmemSet = 48 * 1024;
+// opt-in dynamic shared memory above 48 KB (grow-only, tracked per device: PerDeviceLimit)
 static void ensureRowSmem(size_t rowSmem) {
-  if (rowSmem <= g_rowSmemSet) return;
+  static PerDeviceLimit limit;
   if (rowSmem > 227 * 1024)
     throw Error(HYMLS_B200_ERR_UNSUPPORTED, "subdomain too large for the Schur row kernel (n + m > 29000)");
-  HY_CUDA(cudaFuncSetAttribute(k_schur_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rowSmem));
-  g_rowSmemSet = rowSmem;
+  if (limit.raise(rowSmem)) HY_CUDA(cudaFuncSetAttribute(k_schur_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rowSmem));
+}
+static void ensureBlkSmem(size_t blkSmem) {
+  static PerDeviceLimit limit;
+  if (blkSmem > 200 * 1024)
+    throw Error(HYMLS_B200_ERR_UNSUPPORTED, "linked separator set too large for the block kernel");
+  if (limit.raise(blkSmem)) HY_CUDA(cudaFuncSetAttribute(k_schur_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blkSmem));
 }
 
-void schurAssemble(const SchurArgs& a, int sd0, int sd1, int64_t R0, int64_t R1, int64_t lk0, int64_t lk1, int pass,
-                   size_t rowSmem, size_t blkSmem, cudaStream_t s, int64_t* launches, const int* sdList,
-                   const int64_t* rowList, const int64_t* lkList) {
+void schurRows(const SchurArgs& a, int64_t R0, int64_t R1, int pass, size_t rowSmem, cudaStream_t s,
+               int64_t* launches, const int64_t* rowList) {
+  if (R1 <= R0) return;
   ensureRowSmem(rowSmem);
-  if (blkSmem > g_blkSmemSet) {
-    if (blkSmem > 200 * 1024)
-      throw Error(HYMLS_B200_ERR_UNSUPPORTED, "linked separator set too large for the block kernel");
-    HY_CUDA(cudaFuncSetAttribute(k_schur_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blkSmem));
-    g_blkSmemSet = blkSmem;
-  }
-  if (R1 > R0) {
-    k_schur_rows<<<(unsigned)(R1 - R0), 128, rowSmem, s>>>(a, R0, pass, nullptr, 0, rowList);
+  k_schur_rows<<<(unsigned)(R1 - R0), 128, rowSmem, s>>>(a, R0, pass, nullptr, 0, rowList);
+  ++*launches;
+  HY_CUDA(cudaGetLastError());
+}
+
+void schurScatter(const SchurArgs& a, int pass, int sd0, int sd1, int64_t lk0, int64_t lk1, size_t blkSmem,
+                  cudaStream_t s, int64_t* launches, const int* sdList, const int64_t* lkList) {
+  ensureBlkSmem(blkSmem);
+  if (sd1 > sd0) {
     k_schur_vsum<<<sd1 - sd0, 256, 0, s>>>(a, sd0, pass, sdList);
+    ++*launches;
+  }
+  if (lk1 > lk0) {
     k_schur_blocks<<<(unsigned)(lk1 - lk0), 256, blkSmem, s>>>(a, lk0, pass, lkList);
-    *launches += 3;
+    ++*launches;
   }
   HY_CUDA(cudaGetLastError());
 }
 
 void schurDense(const SchurArgs& a, int64_t R0, int64_t R1, double* denseS, int64_t ldS, size_t rowSmem,
-                cudaStream_t s, int64_t* launches) {
+                cudaStream_t s, int64_t* launches, const int64_t* rowList) {
   if (R1 <= R0) return;
   ensureRowSmem(rowSmem);
-  k_schur_rows<<<(unsigned)(R1 - R0), 128, rowSmem, s>>>(a, R0, 2, denseS, ldS, nullptr);
+  k_schur_rows<<<(unsigned)(R1 - R0), 128, rowSmem, s>>>(a, R0, 2, denseS, ldS, rowList);
   ++*launches;
   HY_CUDA(cudaGetLastError());
 }

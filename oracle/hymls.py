@@ -113,7 +113,7 @@ def householder_dense_cols(X, v):
 
 def householder_w(v):
     """Householder::Construct: normalised reflector w (or None), src/HYMLS_Householder.cpp:128-163"""
-    v = np.array(v, dtype=np.float64)
+    v = np.array(v, dtype=np.result_type(np.asarray(v).dtype, np.float64))
     nrm = np.linalg.norm(v)
     v = v * sign(v[0])
     v[0] += nrm
@@ -127,7 +127,8 @@ def householder_w(v):
 # Coarse solver
 # ---------------------------------------------------------------------------
 class CoarseSolver:
-    def __init__(self, matrix, gids, prec_params, level):
+    def __init__(self, matrix, gids, prec_params, level, factor_sparse=None):
+        self.factor_sparse = factor_sparse or (lambda M: spla.splu(sp.csc_matrix(M)))
         self.matrix = sp.csr_matrix(matrix)
         self.gids = np.asarray(gids, dtype=np.int64)
         self.level = level
@@ -156,13 +157,13 @@ class CoarseSolver:
         if self.V is not None:
             # AugmentedMatrix [S V; W' C], src/HYMLS_CoarseSolver.cpp:200-224
             S = sp.bmat([[S, sp.csr_matrix(self.V)], [sp.csr_matrix(self.W.T), sp.csr_matrix(self.C)]]).tocsc()
-        self.lu = spla.splu(sp.csc_matrix(S))
+        self.lu = self.factor_sparse(sp.csc_matrix(S))
         self._lid = lid
 
     def apply_inverse(self, X):
         if self.matrix.shape[0] == 0:
             return X.copy()
-        rhs = np.array(X, dtype=np.float64, copy=True)
+        rhs = np.array(X, copy=True)
         for g in self.fix_gid:
             l = self._lid.get(g, -1)
             if l > 0:  # sic: 'lid > 0', src/HYMLS_CoarseSolver.cpp:289
@@ -172,7 +173,7 @@ class CoarseSolver:
     def apply_inverse_bordered(self, X, T):
         """[Y;S] = [A V; W' C]^-1 [X;T], src/HYMLS_CoarseSolver.cpp:454-564"""
         n = self.matrix.shape[0]
-        rhs = np.array(X, dtype=np.float64, copy=True)
+        rhs = np.array(X, copy=True)
         # (no Fix-GID zeroing in the augmented solve, :497-509)
         full = np.concatenate([rhs, T], axis=0)
         sol = self.lu.solve(full)
@@ -182,9 +183,30 @@ class CoarseSolver:
 # ---------------------------------------------------------------------------
 # Preconditioner (one level)
 # ---------------------------------------------------------------------------
+class _DenseLU:
+    def __init__(self, M):
+        self.f = sla.lu_factor(M)
+
+    def solve(self, B):
+        return sla.lu_solve(self.f, B)
+
+
 class Preconditioner:
+    # arithmetic hooks: oracle/extended.py overrides them to run the same algorithm in extended precision
+    dtype = np.float64
+
+    @staticmethod
+    def factor_sparse(M):
+        """per-subdomain / coarse sparse LU (Ifpack_SparseContainer<KLU>, Amesos)"""
+        return spla.splu(sp.csc_matrix(M), permc_spec="COLAMD")
+
+    @staticmethod
+    def factor_dense(M):
+        """separator-block LU (Ifpack_DenseContainer -> LAPACK dgetrf/dgetrs)"""
+        return _DenseLU(M)
+
     def __init__(self, A, params, testvector=None, level=0, hid=None, gids=None):
-        self.A = sp.csr_matrix(A)
+        self.A = sp.csr_matrix(A, dtype=self.dtype)
         self.A.sort_indices()
         self.params = params
         self.prec_params = params.sublist("Preconditioner")
@@ -237,6 +259,7 @@ class Preconditioner:
             self.sd_grp_ptr.append(ptr)
         if self.testvector is None:
             self.testvector = np.ones(n)
+        self.testvector = np.asarray(self.testvector, dtype=self.dtype)
         self.tv_sep = self.testvector[self.sep_rows]
         if self.level < self.max_level:
             self.schur_prec = SchurPreconditioner(self)
@@ -252,7 +275,7 @@ class Preconditioner:
         if self.level >= self.max_level:
             S = self.construct_schur()
             self.schur_prec = CoarseSolver(drop_by_value(S, SMALL), self.sep_gids,
-                                           self.prec_params, self.level)
+                                           self.prec_params, self.level, self.factor_sparse)
         self.compute_border()
         self.schur_prec.compute()
         self.computed = True
@@ -275,7 +298,7 @@ class Preconditioner:
                 self.sd_lu.append(None)
                 continue
             blk = A11c[idx[0]:idx[-1] + 1, idx[0]:idx[-1] + 1].tocsc()
-            self.sd_lu.append(spla.splu(blk, permc_spec="COLAMD"))
+            self.sd_lu.append(self.factor_sparse(blk))
 
     def a11_solve(self, B, trans=False):
         """MatrixBlock::ApplyInverse, src/HYMLS_MatrixBlock.cpp:311-385"""
@@ -325,11 +348,11 @@ class Preconditioner:
         if V is None:
             self.V = self.W = self.C = None
         else:
-            V = np.asarray(V, dtype=np.float64).reshape(self.A.shape[0], -1)
+            V = np.asarray(V, dtype=self.dtype).reshape(self.A.shape[0], -1)
             self.V = V
-            self.W = V if W is None else np.asarray(W, dtype=np.float64).reshape(self.A.shape[0], -1)
+            self.W = V if W is None else np.asarray(W, dtype=self.dtype).reshape(self.A.shape[0], -1)
             m = V.shape[1]
-            self.C = np.zeros((m, m)) if C is None else np.asarray(C, dtype=np.float64)
+            self.C = np.zeros((m, m)) if C is None else np.asarray(C, dtype=self.dtype)
         self.computed = False
 
     def compute_border(self):
@@ -373,15 +396,15 @@ class Preconditioner:
 
     def apply_inverse(self, B):
         """Epetra_Operator::ApplyInverse; with a border set: T = 0 and S is discarded (:594-605)"""
-        B = np.asarray(B, dtype=np.float64)
+        B = np.asarray(B, dtype=self.dtype)
         B2 = B.reshape(self.A.shape[0], -1)
         T = None if self.V is None else np.zeros((self.V.shape[1], B2.shape[1]))
         X, _ = self._apply(B2, T)
         return X.reshape(B.shape)
 
     def apply_inverse_bordered(self, B, T):
-        B2 = np.asarray(B, dtype=np.float64).reshape(self.A.shape[0], -1)
-        T2 = np.asarray(T, dtype=np.float64).reshape(-1, B2.shape[1])
+        B2 = np.asarray(B, dtype=self.dtype).reshape(self.A.shape[0], -1)
+        T2 = np.asarray(T, dtype=self.dtype).reshape(-1, B2.shape[1])
         if self.V is None:
             X, _ = self._apply(B2, None)
             return X, np.zeros_like(T2)
@@ -442,8 +465,8 @@ class SchurPreconditioner:
 
     # ApplyOT :1236-1265 + Householder::Apply(MV) :353-363 : v <- 2 T'(T v) - v
     def apply_ot(self, v):
-        out = -np.array(v, dtype=np.float64, copy=True)
-        v2 = np.asarray(v, dtype=np.float64)
+        out = -np.array(v, dtype=self.P.dtype, copy=True)
+        v2 = np.asarray(v, dtype=self.P.dtype)
         for pos, w in zip(self.grp_pos, self.grp_w):
             if w is None:
                 continue
@@ -516,7 +539,7 @@ class SchurPreconditioner:
                 self.block_lu.append(None)
                 continue
             blk = M[rows, :][:, rows].toarray()
-            self.block_lu.append(sla.lu_factor(blk))
+            self.block_lu.append(self.P.factor_dense(blk))
 
     # ComputeNextLevel :520-629
     def compute_next_level(self):
@@ -529,11 +552,12 @@ class SchurPreconditioner:
             ttv = self.apply_ot(P.tv_sep)
             next_tv = ttv[vs]
             nparams = P.params.copy()
-            self.reduced_solver = Preconditioner(red, nparams, next_tv, self.level + 1,
+            self.reduced_solver = type(P)(red, nparams, next_tv, self.level + 1,
                                                  self.next_hid, gids=self.vsum_gids)
             self.reduced_solver.initialize()
         else:
-            self.reduced_solver = CoarseSolver(red, self.vsum_gids, P.prec_params, self.level + 1)
+            self.reduced_solver = CoarseSolver(red, self.vsum_gids, P.prec_params, self.level + 1,
+                                               P.factor_sparse)
         self.compute_border()
         self.reduced_solver.compute()
 
@@ -552,7 +576,7 @@ class SchurPreconditioner:
         for rows, lu in zip(self.blocks, self.block_lu):
             if lu is None:
                 continue
-            Y[rows] = sla.lu_solve(lu, B[rows])
+            Y[rows] = lu.solve(B[rows])
         Y[self.vsum_pos] = B[self.vsum_pos]
         return Y
 

@@ -180,251 +180,251 @@ void CartesianPartitioner::setNextLevelParameters(ParameterList& params) const {
   }
 }
 
-// src/HYMLS_CartesianPartitioner.cpp:80-121
-int CartesianPartitioner::subdomainPosition(int sd, int sx, int sy, int sz, int& x, int& y, int& z) const {
-  int npx = (nx_ - 1) / sx + 1, npy = (ny_ - 1) / sy + 1, npz = (nz_ - 1) / sz + 1;
-  x = (sd % npx) * sx;
-  y = ((sd / npx) % npy) * sy;
-  z = ((sd / npx / npy) % npz) * sz;
+// ---------------------------------------------------------------------------------------------
+// Cartesian brick arithmetic (behaviour of src/HYMLS_CartesianPartitioner.cpp:80-121): bricks of (bx,by,bz)
+// cells numbered x-fastest; the last brick of an axis is short when n is not a multiple of the brick size
+// ---------------------------------------------------------------------------------------------
+static inline int bricksAlong(int n, int b) { return (n - 1) / b + 1; }
+
+int CartesianPartitioner::subdomainPosition(int sd, int bx, int by, int bz, int& x, int& y, int& z) const {
+  const int px = bricksAlong(nx_, bx), py = bricksAlong(ny_, by), pz = bricksAlong(nz_, bz);
+  x = (sd % px) * bx;
+  y = (sd / px % py) * by;
+  z = (sd / px / py % pz) * bz;
   return 0;
 }
-int CartesianPartitioner::subdomainId(int sx, int sy, int sz, int x, int y, int z) const {
-  int npx = (nx_ - 1) / sx + 1, npy = (ny_ - 1) / sy + 1;
-  return (z / sz * npy + y / sy) * npx + x / sx;
+int CartesianPartitioner::subdomainId(int bx, int by, int bz, int x, int y, int z) const {
+  const int px = bricksAlong(nx_, bx), py = bricksAlong(ny_, by);
+  return x / bx + px * (y / by + py * (z / bz));
 }
-int CartesianPartitioner::numGlobalParts(int sx, int sy, int sz) const {
-  return ((nx_ - 1) / sx + 1) * ((ny_ - 1) / sy + 1) * ((nz_ - 1) / sz + 1);
+int CartesianPartitioner::numGlobalParts(int bx, int by, int bz) const {
+  return bricksAlong(nx_, bx) * bricksAlong(ny_, by) * bricksAlong(nz_, bz);
 }
 int CartesianPartitioner::pid(gidx gid) const {
-  gidx rem = gid / dof_;
-  int i = (int)(rem % nx_);
-  rem /= nx_;
-  int j = (int)(rem % ny_);
-  rem /= ny_;
-  int k = (int)(rem % nz_);
-  return pidMap_[subdomainId(sx_, sy_, sz_, i, j, k)];
+  const gidx cell = gid / dof_;
+  return pidMap_[subdomainId(sx_, sy_, sz_, (int)(cell % nx_), (int)(cell / nx_ % ny_), (int)(cell / nx_ / ny_ % nz_))];
 }
 
-static int findCoarseningFactor(int cx) {  // src/HYMLS_BasePartitioner.cpp:348-359
-  int b = 1;
-  while (b < cx) {
-    for (int p = 0; p < cx; ++p)
-      if (std::pow((double)b, (double)p) == (double)cx) return b;
-    b += 1;
+// ---------------------------------------------------------------------------------------------
+// Subdomain -> rank map.  Behaviour of BasePartitioner::CreatePIDMap (src/HYMLS_BasePartitioner.cpp:348-586),
+// written as four phases over a LADDER of brick grids fine * c^k (c = smallest integer root of the coarsening
+// factor), coarsest (one brick) first:
+//   1. walking down the ladder, every brick is represented by its ANCHOR, the fine subdomain holding the
+//      brick's origin; anchors receive ranks in order of first appearance.  The walk stops at the last grid
+//      whose anchors still fit into the P ranks (the "accepted" grid);
+//   2. ranks left over are dealt cyclically to the anchors in ascending subdomain order, so an accepted brick
+//      may own several ranks;
+//   3. the bricks of the next finer grid (the "deal" grid; the accepted one if there is none) take a rank from
+//      their accepted parent brick, round-robin in brick order;
+//   4. every fine subdomain inherits the rank of the deal brick it lies in.
+// Works through the virtual position / id functions, so the skew partitioner shares it.
+// ---------------------------------------------------------------------------------------------
+static int smallestIntegerRoot(int c) {
+  for (int base = 2; base < c; ++base) {
+    long long pw = base;
+    while (pw < c) pw *= base;
+    if (pw == c) return base;
   }
-  return cx;
+  return c;
 }
 
-// src/HYMLS_BasePartitioner.cpp:361-586
+int CartesianPartitioner::brickAnchor(int b, int bx, int by, int bz) const {
+  int x, y, z;
+  subdomainPosition(b, bx, by, bz, x, y, z);
+  x = ((x % nx_) + nx_) % nx_;
+  y = ((y % ny_) + ny_) % ny_;
+  z = ((z % nz_) + nz_) % nz_;
+  return subdomainId(sx_, sy_, sz_, x, y, z);
+}
+
 void CartesianPartitioner::createPidMap() {
-  int sx = sx_, sy = sy_, sz = sz_;
-  int nparts = numGlobalParts(sx, sy, sz);
+  const int nfine = numGlobalParts(sx_, sy_, sz_);
   const int P = nprocsComm_;
-  if (P == 1 || nparts == 1) {
+  if (P == 1 || nfine == 1) {
     nprocs_ = 1;
-    pidMap_.assign(nparts, 0);
+    pidMap_.assign(nfine, 0);
     return;
   }
-  pidMap_.assign(nparts, -1);
-  std::vector<std::vector<int>> pidGroups(nparts);
-  std::vector<int> sdPidNum(nparts, 0);
-  int cx = findCoarseningFactor(cx_), cy = findCoarseningFactor(cy_), cz = findCoarseningFactor(cz_);
-  while (sx < nx_ || sy < ny_ || sz < nz_) {
-    sx *= cx;
-    sy *= cy;
-    if (nz_ > 1) sz *= cz;
+  struct Grid { int bx, by, bz; };
+  std::vector<Grid> ladder(1, Grid{sx_, sy_, sz_});  // ladder[0] = fine grid, back() = a single brick
+  {
+    const int fx = smallestIntegerRoot(cx_), fy = smallestIntegerRoot(cy_), fz = smallestIntegerRoot(cz_);
+    while (ladder.back().bx < nx_ || ladder.back().by < ny_ || ladder.back().bz < nz_) {
+      Grid g = ladder.back();
+      g.bx *= fx;
+      g.by *= fy;
+      if (nz_ > 1) g.bz *= fz;
+      ladder.push_back(g);
+    }
   }
-  int sx2 = sx, sy2 = sy, sz2 = sz;
-  auto wrap = [&](int& x, int& y, int& z) {
-    x = (x % nx_ + nx_) % nx_;
-    y = (y % ny_ + ny_) % ny_;
-    z = (z % nz_ + nz_) % nz_;
+  auto anchorsOf = [&](const Grid& g) {
+    std::vector<int> a(numGlobalParts(g.bx, g.by, g.bz));
+    for (int b = 0; b < (int)a.size(); ++b) a[b] = brickAnchor(b, g.bx, g.by, g.bz);
+    return a;
   };
+  // phase 1
+  std::vector<int> firstRank(nfine, -1);
+  int nOwners = 0;
+  int accepted = (int)ladder.size() - 1, deal = accepted;
+  for (int lv = (int)ladder.size() - 1; lv >= 0; --lv) {
+    std::vector<int> fresh;
+    for (int a : anchorsOf(ladder[lv]))
+      if (firstRank[a] < 0 && std::find(fresh.begin(), fresh.end(), a) == fresh.end()) fresh.push_back(a);
+    deal = lv;
+    if (nOwners + (int)fresh.size() > P) break;  // this grid does not fit: it becomes the deal grid
+    for (int a : fresh) firstRank[a] = nOwners++;
+    accepted = lv;
+  }
+  // phase 2
+  std::vector<int> owners;
+  for (int sd = 0; sd < nfine; ++sd)
+    if (firstRank[sd] >= 0) owners.push_back(sd);
+  std::vector<std::vector<int>> ranksOf(nfine);
+  for (int sd : owners) ranksOf[sd].push_back(firstRank[sd]);
+  for (int r = nOwners, turn = 0; r < P; ++r, ++turn) ranksOf[owners[turn % owners.size()]].push_back(r);
+  // phase 3
+  pidMap_.assign(nfine, -1);
+  std::vector<int> cursor(nfine, 0);
+  const Grid gd = ladder[deal], ga = ladder[accepted];
+  auto wrappedOrigin = [&](int b, const Grid& g, int& x, int& y, int& z) {
+    subdomainPosition(b, g.bx, g.by, g.bz, x, y, z);
+    x = ((x % nx_) + nx_) % nx_;
+    y = ((y % ny_) + ny_) % ny_;
+    z = ((z % nz_) + nz_) % nz_;
+  };
+  const int nDeal = numGlobalParts(gd.bx, gd.by, gd.bz);
+  for (int b = 0; b < nDeal; ++b) {
+    int x, y, z;
+    wrappedOrigin(b, gd, x, y, z);
+    const int a = subdomainId(sx_, sy_, sz_, x, y, z);
+    if (pidMap_[a] >= 0) continue;
+    const int parent = brickAnchor(subdomainId(ga.bx, ga.by, ga.bz, x, y, z), ga.bx, ga.by, ga.bz);
+    if (ranksOf[parent].empty()) throw argError("CreatePIDMap: a brick without an owning rank");
+    pidMap_[a] = ranksOf[parent][cursor[parent]++ % ranksOf[parent].size()];
+  }
+  // phase 4
+  for (int sd = 0; sd < nfine; ++sd) {
+    if (pidMap_[sd] >= 0) continue;
+    int x, y, z;
+    wrappedOrigin(sd, ladder[0], x, y, z);
+    int src = subdomainId(sx_, sy_, sz_, x, y, z);
+    if (pidMap_[src] < 0) src = brickAnchor(subdomainId(gd.bx, gd.by, gd.bz, x, y, z), gd.bx, gd.by, gd.bz);
+    if (pidMap_[src] < 0) throw argError("CreatePIDMap: a subdomain outside every brick");
+    pidMap_[sd] = pidMap_[src];
+  }
+  std::vector<char> seen(P, 0);
   nprocs_ = 0;
-  for (int j = 0; j < 1000; ++j) {
-    nparts = numGlobalParts(sx, sy, sz);
-    int prevNprocs = nprocs_;
-    std::vector<std::vector<int>> prevGroups = pidGroups;
-    for (int i = 0; i < nparts; ++i) {
-      int x, y, z;
-      subdomainPosition(i, sx, sy, sz, x, y, z);
-      wrap(x, y, z);
-      int sd = subdomainId(sx_, sy_, sz_, x, y, z);
-      if (pidGroups[sd].empty()) pidGroups[sd].push_back(nprocs_++);
-    }
-    if (nprocs_ > P) {
-      nprocs_ = prevNprocs;
-      pidGroups = prevGroups;
-      break;
-    }
-    sx2 = sx;
-    sy2 = sy;
-    sz2 = sz;
-    sx /= cx;
-    sy /= cy;
-    if (nz_ > 1) sz /= cz;
-    if (sx < sx_ || sy < sy_ || sz < sz_) {
-      sx = sx2;
-      sy = sy2;
-      sz = sz2;
-      break;
-    }
-  }
-  nparts = numGlobalParts(sx_, sy_, sz_);
-  for (int j = 0; j < 1000; ++j) {
-    if (nprocs_ >= P) break;
-    for (int sd = 0; sd < nparts; ++sd) {
-      if (nprocs_ >= P) break;
-      if (!pidGroups[sd].empty()) pidGroups[sd].push_back(nprocs_++);
-    }
-  }
-  nparts = numGlobalParts(sx, sy, sz);
-  for (int i = 0; i < nparts; ++i) {
-    int x, y, z;
-    subdomainPosition(i, sx, sy, sz, x, y, z);
-    wrap(x, y, z);
-    int sd = subdomainId(sx_, sy_, sz_, x, y, z);
-    if (pidMap_[sd] != -1) continue;
-    int sd2 = subdomainId(sx2, sy2, sz2, x, y, z);
-    subdomainPosition(sd2, sx2, sy2, sz2, x, y, z);
-    wrap(x, y, z);
-    sd2 = subdomainId(sx_, sy_, sz_, x, y, z);
-    if (pidGroups[sd2].empty()) throw argError("CreatePIDMap: invalid subdomain index");
-    pidMap_[sd] = pidGroups[sd2][sdPidNum[sd2]++ % pidGroups[sd2].size()];
-  }
-  nparts = numGlobalParts(sx_, sy_, sz_);
-  for (int i = 0; i < nparts; ++i) {
-    if (pidMap_[i] != -1) continue;
-    int x, y, z;
-    subdomainPosition(i, sx_, sy_, sz_, x, y, z);
-    wrap(x, y, z);
-    int sd = subdomainId(sx_, sy_, sz_, x, y, z);
-    if (pidMap_[sd] != -1) {
-      pidMap_[i] = pidMap_[sd];
-      continue;
-    }
-    sd = subdomainId(sx, sy, sz, x, y, z);
-    subdomainPosition(sd, sx, sy, sz, x, y, z);
-    wrap(x, y, z);
-    sd = subdomainId(sx_, sy_, sz_, x, y, z);
-    if (pidMap_[sd] == -1) throw argError("CreatePIDMap: invalid subdomain index");
-    pidMap_[i] = pidMap_[sd];
-  }
-  std::vector<int> tmp(pidMap_);
-  std::sort(tmp.begin(), tmp.end());
-  nprocs_ = (int)(std::unique(tmp.begin(), tmp.end()) - tmp.begin());
+  for (int r : pidMap_)
+    if (!seen[r]) { seen[r] = 1; ++nprocs_; }
 }
 
 void CartesianPartitioner::partition() {
   createPidMap();
   sdMap_.clear();
-  int nparts = numGlobalParts(sx_, sy_, sz_);
-  for (int sd = 0; sd < nparts; ++sd)
+  for (int sd = 0; sd < (int)pidMap_.size(); ++sd)
     if (pidMap_[sd] == mypid_) sdMap_.push_back(sd);
 }
 
-// src/HYMLS_CartesianPartitioner.cpp:224-263
-static int startAndEnd(int pos, int idx, int idxMax, int dim, int mx, bool perio, int& type, int& start,
-                       int& end) {
-  int len = std::max((mx + idxMax - 1) / idxMax, 1);
-  if (idx == idxMax)
-    type = 2;
-  else if (idx >= 0)
-    type = 1;
-  else
-    type = 0;
-  start = idx;
-  if (idx == idxMax)
-    start = mx;
-  else if (idx > 0)
-    start = std::min(len * idx, mx);
-  end = start + 1;
-  if (type == 1) end = std::min(len * (idx + 1), mx);
-  if (!perio) {
-    if (pos == 0 && idx == -1) return 1;
-    if (pos + mx + 1 == dim) {
-      if (idx == idxMax) return 1;
-      if (idx == idxMax - 1) end += 1;
-    }
+// ---------------------------------------------------------------------------------------------
+// Groups of a Cartesian subdomain.  Behaviour of CartesianPartitioner::GetGroups
+// (src/HYMLS_CartesianPartitioner.cpp:224-408), formulated as a tensor product: every axis of the subdomain
+// is cut into PIECES
+//     [plane of the previous subdomain] [inner piece 0] ... [inner piece r-1] [own separator plane]
+// (no previous plane at a non-periodic near wall; at a non-periodic far wall the own plane does not exist and
+// its cells join the last inner piece).  A (z-piece, y-piece, x-piece, variable) product is interior when all
+// three pieces are inner (pressures: two of three), otherwise one separator group whose type encodes the
+// three piece kinds in base 3.  Products are visited z-piece outermost, variable innermost: that order is the
+// group order of the reference and decides which pressure nodes are retained.
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct AxisPiece {
+  int kind;    // 0 previous plane, 1 inner, 2 own plane
+  int lo, hi;  // cell offsets [lo, hi) from the subdomain origin
+};
+std::vector<AxisPiece> cutAxis(int origin, int extent, int n, int pieces, bool periodic) {
+  std::vector<AxisPiece> out;
+  if (periodic || origin > 0) out.push_back({0, -1, 0});
+  const bool farWall = !periodic && origin + extent + 1 == n;
+  const int width = std::max((extent + pieces - 1) / pieces, 1);
+  for (int q = 0; q < pieces; ++q) {
+    const int lo = std::min(q * width, extent);
+    int hi = std::min((q + 1) * width, extent);
+    if (farWall && q == pieces - 1) ++hi;
+    if (hi > lo) out.push_back({1, lo, hi});
   }
-  if (start == end) return 1;
-  return 0;
+  if (!farWall) out.push_back({2, extent, extent + 1});
+  return out;
 }
+}  // namespace
 
-// src/HYMLS_CartesianPartitioner.cpp:265-408
 void CartesianPartitioner::getGroups(int localSd, std::vector<gidx>& interior,
                                      std::vector<SepGroup>& groups) const {
   interior.clear();
   groups.clear();
+  int ox, oy, oz;
+  subdomainPosition(sdMap_[localSd], sx_, sy_, sz_, ox, oy, oz);
+  const int ex = std::min(nx_ - ox, sx_) - 1, ey = std::min(ny_ - oy, sy_) - 1, ez = std::min(nz_ - oz, sz_) - 1;
+  if (ex == 0 || ey == 0 || (ez == 0 && nz_ > 1)) throw argError("Can't have a subdomain of size 1");
+  const std::vector<AxisPiece> cutX = cutAxis(ox, ex, nx_, std::max(rx_, 1), perio_ & X_PERIO);
+  const std::vector<AxisPiece> cutY = cutAxis(oy, ey, ny_, std::max(ry_, 1), perio_ & Y_PERIO);
+  const std::vector<AxisPiece> cutZ = cutAxis(oz, ez, nz_, std::max(rz_, 1), perio_ & Z_PERIO);
+  // grid coordinates of the offsets -1 .. extent (periodic wrap)
+  auto coords = [](int origin, int extent, int n) {
+    std::vector<gidx> c(extent + 2);
+    for (int o = -1; o <= extent; ++o) c[o + 1] = (gidx)((origin + o + n) % n);
+    return c;
+  };
+  const std::vector<gidx> X = coords(ox, ex, nx_), Y = coords(oy, ey, ny_), Z = coords(oz, ez, nz_);
   std::vector<gidx> retained;
-  int gsd = sdMap_[localSd];
-  int xpos, ypos, zpos;
-  subdomainPosition(gsd, sx_, sy_, sz_, xpos, ypos, zpos);
-  int xmax = std::min(nx_ - xpos - 1, sx_ - 1);
-  int ymax = std::min(ny_ - ypos - 1, sy_ - 1);
-  int zmax = std::min(nz_ - zpos - 1, sz_ - 1);
-  if (xmax == 0 || ymax == 0 || (zmax == 0 && nz_ > 1)) throw argError("Can't have a subdomain of size 1");
-  int iMax = rx_ > 1 ? rx_ : 1, jMax = ry_ > 1 ? ry_ : 1, kMax = rz_ > 1 ? rz_ : 1;
-
-  for (int kidx = -1; kidx <= kMax; ++kidx) {
-    bool kint = kidx >= 0 && kidx < kMax;
-    int ktype, kstart, kend;
-    if (startAndEnd(zpos, kidx, kMax, nz_, zmax, perio_ & Z_PERIO, ktype, kstart, kend)) continue;
-    for (int jidx = -1; jidx <= jMax; ++jidx) {
-      bool jint = jidx >= 0 && jidx < jMax;
-      int jtype, jstart, jend;
-      if (startAndEnd(ypos, jidx, jMax, ny_, ymax, perio_ & Y_PERIO, jtype, jstart, jend)) continue;
-      for (int iidx = -1; iidx <= iMax; ++iidx) {
-        bool iint = iidx >= 0 && iidx < iMax;
-        int itype, istart, iend;
-        if (startAndEnd(xpos, iidx, iMax, nx_, xmax, perio_ & X_PERIO, itype, istart, iend)) continue;
+  for (const AxisPiece& pz : cutZ)
+    for (const AxisPiece& py : cutY)
+      for (const AxisPiece& px : cutX) {
+        const bool touchesPrev = px.kind == 0 || py.kind == 0 || pz.kind == 0;
+        const int innerAxes = (px.kind == 1) + (py.kind == 1) + (pz.kind == 1);
         for (int d = 0; d < dof_; ++d) {
           const int vt = variableType_[d];
-          // destination: -1 interior, otherwise index of the group in `groups`
-          int dst = -1, dst2 = -2;
-          if ((vt == VT_PRESSURE || vt == VT_INTERIOR) && (iidx == -1 || jidx == -1 || kidx == -1)) {
-            continue;
-          } else if ((iint && jint && kint) || vt == VT_INTERIOR ||
-                     (vt == VT_PRESSURE &&
-                      ((iint && jint) || (iint && kint) || (jint && kint) || retainPressures_ > 1))) {
-            dst = -1;
-          } else {
-            int type = -1000;
-            if (linkRetained_) type = 2 * dof_ * (itype + 3 * (jtype + 3 * ktype));
-            bool isVel = vt == VT_U || vt == VT_V || vt == VT_W;
-            if (!((linkVelocities_ && isVel) || (linkTubePressures_ && vt == VT_PRESSURE))) type += 2 * d;
+          const bool cellCentred = vt == VT_PRESSURE || vt == VT_INTERIOR;
+          if (cellCentred && touchesPrev) continue;  // those planes carry the neighbour's cell-centred unknowns
+          const bool isInterior = innerAxes == 3 || vt == VT_INTERIOR ||
+                                  (vt == VT_PRESSURE && (innerAxes == 2 || retainPressures_ > 1));
+          int target = -1, targetOdd = -1;  // group indices (B-grid: odd cells go to a second group)
+          if (!isInterior) {
+            int type = linkRetained_ ? 2 * dof_ * (px.kind + 3 * (py.kind + 3 * pz.kind)) : -1000;
+            const bool velocity = vt == VT_U || vt == VT_V || vt == VT_W;
+            const bool shared = (linkVelocities_ && velocity) || (linkTubePressures_ && vt == VT_PRESSURE);
+            if (!shared) type += 2 * d;
+            target = (int)groups.size();
             groups.emplace_back();
             groups.back().type = type;
-            dst = (int)groups.size() - 1;
             if (bgrid_) {
+              targetOdd = (int)groups.size();
               groups.emplace_back();
               groups.back().type = type + 1;
-              dst2 = (int)groups.size() - 1;
             }
           }
-          for (int k = kstart; k < kend; ++k)
-            for (int j = jstart; j < jend; ++j)
-              for (int i = istart; i < iend; ++i) {
-                gidx gid = d + (gidx)((i + xpos + nx_) % nx_) * dof_ +
-                           (gidx)((j + ypos + ny_) % ny_) * nx_ * dof_ +
-                           (gidx)((k + zpos + nz_) % nz_) * nx_ * ny_ * dof_;
-                if (vt == VT_PRESSURE && i >= 0 && j >= 0 && k >= 0 && (int)retained.size() < retainPressures_) {
+          for (int k = pz.lo; k < pz.hi; ++k)
+            for (int j = py.lo; j < py.hi; ++j)
+              for (int i = px.lo; i < px.hi; ++i) {
+                const gidx gid = d + dof_ * (X[i + 1] + nx_ * (Y[j + 1] + (gidx)ny_ * Z[k + 1]));
+                if (vt == VT_PRESSURE && i >= 0 && j >= 0 && k >= 0 && (int)retained.size() < retainPressures_)
                   retained.push_back(gid);
-                } else if (dst2 >= 0 && (i + xpos + j + ypos) % 2) {
-                  groups[dst2].nodes.push_back(gid);
-                } else if (dst < 0) {
+                else if (targetOdd >= 0 && (i + ox + j + oy) % 2)
+                  groups[targetOdd].nodes.push_back(gid);
+                else if (target < 0)
                   interior.push_back(gid);
-                } else {
-                  groups[dst].nodes.push_back(gid);
-                }
+                else
+                  groups[target].nodes.push_back(gid);
               }
         }
       }
+  size_t kept = 0;
+  for (size_t g = 0; g < groups.size(); ++g)
+    if (!groups[g].nodes.empty()) {
+      if (kept != g) std::swap(groups[kept], groups[g]);
+      ++kept;
     }
-  }
-  groups.erase(std::remove_if(groups.begin(), groups.end(), [](const SepGroup& g) { return g.nodes.empty(); }),
-               groups.end());
-  for (gidx g : retained) {
+  groups.resize(kept);
+  for (gidx g : retained) {  // retained pressures: singleton groups that are never linked
     groups.emplace_back();
     groups.back().type = -1;
     groups.back().nodes.push_back(g);
@@ -527,7 +527,7 @@ void buildHierarchicalMap(const CartesianPartitioner& part, const std::vector<ch
 }  // namespace hymls
 
 // =============================================================================================
-// Skew Cartesian partitioner (src/HYMLS_SkewCartesianPartitioner.cpp)
+// Skew Cartesian partitioner
 // =============================================================================================
 namespace hymls {
 
@@ -538,349 +538,269 @@ CartesianPartitioner* makePartitioner(ParameterList& params, int level, int npro
   throw Error(HYMLS_B200_ERR_ARG, "Up to now we only support Cartesian partitioning");
 }
 
-// :128-160
-int SkewCartesianPartitioner::subdomainPosition(int sd, int sx, int sy, int sz, int& x, int& y, int& z) const {
-  (void)sz;
-  const int npx = nx_ / sx, npy = ny_ / sy;
+// ---------------------------------------------------------------------------------------------
+// Geometry.  In the sheared coordinates  s = x + y,  d = x - y,  t = x - y + z  the skew subdomains of size b
+// are the cubes  S*b - 1 <= s < (S+1)*b - 1,  D*b <= d < (D+1)*b,  T*b <= t < (T+1)*b  (the cells a subdomain
+// owns = the pressure nodes of its template).  The reference numbers them layer by layer (Z = T - D), each
+// layer as interleaved rows: "even" rows of npx subdomains at (col*b, row*b) followed by "odd" rows of npx + 1
+// subdomains at ((col - 1/2) b, (row + 1/2) b).  Checked against the closed forms the reference's unit tests
+// pin (tests/test_oracle_skew.py) and cell by cell against the oracle (tests/test_host_maps.py).
+// ---------------------------------------------------------------------------------------------
+static inline int floorDiv(int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
+
+int SkewCartesianPartitioner::numGlobalParts(int bx, int by, int bz) const {
+  const int npx = nx_ / bx, npy = ny_ / by, npz = nz_ / bz;
   const int perLayer = 2 * npx * npy + npx + npy;
-  const int perRow = 2 * npx + 1;
-  const int Z = perLayer > 0 ? sd / perLayer : 0;
-  int Y = ((sd - Z * perLayer) / perRow) * 2 - 1;
-  int X = ((sd - Z * perLayer) % perRow) * 2;
-  if (X >= npx * 2) {
-    X -= npx * 2 + 1;
-    Y += 1;
+  return std::max(nz_ > 1 ? perLayer * (npz + 1) : perLayer, 1);
+}
+
+int SkewCartesianPartitioner::subdomainPosition(int sd, int bx, int by, int bz, int& x, int& y, int& z) const {
+  (void)bz;
+  const int npx = nx_ / bx, npy = ny_ / by;
+  const int perLayer = 2 * npx * npy + npx + npy, perRowPair = 2 * npx + 1;
+  const int layer = perLayer > 0 ? sd / perLayer : 0;
+  const int inLayer = sd - layer * perLayer;
+  const int pairIdx = inLayer / perRowPair, inPair = inLayer % perRowPair;
+  // a "row pair" is an odd row (npx + 1 subdomains, half a brick lower) stored AFTER the even row above it:
+  // inPair < npx: even row at y = pairIdx*b - b/2 ... written in half-brick units below
+  const int h = bx / 2;
+  if (inPair < npx) {
+    x = 2 * inPair * h;
+    y = (2 * pairIdx - 1) * h + h;
+  } else {
+    x = (2 * (inPair - npx) - 1) * h;
+    y = 2 * pairIdx * h + h;
   }
-  x = (X * sx) / 2;
-  y = (Y * sx) / 2 + sx / 2;
-  z = Z * sx;
-  if (x == nx_ - sx / 2 && (perio_ & X_PERIO)) return 1;
-  if (y == ny_ && (perio_ & Y_PERIO)) return 1;
-  if (z == nz_ && (perio_ & Z_PERIO)) return 1;
+  z = layer * bx;
+  // periodic images: the last odd column / last row pair / top layer coincide with the first ones
+  if ((perio_ & X_PERIO) && x == nx_ - h) return 1;
+  if ((perio_ & Y_PERIO) && y == ny_) return 1;
+  if ((perio_ & Z_PERIO) && z == nz_) return 1;
   return 0;
 }
 
-// :162-207
-int SkewCartesianPartitioner::subdomainId(int sx, int sy, int sz, int x, int y, int z) const {
-  const int npx = nx_ / sx, npy = ny_ / sy, npz = nz_ / sz;
-  const int dir1 = npx + 1, dir2 = npx, dir3 = 2 * npx * npy + npx + npy;
-  const int xc = x / sx, yc = y / sx, zc = z / sx;
-  int sd = zc * dir3 + yc * (dir2 + dir1) + xc;
-  x -= xc * sx - 1;
-  y -= yc * sx;
-  z -= zc * sx;
-  const bool front = y < sx - x;
-  const bool right = y < x;
-  bool below = z <= y - x;
-  if (right) below = z <= sx + y - x;
-  if (!front) sd += dir1;
-  if (!right) sd += dir2;
-  if (!below) sd += dir3;
-  if (!front && right && (perio_ & X_PERIO) && xc == npx - 1) sd -= dir2;
-  if (!front && !right && (perio_ & Y_PERIO) && yc == npy - 1) sd -= dir3 - dir2;
-  if (!below && (perio_ & Z_PERIO) && zc == npz - 1) sd -= npz * dir3;
-  return sd;
+int SkewCartesianPartitioner::subdomainId(int bx, int by, int bz, int x, int y, int z) const {
+  const int b = bx;
+  const int npx = nx_ / bx, npy = ny_ / by, npz = nz_ / bz;
+  const int perLayer = 2 * npx * npy + npx + npy, perRowPair = 2 * npx + 1;
+  const int S = floorDiv(x + y + 1, b), D = floorDiv(x - y, b), T = floorDiv(x - y + z, b);
+  int layer = T - D;
+  // cube (S, D) of the s-d plane: S + D even -> even row at (col, row) = ((S+D)/2, (S-D)/2),
+  //                               S + D odd  -> odd row, col = (S+D+1)/2 in 0..npx, below even row (S-D+1)/2
+  int pairIdx, inPair;
+  if (((S + D) & 1) == 0) {
+    pairIdx = (S - D) / 2;
+    inPair = (S + D) / 2;
+    if ((perio_ & Y_PERIO) && pairIdx == npy) pairIdx = 0;
+  } else {
+    pairIdx = (S - D - 1) / 2;
+    int col = (S + D + 1) / 2;
+    if ((perio_ & X_PERIO) && col == npx) col = 0;
+    inPair = npx + col;
+  }
+  if ((perio_ & Z_PERIO) && layer == npz) layer = 0;
+  return layer * perLayer + pairIdx * perRowPair + inPair;
 }
 
-// :219-238
-int SkewCartesianPartitioner::numGlobalParts(int sx, int sy, int sz) const {
-  const int npx = nx_ / sx, npy = ny_ / sy, npz = nz_ / sz;
-  const int perLayer = 2 * npx * npy + npx + npy;
-  int n = perLayer;
-  if (nz_ > 1) n += perLayer * npz;
-  return std::max(n, 1);
+// ---------------------------------------------------------------------------------------------
+// Template of a subdomain = the nodes it touches (its interior and all separators around it), relative to the
+// subdomain position.  Per variable type the reference's template is exactly the set of lattice points of a
+// polytope in (s, d, t, z) (b = sx; found by fitting the four plane families to the reference's node lists
+// for sx = 4, 6, 8 and asserted equal to the oracle's lists in tests/test_oracle_skew.py):
+//     P:  -1 <= s <= b-2    0 <= d <= b-1    0 <= t <= b-1    |z| <= b-1        (the owned cells)
+//     U:  -2 <= s <= b-2   -1 <= d <= b-1   -1 <= t <= b-1    |z| <= b-1        (+ west faces)
+//     V:  -2 <= s <= b-2    0 <= d <= b      0 <= t <= b      |z| <= b-1        (+ south faces)
+//     W:  -2 <= s <= b-1   -1 <= d <= b     -1 <= t <= b-1   -b <= z <= b-1     (+ bottom faces), without the
+//         nodes of even t on the four side planes s = -2, s = b-1, d = -1, d = b
+// In 2D only z = 0 exists.
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct SkewShape {
+  int b;
+  bool flat;  // nz == 1
+  bool contains(int vt, int x, int y, int z) const {
+    if (flat && z != 0) return false;
+    const int s = x + y, d = x - y, t = d + z;
+    switch (vt) {
+      case VT_PRESSURE: return s >= -1 && s <= b - 2 && d >= 0 && d <= b - 1 && t >= 0 && t <= b - 1 && z > -b && z < b;
+      case VT_U: return s >= -2 && s <= b - 2 && d >= -1 && d <= b - 1 && t >= -1 && t <= b - 1 && z > -b && z < b;
+      case VT_V: return s >= -2 && s <= b - 2 && d >= 0 && d <= b && t >= 0 && t <= b && z > -b && z < b;
+      case VT_W:
+        if (!(s >= -2 && s <= b - 1 && d >= -1 && d <= b && t >= -1 && t <= b - 1 && z >= -b && z < b)) return false;
+        return (t & 1) || !(s == -2 || s == b - 1 || d == -1 || d == b);
+      default: return false;
+    }
+  }
+};
+}  // namespace
+
+// Classifies every template node by the set of neighbouring subdomains (lattice translates a*e1 + b*e2 + c*e3,
+// a, b, c in {-1, 0, 1}, e1 = (h, h, 0), e2 = (-h, h, 2h), e3 = (0, 0, 2h), h = sx/2) whose templates contain it
+// as well.  Class 0 = no neighbour (interior); the other classes are numbered in order of first appearance
+// when the template is scanned by ascending (z, y, x, variable) -- the reference's group order.
+void SkewCartesianPartitioner::classifyTemplate() {
+  const SkewShape shape{sx_, nz_ <= 1};
+  const int b = sx_, h = sx_ / 2;
+  struct Shift { int x, y, z; };
+  std::vector<Shift> shifts;
+  for (int a = -1; a <= 1; ++a)
+    for (int bb = -1; bb <= 1; ++bb)
+      for (int c = -1; c <= 1; ++c)
+        if (a || bb || c) shifts.push_back({a * h - bb * h, a * h + bb * h, bb * b + c * b});
+  std::vector<uint32_t> classMask;  // classMask[k-1] = neighbour set of class k
+  std::vector<TemplateNode> scan;
+  for (int z = -b; z < b; ++z)
+    for (int y = -2 * b; y <= 2 * b; ++y)
+      for (int x = -2 * b; x <= 2 * b; ++x)
+        for (int v = 0; v < dof_; ++v) {
+          const int vt = variableType_[v];
+          if (!shape.contains(vt, x, y, z)) continue;
+          uint32_t mask = 0;
+          for (size_t q = 0; q < shifts.size(); ++q)
+            if (shape.contains(vt, x - shifts[q].x, y - shifts[q].y, z - shifts[q].z)) mask |= 1u << q;
+          int cls = 0;
+          if (mask) {
+            size_t k = 0;
+            while (k < classMask.size() && classMask[k] != mask) ++k;
+            if (k == classMask.size()) classMask.push_back(mask);
+            cls = (int)k + 1;
+          }
+          scan.push_back({x, y, z, v, cls});
+        }
+  ncls_ = (int)classMask.size() + 1;
+  // bucket by (class, variable), keeping the scan order inside a bucket
+  clsVarPtr_.assign((size_t)ncls_ * dof_ + 1, 0);
+  for (const TemplateNode& t : scan) clsVarPtr_[(size_t)t.cls * dof_ + t.var + 1]++;
+  for (size_t q = 1; q < clsVarPtr_.size(); ++q) clsVarPtr_[q] += clsVarPtr_[q - 1];
+  std::vector<int64_t> fill(clsVarPtr_.begin(), clsVarPtr_.end() - 1);
+  tmpl_.resize(scan.size());
+  for (const TemplateNode& t : scan) tmpl_[fill[(size_t)t.cls * dof_ + t.var]++] = t;
 }
 
-// :240-368
 void SkewCartesianPartitioner::partition() {
   if (sx_ != sy_ || (nz_ > 1 && sx_ != sz_)) throw argError("sx, sy and sz should be the same");
-  if ((sx_ / 2) * 2 != sx_) throw argError("sx should be even");
+  if (sx_ % 2) throw argError("sx should be even");
   if (nx_ % sx_ || ny_ % sy_ || nz_ % sz_)
     throw argError("You are trying to partition a domain whose size is not a multiple of the subdomain size");
   createPidMap();
   sdMap_.clear();
   const int nparts = numGlobalParts(sx_, sy_, sz_);
   for (int sd = 0; sd < nparts; ++sd) {
-    int i, j, k;
-    if (subdomainPosition(sd, sx_, sy_, sz_, i, j, k) == 1) continue;
-    i = (i % nx_ + nx_) % nx_;
-    j = (j % ny_ + ny_) % ny_;
-    k = (k % nz_ + nz_) % nz_;
-    if (pidMap_[subdomainId(sx_, sy_, sz_, i, j, k)] == mypid_) sdMap_.push_back(sd);
+    int x, y, z;
+    if (subdomainPosition(sd, sx_, sy_, sz_, x, y, z) == 1) continue;  // periodic image of another subdomain
+    if (pidMap_[brickAnchor(sd, sx_, sy_, sz_)] == mypid_) sdMap_.push_back(sd);
   }
-  buildTemplate();
-  solveGroups();
+  classifyTemplate();
 }
 
-namespace {
-struct Plane45 {
-  std::vector<long long> ptr, plane;
-};
-// :27-78: a diamond of nodes in the xy-plane, row by row
-Plane45 buildPlane45(long long first, int length, long long dirX, long long dirY, int type) {
-  long long left = first, right = first;
-  int height = 2 * length;
-  bool extra = false;
-  const long long dir1 = dirY + dirX, dir2 = dirY - dirX;
-  if (type == 0) {
-    left -= dirX;
-    height++;
-    extra = true;
-  } else if (type == 3) {
-    height++;
-    extra = true;
-  }
-  Plane45 P;
-  P.ptr.push_back(0);
-  for (int i = 0; i < height - 1; ++i) {
-    for (long long j = left; j <= right; j += dirX) P.plane.push_back(j);
-    P.ptr.push_back((long long)P.plane.size());
-    if (i < length - 1) {
-      left += dir2;
-      right += dir1;
-    } else if (extra && i == length - 1) {
-      left += dirY;
-      right += dirY;
-    } else {
-      left += dir1;
-      right += dir2;
-    }
-  }
-  return P;
-}
-}  // namespace
-
-// getTemplate :372-565
-void SkewCartesianPartitioner::buildTemplate() {
-  const int sx = sx_, dof = dof_;
-  const long long nx = sx * 4;
-  const long long dirX = dof, dirY = dof * nx, dirZ = dof * nx * nx;
-  const long long first[4] = {dof * sx / 2 + dirY + dirZ * sx, dof * sx / 2 + dirZ * sx,
-                              dof * sx / 2 + dirY + dirZ * sx, dof * sx / 2 + dirY + dirZ * sx};
-  const int baseLen[4] = {sx / 2, sx / 2 + 1, sx / 2 + 1, sx / 2};
-  const int typeArr[4] = {VT_U, VT_V, VT_W, VT_PRESSURE};
-  std::vector<std::vector<std::vector<long long>>> nodes(4);
-  for (int type = 0; type < 4; ++type) {
-    auto& layers = nodes[type];
-    layers.assign(2 * sx + 1, std::vector<long long>());
-    Plane45 P = buildPlane45(first[type], baseLen[type], dirX, dirY, type);
-    layers[sx] = P.plane;
-    if (nz_ <= 1) continue;
-    std::vector<long long> bottom, top = P.plane, rowLen;
-    for (size_t i = 0; i + 1 < P.ptr.size(); ++i) rowLen.push_back(P.ptr[i + 1] - P.ptr[i] - 1);
-    std::vector<long long> active, offset;
-    for (int i = 0; i < baseLen[type]; ++i) active.push_back(i);
-    for (long long a : active) offset.push_back(rowLen[a]);
-    for (int i = 0; i < sx; ++i) {
-      for (size_t j = 0; j < active.size(); ++j) {
-        const long long val = P.plane[P.ptr[active[j]] + offset[j]];
-        bottom.push_back(val);
-        top.erase(std::remove(top.begin(), top.end(), val), top.end());
-      }
-      if (typeArr[type] == VT_W) {
-        if (i % 2 == 1) {
-          for (long long j : top) layers[sx + i].push_back(j + i * dirZ - dirY);
-          for (long long j : top) layers[sx + 1 + i].push_back(j + (i + 1) * dirZ);
-        } else {
-          for (long long j : bottom) layers[i].push_back(j - (sx - i) * dirZ);
-          if (i > 0) {
-            for (long long j : bottom) layers[i - 1].push_back(j - (sx - i + 1) * dirZ - dirY);
-          } else {
-            for (long long j : P.plane) layers[sx - 1].push_back(j - dirZ - dirY);
-          }
-        }
-      } else {
-        const int isP = typeArr[type] == VT_PRESSURE ? 1 : 0;
-        if (i < sx - isP)
-          for (long long j : bottom) layers[i + isP].push_back(j - (sx - i - isP) * dirZ);
-        for (long long j : top) layers[sx + 1 + i].push_back(j + (i + 1) * dirZ);
-      }
-      if (i < sx - 1) {
-        for (auto& d : offset) d--;
-        if (typeArr[type] == VT_PRESSURE) {
-          if (offset[0] < 0) {
-            active.push_back(active.back() + 1);
-            active.erase(active.begin());
-            offset.push_back(rowLen[active.back()]);
-            offset.erase(offset.begin());
-          }
-        } else {
-          if (offset[0] < 0) {
-            active.erase(active.begin());
-            offset.erase(offset.begin());
-          } else if (offset[0] == 0) {
-            active.push_back(active.back() + 1);
-            offset.push_back(rowLen[active.back()]);
-          }
-        }
-      }
-    }
-  }
-  nodes[0].pop_back();
-  nodes[0].erase(nodes[0].begin());
-  nodes[1].pop_back();
-  nodes[1].erase(nodes[1].begin());
-  nodes[2].pop_back();
-  nodes[3].pop_back();
-  nodes[3].erase(nodes[3].begin());
-  template_.clear();
-  template_.emplace_back();
-  for (int i = 0; i < dof; ++i)
-    if (variableType_[i] == VT_W) {
-      for (long long v : nodes[2].front()) template_.back().push_back(v + i);
-      nodes[2].erase(nodes[2].begin());
-      break;
-    }
-  for (int j = 0; j < 2 * sx - 1; ++j) {
-    template_.emplace_back();
-    for (int i = 0; i < dof; ++i)
-      for (int type = 0; type < 4; ++type)
-        if (variableType_[i] == typeArr[type])
-          for (long long v : nodes[type][j]) template_.back().push_back(v + i);
-    std::sort(template_.back().begin(), template_.back().end());
-  }
-}
-
-// solveGroups :567-654: classify every template node by the set of neighbouring domains it lies in
-void SkewCartesianPartitioner::solveGroups() {
-  const long long nx = sx_ * 4;
-  const long long dirX = (long long)dof_ * sx_, dirY = (long long)dof_ * nx * sx_, dirZ = (long long)dof_ * nx * nx * sx_;
-  const long long first = dirX + dirY + dirZ;
-  const long long d1 = (dirY + dirX) / 2, d2 = (dirY - dirX) / 2 + dirZ, d3 = dirZ;
-  const long long pos[27] = {0, -d3, d3, -d2, -d2 - d3, -d2 + d3, d2, d2 - d3, d2 + d3,
-                             -d1, -d1 - d3, -d1 + d3, -d1 - d2, -d1 - d2 - d3, -d1 - d2 + d3, -d1 + d2,
-                             -d1 + d2 - d3, -d1 + d2 + d3, d1, d1 - d3, d1 + d3, d1 - d2,
-                             d1 - d2 - d3, d1 - d2 + d3, d1 + d2, d1 + d2 - d3, d1 + d2 + d3};
-  std::vector<long long> temp;
-  for (auto& layer : template_)
-    for (long long v : layer) temp.push_back(v + first);
-  std::vector<long long> sorted(temp);
-  std::sort(sorted.begin(), sorted.end());
-  std::vector<std::vector<long long>> groups(1);
-  std::vector<unsigned long> domains(1, 1ul);
-  for (long long node : temp) {
-    unsigned long bits = 0;
-    for (int i = 0; i < 27; ++i)
-      if (std::binary_search(sorted.begin(), sorted.end(), node - pos[i])) bits += 1ul << i;
-    bool found = false;
-    for (size_t g = 0; g < groups.size(); ++g)
-      if (domains[g] == bits) {
-        groups[g].push_back(node);
-        found = true;
-        break;
-      }
-    if (!found) {
-      groups.emplace_back(1, node);
-      domains.push_back(bits);
-    }
-  }
-  groupsT_.clear();
-  groupsT_.emplace_back(1, groups[0]);
-  for (size_t g = 1; g < groups.size(); ++g) {
-    groupsT_.emplace_back(dof_);
-    for (long long node : groups[g]) groupsT_.back()[((node % dof_) + dof_) % dof_].push_back(node);
-  }
-}
-
-// GetGroups :656-812
+// Groups of one subdomain (behaviour of SkewCartesianPartitioner::GetGroups, src/HYMLS_SkewCartesianPartitioner.cpp:
+// 656-812): the classified template translated to the subdomain position and clipped to the grid.  Class 0 is
+// the interior (its first pressure nodes become retained singleton groups); every other (class, variable)
+// bucket is split by the subdomain that owns the node's cell, ascending, optionally subdivided into rx pieces.
+// Velocities on a non-periodic far wall are Dirichlet rows: dropped from the groups, and kept as interior by
+// the subdomain owning the cell.
 void SkewCartesianPartitioner::getGroups(int localSd, std::vector<gidx>& interior,
                                          std::vector<SepGroup>& out) const {
   interior.clear();
   out.clear();
-  const int gsd = sdMap_[localSd];
-  int sdx, sdy, sdz;
-  subdomainPosition(gsd, sx_, sy_, sz_, sdx, sdy, sdz);
-  const long long nx = 4 * sx_;
-  std::vector<std::vector<std::vector<gidx>>> groups;
-  for (auto const& cat : groupsT_) {
-    groups.emplace_back();
-    for (auto const& group : cat) {
-      groups.back().emplace_back();
-      for (long long node : group) {
-        const int var = (int)(node % dof_);
-        int x = (int)((node / dof_) % nx) + sdx - 1 - sx_;
-        int y = (int)((node / dof_ / nx) % nx) + sdy - 1 - 3 * sx_ / 2;
-        int z = (int)(node / dof_ / nx / nx) + sdz - 2 * sx_;
-        if (perio_ & X_PERIO) x = (x + nx_) % nx_;
-        if (perio_ & Y_PERIO) y = (y + ny_) % ny_;
-        if (perio_ & Z_PERIO) z = (z + nz_) % nz_;
-        if (x >= 0 && x < nx_ && y >= 0 && y < ny_ && z >= 0 && z < nz_)
-          groups.back().back().push_back((gidx)x * dof_ + (gidx)nx_ * y * dof_ + (gidx)nx_ * ny_ * z * dof_ + var);
-      }
-    }
-  }
-  // first pressure nodes of the interior become retained (singleton) groups.  The reference erases from
-  // the vector it iterates over, so the element sliding into the erased slot is skipped: same here.
-  {
-    int retained = 0;
-    std::vector<gidx>& in0 = groups[0][0];
-    for (size_t it = 0; it < in0.size(); ++it) {
-      const gidx node = in0[it];
-      if (variableType_[(int)(((node % dof_) + dof_) % dof_)] == VT_PRESSURE) {
-        groups.emplace_back();
-        groups.back().emplace_back(1, node);
-        std::vector<gidx>& in = groups[0][0];  // (emplace_back may have moved the outer vector)
-        in.erase(in.begin() + it);
-        if (++retained >= retainPressures_) break;
-      }
-    }
-  }
-  interior = groups[0][0];
-  auto cellOwner = [&](gidx node) {
-    gidx cell = node / dof_;
-    return subdomainId(sx_, sy_, sz_, (int)(cell % nx_), (int)((cell / nx_) % ny_), (int)(cell / ((gidx)nx_ * ny_)));
+  const int me = sdMap_[localSd];
+  int px, py, pz;
+  subdomainPosition(me, sx_, sy_, sz_, px, py, pz);
+  // translated node: returns false when it falls outside the grid
+  auto place = [&](const TemplateNode& t, int& x, int& y, int& z) {
+    x = t.dx + px;
+    y = t.dy + py;
+    z = t.dz + pz;
+    if (perio_ & X_PERIO) x = (x + nx_) % nx_;
+    if (perio_ & Y_PERIO) y = (y + ny_) % ny_;
+    if (perio_ & Z_PERIO) z = (z + nz_) % nz_;
+    return x >= 0 && x < nx_ && y >= 0 && y < ny_ && z >= 0 && z < nz_;
   };
-  int type = 1;
-  for (size_t i = 1; i < groups.size(); ++i) {
-    type++;
-    for (auto const& group : groups[i]) {
-      std::vector<std::pair<int, SepGroup>> parts;  // keyed by owner subdomain, kept sorted (std::map order)
-      for (gidx node : group) {
-        const int owner = cellOwner(node);
-        auto it = std::lower_bound(parts.begin(), parts.end(), owner,
-                                   [](const std::pair<int, SepGroup>& a, int b) { return a.first < b; });
-        if (it != parts.end() && it->first == owner) {
-          it->second.nodes.push_back(node);
-        } else {
-          SepGroup g;
-          g.type = linkVelocities_ ? type : -1;
-          g.nodes.push_back(node);
-          parts.insert(it, std::make_pair(owner, g));
-        }
-      }
-      for (auto& pr : parts) {
-        if (rx_ > 1) {
-          if (!linkVelocities_) type++;
-          const int len = (int)pr.second.nodes.size();
-          const int newLen = std::max((len + rx_ - 1) / rx_, 1);
-          const int numParts = (len - 1) / newLen + 1;
-          for (int j = 0; j < numParts; ++j) {
-            SepGroup g2;
-            g2.type = (linkVelocities_ || linkRetained_) ? type : -1;
-            for (int q = j * newLen; q < (j + 1) * newLen && q < len; ++q) g2.nodes.push_back(pr.second.nodes[q]);
-            out.push_back(g2);
-          }
-        } else {
-          out.push_back(pr.second);
-        }
-      }
+  auto gidOf = [&](int x, int y, int z, int v) { return v + dof_ * ((gidx)x + nx_ * ((gidx)y + (gidx)ny_ * z)); };
+  auto onFarWall = [&](int x, int y, int z, int vt) {
+    if (dof_ <= 1) return false;
+    return (vt == VT_U && x == nx_ - 1 && !(perio_ & X_PERIO)) || (vt == VT_V && y == ny_ - 1 && !(perio_ & Y_PERIO)) ||
+           (vt == VT_W && nz_ > 1 && z == nz_ - 1 && !(perio_ & Z_PERIO));
+  };
+  // --- class 0: interior, in scan order over all variables
+  struct Placed { int x, y, z, var; };
+  std::vector<Placed> inner;
+  {
+    // the buckets of class 0 are per variable; merge them back into scan order (z, y, x, variable)
+    std::vector<const TemplateNode*> nodes;
+    for (int64_t q = clsVarPtr_[0]; q < clsVarPtr_[dof_]; ++q) nodes.push_back(&tmpl_[q]);
+    std::sort(nodes.begin(), nodes.end(), [](const TemplateNode* a, const TemplateNode* c) {
+      if (a->dz != c->dz) return a->dz < c->dz;
+      if (a->dy != c->dy) return a->dy < c->dy;
+      if (a->dx != c->dx) return a->dx < c->dx;
+      return a->var < c->var;
+    });
+    for (const TemplateNode* t : nodes) {
+      int x, y, z;
+      if (place(*t, x, y, z)) inner.push_back({x, y, z, t->var});
     }
   }
-  // velocity nodes on the far (non-periodic) boundaries are Dirichlet rows, not separators
-  for (auto& g : out) {
-    std::vector<gidx> copy = g.nodes;
-    for (gidx node : copy) {
-      const int x = (int)((node / dof_) % nx_), y = (int)((node / dof_ / nx_) % ny_);
-      const int z = (int)(node / dof_ / nx_ / ny_);
-      const int vt = variableType_[(int)(node % dof_)];
-      const bool hit = (dof_ > 1 && x == nx_ - 1 && vt == VT_U && !(perio_ & X_PERIO)) ||
-                       (dof_ > 1 && y == ny_ - 1 && vt == VT_V && !(perio_ & Y_PERIO)) ||
-                       (nz_ > 1 && dof_ > 1 && z == nz_ - 1 && vt == VT_W && !(perio_ & Z_PERIO));
-      if (hit) {
-        if (subdomainId(sx_, sy_, sz_, x, y, z) == gsd) interior.push_back(node);
-        g.nodes.erase(std::remove(g.nodes.begin(), g.nodes.end(), node), g.nodes.end());
+  std::vector<gidx> retained;
+  {
+    // The first pressure nodes of the interior are retained.  Reference quirk kept on purpose: it erases from
+    // the list it iterates over, so the element right after a retained node is not examined.
+    std::vector<char> taken(inner.size(), 0);
+    for (size_t q = 0; q < inner.size() && (int)retained.size() < retainPressures_; ++q)
+      if (variableType_[inner[q].var] == VT_PRESSURE) {
+        taken[q] = 1;
+        retained.push_back(gidOf(inner[q].x, inner[q].y, inner[q].z, inner[q].var));
+        ++q;
+      }
+    for (size_t q = 0; q < inner.size(); ++q)
+      if (!taken[q]) interior.push_back(gidOf(inner[q].x, inner[q].y, inner[q].z, inner[q].var));
+  }
+  // --- separator classes.  Far-wall velocities take part in the splitting (they count towards the length of a
+  // part and keep its type number alive) and are removed from the emitted groups afterwards, like the reference.
+  int type = 1;
+  struct Part { int owner; std::vector<gidx> nodes; std::vector<char> wall; };
+  std::vector<Part> parts;
+  auto emitParts = [&]() {
+    std::stable_sort(parts.begin(), parts.end(), [](const Part& a, const Part& c) { return a.owner < c.owner; });
+    for (Part& p : parts) {
+      const int len = (int)p.nodes.size();
+      int piece = len, groupType = linkVelocities_ ? type : -1;
+      if (rx_ > 1) {
+        if (!linkVelocities_) ++type;
+        piece = std::max((len + rx_ - 1) / rx_, 1);
+        groupType = (linkVelocities_ || linkRetained_) ? type : -1;
+      }
+      for (int lo = 0; lo < len; lo += piece) {
+        out.emplace_back();  // (may stay empty: the caller drops empty groups)
+        out.back().type = groupType;
+        for (int q = lo; q < std::min(len, lo + piece); ++q)
+          if (!p.wall[q]) out.back().nodes.push_back(p.nodes[q]);
       }
     }
+    parts.clear();
+  };
+  for (int cls = 1; cls < ncls_; ++cls) {
+    ++type;
+    for (int v = 0; v < dof_; ++v) {
+      const int vt = variableType_[v];
+      for (int64_t q = clsVarPtr_[(size_t)cls * dof_ + v]; q < clsVarPtr_[(size_t)cls * dof_ + v + 1]; ++q) {
+        int x, y, z;
+        if (!place(tmpl_[q], x, y, z)) continue;
+        const int owner = subdomainId(sx_, sy_, sz_, x, y, z);
+        const bool wall = onFarWall(x, y, z, vt);
+        if (wall && owner == me) interior.push_back(gidOf(x, y, z, v));
+        size_t k = 0;
+        while (k < parts.size() && parts[k].owner != owner) ++k;
+        if (k == parts.size()) parts.push_back({owner, {}, {}});
+        parts[k].nodes.push_back(gidOf(x, y, z, v));
+        parts[k].wall.push_back(wall ? 1 : 0);
+      }
+      emitParts();
+    }
+  }
+  for (gidx g : retained) {  // retained pressures: one more class each, through the same splitting rules
+    ++type;
+    parts.push_back({me, std::vector<gidx>(1, g), std::vector<char>(1, 0)});
+    emitParts();
   }
   std::sort(interior.begin(), interior.end());
 }

@@ -54,6 +54,8 @@ class CartesianPartitioner {
   void setParameters(ParameterList& params);
   virtual int numGlobalParts(int sx, int sy, int sz) const;
   void createPidMap();
+  // fine-grid subdomain that contains the (periodically wrapped) origin of brick `b` of the brick grid (bx,by,bz)
+  int brickAnchor(int b, int bx, int by, int bz) const;
 
   int level_, nprocsComm_, mypid_;
   int dim_ = 3, nx_ = 0, ny_ = 0, nz_ = 0, dof_ = 1, perio_ = 0, pvar_ = -1;
@@ -66,8 +68,12 @@ class CartesianPartitioner {
   int nprocs_ = 1;
 };
 
-// src/HYMLS_SkewCartesianPartitioner.cpp: 45-degree rotated (octahedral) subdomains built from a
-// template domain and its 26 neighbours.  Same BasePartitioner machinery (parameters, CreatePIDMap).
+// Skew Cartesian partitioner (behaviour of src/HYMLS_SkewCartesianPartitioner.cpp, formulated geometrically):
+// the subdomains are the unit cubes of side sx of the sheared lattice coordinates
+//     s = x + y,   d = x - y,   t = x - y + z,
+// and the node set ("template") a subdomain touches is, per variable type, the set of lattice points of a
+// polytope bounded by planes of constant s, d, t and z (partitioner.cpp: SkewShape).  Same BasePartitioner
+// machinery (parameters, CreatePIDMap) as the Cartesian one.
 class SkewCartesianPartitioner : public CartesianPartitioner {
  public:
   SkewCartesianPartitioner(ParameterList& params, int level, int nprocs = 1, int mypid = 0)
@@ -77,14 +83,18 @@ class SkewCartesianPartitioner : public CartesianPartitioner {
   int subdomainId(int sx, int sy, int sz, int x, int y, int z) const override;
   int subdomainPosition(int sd, int sx, int sy, int sz, int& x, int& y, int& z) const override;
 
+  // one node of the subdomain template: offset from the subdomain position, variable, class
+  // (0 = touched by this subdomain only, k >= 1 = k-th distinct set of neighbouring subdomains met in scan order)
+  struct TemplateNode { int dx, dy, dz, var, cls; };
+
  protected:
   int numGlobalParts(int sx, int sy, int sz) const override;
 
  private:
-  void buildTemplate();
-  void solveGroups();
-  std::vector<std::vector<long long>> template_;                // layers of the template domain
-  std::vector<std::vector<std::vector<long long>>> groupsT_;    // [category][variable][node]
+  void classifyTemplate();
+  std::vector<TemplateNode> tmpl_;      // sorted by (cls, var), scan order (z, y, x) inside
+  std::vector<int64_t> clsVarPtr_;      // (ncls * dof + 1): ranges of tmpl_ per (class, variable)
+  int ncls_ = 0;
 };
 
 // factory: "Cartesian" | "Skew Cartesian" (OverlappingPartitioner::Partition, :96-119)

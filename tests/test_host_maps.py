@@ -183,9 +183,11 @@ def test_domain_decomposition_decouples_interiors():
     assert P.Stats()["interior_couplings"] > 0
 
 
-def _compare_all_levels(eqn, dim, nx, ny, nz, sx, levels, cx, part, extra):
+def _compare_all_levels(eqn, dim, nx, ny, nz, sx, levels, cx, part, extra, problem=None):
     import scipy.sparse as sps
     p = make_params(eqn, dim, nx, sx, levels, cx, ny=ny, nz=nz, Partitioner=part, **extra)
+    for k, v in (problem or {}).items():
+        p.sublist("Problem").set(k, v)
     A = hb.galeri.create_matrix(eqn, dim, nx, ny, nz)
     tv = hb.galeri.create_testvector(A)
     lvl = ohymls.Preconditioner(A, p.copy(), tv)
@@ -267,3 +269,53 @@ def test_random_pid_maps_match_oracle():
         assert np.array_equal(hb.pid_map(_dictify(p), nprocs), ref), (dim, nx, sx, nprocs, part)
         checked += 1
     assert checked >= 30
+
+
+@pytest.mark.parametrize("eqn,dim,n,sx,levels,cx,part,extra,problem", [
+    # periodic directions (the wrap of the group nodes and of the skew subdomain numbering)
+    ("Laplace", 2, (16, 16, 1), 4, 2, 2, "Cartesian", {}, {"x-periodic": True}),
+    ("Laplace", 3, (8, 8, 8), 4, 1, None, "Cartesian", {}, {"x-periodic": True, "y-periodic": True, "z-periodic": True}),
+    ("Stokes-C", 2, (16, 24, 1), 4, 1, None, "Cartesian", {}, {"y-periodic": True}),
+    ("Stokes-C", 2, (16, 16, 1), 4, 2, 2, "Skew Cartesian", {}, {"x-periodic": True}),
+    ("Stokes-C", 2, (24, 16, 1), 4, 1, None, "Skew Cartesian", {}, {"x-periodic": True, "y-periodic": True}),
+    ("Stokes-C", 3, (8, 8, 8), 4, 1, None, "Skew Cartesian", {}, {"z-periodic": True}),
+    ("Stokes-C", 3, (8, 8, 12), 4, 1, None, "Skew Cartesian", {}, {"x-periodic": True, "y-periodic": True, "z-periodic": True}),
+    # retained nodes per separator (rx > 1), two retained pressures, unlinked velocities
+    ("Laplace", 2, (32, 32, 1), 8, 2, 2, "Cartesian", {"Retain_Nodes": 2}, {}),
+    ("Stokes-C", 2, (24, 24, 1), 6, 1, None, "Cartesian", {"Retain_Nodes": 3}, {}),
+    ("Stokes-C", 2, (32, 32, 1), 8, 1, None, "Skew Cartesian", {"Retain_Nodes": 2}, {}),
+    ("Stokes-C", 3, (8, 8, 8), 4, 1, None, "Skew Cartesian", {"Retain_Nodes": 2, "Eliminate_Velocities_Together": False}, {}),
+    ("Stokes-C", 2, (16, 16, 1), 4, 1, None, "Cartesian", {}, {"Retained Pressure Nodes": 2}),
+    ("Stokes-C", 2, (16, 16, 1), 4, 1, None, "Skew Cartesian", {}, {"Retained Pressure Nodes": 2}),
+    ("Stokes-C", 3, (8, 8, 8), 4, 1, None, "Skew Cartesian", {}, {"Retained Pressure Nodes": 3}),
+    ("Stokes-C", 2, (16, 16, 1), 4, 1, None, "Cartesian", {"Eliminate_Velocities_Together": False,
+                                                        "Eliminate_Retained_Nodes_Together": False}, {}),
+    # subdomain sizes that are not powers of two; coarsening factors with integer roots (4 -> 2, 9 -> 3)
+    ("Stokes-C", 2, (36, 36, 1), 6, 2, 3, "Skew Cartesian", {}, {}),
+    ("Stokes-C", 3, (12, 12, 12), 6, 1, None, "Skew Cartesian", {}, {}),
+    ("Stokes-C", 3, (20, 20, 10), 10, 1, None, "Skew Cartesian", {}, {}),
+    ("Laplace", 2, (36, 36, 1), 2, 2, 9, "Cartesian", {}, {}),
+    ("Laplace", 3, (16, 16, 16), 2, 2, 4, "Skew Cartesian", {}, {}),
+    ("Laplace", 2, (27, 18, 1), 3, 2, 3, "Cartesian", {}, {}),
+])
+def test_partitioner_variants_match_oracle(eqn, dim, n, sx, levels, cx, part, extra, problem):
+    """Parameter variants outside the default sweeps (periodicity, Retain Nodes, several retained pressures,
+    unlinked groups, sx = 6 / 10, coarsening 3 / 4 / 9): the geometric formulation of partitioner.cpp gives
+    bit-exact maps against the restated reference algorithm on every level."""
+    assert _compare_all_levels(eqn, dim, n[0], n[1], n[2], sx, levels, cx, part, extra, problem) == "equal"
+
+
+@pytest.mark.parametrize("part", ["Cartesian", "Skew Cartesian"])
+@pytest.mark.parametrize("cx,nprocs", [(2, 5), (4, 8), (4, 3), (9, 4), (3, 27), (2, 64), (8, 7)])
+def test_pid_map_coarsening_factors_match_oracle(part, cx, nprocs):
+    from oracle.skew import SkewCartesianPartitioner
+    for dim, nx, sx in [(2, 72, 2), (3, 16, 2), (2, 64, 8), (3, 24, 4)]:
+        p = make_params("Stokes-C", dim, nx, sx, 1, cx, Partitioner=part)
+        cls = CartesianPartitioner if part == "Cartesian" else SkewCartesianPartitioner
+        try:
+            ref = np.asarray(cls(p.copy(), 0, nprocs, 0).partition().pid_map, dtype=np.int32)
+        except Exception:
+            with pytest.raises(hb.HymlsError):     # configurations the reference refuses are refused here too
+                hb.pid_map(_dictify(p), nprocs)
+            continue
+        assert np.array_equal(hb.pid_map(_dictify(p), nprocs), ref), (dim, nx, sx, cx, nprocs, part)

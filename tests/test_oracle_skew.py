@@ -147,3 +147,41 @@ def test_stokes1_2d_target():  # stokes1.xml: Skew sx=4, 1 level, right-precondi
     x, its, conv, _ = krylov.gmres(lambda v: A @ v, b, np.zeros(A.shape[0]), prec.apply_inverse, side="Right",
                                    tol=1e-6, max_iters=100, max_restarts=1)
     assert conv and its <= 23 and np.linalg.norm(A @ x - b) / np.linalg.norm(b) <= 5e-6
+
+
+@pytest.mark.parametrize("dim,sx", [(2, 4), (2, 6), (2, 8), (3, 4), (3, 6), (3, 8), (3, 10)])
+def test_template_is_a_polytope_in_sheared_coordinates(dim, sx):
+    """hymls_b200/csrc/partitioner.cpp (SkewShape) describes the subdomain template geometrically: per variable
+    type the lattice points of a polytope bounded by planes of constant s = x+y, d = x-y, t = x-y+z and z.  The
+    restated reference construction (oracle/skew.py::_template, src/HYMLS_SkewCartesianPartitioner.cpp:372-565)
+    must produce exactly those node sets."""
+    from oracle.skew import SkewCartesianPartitioner
+    from tests.common import stokes_var_params
+    n = 4 * sx
+    part = SkewCartesianPartitioner(stokes_var_params(dim, n, n, n if dim == 3 else 1, sx), 0, 1, 0).partition()
+    dof, w = part.dof, 4 * sx
+    got = {v: set() for v in range(dof)}
+    for cat in part.groups_template:
+        for grp in cat:
+            for node in grp:
+                got[node % dof].add(((node // dof) % w - 1 - sx, (node // dof // w) % w - 1 - 3 * sx // 2,
+                                     node // dof // w // w - 2 * sx))
+    b = sx
+
+    def inside(kind, x, y, z):
+        if dim == 2 and z != 0:
+            return False
+        s, d, t = x + y, x - y, x - y + z
+        if kind == "P":
+            return -1 <= s <= b - 2 and 0 <= d <= b - 1 and 0 <= t <= b - 1 and abs(z) <= b - 1
+        if kind == "U":
+            return -2 <= s <= b - 2 and -1 <= d <= b - 1 and -1 <= t <= b - 1 and abs(z) <= b - 1
+        if kind == "V":
+            return -2 <= s <= b - 2 and 0 <= d <= b and 0 <= t <= b and abs(z) <= b - 1
+        ok = -2 <= s <= b - 1 and -1 <= d <= b and -1 <= t <= b - 1 and -b <= z <= b - 1
+        return ok and (t % 2 == 1 or not (s in (-2, b - 1) or d in (-1, b)))
+    kinds = ["U", "V", "W", "P"] if dim == 3 else ["U", "V", "P"]
+    r = range(-2 * sx, 2 * sx + 1)
+    for v, kind in enumerate(kinds):
+        want = {(x, y, z) for z in (r if dim == 3 else [0]) for y in r for x in r if inside(kind, x, y, z)}
+        assert got[v] == want, (kind, len(got[v]), len(want))

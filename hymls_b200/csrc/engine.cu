@@ -4,6 +4,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstring>
+#include <functional>
 #include <random>
 #include <thread>
 
@@ -28,7 +29,7 @@ static void validatePreconditionerList(const ParameterList& prec) {
       "Separator Length (y)", "Separator Length (z)", "Subdivide Separators", "Subdivide based on variable",
       "Subdomain Solver Num Threads", "Subdomain Solver Type", "Visualize Solver",
       // extension of this implementation ("Deviations")
-      "Eliminate Tube Pressures With Velocities"};
+      "Eliminate Tube Pressures With Velocities", "Refine Inverses"};
   for (const std::string& name : prec.parameterNames()) {
     bool ok = startsWith(name, "Fix GID ") || startsWith(name, "Retain Nodes");
     for (const char* v : valid) ok = ok || name == v;
@@ -50,6 +51,9 @@ Engine::Engine(const std::string& xml) {
   ParameterList& prec = params_.sublist("Preconditioner");
   validatePreconditionerList(prec);
   maxLevel_ = prec.get("Number of Levels", 1);
+  // extension: one Newton-Schulz step on every explicit inverse (parity section); default on
+  refine_ = prec.get("Refine Inverses", true);
+  if (const char* e = getenv("HYMLS_B200_REFINE")) refine_ = atoi(e) != 0;
   std::string method = prec.get("Partitioner", "Cartesian");
   if (method != "Cartesian" && method != "Skew Cartesian")
     throw Error(HYMLS_B200_ERR_ARG, "Partitioner '" + method + "': Up to now we only support Cartesian partitioning");
@@ -699,9 +703,12 @@ void Engine::compute() {
   computed_ = true;
 }
 
-// inverts the matrices [m0, m1) of `B` whose dense input has been assembled in W (chunk-relative offsets)
+// inverts the matrices [m0, m1) of `B` whose dense input has been assembled in W (chunk-relative offsets).
+// `refill` (optional) writes the original matrices into W again after the inversion: with it and the scratch
+// R (same size as W) every inverse gets one Newton-Schulz step against its original matrix (gj.cu)
 static void invertRange(BatchedInverse& B, int m0, int m1, double* W, DevBuf<int>& piv, DevBuf<int>& perm,
-                        DevBuf<int64_t>& relOff, int* info, cudaStream_t s, int64_t* launches) {
+                        DevBuf<int64_t>& relOff, int* info, cudaStream_t s, int64_t* launches,
+                        const std::function<void()>& refill = nullptr, double* R = nullptr) {
   const int cnt = m1 - m0;
   if (cnt <= 0) return;
   int npMax = 0;
@@ -716,13 +723,19 @@ static void invertRange(BatchedInverse& B, int m0, int m1, double* W, DevBuf<int
   perm.alloc((size_t)cnt * npMax);
   invertBatched(W, B.F.p + B.hMatOff[m0], relOff.p, B.n.p + m0, B.np.p + m0, cnt, npMax, piv.p, perm.p,
                 piv.p + (size_t)cnt * npMax, info, s, launches);
+  if (refill && R) {
+    refill();
+    refineInverseBatched(W, B.F.p + B.hMatOff[m0], R, relOff.p, B.np.p + m0, cnt, npMax, s, launches);
+  }
   HY_CUDA(cudaStreamSynchronize(s));  // relOff is reused by the next chunk
 }
 
-// the same for an arbitrary subset `list` of the matrices of `B` (absolute offsets; W and F share the layout)
+// the same for an arbitrary subset `list` of the matrices of `B` (absolute offsets; W, F, the copy of the
+// originals A0 and the scratch R share the layout)
 static void invertSubset(BatchedInverse& B, const std::vector<int>& list, size_t lo, size_t hi, double* Wbase,
                          DevBuf<int>& piv, DevBuf<int>& perm, DevBuf<int64_t>& offBuf, DevBuf<int>& nBuf,
-                         DevBuf<int>& npBuf, int* info, cudaStream_t s, int64_t* launches) {
+                         DevBuf<int>& npBuf, int* info, cudaStream_t s, int64_t* launches, double* A0 = nullptr,
+                         double* R = nullptr) {
   const int cnt = (int)(hi - lo);
   if (cnt <= 0) return;
   int npMax = 0;
@@ -743,6 +756,7 @@ static void invertSubset(BatchedInverse& B, const std::vector<int>& list, size_t
   perm.alloc((size_t)cnt * npMax);
   invertBatched(Wbase, B.F.p, offBuf.p, nBuf.p, npBuf.p, cnt, npMax, piv.p, perm.p, piv.p + (size_t)cnt * npMax, info,
                 s, launches);
+  if (A0 && R) refineInverseBatched(A0, B.F.p, R, offBuf.p, npBuf.p, cnt, npMax, s, launches);
   HY_CUDA(cudaStreamSynchronize(s));  // the host vectors and offBuf are reused by the next chunk
 }
 
@@ -818,6 +832,11 @@ void Engine::reserveComputeScratch() {
   work = std::max(work, (size_t)(nc * nc));
   batch(1, (int)nc);
   work_.alloc(work);
+  if (refine_) {
+    work2_.alloc(work);
+    blkA_.alloc(std::max(blkW, (size_t)(nc * nc)));
+    blkR_.alloc(blkW);
+  }
   piv_.alloc(piv);
   perm_.alloc(perm);
   blkW_.alloc(blkW);
@@ -849,7 +868,13 @@ void Engine::computeLevel(int l) {
       const int64_t e0 = L.a11ListPtr[k0], e1 = L.a11ListPtr[k1];
       scatterValues(L.val.p, L.a11Src.p + e0, L.a11Dst.p + e0, L.ownOff[k0], work_.p, e1 - e0, s, &launches_);
       pt.lap("  chunk fill");
-      invertRange(L.a11, k0, k1, work_.p, piv_, perm_, relOff, info_.p, s, &launches_);
+      auto fillChunk = [&]() {
+        HY_CUDA(cudaMemsetAsync(work_.p, 0, used * sizeof(double), s));
+        scatterValues(L.val.p, L.a11Src.p + e0, L.a11Dst.p + e0, L.ownOff[k0], work_.p, e1 - e0, s, &launches_);
+      };
+      if (refine_) work2_.alloc((size_t)used);
+      invertRange(L.a11, k0, k1, work_.p, piv_, perm_, relOff, info_.p, s, &launches_,
+                  refine_ ? std::function<void()>(fillChunk) : nullptr, refine_ ? work2_.p : nullptr);
       pt.lap("  chunk inversion");
       for (int k = k0; k < k1; ++k) stats_.flops_compute += 2.0 * std::pow((double)L.a11.hN[k], 3);
     }
@@ -1040,11 +1065,21 @@ void Engine::computeLevel(int l) {
   // separator blocks (SchurPreconditioner::Compute :284-291)
   {
     DevBuf<int64_t>& relOff = relOff_;
+    if (refine_) {  // the assembled blocks are needed again for the Newton-Schulz step
+      blkA_.alloc(blkW.n);
+      blkR_.alloc(blkW.n);
+      HY_CUDA(cudaMemcpyAsync(blkA_.p, blkW.p, blkW.bytes(), cudaMemcpyDeviceToDevice, s));
+    }
     if (!L.sharded) {
       int b0 = 0;
       while (b0 < S.nblk) {
         int b1 = std::min(S.nblk, b0 + 16384);
-        invertRange(L.blk, b0, b1, blkW.p + S.blkOff[b0], piv_, perm_, relOff, info_.p, s, &launches_);
+        const int64_t o0 = S.blkOff[b0], len = S.blkOff[b1] - o0;
+        auto refill = [&]() {
+          HY_CUDA(cudaMemcpyAsync(blkW.p + o0, blkA_.p + o0, len * sizeof(double), cudaMemcpyDeviceToDevice, s));
+        };
+        invertRange(L.blk, b0, b1, blkW.p + o0, piv_, perm_, relOff, info_.p, s, &launches_,
+                    refine_ ? std::function<void()>(refill) : nullptr, refine_ ? blkR_.p + o0 : nullptr);
         b0 = b1;
       }
     } else {
@@ -1054,7 +1089,7 @@ void Engine::computeLevel(int l) {
         if (L.sdRank[S.blkOwnerSd[b]] == comm_.rank()) mine.push_back(b);
       for (size_t lo = 0; lo < mine.size(); lo += 16384)
         invertSubset(L.blk, mine, lo, std::min(mine.size(), lo + 16384), blkW.p, piv_, perm_, relOff, subsetN_,
-                     subsetNp_, info_.p, s, &launches_);
+                     subsetNp_, info_.p, s, &launches_, refine_ ? blkA_.p : nullptr, refine_ ? blkR_.p : nullptr);
     }
     for (int b = 0; b < S.nblk; ++b) stats_.flops_compute += 2.0 * std::pow((double)S.blkN[b], 3);
     checkInfo("separator block of level " + std::to_string(l));
@@ -1124,7 +1159,17 @@ void Engine::augmentAndInvertCoarse(int n, int np, const double* bV, const doubl
   coarseRhs_.alloc(n + bm);
   coarseSol_.alloc(n + bm);
   DevBuf<int64_t>& relOff = relOff_;
-  invertRange(coarse_, 0, 1, work_.p, piv_, perm_, relOff, info_.p, s, &launches_);
+  const size_t clen = (size_t)np * np;
+  if (refine_) {
+    blkA_.alloc(clen);
+    work2_.alloc(clen);
+    HY_CUDA(cudaMemcpyAsync(blkA_.p, work_.p, clen * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  }
+  auto refill = [&]() {
+    HY_CUDA(cudaMemcpyAsync(work_.p, blkA_.p, clen * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  };
+  invertRange(coarse_, 0, 1, work_.p, piv_, perm_, relOff, info_.p, s, &launches_,
+              refine_ ? std::function<void()>(refill) : nullptr, refine_ ? work2_.p : nullptr);
   checkInfo(what);
   stats_.flops_compute += 2.0 * std::pow((double)(n + bm), 3);
 }

@@ -169,6 +169,8 @@ class Engine {
   DevBuf<double> bS_, bTin_, bPartial_, bDots_, bC_, bC0_;
   // scratch
   DevBuf<double> work_;      // inversion workspace
+  DevBuf<double> work2_, blkA_, blkR_;  // Newton-Schulz refinement: residuals, copies of the dense originals
+  bool refine_ = true;
   DevBuf<int> piv_, perm_, info_, subsetN_, subsetNp_;
   DevBuf<double> wsC_, wsSV_, wsSLL_, diagScratch_, blkW_, red2_, blk2_, a21d_, dmat_, a12d_, skd_;
   DevBuf<int64_t> relOff_;

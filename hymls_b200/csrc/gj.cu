@@ -874,4 +874,131 @@ void invertBatched(double* W, double* F, const int64_t* dOff, const int* dN, con
   HY_CUDA(cudaGetLastError());
 }
 
+// ---------------------------------------------------------------------------------------------
+// One Newton-Schulz step  X <- X + X (I - A X)  on every inverse of a batch.
+// Gauss-Jordan elimination with partial pivoting is forward stable only up to cond(U): measured against an
+// extended-precision ground truth (oracle/extended.py) its inverses of the badly scaled Stokes blocks carry
+// up to 60x the error of a LAPACK getrf/getri inverse, and ApplyInverse up to 80x the error of an LU solve
+// (profiles/r02_accuracy_before_refinement.json).  The residual R = I - A X is formed in FP64 from the
+// ORIGINAL matrix, so one step brings X to the O(cond(A) eps) of a backward-stable factorization.
+// Two batched FP64 tensor-core GEMMs (DMMA m8n8k4, cp.async double-buffered 32 x 64 x 32 tiles).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma884r(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+static constexpr int RF_TM = 32, RF_TN = 64, RF_TK = 32, RF_T = 128;
+static constexpr int RF_SA = RF_TK + 4, RF_SB = RF_TN + 4;  // strides = 4 mod 16 doubles: conflict-free fragments
+// mode 0:  C = I - A B      mode 1:  C = A B        (all np x np, row major, the batch's offsets)
+__global__ void __launch_bounds__(RF_T, 4)
+k_refine_gemm(const double* __restrict__ Abase, const double* __restrict__ Bbase, double* __restrict__ Cbase,
+              const int64_t* __restrict__ off, const int* __restrict__ npArr, int tilesN, int mode) {
+  const int mat = blockIdx.y;
+  const int np = npArr[mat];
+  const int i0 = (blockIdx.x / tilesN) * RF_TM, j0 = (blockIdx.x % tilesN) * RF_TN;
+  if (i0 >= np || j0 >= np) return;
+  const double* __restrict__ A = Abase + off[mat];
+  const double* __restrict__ B = Bbase + off[mat];
+  double* __restrict__ Cm = Cbase + off[mat];
+  extern __shared__ __align__(16) double rfSm[];
+  constexpr int SZA = RF_TM * RF_SA, SZB = RF_TK * RF_SB;
+  const int tid = threadIdx.x, lane = tid & 31, wc = tid >> 5;
+  const int fr = lane >> 2, fk = lane & 3;
+  auto stage = [&](int k0, int buf) {
+    for (int e = tid; e < RF_TM * (RF_TK / 2); e += RF_T) {
+      const int r = e / (RF_TK / 2), c = (e % (RF_TK / 2)) * 2;
+      const bool ok = (i0 + r < np) && (k0 + c < np);
+      const double* src = ok ? A + (int64_t)(i0 + r) * np + k0 + c : A;
+      const unsigned saddr = (unsigned)__cvta_generic_to_shared(rfSm + buf * SZA + r * RF_SA + c);
+      const int bytes = ok ? 16 : 0;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(saddr), "l"(src), "r"(bytes));
+    }
+    for (int e = tid; e < RF_TK * (RF_TN / 2); e += RF_T) {
+      const int r = e / (RF_TN / 2), c = (e % (RF_TN / 2)) * 2;
+      const bool ok = (k0 + r < np) && (j0 + c < np);
+      const double* src = ok ? B + (int64_t)(k0 + r) * np + j0 + c : B;
+      const unsigned saddr = (unsigned)__cvta_generic_to_shared(rfSm + 2 * SZA + buf * SZB + r * RF_SB + c);
+      const int bytes = ok ? 16 : 0;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(saddr), "l"(src), "r"(bytes));
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+  };
+  double acc[4][2][2];
+#pragma unroll
+  for (int ti = 0; ti < 4; ++ti)
+#pragma unroll
+    for (int tj = 0; tj < 2; ++tj) acc[ti][tj][0] = acc[ti][tj][1] = 0.0;
+  const int nk = (np + RF_TK - 1) / RF_TK;
+  stage(0, 0);
+  for (int kt = 0; kt < nk; ++kt) {
+    const int buf = kt & 1;
+    const bool more = kt + 1 < nk;
+    if (more) stage((kt + 1) * RF_TK, buf ^ 1);
+    if (more) asm volatile("cp.async.wait_group 1;\n" ::); else asm volatile("cp.async.wait_group 0;\n" ::);
+    __syncthreads();
+    const double* cA = rfSm + buf * SZA;
+    const double* cB = rfSm + 2 * SZA + buf * SZB;
+#pragma unroll
+    for (int kk = 0; kk < RF_TK / 4; ++kk) {
+      double av[4], bv[2];
+#pragma unroll
+      for (int ti = 0; ti < 4; ++ti) av[ti] = cA[(ti * 8 + fr) * RF_SA + kk * 4 + fk];
+#pragma unroll
+      for (int tj = 0; tj < 2; ++tj) bv[tj] = cB[(kk * 4 + fk) * RF_SB + (wc * 2 + tj) * 8 + fr];
+#pragma unroll
+      for (int ti = 0; ti < 4; ++ti)
+#pragma unroll
+        for (int tj = 0; tj < 2; ++tj) dmma884r(acc[ti][tj][0], acc[ti][tj][1], av[ti], bv[tj]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int ti = 0; ti < 4; ++ti) {
+    const int row = i0 + ti * 8 + fr;
+#pragma unroll
+    for (int tj = 0; tj < 2; ++tj) {
+      const int col = j0 + (wc * 2 + tj) * 8 + 2 * fk;
+      if (row < np && col < np) {
+        double v0 = acc[ti][tj][0], v1 = acc[ti][tj][1];
+        if (mode == 0) {
+          v0 = (row == col ? 1.0 : 0.0) - v0;
+          v1 = (row == col + 1 ? 1.0 : 0.0) - v1;
+        }
+        *reinterpret_cast<double2*>(Cm + (int64_t)row * np + col) = make_double2(v0, v1);
+      }
+    }
+  }
+}
+// X += T for every matrix of the batch
+__global__ void k_refine_add(double* __restrict__ Xbase, const double* __restrict__ Tbase,
+                             const int64_t* __restrict__ off, const int* __restrict__ npArr) {
+  const int mat = blockIdx.y;
+  const int64_t len = (int64_t)npArr[mat] * npArr[mat];
+  double* __restrict__ X = Xbase + off[mat];
+  const double* __restrict__ T = Tbase + off[mat];
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < len; e += (int64_t)gridDim.x * blockDim.x)
+    X[e] += T[e];
+}
+
+void refineInverseBatched(double* A, double* F, double* R, const int64_t* dOff, const int* dNp, int count, int npMax,
+                          cudaStream_t s, int64_t* launches) {
+  if (count == 0 || npMax == 0) return;
+  constexpr size_t smem = (size_t)(2 * RF_TM * RF_SA + 2 * RF_TK * RF_SB) * sizeof(double);
+  static PerDeviceLimit limit;
+  if (limit.raise(smem + 48 * 1024))
+    HY_CUDA(cudaFuncSetAttribute(k_refine_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int tilesM = (npMax + RF_TM - 1) / RF_TM, tilesN = (npMax + RF_TN - 1) / RF_TN;
+  for (int c0 = 0; c0 < count; c0 += 32768) {  // grid.y limit
+    const int cnt = std::min(count - c0, 32768);
+    dim3 g((unsigned)(tilesM * tilesN), (unsigned)cnt);
+    k_refine_gemm<<<g, RF_T, smem, s>>>(A, F, R, dOff + c0, dNp + c0, tilesN, 0);  // R = I - A X
+    k_refine_gemm<<<g, RF_T, smem, s>>>(F, R, A, dOff + c0, dNp + c0, tilesN, 1);  // T = X R  (A is dead: reused)
+    const int blocks = std::max(1, std::min(64, (npMax * npMax + 1023) / 1024));
+    k_refine_add<<<dim3((unsigned)blocks, (unsigned)cnt), 256, 0, s>>>(F, A, dOff + c0, dNp + c0);
+    *launches += 3;
+  }
+  HY_CUDA(cudaGetLastError());
+}
+
 }  // namespace hymls

@@ -10,6 +10,12 @@ namespace hymls {
 void invertBatched(double* W, double* F, const int64_t* dOff, const int* dN, const int* dNp, int count, int npMax,
                    int* dPiv, int* dPerm, int* dSwap, int* dInfo, cudaStream_t s, int64_t* launches);
 
+// One Newton-Schulz step X <- X + X (I - A X) on the inverses F of a batch (same offsets for A, F and the
+// scratch R; A holds the ORIGINAL matrices and is destroyed).  Restores O(cond(A) eps) accuracy after the
+// Gauss-Jordan inversion (whose forward error grows with cond(U)).
+void refineInverseBatched(double* A, double* F, double* R, const int64_t* dOff, const int* dNp, int count, int npMax,
+                          cudaStream_t s, int64_t* launches);
+
 // ---- schur.cu ----
 struct SchurArgs {
   // per local separator row R (row i of subdomain sd: R = sdRowPtr[sd] + i)

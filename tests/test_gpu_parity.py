@@ -5,17 +5,22 @@ import pytest
 import scipy.sparse as sp
 
 import hymls_b200 as hb
-from oracle import hymls as oh, krylov as ok
+from oracle import extended as ox, hymls as oh, krylov as ok
 from tests.common import make_params
 from tests.conftest import load_fixture
 
 pytestmark = pytest.mark.gpu
 
-# ApplyInverse tolerances.  The north star asks for 1e-12 relative; two different FP64 factorizations of
-# the A11 blocks (oracle: SuperLU solve, GPU: pivoted Gauss-Jordan inverse) agree to about cond(A11)*eps,
-# which is ~1e-15 for Laplace and 1e-11..1e-10 for the badly scaled Stokes blocks (a = nx^2 vs b = 1).
+# ApplyInverse tolerances.  The north star asks for 1e-12 relative against the reference's own FP64 path.  No two
+# FP64 evaluations of this preconditioner agree better than their own rounding error, and that error is 1e-12 ..
+# 8e-12 for the FP64 oracle itself on the badly scaled Stokes blocks (a = nx^2 vs b = 1), measured against the
+# extended-precision ground truth of oracle/extended.py (profiles/r02_accuracy.md).  The tests therefore check
+#   (1) err(GPU vs truth) <= max(2 err(oracle vs truth), 1e-12): the GPU is as close to the exact-arithmetic
+#       preconditioner as the reference-style LU evaluation (or meets the north star's 1e-12 outright), and
+#   (2) GPU vs FP64 oracle within the cap below (<= err(GPU) + err(oracle) by the triangle inequality).
 TOL_LAPLACE = 1e-13
-TOL_STOKES = 5e-10
+TOL_STOKES = 2e-11
+TRUTH_FACTOR, TRUTH_FLOOR = 2.0, 1e-12
 
 
 def dictify(p):
@@ -75,6 +80,14 @@ def test_apply_inverse_matches_oracle(eqn, dim, nx, sx, levels, cx, extra, tol):
     X = P.ApplyInverse(B)                 # two right-hand sides in one call (Epetra_MultiVector)
     for k in range(2):
         assert rel(X[:, k], O.apply_inverse(B[:, k])) < tol
+    # ground truth: the same algorithm in extended precision (oracle/extended.py)
+    T = ox.Preconditioner(A, make_params(eqn, dim, nx, sx, levels, cx, **extra), hb.galeri.create_testvector(A))
+    T.initialize()
+    T.compute()
+    xt = T.apply_inverse(B[:, 0])
+    e_gpu = float(np.linalg.norm(X[:, 0] - xt) / np.linalg.norm(xt))
+    e_ora = float(np.linalg.norm(O.apply_inverse(B[:, 0]) - xt) / np.linalg.norm(xt))
+    assert e_gpu <= max(TRUTH_FACTOR * e_ora, TRUTH_FLOOR), (e_gpu, e_ora)
     # linearity, a size-independent property
     y = P.ApplyInverse(2.0 * B[:, 0] - 3.0 * B[:, 1])
     assert rel(y, 2.0 * X[:, 0] - 3.0 * X[:, 1]) < 1e-12

@@ -1,0 +1,101 @@
+"""The C++/OpenMP CPU restatement (oracle/cpp/hymls_oracle.cpp: the timed CPU baseline and the oracle for sizes the
+numpy oracle cannot reach) against the numpy oracle, which in turn is pinned to the reference's fixtures and
+integration targets (tests/test_oracle_solver.py).  Two independent FP64 sparse-LU evaluations of the same
+algorithm: they agree to their rounding error (<= 2e-11 on the Stokes cases, tests/test_gpu_parity.py)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import hymls_b200 as hb
+from oracle import cpp_oracle as oc, hymls as oh, krylov as ok
+from tests.common import make_params
+from tests.conftest import load_fixture
+
+CASES = [
+    ("Laplace", 2, 32, 4, 2, None, {}, 1e-13),
+    ("Laplace", 3, 16, 4, 2, None, {}, 1e-13),
+    ("Stokes-C", 2, 32, 4, 1, None, {}, 2e-11),
+    ("Stokes-C", 2, 32, 4, 3, 2, {}, 2e-11),
+    ("Stokes-C", 3, 8, 4, 1, None, {"Partitioner": "Skew Cartesian"}, 2e-11),
+    ("Stokes-C", 3, 16, 4, 2, 2, {"Partitioner": "Skew Cartesian"}, 2e-11),
+    ("Stokes-C", 3, 16, 4, 2, 2, {"Eliminate_Tube_Pressures_With_Velocities": True}, 2e-11),
+]
+
+
+def _build(eqn, dim, nx, sx, levels, cx, extra, A=None):
+    p = make_params(eqn, dim, nx, sx, levels, cx, **extra)
+    if A is None:
+        A = hb.galeri.create_matrix(eqn, dim, nx)
+        if eqn == "Stokes-C":
+            A = -A
+    A = sp.csr_matrix(A)
+    tv = hb.galeri.create_testvector(A)
+    O = oh.Preconditioner(A, p.copy(), tv)
+    O.initialize()
+    O.compute()
+    Cp = oc.Preconditioner(A, p.copy(), tv, oc.maps_from_python_oracle(A, p.copy(), tv))
+    Cp.compute()
+    return A, O, Cp
+
+
+@pytest.mark.parametrize("eqn,dim,nx,sx,levels,cx,extra,tol", CASES)
+def test_cpp_oracle_matches_numpy_oracle(eqn, dim, nx, sx, levels, cx, extra, tol):
+    A, O, Cp = _build(eqn, dim, nx, sx, levels, cx, extra)
+    R, Ro = Cp.reduced(0), O.schur_prec.reduced
+    assert abs(R - Ro).max() <= tol * abs(Ro).max()           # transformed + dropped Schur complement on the V-sums
+    b = np.random.default_rng(1).uniform(-1, 1, A.shape[0])
+    x, xo = Cp.apply_inverse(b), O.apply_inverse(b)
+    assert np.linalg.norm(x - xo) <= tol * np.linalg.norm(xo)
+
+
+def test_cpp_oracle_with_library_maps_and_threads():
+    """maps from the library's host partitioner (what the CPU baseline uses at 64^3 / 128^3) give the same
+    preconditioner as maps from oracle/partitioner.py; the result does not depend on the thread count."""
+    from tests.test_host_maps import _dictify
+    p = make_params("Stokes-C", 3, 16, 4, 2, 2, Partitioner="Skew Cartesian")
+    A = sp.csr_matrix(-hb.galeri.create_matrix("Stokes-C", 3, 16))
+    tv = hb.galeri.create_testvector(A)
+    P = hb.Preconditioner(A, _dictify(p), tv, pattern_only=True)
+    P.Initialize()
+    b = np.random.default_rng(2).uniform(-1, 1, A.shape[0])
+    xs = []
+    for maps, threads in [(oc.maps_from_library(P), 1), (oc.maps_from_library(P), 4),
+                          (oc.maps_from_python_oracle(A, p.copy(), tv), 2)]:
+        Cp = oc.Preconditioner(A, p.copy(), tv, maps, threads=threads)
+        Cp.compute()
+        xs.append(Cp.apply_inverse(b))
+    assert np.array_equal(xs[0], xs[1]) and np.array_equal(xs[0], xs[2])
+
+
+@pytest.mark.parametrize("eqn,dim,nx,sx,levels,cx,extra", [
+    ("Laplace", 2, 64, 4, 2, None, {}),
+    ("Stokes-C", 2, 32, 4, 2, None, {}),
+    ("Stokes-C", 3, 16, 4, 2, 2, {"Partitioner": "Skew Cartesian"}),
+])
+def test_cpp_krylov_matches_numpy_krylov(eqn, dim, nx, sx, levels, cx, extra):
+    A, O, Cp = _build(eqn, dim, nx, sx, levels, cx, extra)
+    n = A.shape[0]
+    b = A @ np.random.default_rng(42).uniform(-1, 1, n)
+    if eqn == "Laplace":
+        xo, its, conv, h = ok.cg(lambda v: A @ v, b, np.zeros(n), O.apply_inverse, tol=1e-8, max_iters=300)
+        x, itc, convc, hc, _ = Cp.solve(b, method="CG", tol=1e-8, max_iters=300)
+    else:
+        xo, its, conv, h = ok.gmres(lambda v: A @ v, b, np.zeros(n), O.apply_inverse, side="Right", tol=1e-8,
+                                    max_iters=300, max_restarts=1, imp_scaling="Norm of Initial Residual")
+        x, itc, convc, hc, _ = Cp.solve(b, method="GMRES", tol=1e-8, max_iters=300, max_restarts=1)
+    assert conv and convc and abs(its - itc) <= 1
+    k = min(len(h), len(hc), 15)
+    assert np.allclose(hc[:k], h[:k], rtol=1e-6)
+    assert np.linalg.norm(A @ x - b) <= 2e-8 * np.linalg.norm(b)
+
+
+def test_cpp_oracle_on_reference_fixture_target():
+    """integration_tests/stokes1.xml-style target on the shipped 32x32/Re0 fixture (Cartesian sx=4, 2 levels):
+    the C++ oracle converges within the reference's iteration bound, like the numpy oracle does."""
+    A, b, sol = load_fixture("cavity2d_32_Re0")
+    A, O, Cp = _build("Stokes-C", 2, 32, 4, 2, None, {}, A=A)
+    n = A.shape[0]
+    xo, its, conv, h = ok.gmres(lambda v: A @ v, b, np.zeros(n), O.apply_inverse, side="Right", tol=1e-8,
+                                max_iters=100, imp_scaling="Norm of Initial Residual")
+    x, itc, convc, hc, _ = Cp.solve(b, tol=1e-8, max_iters=100)
+    assert conv and convc and abs(its - itc) <= 1

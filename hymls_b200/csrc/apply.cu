@@ -414,6 +414,109 @@ void scatterVec(const double* x, const int* idx, double* y, int64_t n, cudaStrea
 }
 
 // ---------------------------------------------------------------------------------------------
+// Row-list / group-list variants for the owner-computes multi-GPU path (dist.cu): a rank touches only the
+// rows it owns (plus its halo), addressed through index lists into the global-length work vectors.
+// ---------------------------------------------------------------------------------------------
+// r = rows[i]:  y[compact ? i : r] = alpha * b[bidx ? bidx[r] : r] + beta * sum_e val[e] x[col[e]]
+__global__ void k_spmv_rows(const int64_t* __restrict__ ptr, const int* __restrict__ col, const double* __restrict__ val,
+                            const double* __restrict__ x, double* __restrict__ y, const int* __restrict__ rows,
+                            int64_t nrows, double alpha, const double* __restrict__ b, const int* __restrict__ bidx,
+                            double beta, int compact) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nrows) return;
+  const int r = rows[i];
+  double s = 0.0;
+  for (int64_t e = ptr[r]; e < ptr[r + 1]; ++e) s += val[e] * x[col[e]];
+  double base = 0.0;
+  if (b) base = alpha * b[bidx ? bidx[r] : r];
+  y[compact ? i : (int64_t)r] = base + beta * s;
+}
+void spmvRows(const int64_t* ptr, const int* col, const double* val, const double* x, double* y, const int* rows,
+              int64_t nrows, double alpha, const double* b, const int* bidx, double beta, int compact, cudaStream_t s,
+              int64_t* launches) {
+  if (nrows == 0) return;
+  k_spmv_rows<<<(unsigned)((nrows + 255) / 256), 256, 0, s>>>(ptr, col, val, x, y, rows, nrows, alpha, b, bidx, beta,
+                                                               compact);
+  ++*launches;
+}
+// k_householder over a list of unique groups
+__global__ void k_householder_list(const int* __restrict__ uniqStart, const int* __restrict__ list, int nlist,
+                                   const double* __restrict__ w, const double* __restrict__ in, double* __restrict__ out,
+                                   double* __restrict__ vsumOut, const double* __restrict__ vsumIn,
+                                   double* __restrict__ X, const int* __restrict__ sepRow) {
+  const int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (idx >= nlist) return;
+  const int u = list[idx];
+  const int lane = threadIdx.x & 31;
+  const int a = uniqStart[u], z = uniqStart[u + 1];
+  double t = 0.0;
+  for (int p = a + lane; p < z; p += 32) {
+    double v = (vsumIn && p == a) ? vsumIn[u] : in[p];
+    t += w[p] * v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  for (int p = a + lane; p < z; p += 32) {
+    double v = (vsumIn && p == a) ? vsumIn[u] : in[p];
+    double r = 2.0 * w[p] * t - v;
+    out[p] = r;
+    if (vsumOut && p == a) vsumOut[u] = r;
+    if (X) X[sepRow[p]] = r;
+  }
+}
+void householderList(const int* uniqStart, const int* list, int nlist, const double* w, const double* in, double* out,
+                     double* vsumOut, const double* vsumIn, double* X, const int* sepRow, cudaStream_t s,
+                     int64_t* launches) {
+  if (nlist == 0) return;
+  const int wpb = 8;
+  k_householder_list<<<(nlist + wpb - 1) / wpb, wpb * 32, 0, s>>>(uniqStart, list, nlist, w, in, out, vsumOut, vsumIn,
+                                                                  X, sepRow);
+  ++*launches;
+}
+// out[i] = x[idx[i]]  (halo pack, compact gather)
+__global__ void k_pack_idx(const double* __restrict__ x, const int* __restrict__ idx, double* __restrict__ out,
+                           int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = x[idx[i]];
+}
+void packIdx(const double* x, const int* idx, double* out, int64_t n, cudaStream_t s, int64_t* launches) {
+  if (n == 0) return;
+  k_pack_idx<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, idx, out, n);
+  ++*launches;
+}
+// z[node[i]] = (base ? base[bidx[node[i]]] : 0) + z[node[i]] + sum_{e in [ptr[i], ptr[i+1])} buf[src[e]]: the partial
+// sums received from the neighbouring ranks are added in a fixed order (by rank), one thread per node
+__global__ void k_halo_add(double* __restrict__ z, const int* __restrict__ node, const int64_t* __restrict__ ptr,
+                           const int64_t* __restrict__ src, const double* __restrict__ buf, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double t = z[node[i]];
+  for (int64_t e = ptr[i]; e < ptr[i + 1]; ++e) t += buf[src[e]];
+  z[node[i]] = t;
+}
+void haloAdd(double* z, const int* node, const int64_t* ptr, const int64_t* src, const double* buf, int64_t n,
+             cudaStream_t s, int64_t* launches) {
+  if (n == 0) return;
+  k_halo_add<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(z, node, ptr, src, buf, n);
+  ++*launches;
+}
+// y[p] = b[bidx[p]] + t[p] for p = list[i]
+__global__ void k_gather_add_list(const double* __restrict__ b, const int* __restrict__ bidx,
+                                  const double* __restrict__ t, double* __restrict__ y, const int* __restrict__ list,
+                                  int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int p = list[i];
+  y[p] = b[bidx[p]] + t[p];
+}
+void gatherAddList(const double* b, const int* bidx, const double* t, double* y, const int* list, int64_t n,
+                   cudaStream_t s, int64_t* launches) {
+  if (n == 0) return;
+  k_gather_add_list<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(b, bidx, t, y, list, n);
+  ++*launches;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Kernels of the bordered variant (Preconditioner::ComputeBorder src/HYMLS_Preconditioner.cpp:519-588,
 // SchurPreconditioner::ComputeBorder src/HYMLS_SchurPreconditioner.cpp:631-664, CoarseSolver's
 // AugmentedMatrix src/HYMLS_CoarseSolver.cpp:200-224).  Borders have m <= a few columns and these run

@@ -143,6 +143,12 @@ int hymls_b200_local_rows(hymls_b200_t* h, int64_t* r0, int64_t* r1) {
   HY_CATCH
 }
 
+int64_t hymls_b200_owned_rows(hymls_b200_t* h, int64_t* rows, int64_t cap) {
+  HY_TRY
+  return h->eng->ownedRows(rows, cap);
+  HY_CATCH
+}
+
 int hymls_b200_apply_inverse_dist(hymls_b200_t* h, const double* Bl, double* Xl, int where) {
   HY_TRY
   h->eng->applyInverseDist(Bl, Xl, where);

@@ -19,6 +19,9 @@ typedef int (*CommDestroyFn)(void*);
 typedef int (*AllGatherFn)(const void*, void*, size_t, int, void*, cudaStream_t);
 typedef int (*BroadcastFn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
 typedef const char* (*GetErrorStringFn)(int);
+typedef int (*SendFn)(const void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*RecvFn)(void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*GroupFn)(void);
 
 struct Api {
   void* lib = nullptr;
@@ -29,6 +32,9 @@ struct Api {
   BroadcastFn broadcast = nullptr;
   AllGatherFn allGather = nullptr;
   GetErrorStringFn errorString = nullptr;
+  SendFn send = nullptr;
+  RecvFn recv = nullptr;
+  GroupFn groupStart = nullptr, groupEnd = nullptr;
 };
 
 Api& api() {
@@ -47,7 +53,12 @@ Api& api() {
   a.broadcast = (BroadcastFn)dlsym(a.lib, "ncclBroadcast");
   a.allGather = (AllGatherFn)dlsym(a.lib, "ncclAllGather");
   a.errorString = (GetErrorStringFn)dlsym(a.lib, "ncclGetErrorString");
-  if (!a.getUniqueId || !a.commInitRank || !a.allReduce || !a.commDestroy || !a.broadcast || !a.allGather)
+  a.send = (SendFn)dlsym(a.lib, "ncclSend");
+  a.recv = (RecvFn)dlsym(a.lib, "ncclRecv");
+  a.groupStart = (GroupFn)dlsym(a.lib, "ncclGroupStart");
+  a.groupEnd = (GroupFn)dlsym(a.lib, "ncclGroupEnd");
+  if (!a.getUniqueId || !a.commInitRank || !a.allReduce || !a.commDestroy || !a.broadcast || !a.allGather ||
+      !a.send || !a.recv || !a.groupStart || !a.groupEnd)
     throw Error(HYMLS_B200_ERR_CUDA, "NCCL library lacks the expected symbols");
   return a;
 }
@@ -95,5 +106,23 @@ void Comm::broadcast(double* buf, size_t count, int root, cudaStream_t s) const 
   if (!comm_ || count == 0) return;
   const int ncclDouble = 8;
   check(api().broadcast(buf, buf, count, ncclDouble, root, comm_, s), "ncclBroadcast");
+}
+}  // namespace hymls
+
+namespace hymls {
+// One grouped neighbour exchange (the halo Import/Export of Epetra_CrsMatrix::Apply): for every peer k the range
+// [sendPtr[k], sendPtr[k+1]) of sendBuf goes to peers[k] and [recvPtr[k], recvPtr[k+1]) of recvBuf comes from it.
+void Comm::neighbourExchange(const std::vector<int>& peers, const double* sendBuf, const std::vector<int64_t>& sendPtr,
+                             double* recvBuf, const std::vector<int64_t>& recvPtr, cudaStream_t s) const {
+  if (!comm_ || peers.empty()) return;
+  const int ncclDouble = 8;
+  Api& a = api();
+  check(a.groupStart(), "ncclGroupStart");
+  for (size_t k = 0; k < peers.size(); ++k) {
+    const size_t ns = (size_t)(sendPtr[k + 1] - sendPtr[k]), nr = (size_t)(recvPtr[k + 1] - recvPtr[k]);
+    if (ns) check(a.send(sendBuf + sendPtr[k], ns, ncclDouble, peers[k], comm_, s), "ncclSend");
+    if (nr) check(a.recv(recvBuf + recvPtr[k], nr, ncclDouble, peers[k], comm_, s), "ncclRecv");
+  }
+  check(a.groupEnd(), "ncclGroupEnd");
 }
 }  // namespace hymls

@@ -7,6 +7,7 @@
 
 #include <cstddef>
 #include <cstdint>
+#include <vector>
 
 namespace hymls {
 
@@ -24,6 +25,9 @@ class Comm {
   void broadcast(double* buf, size_t count, int root, cudaStream_t s) const;  // in place
   // recv[rank * count + i] = send_rank[i]; recv may alias send at offset rank*count
   void allGather(const double* send, double* recv, size_t count, cudaStream_t s) const;
+  // grouped ncclSend / ncclRecv with a set of neighbour ranks (halo exchange)
+  void neighbourExchange(const std::vector<int>& peers, const double* sendBuf, const std::vector<int64_t>& sendPtr,
+                         double* recvBuf, const std::vector<int64_t>& recvPtr, cudaStream_t s) const;
 
  private:
   void* comm_ = nullptr;

@@ -633,6 +633,7 @@ void Engine::uploadLevel(Level& L) {
     L.blk.setup(S.blkN, S.blkNp, S.blkOff, blkVecOff, s);
   }
   L.blkRows.upload(S.blkRows, s);
+  if (L.sharded && S.level == 0 && !L.exact) buildDistPlan(L); else L.dist.ready = false;
   // work vectors
   L.x1.alloc(S.nI);
   L.y1.alloc(S.nI);
@@ -725,7 +726,7 @@ static void invertRange(BatchedInverse& B, int m0, int m1, double* W, DevBuf<int
                 piv.p + (size_t)cnt * npMax, info, s, launches);
   if (refill && R) {
     refill();
-    refineInverseBatched(W, B.F.p + B.hMatOff[m0], R, relOff.p, B.np.p + m0, cnt, npMax, s, launches);
+    refineInverseBatched(W, B.F.p + B.hMatOff[m0], R, relOff.p, B.n.p + m0, B.np.p + m0, cnt, npMax, s, launches);
   }
   HY_CUDA(cudaStreamSynchronize(s));  // relOff is reused by the next chunk
 }
@@ -756,7 +757,7 @@ static void invertSubset(BatchedInverse& B, const std::vector<int>& list, size_t
   perm.alloc((size_t)cnt * npMax);
   invertBatched(Wbase, B.F.p, offBuf.p, nBuf.p, npBuf.p, cnt, npMax, piv.p, perm.p, piv.p + (size_t)cnt * npMax, info,
                 s, launches);
-  if (A0 && R) refineInverseBatched(A0, B.F.p, R, offBuf.p, npBuf.p, cnt, npMax, s, launches);
+  if (A0 && R) refineInverseBatched(A0, B.F.p, R, offBuf.p, nBuf.p, npBuf.p, cnt, npMax, s, launches);
   HY_CUDA(cudaStreamSynchronize(s));  // the host vectors and offBuf are reused by the next chunk
 }
 
@@ -1489,6 +1490,15 @@ void Engine::applyLevel(int l, const double* B, double* X, const double* T) {
 }
 
 void Engine::applyDevice(const double* dB, double* dX, const double* dT, double* dS) {
+  if (useDist() && !dT) {
+    // replicated argument / result around the owner-computes path: every rank applies to its own rows, the
+    // owned parts of the result are all-gathered
+    bufD_.alloc(n_);
+    applyLevel0Dist(dB, bufD_.p);
+    gatherOwned(bufD_.p, dX);
+    stats_.num_apply_inverse++;
+    return;
+  }
   applyLevel(0, dB, dX, dT);
   if (dS && borderM_)
     HY_CUDA(cudaMemcpyAsync(dS, bS_.p, borderM_ * sizeof(double), cudaMemcpyDeviceToDevice, stream_));
@@ -1548,31 +1558,48 @@ void Engine::applyInverse(const double* B, int64_t ldb, double* X, int64_t ldx, 
 }
 
 void Engine::localRows(int64_t* r0, int64_t* r1) const {
-  const int P = comm_.size();
-  const int64_t chunk = (n_ + P - 1) / P;
-  *r0 = std::min<int64_t>(n_, (int64_t)comm_.rank() * chunk);
-  *r1 = std::min<int64_t>(n_, *r0 + chunk);
+  if (comm_.size() > 1)
+    throw Error(HYMLS_B200_ERR_STATE,
+                "local_rows: with several ranks the rows are distributed by owner, not in contiguous blocks: use "
+                "hymls_b200_owned_rows");
+  *r0 = 0;
+  *r1 = n_;
 }
 
+// Distributed-vector ApplyInverse: Bloc / Xloc hold the rows hymls_b200_owned_rows lists (ascending), i.e. the
+// distribution the subdomain -> rank map of the reference induces
 void Engine::applyInverseDist(const double* Bloc, double* Xloc, int where) {
   needDevice();
   needComm();
   if (!computed_) throw Error(HYMLS_B200_ERR_STATE, "The preconditioner has not yet been computed.");
-  const int P = comm_.size();
-  const int64_t chunk = (n_ + P - 1) / P;
-  int64_t r0, r1;
-  localRows(&r0, &r1);
-  const int64_t nloc = r1 - r0;
-  bufG_.alloc((size_t)P * chunk);
+  if (comm_.size() <= 1) {
+    applyInverse(Bloc, n_, Xloc, n_, 1, where);
+    return;
+  }
+  DistPlan& D = levels_[0]->dist;
+  if (!D.ready) throw Error(HYMLS_B200_ERR_STATE, "apply_inverse_dist: no distributed plan (Number of Levels = 0?)");
+  cudaStream_t s = stream_;
+  const int64_t ld = (D.maxOwn + 7) & ~(int64_t)7;
+  bufB_.alloc(n_);
   bufX_.alloc(n_);
-  double* mine = bufG_.p + (int64_t)comm_.rank() * chunk;
-  HY_CUDA(cudaMemcpyAsync(mine, Bloc, nloc * sizeof(double),
-                          where == HYMLS_B200_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, stream_));
-  if (comm_.active()) comm_.allGather(mine, bufG_.p, (size_t)chunk, stream_);
-  applyDevice(bufG_.p, bufX_.p);
-  HY_CUDA(cudaMemcpyAsync(Xloc, bufX_.p + r0, nloc * sizeof(double),
-                          where == HYMLS_B200_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, stream_));
-  if (where == HYMLS_B200_HOST) HY_CUDA(cudaStreamSynchronize(stream_));
+  bufG_.alloc(2 * ld);
+  double* cB = bufG_.p;
+  double* cX = bufG_.p + ld;
+  const auto in = where == HYMLS_B200_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  const auto out = where == HYMLS_B200_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  HY_CUDA(cudaMemcpyAsync(cB, Bloc, D.nOwn * sizeof(double), in, s));
+  scatterVec(cB, D.ownRows.p, bufB_.p, D.nOwn, s, &launches_);
+  if (useDist()) {
+    applyLevel0Dist(bufB_.p, bufX_.p);
+  } else {  // bordered / fallback path works on replicated vectors
+    bufD_.alloc(n_);
+    gatherOwned(bufB_.p, bufD_.p);
+    applyLevel(0, bufD_.p, bufX_.p, nullptr);
+  }
+  stats_.num_apply_inverse++;
+  packIdx(bufX_.p, D.ownRows.p, cX, D.nOwn, s, &launches_);
+  HY_CUDA(cudaMemcpyAsync(Xloc, cX, D.nOwn * sizeof(double), out, s));
+  if (where == HYMLS_B200_HOST) HY_CUDA(cudaStreamSynchronize(s));
 }
 
 void Engine::applyMatrix(const double* x, double* y, int where) {
@@ -1601,10 +1628,20 @@ void Engine::timeApply(int reps, double* msApply, double* msA11) {
   std::mt19937_64 rng(7);
   for (auto& v : h) v = (double)(rng() >> 11) * (1.0 / 9007199254740992.0) * 2.0 - 1.0;
   HY_CUDA(cudaMemcpyAsync(bufB_.p, h.data(), n_ * sizeof(double), cudaMemcpyHostToDevice, stream_));
-  for (int i = 0; i < 3; ++i) applyDevice(bufB_.p, bufX_.p);
+  // sharded: the distributed-vector apply (what the Krylov loop calls), every rank on the rows it owns
+  const bool dist = useDist();
+  auto applyOnce = [&]() {
+    if (dist) {
+      applyLevel0Dist(bufB_.p, bufX_.p);
+      stats_.num_apply_inverse++;
+    } else {
+      applyDevice(bufB_.p, bufX_.p);
+    }
+  };
+  for (int i = 0; i < 3; ++i) applyOnce();
   HY_CUDA(cudaStreamSynchronize(stream_));
   HY_CUDA(cudaEventRecord(ev0_, stream_));
-  for (int i = 0; i < reps; ++i) applyDevice(bufB_.p, bufX_.p);
+  for (int i = 0; i < reps; ++i) applyOnce();
   HY_CUDA(cudaEventRecord(ev1_, stream_));
   HY_CUDA(cudaStreamSynchronize(stream_));
   float ms = 0;
@@ -1615,7 +1652,7 @@ void Engine::timeApply(int reps, double* msApply, double* msA11) {
   a11Ms_ = 0;
   a11LeadMs_ = 0;
   a11Launches_ = 0;
-  for (int i = 0; i < reps; ++i) applyDevice(bufB_.p, bufX_.p);
+  for (int i = 0; i < reps; ++i) applyOnce();
   HY_CUDA(cudaStreamSynchronize(stream_));
   timeA11_ = false;
   if (msA11) *msA11 = a11Launches_ ? a11Ms_ / a11Launches_ : 0.0;
@@ -1653,6 +1690,12 @@ void Engine::solve(const double* b, double* x, int where, uint64_t seed, hymls_b
   needDevice();
   needComm();
   if (!computed_) throw Error(HYMLS_B200_ERR_STATE, "The preconditioner has not yet been computed.");
+  if (params_.sublist("Solver").get("Use Deflation", false))
+    throw Error(HYMLS_B200_ERR_UNSUPPORTED, "deflated solvers are not implemented");
+  if (useDist()) {
+    solveDist(b, x, where, seed, info, hist, histCap);
+    return;
+  }
   ParameterList& sol = params_.sublist("Solver");
   ParameterList& it = sol.sublist("Iterative Solver");
   const std::string method = sol.get("Krylov Method", "GMRES");

@@ -28,8 +28,34 @@ struct BatchedInverse {  // a set of dense inverses + the GEMV work list over th
   GemvArgs args() const;
 };
 
+// one sparse neighbour exchange (grouped ncclSend / ncclRecv): positions to pack per peer, positions to unpack
+struct Halo {
+  std::vector<int> peers;                 // ranks exchanged with, ascending
+  std::vector<int64_t> sendPtr, recvPtr;  // peers+1: ranges of the packed buffers
+  DevBuf<int> sendIdx, recvIdx;
+  DevBuf<double> sendBuf, recvBuf;
+};
+
+// Owner-computes plan of a sharded level 0 (dist.cu): every rank works on the interiors of its subdomains and on
+// the separator groups it owns; only separator values on the interfaces between ranks are exchanged.
+struct DistPlan {
+  bool ready = false, matReady = false;
+  Halo rev;   // partial sums of A21 x1 at the ghost separators -> their owners
+  Halo fwd;   // x2 of owned separators -> the ranks whose subdomains touch them
+  Halo mat;   // columns of the owned matrix rows that other ranks own (operator apply of the Krylov loop)
+  DevBuf<int> addNode;                    // owned separators receiving partial sums, with their sources in
+  DevBuf<int64_t> addPtr, addSrc;         // rev.recvBuf in rank order (deterministic sum)
+  int64_t nAdd = 0;
+  DevBuf<int> rows21, rows12, ownUniq, ownSepPos, ownRows, allRows;
+  int64_t nRows21 = 0, nRows12 = 0, nOwnUniq = 0, nOwnSep = 0, nOwn = 0, maxOwn = 0;
+  std::vector<int> hOwnRows;              // matrix rows this rank owns, ascending
+  std::vector<int> rowOwner;              // owner rank of every matrix row
+  DevBuf<double> gath;                    // nranks * maxOwn: all-gather target for replicated output
+};
+
 struct Level {
   LevelSym sym;
+  DistPlan dist;
   bool exact = false;  // Number of Levels == 0: dense Schur complement instead of transform + drop
   // matrix of this level
   DevBuf<int64_t> rowptr;
@@ -118,6 +144,7 @@ class Engine {
   void applyMatrix(const double* x, double* y, int where);
   void localRows(int64_t* r0, int64_t* r1) const;
   void applyInverseDist(const double* Bloc, double* Xloc, int where);
+  int64_t ownedRows(int64_t* rows, int64_t cap);
   void solve(const double* b, double* x, int where, uint64_t seed, hymls_b200_solve_info* info, double* hist,
              int histCap);
   void timeApply(int reps, double* msApply, double* msA11);
@@ -142,6 +169,15 @@ class Engine {
                               const char* what);
   void coarseSolveBordered(const double* rhs, const double* T, double* sol, int n);
   void uploadLevel(Level& L);
+  // owner-computes multi-GPU path (dist.cu)
+  bool useDist() const;
+  void buildDistPlan(Level& L);
+  void buildMatrixHalo();
+  void haloExchange(Halo& h, const double* src, double* dst, bool scatter);
+  void applyLevel0Dist(const double* B, double* X);
+  void gatherOwned(const double* Xowned, double* Xfull);
+  void solveDist(const double* b, double* x, int where, uint64_t seed, hymls_b200_solve_info* info, double* hist,
+                 int histCap);
   void applyDevice(const double* dB, double* dX, const double* dT = nullptr, double* dS = nullptr);
   // rows [r0, r1) of the (bordered) operator [K V; W' C] applied to the replicated vector `full`
   void operatorRows(const double* full, double* out, int64_t r0, int64_t r1);
@@ -176,7 +212,8 @@ class Engine {
   DevBuf<int64_t> relOff_;
   DevBuf<double> flag_;
   DevBuf<double> bufB_, bufX_;  // staging for host vectors
-  DevBuf<double> bufG_;          // all-gather target of the distributed-vector entry point
+  DevBuf<double> bufG_;          // compact staging of the distributed-vector entry point
+  DevBuf<double> bufD_;          // global-length scratch of the owner-computes path
   // Krylov workspace
   DevBuf<double> kV_, kW_, kZ_, kH_, kPartial_, kX_, kB_, kR_;
   int kCap_ = 0;

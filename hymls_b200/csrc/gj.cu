@@ -981,9 +981,11 @@ __global__ void k_refine_add(double* __restrict__ Xbase, const double* __restric
     X[e] += T[e];
 }
 
-void refineInverseBatched(double* A, double* F, double* R, const int64_t* dOff, const int* dNp, int count, int npMax,
-                          cudaStream_t s, int64_t* launches) {
+void refineInverseBatched(double* A, double* F, double* R, const int64_t* dOff, const int* dN, const int* dNp, int count,
+                          int npMax, cudaStream_t s, int64_t* launches) {
   if (count == 0 || npMax == 0) return;
+  k_pad_identity<<<count, 64, 0, s>>>(A, dOff, dN, dNp, count);  // the originals come without the padding identity
+  ++*launches;
   constexpr size_t smem = (size_t)(2 * RF_TM * RF_SA + 2 * RF_TK * RF_SB) * sizeof(double);
   static PerDeviceLimit limit;
   if (limit.raise(smem + 48 * 1024))

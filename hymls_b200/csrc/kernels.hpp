@@ -13,8 +13,8 @@ void invertBatched(double* W, double* F, const int64_t* dOff, const int* dN, con
 // One Newton-Schulz step X <- X + X (I - A X) on the inverses F of a batch (same offsets for A, F and the
 // scratch R; A holds the ORIGINAL matrices and is destroyed).  Restores O(cond(A) eps) accuracy after the
 // Gauss-Jordan inversion (whose forward error grows with cond(U)).
-void refineInverseBatched(double* A, double* F, double* R, const int64_t* dOff, const int* dNp, int count, int npMax,
-                          cudaStream_t s, int64_t* launches);
+void refineInverseBatched(double* A, double* F, double* R, const int64_t* dOff, const int* dN, const int* dNp, int count,
+                          int npMax, cudaStream_t s, int64_t* launches);
 
 // ---- schur.cu ----
 struct SchurArgs {
@@ -126,6 +126,19 @@ void gatherAdd(const double* b, const int* idx, const double* t, double* y, int6
 void scatterVec(const double* x, const int* idx, double* y, int64_t n, cudaStream_t s, int64_t* launches);
 // y[idx[i]] = x[i] for idx[i] >= 0
 void scatterVecMasked(const double* x, const int* idx, double* y, int64_t n, cudaStream_t s, int64_t* launches);
+
+// ---- owner-computes multi-GPU path (apply.cu; used by dist.cu) ----
+void spmvRows(const int64_t* ptr, const int* col, const double* val, const double* x, double* y, const int* rows,
+              int64_t nrows, double alpha, const double* b, const int* bidx, double beta, int compact, cudaStream_t s,
+              int64_t* launches);
+void householderList(const int* uniqStart, const int* list, int nlist, const double* w, const double* in, double* out,
+                     double* vsumOut, const double* vsumIn, double* X, const int* sepRow, cudaStream_t s,
+                     int64_t* launches);
+void packIdx(const double* x, const int* idx, double* out, int64_t n, cudaStream_t s, int64_t* launches);
+void haloAdd(double* z, const int* node, const int64_t* ptr, const int64_t* src, const double* buf, int64_t n,
+             cudaStream_t s, int64_t* launches);
+void gatherAddList(const double* b, const int* bidx, const double* t, double* y, const int* list, int64_t n,
+                   cudaStream_t s, int64_t* launches);
 
 // ---- bordered variant (apply.cu) ----
 void batchedGemvT(const GemvArgs& a, int count, int npMax, cudaStream_t s, int64_t* launches);  // out = Ainv^T x

@@ -97,11 +97,16 @@ int hymls_b200_apply_inverse(hymls_b200_t* h, const double* B, int64_t ldb, doub
                              int nvec, int where);
 
 /*
- * Distributed-vector variant for multi-GPU use (the reference's vectors are distributed Epetra_MultiVectors):
- * rank r passes / receives only rows [r0, r1) of B and X (hymls_b200_local_rows; contiguous row blocks of
- * ceil(n / nranks) rows).  The library all-gathers B over NVLink, so each rank moves n/nranks values over
- * PCIe instead of n.  With one rank it is the same as hymls_b200_apply_inverse.
+ * Distributed-vector variant for multi-GPU use (the reference's vectors are distributed Epetra_MultiVectors on the
+ * map its partitioner induces, src/HYMLS_Preconditioner.cpp:978-979, 1050-1052).  A rank owns the rows of the
+ * interiors of its subdomains (BasePartitioner::CreatePIDMap) and of the separator groups whose owner subdomain is
+ * its own; hymls_b200_owned_rows lists them (ascending GIDs; returns the count, rows may be NULL to query it).
+ * hymls_b200_apply_inverse_dist takes / returns exactly those rows, in that order.  Nothing but separator values on
+ * the interfaces between ranks, the V-sums and (in hymls_b200_solve) dot products cross NVLink.
+ * With one rank: all rows, the same as hymls_b200_apply_inverse.
+ * hymls_b200_local_rows (contiguous row blocks) is kept for one rank only and fails with several.
  */
+int64_t hymls_b200_owned_rows(hymls_b200_t* h, int64_t* rows, int64_t cap);
 int hymls_b200_local_rows(hymls_b200_t* h, int64_t* r0, int64_t* r1);
 int hymls_b200_apply_inverse_dist(hymls_b200_t* h, const double* B_local, double* X_local, int where);
 

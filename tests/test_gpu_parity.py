@@ -13,14 +13,16 @@ pytestmark = pytest.mark.gpu
 
 # ApplyInverse tolerances.  The north star asks for 1e-12 relative against the reference's own FP64 path.  No two
 # FP64 evaluations of this preconditioner agree better than their own rounding error, and that error is 1e-12 ..
-# 8e-12 for the FP64 oracle itself on the badly scaled Stokes blocks (a = nx^2 vs b = 1), measured against the
-# extended-precision ground truth of oracle/extended.py (profiles/r02_accuracy.md).  The tests therefore check
-#   (1) err(GPU vs truth) <= max(2 err(oracle vs truth), 1e-12): the GPU is as close to the exact-arithmetic
-#       preconditioner as the reference-style LU evaluation (or meets the north star's 1e-12 outright), and
-#   (2) GPU vs FP64 oracle within the cap below (<= err(GPU) + err(oracle) by the triangle inequality).
+# 8e-12 for a reference-style sparse-LU evaluation (the FP64 oracle) on the badly scaled Stokes blocks (a = nx^2 vs
+# b = 1), measured against the extended-precision ground truth of oracle/extended.py.  The GPU path (explicit inverses
+# + one Newton-Schulz step each, gj.cu) is 3e-16 .. 2e-14 away from that ground truth (profiles/r02_accuracy.md).
+# The tests therefore check
+#   (1) err(GPU vs truth) <= 1e-12, the north star's tolerance, against the exact-arithmetic preconditioner, and
+#       err(GPU vs truth) <= 2 err(FP64 oracle vs truth) + 1e-14: never less accurate than the reference-style path;
+#   (2) GPU vs FP64 oracle within the cap below, which is the oracle's own distance to the truth.
 TOL_LAPLACE = 1e-13
 TOL_STOKES = 2e-11
-TRUTH_FACTOR, TRUTH_FLOOR = 2.0, 1e-12
+TRUTH_TOL = 1e-12
 
 
 def dictify(p):
@@ -87,7 +89,7 @@ def test_apply_inverse_matches_oracle(eqn, dim, nx, sx, levels, cx, extra, tol):
     xt = T.apply_inverse(B[:, 0])
     e_gpu = float(np.linalg.norm(X[:, 0] - xt) / np.linalg.norm(xt))
     e_ora = float(np.linalg.norm(O.apply_inverse(B[:, 0]) - xt) / np.linalg.norm(xt))
-    assert e_gpu <= max(TRUTH_FACTOR * e_ora, TRUTH_FLOOR), (e_gpu, e_ora)
+    assert e_gpu <= TRUTH_TOL and e_gpu <= 2.0 * e_ora + 1e-14, (e_gpu, e_ora)
     # linearity, a size-independent property
     y = P.ApplyInverse(2.0 * B[:, 0] - 3.0 * B[:, 1])
     assert rel(y, 2.0 * X[:, 0] - 3.0 * X[:, 1]) < 1e-12

@@ -1,22 +1,26 @@
-"""Stage-by-stage parity of Compute against the oracle: the explicit subdomain inverses (row a7 of SURVEY 8a),
-the transformed + dropped reduced Schur complement on the V-sums (a10-a12, a14) and the separator-block inverses
-(a13), read back through the C ABI's test hook.  ApplyInverse parity (test_gpu_parity.py) only sees their product."""
+"""Stage-by-stage parity of Compute: the explicit subdomain inverses (row a7 of SURVEY 8a), the transformed +
+dropped reduced Schur complement on the V-sums (a10-a12, a14) and the separator-block inverses (a13), read back
+through the C ABI's test hook and compared with the EXTENDED-PRECISION evaluation of the restated reference
+algorithm (oracle/extended.py).  Measured distances (profiles/r02_accuracy.md): <= 1.2e-15 for every stage on the
+GPU (after the Newton-Schulz step), against 1e-13 .. 5e-12 for FP64 LAPACK / the FP64 oracle -- so the bound below
+is a real bound, not slack.  ApplyInverse parity (test_gpu_parity.py) only sees the product of the stages."""
 import numpy as np
 import pytest
 import scipy.sparse as sp
 
 import hymls_b200 as hb
-from oracle import hymls as oh
+from oracle import extended as ox, hymls as oh
 from tests.common import make_params
 from tests.test_gpu_parity import dictify
 
 pytestmark = pytest.mark.gpu
 
+STAGE_TOL = 1e-13   # relative, against the extended-precision stage values
 CASES = [
-    ("Laplace", 2, 32, 4, 2, None, {}, 1e-13),
-    ("Stokes-C", 2, 32, 4, 2, None, {}, 1e-9),
-    ("Stokes-C", 3, 8, 4, 1, None, {"Partitioner": "Skew Cartesian"}, 1e-9),
-    ("Stokes-C", 3, 16, 4, 2, 2, {"Eliminate_Tube_Pressures_With_Velocities": True}, 1e-9),
+    ("Laplace", 2, 32, 4, 2, None, {}, STAGE_TOL),
+    ("Stokes-C", 2, 32, 4, 2, None, {}, STAGE_TOL),
+    ("Stokes-C", 3, 8, 4, 1, None, {"Partitioner": "Skew Cartesian"}, STAGE_TOL),
+    ("Stokes-C", 3, 16, 4, 2, 2, {"Eliminate_Tube_Pressures_With_Velocities": True}, STAGE_TOL),
 ]
 
 
@@ -31,9 +35,16 @@ def test_compute_stages_match_oracle(eqn, dim, nx, sx, levels, cx, extra, tol):
     O = oh.Preconditioner(A, p.copy(), tv)
     O.initialize()
     O.compute()
+    T = ox.Preconditioner(A, p.copy(), tv)      # ground truth: the same algorithm in extended precision
+    T.initialize()
+    T.compute()
     P = hb.Preconditioner(A, dictify(p), tv)
     P.Initialize()
     P.Compute()
+
+    def dist(G, ref):
+        ref = np.asarray(ref, dtype=np.longdouble)
+        return float(np.linalg.norm(np.asarray(G, dtype=np.longdouble) - ref) / np.linalg.norm(ref))
 
     # (1) A11^-1 blocks.  The library orders the interior of a subdomain "nodes coupled to separators first"
     # (DESIGN.md 3); "introw" gives the matrix row of every interior position, the oracle keeps GID order.
@@ -56,19 +67,19 @@ def test_compute_stages_match_oracle(eqn, dim, nx, sx, levels, cx, extra, tol):
         perm = np.array([where[int(r)] for r in rows_gpu])                  # library position -> oracle position
         blk = (dense11[np.ix_(idx, idx)] if dense11 is not None
                else O.A11[idx[0]:idx[-1] + 1, idx[0]:idx[-1] + 1].toarray())
-        inv = np.linalg.inv(blk)[np.ix_(perm, perm)]
+        inv = ox._RefinedDenseLU(blk).solve(np.eye(k))[np.ix_(perm, perm)]
         npad = (k + 7) // 8 * 8
         G = F[off[sd]:off[sd] + npad * npad].reshape(npad, npad)
-        assert np.linalg.norm(G[:k, :k] - inv) <= tol * np.linalg.norm(inv)
+        assert dist(G[:k, :k], inv) <= tol
         assert np.allclose(G[k:, k:], np.eye(npad - k), rtol=0, atol=1e-14)  # identity in the padding
 
     # (2) reduced Schur complement on the V-sums after transformation and dropping
-    S = O.schur_prec
+    S = T.schur_prec
     ptr = P.DebugArray("redptr").astype(np.int64)
     col = P.DebugArray("redcol").astype(np.int64)
     val = P.DebugArray("redval")
     R = sp.csr_matrix((val, col, ptr), shape=(len(ptr) - 1, len(ptr) - 1))
-    assert abs(R - S.reduced).max() <= tol * abs(S.reduced).max()
+    assert float(abs(R - S.reduced).max()) <= tol * float(abs(S.reduced).max())
 
     # (3) inverses of the non-V-sum separator blocks
     boff = P.DebugArray("blkoff").astype(np.int64)
@@ -79,16 +90,16 @@ def test_compute_stages_match_oracle(eqn, dim, nx, sx, levels, cx, extra, tol):
         if k == 0:
             continue
         npad = (k + 7) // 8 * 8
-        inv = np.linalg.inv(S.matrix[rows, :][:, rows].toarray())
+        inv = ox._RefinedDenseLU(S.matrix[rows, :][:, rows].toarray()).solve(np.eye(k))
         G = BF[boff[b]:boff[b] + npad * npad].reshape(npad, npad)[:k, :k]
-        assert np.linalg.norm(G - inv) <= 100 * tol * np.linalg.norm(inv)
+        assert dist(G, inv) <= tol
         nb += 1
     assert nb > 0
 
 
 @pytest.mark.parametrize("eqn,dim,nx,sx,levels,cx,extra,tol", [
-    ("Stokes-C", 2, 32, 4, 2, None, {}, 1e-9),
-    ("Stokes-C", 3, 16, 4, 2, 2, {"Partitioner": "Skew Cartesian"}, 1e-9),
+    ("Stokes-C", 2, 32, 4, 2, None, {}, STAGE_TOL),
+    ("Stokes-C", 3, 16, 4, 2, 2, {"Partitioner": "Skew Cartesian"}, STAGE_TOL),
 ])
 def test_dense_schur_rows_path_matches_oracle(monkeypatch, eqn, dim, nx, sx, levels, cx, extra, tol):
     """The coarser levels form the rows of A21 A11^-1 with a DMMA GEMM per subdomain instead of the sparse
@@ -108,4 +119,4 @@ def test_dense_schur_rows_path_matches_oracle(monkeypatch, eqn, dim, nx, sx, lev
     P.Compute()
     b = np.random.default_rng(7).uniform(-1, 1, A.shape[0])
     x, xo = P.ApplyInverse(b), O.apply_inverse(b)
-    assert np.linalg.norm(x - xo) <= 5e-10 * np.linalg.norm(xo)
+    assert np.linalg.norm(x - xo) <= 2e-11 * np.linalg.norm(xo)

@@ -71,6 +71,8 @@ def load_library():
     lib.hymls_b200_compute.argtypes = [vp]
     lib.hymls_b200_apply_inverse.argtypes = [vp, vp, i64, vp, i64, C.c_int, C.c_int]
     lib.hymls_b200_local_rows.argtypes = [vp, P(i64), P(i64)]
+    lib.hymls_b200_owned_rows.argtypes = [vp, vp, i64]
+    lib.hymls_b200_owned_rows.restype = i64
     lib.hymls_b200_apply_inverse_dist.argtypes = [vp, vp, vp, C.c_int]
     lib.hymls_b200_set_border.argtypes = [vp, vp, vp, vp, C.c_int]
     lib.hymls_b200_apply_inverse_bordered.argtypes = [vp, vp, i64, vp, vp, i64, vp, C.c_int, C.c_int]
@@ -244,11 +246,25 @@ class Preconditioner:
         _check(self._lib, self._lib.hymls_b200_local_rows(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
 
+    def OwnedRows(self):
+        """rows (GIDs, ascending) this rank owns: interiors of its subdomains + the separator groups it owns"""
+        n = int(self._lib.hymls_b200_owned_rows(self._h, None, 0))
+        _check(self._lib, n)
+        out = np.zeros(n, dtype=np.int64)
+        _check(self._lib, int(self._lib.hymls_b200_owned_rows(self._h, out.ctypes.data, n)))
+        return out
+
     def ApplyInverseDist(self, b_local):
-        """distributed-vector ApplyInverse: this rank's rows in, this rank's rows out (numpy, host)"""
-        bl = np.ascontiguousarray(b_local, dtype=np.float64)
-        xl = np.zeros_like(bl)
-        _check(self._lib, self._lib.hymls_b200_apply_inverse_dist(self._h, bl.ctypes.data, xl.ctypes.data, HOST))
+        """distributed-vector ApplyInverse: the rows of OwnedRows() in, the same rows out (numpy: host buffers,
+        torch CUDA tensors: device buffers)"""
+        if isinstance(b_local, np.ndarray):
+            bl = np.ascontiguousarray(b_local, dtype=np.float64)
+            xl = np.zeros_like(bl)
+            _check(self._lib, self._lib.hymls_b200_apply_inverse_dist(self._h, bl.ctypes.data, xl.ctypes.data, HOST))
+            return xl
+        import torch
+        xl = torch.empty_like(b_local)
+        _check(self._lib, self._lib.hymls_b200_apply_inverse_dist(self._h, b_local.data_ptr(), xl.data_ptr(), DEVICE))
         return xl
 
     def Apply(self, X, Y):  # Preconditioner::Apply returns -1 (:122-123)

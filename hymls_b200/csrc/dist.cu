@@ -33,7 +33,7 @@ bool Engine::useDist() const {
 }
 
 static void uploadHalo(Halo& h, const std::vector<std::vector<int>>& send, const std::vector<std::vector<int>>& recv,
-                       cudaStream_t s) {
+                       cudaStream_t s, bool device = true) {
   const int P = (int)send.size();
   h.peers.clear();
   h.sendPtr.assign(1, 0);
@@ -47,6 +47,7 @@ static void uploadHalo(Halo& h, const std::vector<std::vector<int>>& send, const
     h.sendPtr.push_back((int64_t)si.size());
     h.recvPtr.push_back((int64_t)ri.size());
   }
+  if (!device) return;
   h.sendIdx.upload(si, s);
   h.recvIdx.upload(ri, s);
   h.sendBuf.alloc(std::max<size_t>(si.size(), 1));
@@ -95,8 +96,9 @@ void Engine::buildDistPlan(Level& L) {
     sortUnique(sendRev[q]);
     sortUnique(recvRev[q]);
   }
-  uploadHalo(D.rev, sendRev, recvRev, s);
-  uploadHalo(D.fwd, recvRev, sendRev, s);  // the same lists, opposite direction
+  const bool dev = deviceOk_;  // without a device only the host side of the plan exists (owned_rows, tests)
+  uploadHalo(D.rev, sendRev, recvRev, s, dev);
+  uploadHalo(D.fwd, recvRev, sendRev, s, dev);  // the same lists, opposite direction
   // deterministic accumulation of the received partial sums: per owned node its sources in rank order
   {
     std::vector<std::pair<int, int64_t>> ent;  // (node, index in rev.recvBuf)
@@ -118,9 +120,11 @@ void Engine::buildDistPlan(Level& L) {
     }
     if (!node.empty()) ptr.push_back((int64_t)src.size());
     D.nAdd = (int64_t)node.size();
-    D.addNode.upload(node, s);
-    D.addPtr.upload(ptr, s);
-    D.addSrc.upload(src, s);
+    if (dev) {
+      D.addNode.upload(node, s);
+      D.addPtr.upload(ptr, s);
+      D.addSrc.upload(src, s);
+    }
   }
   std::vector<int> rows12;
   for (int sd : L.ownSd)
@@ -146,14 +150,16 @@ void Engine::buildDistPlan(Level& L) {
   D.nRows12 = (int64_t)rows12.size();
   D.nOwnUniq = (int64_t)ownUniq.size();
   D.nOwnSep = (int64_t)ownSepPos.size();
-  D.rows21.upload(rows21, s);
-  D.rows12.upload(rows12, s);
-  D.ownUniq.upload(ownUniq, s);
-  D.ownSepPos.upload(ownSepPos, s);
-  D.ownRows.upload(D.hOwnRows, s);
-  D.allRows.upload(allRows, s);
-  D.gath.alloc((size_t)P * D.maxOwn);
-  HY_CUDA(cudaStreamSynchronize(s));
+  if (dev) {
+    D.rows21.upload(rows21, s);
+    D.rows12.upload(rows12, s);
+    D.ownUniq.upload(ownUniq, s);
+    D.ownSepPos.upload(ownSepPos, s);
+    D.ownRows.upload(D.hOwnRows, s);
+    D.allRows.upload(allRows, s);
+    D.gath.alloc((size_t)P * D.maxOwn);
+    HY_CUDA(cudaStreamSynchronize(s));
+  }
   D.ready = true;
   D.matReady = false;
 }
@@ -310,7 +316,7 @@ int64_t Engine::ownedRows(int64_t* rows, int64_t cap) {
     return n_;
   }
   DistPlan& D = levels_[0]->dist;
-  if (!D.ready) throw Error(HYMLS_B200_ERR_STATE, "owned_rows: the distributed plan needs a device (Initialize on a GPU)");
+  if (!D.ready) throw Error(HYMLS_B200_ERR_STATE, "owned_rows: no distributed plan (Number of Levels = 0 is single-GPU only)");
   if (rows && cap >= D.nOwn)
     for (int64_t i = 0; i < D.nOwn; ++i) rows[i] = D.hOwnRows[i];
   return D.nOwn;

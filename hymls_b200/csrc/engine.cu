@@ -298,6 +298,8 @@ void Engine::initialize() {
     }
     // parameters of the next level (SetNextLevelParameters; sx *= cx)
     part.setNextLevelParameters(levelParams);
+    L.dist.ready = false;
+    if (L.sharded && l == 0 && !L.exact) buildDistPlan(L);  // host lists always, device copies with a device
     if (deviceOk_) uploadLevel(L);
   }
   if (deviceOk_) {
@@ -633,7 +635,6 @@ void Engine::uploadLevel(Level& L) {
     L.blk.setup(S.blkN, S.blkNp, S.blkOff, blkVecOff, s);
   }
   L.blkRows.upload(S.blkRows, s);
-  if (L.sharded && S.level == 0 && !L.exact) buildDistPlan(L); else L.dist.ready = false;
   // work vectors
   L.x1.alloc(S.nI);
   L.y1.alloc(S.nI);

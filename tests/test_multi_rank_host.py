@@ -40,12 +40,20 @@ def _worker(rank, world, port, nx, sx, out):
     ok = ok and int(n1.item()) == P.NumMySubdomains(1) and 0 < len(P.OwnedSubdomains(1)) < P.NumMySubdomains(1)
     # the index maps do not depend on the number of ranks
     ok = ok and P.GetMap(hb.api.MAP_SEPARATOR, 0).shape[0] > 0
-    # row blocks of the distributed-vector entry point (hymls_b200_local_rows) tile [0, n) in rank order
-    r0, r1 = P.LocalRows()
-    rows = [torch.zeros(2, dtype=torch.int64) for _ in range(world)]
-    dist.all_gather(rows, torch.tensor([r0, r1], dtype=torch.int64))
-    ok = ok and int(rows[0][0]) == 0 and int(rows[-1][1]) == A.shape[0]
-    ok = ok and all(int(rows[q][1]) == int(rows[q + 1][0]) for q in range(world - 1))
+    # rows of the distributed-vector entry point (hymls_b200_owned_rows): every row has exactly one owner, and a
+    # rank owns the interior rows of its subdomains
+    rows = P.OwnedRows()
+    cnt = torch.zeros(A.shape[0], dtype=torch.int32)
+    cnt[torch.from_numpy(rows)] += 1
+    dist.all_reduce(cnt)
+    ok = ok and bool((cnt == 1).all()) and bool(np.all(np.diff(rows) > 0))
+    mine = set(rows.tolist())
+    ok = ok and all(int(g) in mine for sd in P.OwnedSubdomains(0)[:5] for g in P.GetInteriorGroup(int(sd), 0))
+    try:
+        P.LocalRows()
+        ok = False                 # contiguous row blocks no longer exist with several ranks
+    except hb.HymlsError:
+        pass
     # the skew partitioner (the bench configuration) shards by the same map
     p2 = make_params("Stokes-C", 3, nx, sx, 2, 2, Partitioner="Skew Cartesian")
     Q = hb.Preconditioner(A, _dictify(p2), pattern_only=True)

@@ -1,4 +1,9 @@
-"""Sharded (NCCL) vs single-GPU ApplyInverse / solve on the same problem.  Run with torchrun."""
+"""Sharded (NCCL, owner-computes halo path) vs single-GPU ApplyInverse / solve on the same problem.
+Run under torchrun; prints one JSON line on rank 0 (also used by `bench.py --check`).
+
+    torchrun --nproc-per-node 2 tools/mgpu_check.py [nx sx levels cx partitioner]
+"""
+import json
 import os
 import sys
 
@@ -11,68 +16,88 @@ sys.path.insert(0, ROOT)
 import hymls_b200 as hb  # noqa: E402
 
 
-def main():
-    rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); lr = int(os.environ["LOCAL_RANK"])
-    torch.cuda.set_device(lr)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
-    nx = int(sys.argv[1]) if len(sys.argv) > 1 else 16
-    sx = int(sys.argv[2]) if len(sys.argv) > 2 else 4
-    levels = int(sys.argv[3]) if len(sys.argv) > 3 else 2
+def run_check(nx, sx, levels, cx, partitioner, rank, world, border=False, schur_gemm=None):
+    prec = {"Partitioner": partitioner, "Separator Length": sx, "Number of Levels": levels, "Coarsening Factor": cx}
+    if partitioner == "Cartesian":
+        prec["Eliminate Tube Pressures With Velocities"] = True
     params = {"Problem": {"Equations": "Stokes-C", "Dimension": 3, "nx": nx, "ny": nx, "nz": nx},
-              "Preconditioner": {"Separator Length": sx, "Number of Levels": levels, "Coarsening Factor": int(sys.argv[4]) if len(sys.argv) > 4 else 2,
-                                 "Eliminate Tube Pressures With Velocities": True},
+              "Preconditioner": prec,
               "Solver": {"Krylov Method": "GMRES", "Initial Vector": "Zero",
-                         "Iterative Solver": {"Maximum Iterations": 300, "Convergence Tolerance": 1e-8}}}
+                         "Iterative Solver": {"Maximum Iterations": 400, "Convergence Tolerance": 1e-8}}}
+    if schur_gemm is not None:
+        os.environ["HYMLS_B200_SCHUR_GEMM"] = str(schur_gemm)
     A = -hb.galeri.create_matrix("Stokes-C", 3, nx)
     tv = hb.galeri.create_testvector(A)
     n = A.shape[0]
-    # unique id from rank 0
     idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
     if rank == 0:
         idt.copy_(torch.frombuffer(bytearray(hb.Preconditioner.CommUniqueId()), dtype=torch.uint8))
     dist.broadcast(idt, 0)
-    uid = bytes(idt.cpu().numpy().tobytes())
     P = hb.Preconditioner(A, params, tv)
-    P.CommInit(uid, rank, world)
+    P.CommInit(bytes(idt.cpu().numpy().tobytes()), rank, world)
     P.Initialize()
-    own = P.OwnedSubdomains()
     P.Compute()
-    Q = hb.Preconditioner(A, params, tv)   # single-GPU replica for comparison
-    Q.Initialize(); Q.Compute()
-    b = np.random.default_rng(0).uniform(-1, 1, n)
-    xs = P.ApplyInverse(b)
+    os.environ.pop("HYMLS_B200_SCHUR_GEMM", None)
+    Q = hb.Preconditioner(A, params, tv)   # single-GPU replica of the same problem for comparison
+    Q.Initialize()
+    Q.Compute()
+    rng = np.random.default_rng(0)
+    b = rng.uniform(-1, 1, n)
     xq = Q.ApplyInverse(b)
-    err = np.linalg.norm(xs - xq) / np.linalg.norm(xq)
-    # sequence of device-resident applies (what GMRES does)
-    rng = np.random.default_rng(5)
-    for k in range(4):
-        v = torch.from_numpy(rng.uniform(-1, 1, n)).cuda()
-        d = (P.ApplyInverse(v) - Q.ApplyInverse(v)).norm().item() / Q.ApplyInverse(v).norm().item()
-        print("rank %d device apply %d rel diff %.2e" % (rank, k, d), flush=True)
-    v = rng.uniform(-1, 1, n)
-    print("rank %d ApplyMatrix diff %.2e" % (rank, np.linalg.norm(P.ApplyMatrix(v) - A @ v) / np.linalg.norm(A @ v)), flush=True)
-    from oracle import krylov as ok
-    log = []
-    def both(z):
-        a_ = P.ApplyInverse(z); b_ = Q.ApplyInverse(z)
-        d_ = a_ - b_
-        log.append((np.linalg.norm(d_) / np.linalg.norm(b_), np.abs(d_).max(), int(np.abs(d_).argmax()) % 4,
-                    np.linalg.norm(d_[3::4]) / max(np.linalg.norm(b_[3::4]), 1e-300)))
-        return a_
-    xo, its_o, conv_o, h_o = ok.gmres(lambda z: A @ z, A @ b, np.zeros(n), both, side="Right", tol=1e-8,
-                                      max_iters=40, max_restarts=0)
+    xs = P.ApplyInverse(b)                       # replicated in / out
+    rows = P.OwnedRows()
+    xd = P.ApplyInverseDist(b[rows])             # distributed in / out (host buffers)
+    xdd = P.ApplyInverseDist(torch.from_numpy(b[rows]).cuda()).cpu().numpy()
+    rel = lambda a, r: float(np.linalg.norm(a - r) / np.linalg.norm(r))   # noqa: E731
+    res = {"apply_rel_diff": rel(xs, xq), "dist_rel_diff": float(np.linalg.norm(xd - xq[rows]) / np.linalg.norm(xq)),
+           "dist_host_eq_device": bool(np.array_equal(xd, xdd)), "owned_rows": int(len(rows)), "n": int(n)}
+    # every row has exactly one owner
+    cnt = torch.zeros(n, dtype=torch.int32, device="cuda")
+    cnt[torch.from_numpy(rows).cuda()] += 1
+    dist.all_reduce(cnt)
+    res["rows_partitioned"] = bool((cnt == 1).all().item())
+    rhs = A @ rng.uniform(-1, 1, n)
+    S = hb.Solver(P)
+    x = S.ApplyInverse(rhs)
+    T = hb.Solver(Q)
+    y = T.ApplyInverse(rhs)
+    k = min(len(S.history), len(T.history), 15)
+    res.update({"iterations_sharded": int(S.num_iter), "iterations_single": int(T.num_iter),
+                "history_first15_max_rel_diff": float(np.max(np.abs(S.history[:k] - T.history[:k]) / T.history[:k])),
+                "solution_rel_diff": rel(x, y), "converged": bool(S.info["converged"]),
+                "explicit_rel_residual": float(S.info["explicit_rel_residual"])})
+    if border:
+        # bordered variant (constant-pressure null space) takes the replicated fallback path
+        V = np.zeros((n, 1))
+        V[3::4, 0] = 1.0
+        V /= np.linalg.norm(V)
+        for R in (P, Q):
+            R.SetBorder(V)
+            R.Compute()
+        xb, sb = P.ApplyInverseBordered(b, np.zeros(1))
+        xr, sr = Q.ApplyInverseBordered(b, np.zeros(1))
+        res["bordered_rel_diff"] = rel(xb, xr)
+    ta, tb = P.TimeApply(10), Q.TimeApply(10)
+    res.update({"apply_ms_sharded": ta[0], "apply_ms_single": tb[0], "world": world})
+    return res
+
+
+def main():
+    rank = int(os.environ["RANK"])
+    world = int(os.environ["WORLD_SIZE"])
+    lr = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(lr)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+    a = sys.argv[1:]
+    nx = int(a[0]) if len(a) > 0 else 16
+    sx = int(a[1]) if len(a) > 1 else 4
+    levels = int(a[2]) if len(a) > 2 else 2
+    cx = int(a[3]) if len(a) > 3 else 2
+    part = a[4] if len(a) > 4 else "Skew Cartesian"
+    res = run_check(nx, sx, levels, cx, part, rank, world, border="--border" in a,
+                    schur_gemm=1 if "--schur-gemm" in a else None)
     if rank == 0:
-        for k, l_ in enumerate(log[:40:3]):
-            print("  apply %d: rel diff %.2e maxabs %.2e at var %d, pressure rel diff %.2e" % ((3 * k,) + l_), flush=True)
-    print("rank %d python GMRES with sharded ApplyInverse: its %d conv %s" % (rank, its_o, conv_o), flush=True)
-    S = hb.Solver(P); x = S.ApplyInverse(A @ b)
-    T = hb.Solver(Q); y = T.ApplyInverse(A @ b)
-    print("rank %d hist sharded" % rank, S.history[::12], "single", T.history[::12], flush=True)
-    ta = P.TimeApply(10); tb = Q.TimeApply(10)
-    print("rank %d/%d owns %d of %d sds | sharded vs single apply rel diff %.2e | its %d vs %d | x diff %.2e | "
-          "apply ms sharded %.3f single %.3f" % (rank, world, len(own), P.NumMySubdomains(0), err, S.num_iter,
-                                                  T.num_iter, np.linalg.norm(x - y) / np.linalg.norm(y), ta[0], tb[0]),
-          flush=True)
+        print("MGPU_CHECK " + json.dumps(res), flush=True)
     dist.barrier()
     dist.destroy_process_group()
 

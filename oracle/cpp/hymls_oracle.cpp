@@ -904,7 +904,12 @@ static void gmres(const Csr& A, const Level& M, const double* b, double* x, doub
   // right preconditioning, implicit residual scaled by the norm of the initial residual, zero or given x
   const int64_t n = A.n;
   const int m = std::max(1, std::min(numBlocks, maxIters));
-  std::vector<double> r(n), w(n), z(n), V((size_t)(m + 1) * n);
+  std::vector<double> r(n), w(n), z(n);
+  std::vector<std::vector<double>> V;  // basis vectors, allocated as the iteration proceeds
+  auto basis = [&](int i) -> std::vector<double>& {
+    while ((int)V.size() <= i) V.emplace_back(n);
+    return V[i];
+  };
   std::vector<double> H((size_t)(m + 1) * m, 0.0), cs(m), sn(m), g(m + 1), h(m + 1), h2(m + 1);
   auto t0 = std::chrono::steady_clock::now();
   A.matvec(x, r.data());
@@ -919,27 +924,52 @@ static void gmres(const Csr& A, const Level& M, const double* b, double* x, doub
     if (beta / scale <= tol) { res.converged = 1; break; }
     std::fill(g.begin(), g.end(), 0.0);
     g[0] = beta;
-    for (int64_t i = 0; i < n; ++i) V[i] = r[i] / beta;
+    {
+      std::vector<double>& v0 = basis(0);
+      for (int64_t i = 0; i < n; ++i) v0[i] = r[i] / beta;
+    }
     int kDone = 0;
     for (int k = 0; k < m && res.iters < maxIters; ++k) {
-      double* vk = V.data() + (size_t)k * n;
+      double* vk = basis(k).data();
+      basis(k + 1);
       M.applyInverse(vk, z.data());
       A.matvec(z.data(), w.data());
       for (int pass = 0; pass < 2; ++pass) {  // two passes of classical Gram-Schmidt (Belos ICGS)
         std::vector<double>& hh = pass ? h2 : h;
-        for (int i = 0; i <= k; ++i) hh[i] = dotp(V.data() + (size_t)i * n, w.data(), n);
+        // all k+1 dot products in one sweep over row chunks (w stays in cache); chunk partial sums are combined
+        // in chunk order, so the result does not depend on the thread count
+        const int64_t CH = 2048, nch = (n + CH - 1) / CH;
+        std::vector<double> part((size_t)nch * (k + 1));
 #pragma omp parallel for schedule(static)
-        for (int64_t q = 0; q < n; ++q) {
-          double t = w[q];
-          for (int i = 0; i <= k; ++i) t -= hh[i] * V[(size_t)i * n + q];
-          w[q] = t;
+        for (int64_t c = 0; c < nch; ++c) {
+          const int64_t q0 = c * CH, q1 = std::min(n, q0 + CH);
+          for (int i = 0; i <= k; ++i) {
+            const double* vi = V[i].data();
+            double t = 0;
+            for (int64_t q = q0; q < q1; ++q) t += vi[q] * w[q];
+            part[(size_t)c * (k + 1) + i] = t;
+          }
+        }
+        for (int i = 0; i <= k; ++i) {
+          double t = 0;
+          for (int64_t c = 0; c < nch; ++c) t += part[(size_t)c * (k + 1) + i];
+          hh[i] = t;
+        }
+#pragma omp parallel for schedule(static)
+        for (int64_t c = 0; c < nch; ++c) {
+          const int64_t q0 = c * CH, q1 = std::min(n, q0 + CH);
+          for (int i = 0; i <= k; ++i) {
+            const double* vi = V[i].data();
+            const double hi = hh[i];
+            for (int64_t q = q0; q < q1; ++q) w[q] -= hi * vi[q];
+          }
         }
       }
       const double hn = std::sqrt(dotp(w.data(), w.data(), n));
       for (int i = 0; i <= k; ++i) H[(size_t)i * m + k] = h[i] + h2[i];
       H[(size_t)(k + 1) * m + k] = hn;
       if (hn > 0) {
-        double* vn = V.data() + (size_t)(k + 1) * n;
+        double* vn = V[k + 1].data();
         for (int64_t q = 0; q < n; ++q) vn[q] = w[q] / hn;
       }
       for (int i = 0; i < k; ++i) {
@@ -969,7 +999,7 @@ static void gmres(const Csr& A, const Level& M, const double* b, double* x, doub
       }
       std::fill(w.begin(), w.end(), 0.0);
       for (int i = 0; i < kDone; ++i)
-        for (int64_t q = 0; q < n; ++q) w[q] += y[i] * V[(size_t)i * n + q];
+        for (int64_t q = 0; q < n; ++q) w[q] += y[i] * V[i][q];
       M.applyInverse(w.data(), z.data());
       for (int64_t q = 0; q < n; ++q) x[q] += z[q];
     }

@@ -67,6 +67,13 @@ def load_library():
     lib.hymls_b200_get_owned_subdomains.argtypes = [vp, C.c_int, vp, C.c_int]
     lib.hymls_b200_set_matrix_csr.argtypes = [vp, i64, vp, vp, vp, C.c_int]
     lib.hymls_b200_set_testvector.argtypes = [vp, vp]
+    lib.hymls_b200_set_matrix_csr_dist.argtypes = [vp, i64, i64, vp, vp, vp, vp]
+    lib.hymls_b200_set_parameters.argtypes = [vp, C.c_char_p]
+    lib.hymls_b200_set_row_map.argtypes = [vp, i64, vp]
+    lib.hymls_b200_apply_inverse_map.argtypes = [vp, vp, i64, vp, i64, C.c_int, C.c_int]
+    lib.hymls_b200_apply_inverse_bordered_map.argtypes = [vp, vp, i64, vp, vp, i64, vp, C.c_int, C.c_int]
+    lib.hymls_b200_set_testvector_dist.argtypes = [vp, i64, vp, vp]
+    lib.hymls_b200_set_border_dist.argtypes = [vp, i64, vp, vp, vp, vp, C.c_int]
     lib.hymls_b200_initialize.argtypes = [vp]
     lib.hymls_b200_compute.argtypes = [vp]
     lib.hymls_b200_apply_inverse.argtypes = [vp, vp, i64, vp, i64, C.c_int, C.c_int]
@@ -193,6 +200,41 @@ class Preconditioner:
                 self._h, n, rp.ctypes.data, ci.ctypes.data, None if pattern_only else v.ctypes.data, HOST))
         self.n = n
         return 0
+
+    # -- distributed caller (one MPI rank per GPU): rows / vectors on the caller's map --------------------
+    def SetMatrixDist(self, n_global, row_gids, K_local, pattern_only=False):
+        """this rank's rows (scipy CSR with GLOBAL column ids, row i <-> row_gids[i]); collective"""
+        K = K_local.tocsr()
+        g = np.ascontiguousarray(row_gids, dtype=np.int64)
+        rp = np.ascontiguousarray(K.indptr, dtype=np.int64)
+        ci = np.ascontiguousarray(K.indices, dtype=np.int64)
+        v = np.ascontiguousarray(K.data, dtype=np.float64)
+        _check(self._lib, self._lib.hymls_b200_set_matrix_csr_dist(
+            self._h, n_global, len(g), g.ctypes.data, rp.ctypes.data, ci.ctypes.data,
+            None if pattern_only else v.ctypes.data))
+        self.n = n_global
+        return 0
+
+    def SetParameters(self, params):
+        return _check(self._lib, self._lib.hymls_b200_set_parameters(self._h, params_to_xml(params).encode()))
+
+    def SetTestVectorDist(self, row_gids, tv_local):
+        g = np.ascontiguousarray(row_gids, dtype=np.int64)
+        t = np.ascontiguousarray(tv_local, dtype=np.float64)
+        return _check(self._lib, self._lib.hymls_b200_set_testvector_dist(self._h, len(g), g.ctypes.data, t.ctypes.data))
+
+    def SetRowMap(self, row_gids):
+        g = np.ascontiguousarray(row_gids, dtype=np.int64)
+        self._nlocal = len(g)
+        return _check(self._lib, self._lib.hymls_b200_set_row_map(self._h, len(g), g.ctypes.data))
+
+    def ApplyInverseMap(self, B_local):
+        """vectors on the map given to SetRowMap (numpy, host; n_local or n_local x nvec)"""
+        Bc = np.asfortranarray(np.asarray(B_local, dtype=np.float64).reshape(self._nlocal, -1))
+        Xc = np.zeros_like(Bc, order="F")
+        _check(self._lib, self._lib.hymls_b200_apply_inverse_map(self._h, Bc.ctypes.data, self._nlocal, Xc.ctypes.data,
+                                                                  self._nlocal, Bc.shape[1], HOST))
+        return Xc.reshape(np.shape(B_local))
 
     # -- multi-GPU (one process per GPU) -------------------------------------------------------------
     @staticmethod

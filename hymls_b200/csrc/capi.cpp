@@ -106,6 +106,61 @@ int hymls_b200_set_matrix_csr(hymls_b200_t* h, int64_t n, const int64_t* rowptr,
   HY_CATCH
 }
 
+int hymls_b200_set_matrix_csr_dist(hymls_b200_t* h, int64_t n_global, int64_t n_local, const int64_t* row_gids,
+                                   const int64_t* rowptr, const int64_t* col_gids, const double* values) {
+  HY_TRY
+  h->eng->setMatrixDist(n_global, n_local, row_gids, rowptr, col_gids, values);
+  return 0;
+  HY_CATCH
+}
+
+int hymls_b200_set_parameters(hymls_b200_t* h, const char* xml) {
+  HY_TRY
+  if (!xml) throw Error(HYMLS_B200_ERR_ARG, "set_parameters: null argument");
+  h->eng->setParameters(xml);
+  return 0;
+  HY_CATCH
+}
+
+int hymls_b200_set_row_map(hymls_b200_t* h, int64_t n_local, const int64_t* row_gids) {
+  HY_TRY
+  h->eng->setRowMap(n_local, row_gids);
+  return 0;
+  HY_CATCH
+}
+
+int hymls_b200_apply_inverse_map(hymls_b200_t* h, const double* B, int64_t ldb, double* X, int64_t ldx, int nvec,
+                                 int where) {
+  HY_TRY
+  h->eng->applyInverseMap(B, ldb, X, ldx, nvec, where);
+  return 0;
+  HY_CATCH
+}
+
+int hymls_b200_apply_inverse_bordered_map(hymls_b200_t* h, const double* B, int64_t ldb, const double* T, double* X,
+                                          int64_t ldx, double* S, int nvec, int where) {
+  HY_TRY
+  if (!T || !S) throw Error(HYMLS_B200_ERR_ARG, "apply_inverse_bordered_map: T and S are required");
+  h->eng->applyInverseMap(B, ldb, X, ldx, nvec, where, T, S);
+  return 0;
+  HY_CATCH
+}
+
+int hymls_b200_set_testvector_dist(hymls_b200_t* h, int64_t n_local, const int64_t* row_gids, const double* tv) {
+  HY_TRY
+  h->eng->setTestVectorDist(n_local, row_gids, tv);
+  return 0;
+  HY_CATCH
+}
+
+int hymls_b200_set_border_dist(hymls_b200_t* h, int64_t n_local, const int64_t* row_gids, const double* V,
+                               const double* W, const double* C, int m) {
+  HY_TRY
+  h->eng->setBorderDist(n_local, row_gids, V, W, C, m);
+  return 0;
+  HY_CATCH
+}
+
 int hymls_b200_set_testvector(hymls_b200_t* h, const double* tv) {
   HY_TRY
   h->eng->setTestVector(tv);

@@ -114,11 +114,20 @@ namespace hymls {
 // [sendPtr[k], sendPtr[k+1]) of sendBuf goes to peers[k] and [recvPtr[k], recvPtr[k+1]) of recvBuf comes from it.
 void Comm::neighbourExchange(const std::vector<int>& peers, const double* sendBuf, const std::vector<int64_t>& sendPtr,
                              double* recvBuf, const std::vector<int64_t>& recvPtr, cudaStream_t s) const {
-  if (!comm_ || peers.empty()) return;
+  if (peers.empty()) return;
+  // the part a rank "sends to itself" is a device copy (also the whole exchange of a single-rank run)
+  bool others = false;
+  for (size_t k = 0; k < peers.size(); ++k) {
+    if (peers[k] != rank_) { others = true; continue; }
+    const size_t ns = (size_t)(sendPtr[k + 1] - sendPtr[k]);
+    if (ns) cudaMemcpyAsync(recvBuf + recvPtr[k], sendBuf + sendPtr[k], ns * sizeof(double), cudaMemcpyDeviceToDevice, s);
+  }
+  if (!comm_ || !others) return;
   const int ncclDouble = 8;
   Api& a = api();
   check(a.groupStart(), "ncclGroupStart");
   for (size_t k = 0; k < peers.size(); ++k) {
+    if (peers[k] == rank_) continue;
     const size_t ns = (size_t)(sendPtr[k + 1] - sendPtr[k]), nr = (size_t)(recvPtr[k + 1] - recvPtr[k]);
     if (ns) check(a.send(sendBuf + sendPtr[k], ns, ncclDouble, peers[k], comm_, s), "ncclSend");
     if (nr) check(a.recv(recvBuf + recvPtr[k], nr, ncclDouble, peers[k], comm_, s), "ncclRecv");

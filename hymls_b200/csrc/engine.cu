@@ -48,6 +48,18 @@ Engine::Engine(const std::string& xml) {
   int ndev = 0;
   deviceOk_ = (cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0);
   if (!deviceOk_) cudaGetLastError();
+  readParameters();
+  if (deviceOk_) {
+    HY_CUDA(cudaEventCreate(&ev0_));
+    HY_CUDA(cudaEventCreate(&ev1_));
+    HY_CUDA(cudaEventCreate(&evA_));
+    HY_CUDA(cudaEventCreate(&evB_));
+  }
+}
+
+// validates the list and reads what the engine itself needs (setParameterList / validateParameters,
+// src/HYMLS_Preconditioner.cpp:45-130); everything else is read where it is used
+void Engine::readParameters() {
   ParameterList& prec = params_.sublist("Preconditioner");
   validatePreconditionerList(prec);
   maxLevel_ = prec.get("Number of Levels", 1);
@@ -63,12 +75,22 @@ Engine::Engine(const std::string& xml) {
   if (variant != "Block Diagonal" || !dropping || !ot)
     throw Error(HYMLS_B200_ERR_UNSUPPORTED,
                 "only 'Block Diagonal' with dropping and orthogonal transformation is implemented");
-  if (deviceOk_) {
-    HY_CUDA(cudaEventCreate(&ev0_));
-    HY_CUDA(cudaEventCreate(&ev1_));
-    HY_CUDA(cudaEventCreate(&evA_));
-    HY_CUDA(cudaEventCreate(&evB_));
+}
+
+// Preconditioner::SetParameters (src/HYMLS_Preconditioner.cpp:87-114): a new list; Initialize() has to follow
+void Engine::setParameters(const std::string& xml) {
+  ParameterList fresh = ParameterList::fromXml(xml);
+  ParameterList old = params_;
+  params_ = fresh;
+  try {
+    readParameters();
+  } catch (...) {
+    params_ = old;
+    readParameters();
+    throw;
   }
+  initialized_ = false;
+  computed_ = false;
 }
 
 void Engine::commInit(const void* id128, int rank, int nranks) {
@@ -1590,17 +1612,25 @@ void Engine::applyInverseDist(const double* Bloc, double* Xloc, int where) {
   const auto out = where == HYMLS_B200_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
   HY_CUDA(cudaMemcpyAsync(cB, Bloc, D.nOwn * sizeof(double), in, s));
   scatterVec(cB, D.ownRows.p, bufB_.p, D.nOwn, s, &launches_);
-  if (useDist()) {
-    applyLevel0Dist(bufB_.p, bufX_.p);
-  } else {  // bordered / fallback path works on replicated vectors
-    bufD_.alloc(n_);
-    gatherOwned(bufB_.p, bufD_.p);
-    applyLevel(0, bufD_.p, bufX_.p, nullptr);
-  }
-  stats_.num_apply_inverse++;
+  applyOwned(bufB_.p, bufX_.p);
   packIdx(bufX_.p, D.ownRows.p, cX, D.nOwn, s, &launches_);
   HY_CUDA(cudaMemcpyAsync(Xloc, cX, D.nOwn * sizeof(double), out, s));
   if (where == HYMLS_B200_HOST) HY_CUDA(cudaStreamSynchronize(s));
+}
+
+void Engine::applyOwned(const double* Bglobal, double* Xglobal, const double* dT) {
+  if (comm_.size() <= 1) {
+    applyDevice(Bglobal, Xglobal, dT, nullptr);  // (S stays in bS_)
+    return;
+  }
+  if (useDist() && !dT) {
+    applyLevel0Dist(Bglobal, Xglobal);
+  } else {  // bordered / fallback path works on replicated vectors
+    bufD_.alloc(n_);
+    gatherOwned(Bglobal, bufD_.p);
+    applyLevel(0, bufD_.p, Xglobal, dT);
+  }
+  stats_.num_apply_inverse++;
 }
 
 void Engine::applyMatrix(const double* x, double* y, int where) {

@@ -124,6 +124,20 @@ struct Level {
   std::vector<double> hC;     // C of this level (m x m, column major)
 };
 
+// the caller's distribution of vectors <-> the owner distribution (boundary.cu)
+struct RowMapPlan {
+  bool ready = false;
+  int64_t nLocal = 0;
+  Halo toOwner, fromOwner;
+  DevBuf<double> stage;
+};
+// assembly map of a distributed matrix input (boundary.cu)
+struct DistMatrixCache {
+  bool ready = false;
+  std::vector<int64_t> signature, ptr, slot;
+  std::vector<int> col;
+};
+
 class Engine {
  public:
   explicit Engine(const std::string& xml);
@@ -133,6 +147,14 @@ class Engine {
   void setRankOnly(int rank, int nranks);
   const std::vector<int>& ownedSubdomains(int level) const { return levels_.at(level)->ownSd; }
   void setMatrix(int64_t n, const int64_t* rowptr, const int32_t* colidx, const double* values, int where);
+  void setMatrixDist(int64_t nGlobal, int64_t nLocal, const int64_t* rowGids, const int64_t* rowptr,
+                     const int64_t* colGids, const double* values);
+  void setRowMap(int64_t nLocal, const int64_t* rowGids);
+  void applyInverseMap(const double* B, int64_t ldb, double* X, int64_t ldx, int nvec, int where,
+                       const double* T = nullptr, double* S = nullptr);
+  void setTestVectorDist(int64_t nLocal, const int64_t* gids, const double* tv);
+  void setBorderDist(int64_t nLocal, const int64_t* gids, const double* V, const double* W, const double* C, int m);
+  void setParameters(const std::string& xml);
   void setTestVector(const double* tv);
   void initialize();
   void compute();
@@ -169,6 +191,11 @@ class Engine {
                               const char* what);
   void coarseSolveBordered(const double* rhs, const double* T, double* sol, int n);
   void uploadLevel(Level& L);
+  void readParameters();
+  // global-length vectors with the owned rows valid in, the same out (one rank: the whole vector)
+  void applyOwned(const double* Bglobal, double* Xglobal, const double* dT = nullptr);
+  RowMapPlan rowMap_;
+  DistMatrixCache distMat_;
   // owner-computes multi-GPU path (dist.cu)
   bool useDist() const;
   void buildDistPlan(Level& L);

@@ -4,14 +4,22 @@
 // HYMLS::BorderedSolver (src/HYMLS_BorderedSolver.cpp:100-219), hymls_main (src/main.cpp:330-372) and
 // NOX_Epetra_LinearSystem_Hymls (src/NOX_Epetra_LinearSystem_Hymls.cpp:177-220) take it unchanged as `precPtr`.
 //
-// Needs Trilinos (Epetra, Ifpack, Teuchos) headers, which this repository's build image does not have: the
-// header is compiled inside the reference tree (add it to src/, link -lhymls_b200), not by this repo's tests.
-// One MPI rank per GPU: call CommInit() on every rank before Initialize() (rank 0 creates the NCCL id and
-// broadcasts it with MPI_Bcast); vectors are then passed as distributed row blocks (hymls_b200_local_rows).
+// Needs the Trilinos headers (Epetra, Ifpack, Teuchos) and two headers of the reference tree; inside the reference
+// tree it is added to src/ and linked with -lhymls_b200.  This repository has no Trilinos: tests/shim/ holds
+// minimal stand-ins for exactly the declarations used here, and tests/test_adapter_shim.py compiles this header
+// against them, links it with the library and runs it (construction, SetParameters, Initialize, Compute,
+// ApplyInverse on a serial Epetra_CrsMatrix stand-in).
+// Matrix and vectors may live on ANY Epetra map: rows go through hymls_b200_set_matrix_csr_dist (rows of this rank
+// with their GIDs), vectors through hymls_b200_set_row_map / hymls_b200_apply_inverse_map (the matrix' row map).
+// One MPI rank per GPU: call CommInit() on every rank before Initialize() (rank 0 creates the NCCL id with
+// hymls_b200_comm_get_unique_id and broadcasts it with MPI_Bcast).
 #ifndef HYMLS_B200_PRECONDITIONER_HPP
 #define HYMLS_B200_PRECONDITIONER_HPP
 
+#include <algorithm>
+#include <cstdint>
 #include <sstream>
+#include <string>
 #include <vector>
 
 #include "Epetra_CrsMatrix.h"
@@ -34,16 +42,25 @@ class B200Preconditioner : public Ifpack_Preconditioner, public BorderedOperator
   B200Preconditioner(Teuchos::RCP<const Epetra_RowMatrix> K, Teuchos::RCP<Teuchos::ParameterList> params,
                      Teuchos::RCP<Epetra_Vector> testVector = Teuchos::null)
       : K_(Teuchos::rcp_dynamic_cast<const Epetra_CrsMatrix>(K, true)), params_(params) {
+    commPending_ = K_->Comm().NumProc() > 1;
     std::ostringstream xml;  // the list the reference's XML files are parsed into
     Teuchos::writeParameterListToXmlOStream(*params, xml);
     Check(hymls_b200_create(xml.str().c_str(), &h_));
     Check(PushMatrix());
-    if (testVector != Teuchos::null) Check(hymls_b200_set_testvector(h_, testVector->Values()));
+    testVector_ = testVector;
+    PushTestVector();
   }
   virtual ~B200Preconditioner() { hymls_b200_destroy(h_); }
 
   // one process per GPU: id128 from hymls_b200_comm_get_unique_id on rank 0, shipped with MPI_Bcast
-  int CommInit(const void* id128, int rank, int nranks) { return hymls_b200_comm_init(h_, id128, rank, nranks); }
+  int CommInit(const void* id128, int rank, int nranks) {
+    int e = hymls_b200_comm_init(h_, id128, rank, nranks);
+    if (e == 0) {
+      commPending_ = false;
+      e = PushMatrix();  // the rows of the other ranks can be gathered now
+    }
+    return e;
+  }
 
   // SetMatrix + Initialize reuses the ordering when the pattern is unchanged (:250-254)
   int SetMatrix(Teuchos::RCP<const Epetra_CrsMatrix> K) {
@@ -51,9 +68,22 @@ class B200Preconditioner : public Ifpack_Preconditioner, public BorderedOperator
     computed_ = false;
     return PushMatrix();
   }
-  int SetParameters(Teuchos::ParameterList&) { return 0; }  // the list is fixed at construction
+  int SetMatrix(Teuchos::RCP<const Epetra_RowMatrix> K) {
+    return SetMatrix(Teuchos::rcp_dynamic_cast<const Epetra_CrsMatrix>(K, true));
+  }
+  // Preconditioner::SetParameters (src/HYMLS_Preconditioner.cpp:87-114): a new list; Initialize() has to follow
+  int SetParameters(Teuchos::ParameterList& list) {
+    params_->setParameters(list);
+    std::ostringstream xml;
+    Teuchos::writeParameterListToXmlOStream(*params_, xml);
+    initialized_ = computed_ = false;
+    return hymls_b200_set_parameters(h_, xml.str().c_str());
+  }
   int Initialize() {
+    if (commPending_) return -1;  // several MPI ranks but CommInit() has not been called
+    PushTestVector();             // (collective with several ranks: the communicator exists by now)
     int e = hymls_b200_initialize(h_);
+    if (e == 0) e = hymls_b200_set_row_map(h_, (int64_t)gids_.size(), gids_.data());  // vectors live on the row map
     initialized_ = (e == 0);
     return e;
   }
@@ -67,8 +97,8 @@ class B200Preconditioner : public Ifpack_Preconditioner, public BorderedOperator
 
   // Epetra_Operator
   int ApplyInverse(const Epetra_MultiVector& B, Epetra_MultiVector& X) const {
-    return hymls_b200_apply_inverse(h_, B.Values(), B.Stride(), X.Values(), X.Stride(), B.NumVectors(),
-                                    HYMLS_B200_HOST);
+    return hymls_b200_apply_inverse_map(h_, B.Values(), B.Stride(), X.Values(), X.Stride(), B.NumVectors(),
+                                        HYMLS_B200_HOST);
   }
   int Apply(const Epetra_MultiVector&, Epetra_MultiVector&) const { return -1; }  // as the reference (:122-123)
   int SetUseTranspose(bool) { return -1; }                                        // (:162-166)
@@ -98,7 +128,8 @@ class B200Preconditioner : public Ifpack_Preconditioner, public BorderedOperator
       for (int j = 0; j < m; ++j)
         for (int i = 0; i < m; ++i) c[i + (size_t)j * m] = (*C)(i, j);
     }
-    return hymls_b200_set_border(h_, v.data(), w.empty() ? nullptr : w.data(), c.empty() ? nullptr : c.data(), m);
+    return hymls_b200_set_border_dist(h_, (int64_t)gids_.size(), gids_.data(), v.data(), w.empty() ? nullptr : w.data(),
+                                      c.empty() ? nullptr : c.data(), m);
   }
   // [Y; S] = [K V; W' C] \ [X; T]
   int ApplyInverse(const Epetra_MultiVector& X, const Epetra_SerialDenseMatrix& T, Epetra_MultiVector& Y,
@@ -106,8 +137,8 @@ class B200Preconditioner : public Ifpack_Preconditioner, public BorderedOperator
     std::vector<double> t((size_t)T.M() * T.N()), s(t.size());
     for (int j = 0; j < T.N(); ++j)
       for (int i = 0; i < T.M(); ++i) t[i + (size_t)j * T.M()] = T(i, j);
-    int e = hymls_b200_apply_inverse_bordered(h_, X.Values(), X.Stride(), t.data(), Y.Values(), Y.Stride(),
-                                              s.data(), X.NumVectors(), HYMLS_B200_HOST);
+    int e = hymls_b200_apply_inverse_bordered_map(h_, X.Values(), X.Stride(), t.data(), Y.Values(), Y.Stride(),
+                                                  s.data(), X.NumVectors(), HYMLS_B200_HOST);
     for (int j = 0; j < S.N(); ++j)
       for (int i = 0; i < S.M(); ++i) S(i, j) = s[i + (size_t)j * S.M()];
     return e;
@@ -141,10 +172,13 @@ class B200Preconditioner : public Ifpack_Preconditioner, public BorderedOperator
   hymls_b200_t* Handle() const { return h_; }
 
  private:
-  int PushMatrix() {  // rows on the linear (GID-ordered) map, one rank: Epetra_CrsMatrix::ExtractMyRowView
+  // rows of this rank with their global ids: Epetra_CrsMatrix::ExtractMyRowView + RowMap().GID64 + GCID64
+  int PushMatrix() {
     const int n = K_->NumMyRows();
-    std::vector<int64_t> ptr(n + 1, 0);
-    std::vector<int32_t> col;
+    gids_.resize(n);
+    for (int i = 0; i < n; ++i) gids_[i] = (int64_t)K_->RowMap().GID64(i);
+    if (K_->Comm().NumProc() > 1 && commPending_) return 0;  // gathered in CommInit()
+    std::vector<int64_t> ptr(n + 1, 0), col;
     std::vector<double> val;
     col.reserve(K_->NumMyNonzeros());
     val.reserve(K_->NumMyNonzeros());
@@ -153,16 +187,20 @@ class B200Preconditioner : public Ifpack_Preconditioner, public BorderedOperator
       double* v;
       int* c;
       K_->ExtractMyRowView(i, len, v, c);
-      std::vector<std::pair<int32_t, double>> row(len);
-      for (int k = 0; k < len; ++k) row[k] = std::make_pair((int32_t)K_->GCID64(c[k]), v[k]);
-      std::sort(row.begin(), row.end());
       for (int k = 0; k < len; ++k) {
-        col.push_back(row[k].first);
-        val.push_back(row[k].second);
+        col.push_back((int64_t)K_->GCID64(c[k]));
+        val.push_back(v[k]);
       }
       ptr[i + 1] = (int64_t)col.size();
     }
-    return hymls_b200_set_matrix_csr(h_, n, ptr.data(), col.data(), val.data(), HYMLS_B200_HOST);
+    return hymls_b200_set_matrix_csr_dist(h_, (int64_t)K_->NumGlobalRows64(), n, gids_.data(), ptr.data(), col.data(),
+                                          val.data());
+  }
+  void PushTestVector() {
+    if (testVector_ == Teuchos::null || testVectorPushed_) return;
+    if (K_->Comm().NumProc() > 1 && commPending_) return;
+    Check(hymls_b200_set_testvector_dist(h_, (int64_t)gids_.size(), gids_.data(), testVector_->Values()));
+    testVectorPushed_ = true;
   }
   hymls_b200_stats Stats() const {
     hymls_b200_stats st;
@@ -175,7 +213,10 @@ class B200Preconditioner : public Ifpack_Preconditioner, public BorderedOperator
   hymls_b200_t* h_ = nullptr;
   Teuchos::RCP<const Epetra_CrsMatrix> K_;
   Teuchos::RCP<Teuchos::ParameterList> params_;
-  bool initialized_ = false, computed_ = false;
+  Teuchos::RCP<Epetra_Vector> testVector_;
+  std::vector<int64_t> gids_;  // global ids of the rows of this rank (the matrix' row map)
+  bool initialized_ = false, computed_ = false, testVectorPushed_ = false;
+  bool commPending_ = false;   // several MPI ranks: the matrix is gathered once the NCCL communicator exists
 };
 
 }  // namespace HYMLS

@@ -82,6 +82,21 @@ int hymls_b200_get_owned_subdomains(hymls_b200_t* h, int level, int32_t* sd, int
 int hymls_b200_set_matrix_csr(hymls_b200_t* h, int64_t n, const int64_t* rowptr, const int32_t* colidx,
                               const double* values, int where);
 
+/*
+ * Distributed matrix input (one MPI rank per GPU): every rank passes the rows it holds -- n_local rows with global
+ * ids row_gids (any distribution that tiles [0, n_global)), CSR with GLOBAL column ids, host pointers -- exactly what
+ * Epetra_CrsMatrix::ExtractMyRowView + RowMap().MyGlobalElements() + ColMap().GID() give.  Collective.  Replaces
+ * the import of the matrix to the partitioner's map (src/HYMLS_Preconditioner.cpp:420-431): rows are gathered over
+ * NCCL (the symbolic phase is replicated on every rank).  Same pattern again: only values move.  values == NULL:
+ * pattern only.  With one rank it is hymls_b200_set_matrix_csr up to the row permutation.
+ */
+int hymls_b200_set_matrix_csr_dist(hymls_b200_t* h, int64_t n_global, int64_t n_local, const int64_t* row_gids,
+                                   const int64_t* rowptr, const int64_t* col_gids, const double* values);
+
+/* Preconditioner::SetParameters (src/HYMLS_Preconditioner.cpp:87-114): replaces the parameter list (XML text as in
+ * hymls_b200_create); Initialize() has to follow.  An invalid list is rejected and the old one kept. */
+int hymls_b200_set_parameters(hymls_b200_t* h, const char* xml);
+
 /* Test vector (length n, host); NULL = ones (Preconditioner::CreateTestVector, .cpp:780-790). */
 int hymls_b200_set_testvector(hymls_b200_t* h, const double* tv);
 
@@ -109,6 +124,25 @@ int hymls_b200_apply_inverse(hymls_b200_t* h, const double* B, int64_t ldb, doub
 int64_t hymls_b200_owned_rows(hymls_b200_t* h, int64_t* rows, int64_t cap);
 int hymls_b200_local_rows(hymls_b200_t* h, int64_t* r0, int64_t* r1);
 int hymls_b200_apply_inverse_dist(hymls_b200_t* h, const double* B_local, double* X_local, int where);
+
+/*
+ * Vectors in the CALLER's distribution (Epetra_Operator::ApplyInverse on the matrix' row map, any map):
+ * hymls_b200_set_row_map declares the rows this rank holds, in its local order (collective, after Initialize);
+ * hymls_b200_apply_inverse_map then takes B_local / X_local (n_local x nvec, column major, leading dimensions
+ * ldb / ldx) in that order.  Values travel to the rows' owners and back with one grouped ncclSend/ncclRecv each
+ * way; when the caller's map is the owner map (hymls_b200_owned_rows) this is a local permutation.
+ */
+int hymls_b200_set_row_map(hymls_b200_t* h, int64_t n_local, const int64_t* row_gids);
+int hymls_b200_apply_inverse_map(hymls_b200_t* h, const double* B_local, int64_t ldb, double* X_local, int64_t ldx,
+                                 int nvec, int where);
+/* BorderedOperator::ApplyInverse(X, T, Y, S) on the caller's map; T and S (m x nvec, column major) are replicated */
+int hymls_b200_apply_inverse_bordered_map(hymls_b200_t* h, const double* B_local, int64_t ldb, const double* T,
+                                          double* X_local, int64_t ldx, double* S, int nvec, int where);
+/* distributed forms of hymls_b200_set_testvector / hymls_b200_set_border: this rank's entries (rows row_gids, V and
+ * W with leading dimension n_local); collective */
+int hymls_b200_set_testvector_dist(hymls_b200_t* h, int64_t n_local, const int64_t* row_gids, const double* tv);
+int hymls_b200_set_border_dist(hymls_b200_t* h, int64_t n_local, const int64_t* row_gids, const double* V,
+                               const double* W, const double* C, int m);
 
 /*
  * BorderedOperator interface (src/HYMLS_Preconditioner.cpp:844-918): V, W are n x m (column major,

@@ -364,7 +364,10 @@ def main():
     if world > 1 and not args.no_check:
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         from mgpu_check import run_check
-        check = run_check(32, 8, 2, 2, PARTITIONER, rank, world)
+        try:
+            check = run_check(32, 8, 2, 2, PARTITIONER, rank, world)
+        except Exception as e:   # the check must not cost the bench line
+            check = {"error": repr(e)}
 
     tm = torch.tensor([ms, e2e_ms, ms_a11, t_compute, gm["solve_s"] if gm else 0.0], dtype=torch.float64, device="cuda")
     if dist is not None:

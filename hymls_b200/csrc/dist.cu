@@ -261,13 +261,7 @@ void Engine::applyLevel0Dist(const double* B, double* X) {
   if (levels_.size() > 1) {
     applyLevel(1, L.vsRhs.p, L.vsSol.p, nullptr);
   } else {
-    for (int row : coarseFix_)
-      if (row > 0) setValue(L.vsRhs.p, row, 0.0, s, &launches_);
-    GemvArgs c = coarse_.args();
-    c.xin = L.vsRhs.p;
-    c.out = L.vsSol.p;
-    c.mode = 0;
-    batchedGemv(c, coarse_.numItems, coarse_.npMax, s, &launches_);
+    coarseSolve(L.vsRhs.p, L.vsSol.p, S.nuniq);
     comm_.broadcast(L.vsSol.p, (size_t)S.nuniq, 0, s);
   }
   mark("next level / coarse");

@@ -260,6 +260,7 @@ void Engine::initialize() {
     if (l > 0) levels_.emplace_back(new Level());
     Level& L = *levels_[l];
     L.sym = LevelSym();  // a re-Initialize starts from scratch
+    coarseBT_.planned = coarseBT_.active = false;
     L.t12Ptr.release();
     LevelSym& S = L.sym;
     S.level = l;
@@ -1125,8 +1126,10 @@ void Engine::computeLevel(int l) {
   if (!next) {
     std::vector<gidx> rowGid(S.nuniq);
     for (int u = 0; u < S.nuniq; ++u) rowGid[u] = S.H.sepGid[S.H.uniqPtr[u]];
-    if (borderM_ > 0) computeCoarse(L.redPtr.p, L.redCol.p, redVal, S.nuniq, rowGid, L.cV.p, L.cW.p, &L.hC);
-    else computeCoarse(L.redPtr.p, L.redCol.p, redVal, S.nuniq, rowGid);
+    if (borderM_ > 0)
+      computeCoarse(L.redPtr.p, L.redCol.p, redVal, S.nuniq, rowGid, S.redPtr, S.redCol, L.cV.p, L.cW.p, &L.hC);
+    else
+      computeCoarse(L.redPtr.p, L.redCol.p, redVal, S.nuniq, rowGid, S.redPtr, S.redCol);
   }
   pt.lap("drop + coarse solver");
   HY_CUDA(cudaStreamSynchronize(s));
@@ -1134,11 +1137,19 @@ void Engine::computeLevel(int l) {
 
 // CoarseSolver::Compute (src/HYMLS_CoarseSolver.cpp:131-248): drop (RelFullDiag), Dirichlet rows for the
 // "Fix GID k" entries, dense inverse.
+// largest coarse system that is inverted densely; beyond it the block-tridiagonal factorization of coarse.cu
+static int coarseDenseMax() {
+  if (const char* e = getenv("HYMLS_B200_COARSE_DENSE_MAX")) return atoi(e);
+  return 8192;
+}
+
 void Engine::computeCoarse(const int64_t* ptr, const int* col, double* val, int n, const std::vector<gidx>& rowGid,
-                           const double* bV, const double* bW, const std::vector<double>* bC) {
+                           const std::vector<int64_t>& hPtr, const std::vector<int>& hCol, const double* bV,
+                           const double* bW, const std::vector<double>* bC) {
   cudaStream_t s = stream_;
   const int bm = bV ? borderM_ : 0;
   const int np = (n + bm + 7) & ~7;
+  coarseBT_.active = false;
   if (n == 0) {
     std::vector<int> z(1, 0);
     std::vector<int64_t> off{0, 0}, voff(1, 0);
@@ -1148,9 +1159,6 @@ void Engine::computeCoarse(const int64_t* ptr, const int* col, double* val, int 
   }
   diagScratch_.alloc(n);
   dropByValue(val, ptr, col, diagScratch_.p, n, SMALL_ENTRY, s, &launches_);
-  work_.alloc((size_t)np * np);
-  HY_CUDA(cudaMemsetAsync(work_.p, 0, (size_t)np * np * sizeof(double), s));
-  csrToDense(ptr, col, val, work_.p, n, np, s, &launches_);
   coarseFix_.clear();
   ParameterList& prec = params_.sublist("Preconditioner");
   for (int pos = 1; prec.isParameter("Fix GID " + std::to_string(pos)); ++pos) {
@@ -1160,9 +1168,42 @@ void Engine::computeCoarse(const int64_t* ptr, const int* col, double* val, int 
       if (rowGid[r] == g) row = r;
     if (row < 0) throw Error(HYMLS_B200_ERR_ARG, "fix GID: " + std::to_string(g) + " not in matrix row map");
     coarseFix_.push_back(row);
-    putDirichlet(work_.p, n, np, row, s, &launches_);
   }
+  if (n + bm > coarseDenseMax()) {
+    // sparse route: block-tridiagonal factorization on BFS level sets (coarse.cu)
+    if (bm)
+      throw Error(HYMLS_B200_ERR_UNSUPPORTED,
+                  "a bordered coarse system with more than " + std::to_string(coarseDenseMax()) +
+                      " rows is not supported: use one more level");
+    for (int row : coarseFix_) putDirichletCsr(val, ptr, col, row, s, &launches_);
+    if (!coarseBT_.planned) planCoarseBT(hPtr, hCol, n);
+    factorCoarseBT(ptr, col, val);
+    coarseN_ = n;
+    coarseM_ = 0;
+    return;
+  }
+  work_.alloc((size_t)np * np);
+  HY_CUDA(cudaMemsetAsync(work_.p, 0, (size_t)np * np * sizeof(double), s));
+  csrToDense(ptr, col, val, work_.p, n, np, s, &launches_);
+  for (int row : coarseFix_) putDirichlet(work_.p, n, np, row, s, &launches_);
   augmentAndInvertCoarse(n, np, bV, bW, bC, "coarse solver");
+}
+
+// CoarseSolver::ApplyInverse (src/HYMLS_CoarseSolver.cpp:268-323) without a border
+void Engine::coarseSolve(double* rhs, double* sol, int n) {
+  cudaStream_t s = stream_;
+  for (int row : coarseFix_)
+    if (row > 0) setValue(rhs, row, 0.0, s, &launches_);  // sic: 'lid > 0'
+  if (coarseBT_.active) {
+    solveCoarseBT(rhs, sol);
+    return;
+  }
+  GemvArgs c = coarse_.args();
+  c.xin = rhs;
+  c.out = sol;
+  c.mode = 0;
+  batchedGemv(c, coarse_.numItems, coarse_.npMax, s, &launches_);
+  (void)n;
 }
 
 // work_ holds the n x n coarse matrix (leading dimension np >= n + m): append the border
@@ -1461,13 +1502,7 @@ void Engine::applyLevel(int l, const double* B, double* X, const double* T) {
         comm_.broadcast(bS_.p, (size_t)bm, 0, s);
       }
     } else {
-      for (int row : coarseFix_)
-        if (row > 0) setValue(L.vsRhs.p, row, 0.0, s, &launches_);
-      GemvArgs c = coarse_.args();
-      c.xin = L.vsRhs.p;
-      c.out = L.vsSol.p;
-      c.mode = 0;
-      batchedGemv(c, coarse_.numItems, coarse_.npMax, s, &launches_);
+      coarseSolve(L.vsRhs.p, L.vsSol.p, S.nuniq);
       // the coarse solve is replicated; rank 0's copy becomes the common one so that every rank
       // continues with bit-identical data (replicas may differ in the last bit, which a Krylov method
       // mixing per-rank partial results would amplify)
@@ -2088,7 +2123,11 @@ void Engine::getStats(hymls_b200_stats* st) {
       bytes += 8.0 * (T.sumNsq + T.sumNNb) + 12.0 * (double)(T.A12.nnz() + T.A21.nnz()) +
                4.0 * (double)(T.nI + T.nS + 2) + sb + 2.0 * 12.0 * (double)T.nS * 2.0 + 8.0 * (10.0 * T.nI + 14.0 * T.nS);
     }
-    bytes += 8.0 * (double)coarseN_ * coarseN_;
+    if (coarseBT_.active) {
+      for (int b = 0; b < coarseBT_.m; ++b) bytes += 2.0 * 8.0 * (double)coarseBT_.inv.hN[b] * coarseBT_.inv.hN[b];
+    } else {
+      bytes += 8.0 * (double)coarseN_ * coarseN_;
+    }
     st->bytes_apply = bytes;
   }
 }

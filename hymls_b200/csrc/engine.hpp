@@ -138,6 +138,18 @@ struct DistMatrixCache {
   std::vector<int> col;
 };
 
+// block-tridiagonal coarse factorization on BFS level sets (coarse.cu)
+struct CoarseBT {
+  bool planned = false, active = false;
+  int n = 0, m = 0;
+  std::vector<int> lvlPtr, perm, itemPtr;
+  std::vector<int64_t> dListPtr;
+  BatchedInverse inv;                    // F_i = inv(D_i')
+  DevBuf<int> dPerm, loCol, upCol;
+  DevBuf<int64_t> dSrc, dDst, loPtr, upPtr, loSrc, upSrc;
+  DevBuf<double> loVal, upVal, y, t, r, xp;
+};
+
 class Engine {
  public:
   explicit Engine(const std::string& xml);
@@ -186,7 +198,13 @@ class Engine {
   void reserveComputeScratch();
   void checkInfo(const std::string& what);
   void computeCoarse(const int64_t* ptr, const int* col, double* val, int n, const std::vector<gidx>& rowGid,
-                     const double* bV = nullptr, const double* bW = nullptr, const std::vector<double>* bC = nullptr);
+                     const std::vector<int64_t>& hPtr, const std::vector<int>& hCol, const double* bV = nullptr,
+                     const double* bW = nullptr, const std::vector<double>* bC = nullptr);
+  void coarseSolve(double* rhs, double* sol, int n);  // unbordered coarse solve (zeroes the fixed rows of rhs)
+  void planCoarseBT(const std::vector<int64_t>& ptr, const std::vector<int>& col, int n);
+  void factorCoarseBT(const int64_t* ptr, const int* col, const double* val);
+  void solveCoarseBT(const double* rhs, double* sol);
+  CoarseBT coarseBT_;
   void augmentAndInvertCoarse(int n, int np, const double* bV, const double* bW, const std::vector<double>* bC,
                               const char* what);
   void coarseSolveBordered(const double* rhs, const double* T, double* sol, int n);

@@ -1003,4 +1003,95 @@ void refineInverseBatched(double* A, double* F, double* R, const int64_t* dOff, 
   HY_CUDA(cudaGetLastError());
 }
 
+// ---------------------------------------------------------------------------------------------
+// General dense FP64 GEMM on the tensor cores:  C (M x N, ldc) = alpha * A (M x K, lda) * B (K x N, ldb) + beta * C
+// (row major; same 32 x 64 x 32 DMMA tiling as the refinement kernel; out-of-range tiles read zeros).
+// Used by the block-tridiagonal coarse factorization (coarse.cu).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(RF_T, 4)
+k_dense_gemm(const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb, double* __restrict__ C,
+             int ldc, int M, int N, int K, double alpha, double beta, int tilesN) {
+  const int i0 = (blockIdx.x / tilesN) * RF_TM, j0 = (blockIdx.x % tilesN) * RF_TN;
+  if (i0 >= M || j0 >= N) return;
+  extern __shared__ __align__(16) double rfSm[];
+  constexpr int SZA = RF_TM * RF_SA, SZB = RF_TK * RF_SB;
+  const int tid = threadIdx.x, lane = tid & 31, wc = tid >> 5;
+  const int fr = lane >> 2, fk = lane & 3;
+  auto stage = [&](int k0, int buf) {
+    for (int e = tid; e < RF_TM * (RF_TK / 2); e += RF_T) {
+      const int r = e / (RF_TK / 2), c = (e % (RF_TK / 2)) * 2;
+      const bool ok = (i0 + r < M) && (k0 + c < K);
+      const double* src = ok ? A + (int64_t)(i0 + r) * lda + k0 + c : A;
+      const unsigned saddr = (unsigned)__cvta_generic_to_shared(rfSm + buf * SZA + r * RF_SA + c);
+      const int bytes = ok ? 16 : 0;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(saddr), "l"(src), "r"(bytes));
+    }
+    for (int e = tid; e < RF_TK * (RF_TN / 2); e += RF_T) {
+      const int r = e / (RF_TN / 2), c = (e % (RF_TN / 2)) * 2;
+      const bool ok = (k0 + r < K) && (j0 + c < N);
+      const double* src = ok ? B + (int64_t)(k0 + r) * ldb + j0 + c : B;
+      const unsigned saddr = (unsigned)__cvta_generic_to_shared(rfSm + 2 * SZA + buf * SZB + r * RF_SB + c);
+      const int bytes = ok ? 16 : 0;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(saddr), "l"(src), "r"(bytes));
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+  };
+  double acc[4][2][2];
+#pragma unroll
+  for (int ti = 0; ti < 4; ++ti)
+#pragma unroll
+    for (int tj = 0; tj < 2; ++tj) acc[ti][tj][0] = acc[ti][tj][1] = 0.0;
+  const int nk = (K + RF_TK - 1) / RF_TK;
+  stage(0, 0);
+  for (int kt = 0; kt < nk; ++kt) {
+    const int buf = kt & 1;
+    const bool more = kt + 1 < nk;
+    if (more) stage((kt + 1) * RF_TK, buf ^ 1);
+    if (more) asm volatile("cp.async.wait_group 1;\n" ::); else asm volatile("cp.async.wait_group 0;\n" ::);
+    __syncthreads();
+    const double* cA = rfSm + buf * SZA;
+    const double* cB = rfSm + 2 * SZA + buf * SZB;
+#pragma unroll
+    for (int kk = 0; kk < RF_TK / 4; ++kk) {
+      double av[4], bv[2];
+#pragma unroll
+      for (int ti = 0; ti < 4; ++ti) av[ti] = cA[(ti * 8 + fr) * RF_SA + kk * 4 + fk];
+#pragma unroll
+      for (int tj = 0; tj < 2; ++tj) bv[tj] = cB[(kk * 4 + fk) * RF_SB + (wc * 2 + tj) * 8 + fr];
+#pragma unroll
+      for (int ti = 0; ti < 4; ++ti)
+#pragma unroll
+        for (int tj = 0; tj < 2; ++tj) dmma884r(acc[ti][tj][0], acc[ti][tj][1], av[ti], bv[tj]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int ti = 0; ti < 4; ++ti) {
+    const int row = i0 + ti * 8 + fr;
+#pragma unroll
+    for (int tj = 0; tj < 2; ++tj) {
+      const int col = j0 + (wc * 2 + tj) * 8 + 2 * fk;
+      if (row < M && col < N) {
+        double2* dst = reinterpret_cast<double2*>(C + (int64_t)row * ldc + col);
+        double2 old = beta != 0.0 ? *dst : make_double2(0.0, 0.0);
+        *dst = make_double2(alpha * acc[ti][tj][0] + beta * old.x, alpha * acc[ti][tj][1] + beta * old.y);
+      }
+    }
+  }
+}
+
+// all dimensions and leading dimensions must be even (they are multiples of 8 here: padded blocks)
+void denseGemm(const double* A, int lda, const double* B, int ldb, double* C, int ldc, int M, int N, int K, double alpha,
+               double beta, cudaStream_t s, int64_t* launches) {
+  if (M <= 0 || N <= 0) return;
+  constexpr size_t smem = (size_t)(2 * RF_TM * RF_SA + 2 * RF_TK * RF_SB) * sizeof(double);
+  static PerDeviceLimit limit;
+  if (limit.raise(smem + 48 * 1024))
+    HY_CUDA(cudaFuncSetAttribute(k_dense_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int tilesM = (M + RF_TM - 1) / RF_TM, tilesN = (N + RF_TN - 1) / RF_TN;
+  k_dense_gemm<<<(unsigned)(tilesM * tilesN), RF_T, smem, s>>>(A, lda, B, ldb, C, ldc, M, N, K, alpha, beta, tilesN);
+  ++*launches;
+  HY_CUDA(cudaGetLastError());
+}
+
 }  // namespace hymls

@@ -16,6 +16,10 @@ void invertBatched(double* W, double* F, const int64_t* dOff, const int* dN, con
 void refineInverseBatched(double* A, double* F, double* R, const int64_t* dOff, const int* dN, const int* dNp, int count,
                           int npMax, cudaStream_t s, int64_t* launches);
 
+// C (M x N) = alpha A (M x K) B (K x N) + beta C, row major, FP64 tensor cores; even dimensions / leading dimensions
+void denseGemm(const double* A, int lda, const double* B, int ldb, double* C, int ldc, int M, int N, int K, double alpha,
+               double beta, cudaStream_t s, int64_t* launches);
+
 // ---- schur.cu ----
 struct SchurArgs {
   // per local separator row R (row i of subdomain sd: R = sdRowPtr[sd] + i)
@@ -139,6 +143,9 @@ void haloAdd(double* z, const int* node, const int64_t* ptr, const int64_t* src,
              cudaStream_t s, int64_t* launches);
 void gatherAddList(const double* b, const int* bidx, const double* t, double* y, const int* list, int64_t n,
                    cudaStream_t s, int64_t* launches);
+
+// ---- coarse.cu ----
+void putDirichletCsr(double* val, const int64_t* ptr, const int* col, int row, cudaStream_t s, int64_t* launches);
 
 // ---- bordered variant (apply.cu) ----
 void batchedGemvT(const GemvArgs& a, int count, int npMax, cudaStream_t s, int64_t* launches);  // out = Ainv^T x

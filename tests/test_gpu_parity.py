@@ -244,3 +244,26 @@ def test_large_problem_properties(nx, sx, cx, extra):
     assert np.array_equal(P.ApplyInverse(b), xh)
     S.ApplyInverse(b)
     assert S.num_iter == its
+
+
+@pytest.mark.parametrize("eqn,dim,nx,sx,levels,cx,extra,tol", [
+    ("Laplace", 2, 64, 4, 1, None, {}, TOL_LAPLACE),
+    ("Stokes-C", 2, 64, 4, 1, None, {}, TOL_STOKES),
+    ("Stokes-C", 3, 16, 4, 1, None, {"Partitioner": "Skew Cartesian"}, TOL_STOKES),
+    ("Stokes-C", 3, 16, 4, 2, 2, {"Partitioner": "Skew Cartesian"}, TOL_STOKES),
+])
+def test_block_tridiagonal_coarse_solver(monkeypatch, eqn, dim, nx, sx, levels, cx, extra, tol):
+    """Coarse systems too large for a dense inverse (e.g. the 95 356 V-sums of a 1-level 128^3 run) are factored
+    block-tridiagonally on BFS level sets (coarse.cu).  Forced on here with small blocks; the result must agree with
+    the oracle's sparse LU of the same matrix and with the library's own dense coarse inverse."""
+    A, Pd, O = build(eqn, dim, nx, sx, levels, cx, **extra)        # dense coarse inverse
+    monkeypatch.setenv("HYMLS_B200_COARSE_DENSE_MAX", "32")
+    monkeypatch.setenv("HYMLS_B200_COARSE_MIN_BLOCK", "96")
+    A, Pb, _ = build(eqn, dim, nx, sx, levels, cx, **extra)        # block-tridiagonal route
+    b = np.random.default_rng(11).uniform(-1, 1, A.shape[0])
+    xb, xd, xo = Pb.ApplyInverse(b), Pd.ApplyInverse(b), O.apply_inverse(b)
+    assert rel(xb, xo) < tol
+    assert rel(xb, xd) < 1e-12
+    S = hb.Solver(Pb)
+    x = S.ApplyInverse(A @ b)
+    assert S.info["converged"]

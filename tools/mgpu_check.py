@@ -29,12 +29,15 @@ def run_check(nx, sx, levels, cx, partitioner, rank, world, border=False, schur_
     A = -hb.galeri.create_matrix("Stokes-C", 3, nx)
     tv = hb.galeri.create_testvector(A)
     n = A.shape[0]
-    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
-    if rank == 0:
-        idt.copy_(torch.frombuffer(bytearray(hb.Preconditioner.CommUniqueId()), dtype=torch.uint8))
-    dist.broadcast(idt, 0)
+    def fresh_comm_id():   # an NCCL unique id serves ONE communicator
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(hb.Preconditioner.CommUniqueId()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        return bytes(idt.cpu().numpy().tobytes())
+
     P = hb.Preconditioner(A, params, tv)
-    P.CommInit(bytes(idt.cpu().numpy().tobytes()), rank, world)
+    P.CommInit(fresh_comm_id(), rank, world)
     P.Initialize()
     P.Compute()
     os.environ.pop("HYMLS_B200_SCHUR_GEMM", None)
@@ -72,7 +75,7 @@ def run_check(nx, sx, levels, cx, partitioner, rank, world, border=False, schur_
     mine = np.arange(rank, n, world, dtype=np.int64)[::-1].copy()      # descending: not even sorted
     Ac = sp.csr_matrix(A)
     R = hb.Preconditioner(None, params)
-    R.CommInit(bytes(idt.cpu().numpy().tobytes()), rank, world)
+    R.CommInit(fresh_comm_id(), rank, world)
     R.SetMatrixDist(n, mine, Ac[mine, :])
     R.SetTestVectorDist(mine, tv[mine])
     R.Initialize()

@@ -6,7 +6,7 @@ kernels inside that library; there is no CPU fallback and no dependence on the t
 """
 from .api import (HymlsError, Preconditioner, Solver, lib_path, load_library, params_to_xml,  # noqa: F401
                   pid_map)
-from . import galeri  # noqa: F401
+from . import galeri, io  # noqa: F401
 
-__all__ = ["Preconditioner", "Solver", "HymlsError", "galeri", "params_to_xml", "load_library", "lib_path",
+__all__ = ["Preconditioner", "Solver", "HymlsError", "galeri", "io", "params_to_xml", "load_library", "lib_path",
            "pid_map"]

@@ -262,7 +262,16 @@ class Preconditioner:
         return _check(self._lib, self._lib.hymls_b200_initialize(self._h))
 
     def Compute(self):
-        return _check(self._lib, self._lib.hymls_b200_compute(self._h))
+        rc = _check(self._lib, self._lib.hymls_b200_compute(self._h))
+        # "Visualize Solver" (src/HYMLS_Preconditioner.cpp:510-514): MATLAB file with the partitioning
+        if 'name="Visualize Solver" type="bool" value="true"' in self.params_xml:
+            self.Visualize("hid_data.m")
+        return rc
+
+    def Visualize(self, mfilename, no_recurse=False):
+        """Preconditioner::Visualize (src/HYMLS_Preconditioner.cpp:753-779)"""
+        from . import io
+        io.visualize(self, mfilename, no_recurse)
 
     def ApplyInverse(self, B, X=None):
         """X = P^-1 B.  numpy (host) or torch CUDA tensors (device, column major: shape (nvec, n) contiguous

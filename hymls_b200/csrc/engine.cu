@@ -303,7 +303,12 @@ void Engine::initialize() {
     // ownership: every level is sharded by the reference's subdomain -> rank map of that level
     // (BasePartitioner::CreatePIDMap); with fewer subdomains than ranks some ranks own nothing there
     L.ownSd.clear();
-    L.sharded = comm_.size() > 1;
+    // Level 0 is distributed over the ranks.  The coarser levels are 100x smaller: their collectives (3 per level
+    // and ApplyInverse, each a few 10 us of latency) cost more than their whole replicated computation (0.65 GB of
+    // inverses at 128^3 = 0.1 ms), so they run replicated on every rank, bitwise identical everywhere
+    // (HYMLS_B200_SHARD_LEVELS=k distributes the first k levels instead).
+    static const int shardLevels = getenv("HYMLS_B200_SHARD_LEVELS") ? atoi(getenv("HYMLS_B200_SHARD_LEVELS")) : 1;
+    L.sharded = comm_.size() > 1 && l < shardLevels;
     if (L.sharded) {
       if (maxLevel_ == 0) throw Error(HYMLS_B200_ERR_UNSUPPORTED, "Number of Levels = 0 is single-GPU only");
       ParameterList pp = levelParams.deepCopy();

@@ -262,8 +262,17 @@ def test_block_tridiagonal_coarse_solver(monkeypatch, eqn, dim, nx, sx, levels, 
     A, Pb, _ = build(eqn, dim, nx, sx, levels, cx, **extra)        # block-tridiagonal route
     b = np.random.default_rng(11).uniform(-1, 1, A.shape[0])
     xb, xd, xo = Pb.ApplyInverse(b), Pd.ApplyInverse(b), O.apply_inverse(b)
-    assert rel(xb, xo) < tol
     assert rel(xb, xd) < 1e-12
+    # against the extended-precision ground truth (the FP64 oracle itself is up to 1e-10 away from it on the
+    # one-level cases, whose coarse systems are large and badly conditioned)
+    T = ox.Preconditioner(A, make_params(eqn, dim, nx, sx, levels, cx, **extra), hb.galeri.create_testvector(A))
+    T.initialize()
+    T.compute()
+    xt = T.apply_inverse(b)
+    e_bt = float(np.linalg.norm(xb - xt) / np.linalg.norm(xt))
+    e_ora = float(np.linalg.norm(xo - xt) / np.linalg.norm(xt))
+    assert e_bt <= TRUTH_TOL and e_bt <= 2.0 * e_ora + 1e-14, (e_bt, e_ora)
+    assert rel(xb, xo) < max(tol, 3.0 * e_ora)
     S = hb.Solver(Pb)
     x = S.ApplyInverse(A @ b)
     assert S.info["converged"]

@@ -391,6 +391,7 @@ void Engine::uploadLevel(Level& L) {
     }
     L.a11Src.upload(src, s);
     L.a11Dst.upload(dst, s);
+    L.a11ListPtrDev.upload(L.a11ListPtr, s);
   }
   // A12 / A21 / A22 (A21 restricted to the columns of owned interiors when sharded: partial products
   // are summed over the ranks)
@@ -903,8 +904,21 @@ void Engine::computeLevel(int l) {
         scatterValues(L.val.p, L.a11Src.p + e0, L.a11Dst.p + e0, L.ownOff[k0], work_.p, e1 - e0, s, &launches_);
       };
       if (refine_) work2_.alloc((size_t)used);
+      // Newton-Schulz step: with a sparse original (level 0: ~8 entries per row) the residual I - A X comes from
+      // the dense-fill list directly (one GEMM per inverse instead of two); denser levels use two GEMMs
+      const double avgNnz = S.nI ? (double)S.a11Src.size() / (double)S.nI : 0.0;
+      const bool sparseResidual = refine_ && avgNnz * 8.0 < (double)L.a11.npMax;
       invertRange(L.a11, k0, k1, work_.p, piv_, perm_, relOff, info_.p, s, &launches_,
-                  refine_ ? std::function<void()>(fillChunk) : nullptr, refine_ ? work2_.p : nullptr);
+                  (refine_ && !sparseResidual) ? std::function<void()>(fillChunk) : nullptr,
+                  (refine_ && !sparseResidual) ? work2_.p : nullptr);
+      if (sparseResidual) {
+        int npMax = 0;
+        for (int k = k0; k < k1; ++k) npMax = std::max(npMax, L.a11.hNp[k]);
+        refineInverseSparse(L.val.p, L.a11Src.p, L.a11Dst.p, L.a11ListPtrDev.p + k0, L.ownOff[k0], work_.p,
+                            L.a11.F.p + L.ownOff[k0], work2_.p, relOff.p, L.a11.n.p + k0, L.a11.np.p + k0, k1 - k0, npMax,
+                            s, &launches_);
+        HY_CUDA(cudaStreamSynchronize(s));
+      }
       pt.lap("  chunk inversion");
       for (int k = k0; k < k1; ++k) stats_.flops_compute += 2.0 * std::pow((double)L.a11.hN[k], 3);
     }

@@ -72,6 +72,7 @@ struct Level {
   DevBuf<int64_t> a11OffG;          // per (global) subdomain: compact offset (undefined if not owned)
   DevBuf<int64_t> a11Src, a11Dst;
   std::vector<int64_t> a11ListPtr;  // per owned sd: range of the scatter list
+  DevBuf<int64_t> a11ListPtrDev;
   bool sharded = false;
   DevBuf<int> ownSdList;            // device copies of the owned lists for the pass-2 Schur kernels
   DevBuf<int64_t> ownRowList, ownLinkList;

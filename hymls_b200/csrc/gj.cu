@@ -981,6 +981,64 @@ __global__ void k_refine_add(double* __restrict__ Xbase, const double* __restric
     X[e] += T[e];
 }
 
+// R = I - A X for a batch whose ORIGINAL matrices are sparse and given as the dense-fill list of their entries
+// (value index `src[e]` into `val`, dense position `dst[e]`, ascending, i.e. row by row): row r of R is e_r minus a
+// combination of the few rows of X that row r of A touches.  One CTA per (matrix, row); instead of a 2 n^3 GEMM the
+// residual costs (nnz/row + 1) n^2 memory accesses, most of them L2 hits.  listPtr[m], listPtr[m+1]: range of the
+// list for matrix m; dstBase: offset subtracted from dst (chunk-relative layout like dOff).
+__global__ void __launch_bounds__(128)
+k_refine_residual_sparse(const double* __restrict__ val, const int64_t* __restrict__ src, const int64_t* __restrict__ dst,
+                         const int64_t* __restrict__ listPtr, int64_t dstBase, const double* __restrict__ X,
+                         double* __restrict__ R, const int64_t* __restrict__ off, const int* __restrict__ nArr,
+                         const int* __restrict__ npArr) {
+  const int mat = blockIdx.y, r = blockIdx.x;
+  const int n = nArr[mat], np = npArr[mat];
+  if (r >= np) return;
+  const int64_t o = off[mat];
+  double* __restrict__ Rrow = R + o + (int64_t)r * np;
+  const double* __restrict__ Xm = X + o;
+  // entries of row r: binary search in the sorted destination list
+  int64_t lo = listPtr[mat], hi = listPtr[mat + 1];
+  const int64_t rowStart = dstBase + o + (int64_t)r * np, rowEnd = rowStart + np;
+  int64_t a = lo, b = hi;
+  while (a < b) { const int64_t mid = (a + b) >> 1; if (dst[mid] < rowStart) a = mid + 1; else b = mid; }
+  const int64_t e0 = a;
+  b = hi;
+  while (a < b) { const int64_t mid = (a + b) >> 1; if (dst[mid] < rowEnd) a = mid + 1; else b = mid; }
+  const int64_t e1 = a;
+  for (int c = threadIdx.x; c < np; c += blockDim.x) {
+    double t = (c == r) ? 1.0 : 0.0;
+    if (r < n) {
+      for (int64_t e = e0; e < e1; ++e) t -= val[src[e]] * Xm[(int64_t)(dst[e] - rowStart) * np + c];
+    } else {
+      t -= Xm[(int64_t)r * np + c];  // padding rows of A are rows of the identity
+    }
+    Rrow[c] = t;
+  }
+}
+
+void refineInverseSparse(const double* val, const int64_t* src, const int64_t* dst, const int64_t* listPtr,
+                         int64_t dstBase, double* T, double* F, double* R, const int64_t* dOff, const int* dN,
+                         const int* dNp, int count, int npMax, cudaStream_t s, int64_t* launches) {
+  if (count == 0 || npMax == 0) return;
+  constexpr size_t smem = (size_t)(2 * RF_TM * RF_SA + 2 * RF_TK * RF_SB) * sizeof(double);
+  static PerDeviceLimit limit;
+  if (limit.raise(smem + 48 * 1024))
+    HY_CUDA(cudaFuncSetAttribute(k_refine_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int tilesM = (npMax + RF_TM - 1) / RF_TM, tilesN = (npMax + RF_TN - 1) / RF_TN;
+  for (int c0 = 0; c0 < count; c0 += 32768) {
+    const int cnt = std::min(count - c0, 32768);
+    k_refine_residual_sparse<<<dim3((unsigned)npMax, (unsigned)cnt), 128, 0, s>>>(val, src, dst, listPtr + c0, dstBase, F, R,
+                                                                                 dOff + c0, dN + c0, dNp + c0);
+    dim3 g((unsigned)(tilesM * tilesN), (unsigned)cnt);
+    k_refine_gemm<<<g, RF_T, smem, s>>>(F, R, T, dOff + c0, dNp + c0, tilesN, 1);  // T = X R
+    const int blocks = std::max(1, std::min(64, (npMax * npMax + 1023) / 1024));
+    k_refine_add<<<dim3((unsigned)blocks, (unsigned)cnt), 256, 0, s>>>(F, T, dOff + c0, dNp + c0);
+    *launches += 3;
+  }
+  HY_CUDA(cudaGetLastError());
+}
+
 void refineInverseBatched(double* A, double* F, double* R, const int64_t* dOff, const int* dN, const int* dNp, int count,
                           int npMax, cudaStream_t s, int64_t* launches) {
   if (count == 0 || npMax == 0) return;

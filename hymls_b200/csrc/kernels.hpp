@@ -16,6 +16,11 @@ void invertBatched(double* W, double* F, const int64_t* dOff, const int* dN, con
 void refineInverseBatched(double* A, double* F, double* R, const int64_t* dOff, const int* dN, const int* dNp, int count,
                           int npMax, cudaStream_t s, int64_t* launches);
 
+// the same step with the residual R = I - A X formed from the SPARSE original (dense-fill list src/dst of its entries,
+// range listPtr[m]..listPtr[m+1] per matrix, dst relative to dstBase): one GEMM instead of two.  T: scratch (layout of R)
+void refineInverseSparse(const double* val, const int64_t* src, const int64_t* dst, const int64_t* listPtr,
+                         int64_t dstBase, double* T, double* F, double* R, const int64_t* dOff, const int* dN,
+                         const int* dNp, int count, int npMax, cudaStream_t s, int64_t* launches);
 // C (M x N) = alpha A (M x K) B (K x N) + beta C, row major, FP64 tensor cores; even dimensions / leading dimensions
 void denseGemm(const double* A, int lda, const double* B, int ldb, double* C, int ldc, int M, int N, int K, double alpha,
                double beta, cudaStream_t s, int64_t* launches);

@@ -213,6 +213,28 @@ struct SparseLU {
   int64_t nnzFactors() const { return (int64_t)Li.size() + (int64_t)Ui.size(); }
 };
 
+// Optional iterative refinement of the direct solves (ho_set_refinement): residuals in x87 extended precision
+// (long double), corrections with the FP64 factors.  Used by tests that compare with the GPU path at sizes where
+// the plain FP64 LU solves of this oracle are themselves 1e-10 away from the exact-arithmetic result
+// (tests/test_gpu_baseline_sizes.py); never by the timed CPU baseline.
+static void refinedSolve(const SparseLU& lu, const std::vector<int64_t>& ptr, const std::vector<int>& col,
+                         const std::vector<double>& val, int steps, double* b, double* work, std::vector<double>& tmp) {
+  const int n = lu.n;
+  if (steps <= 0) { lu.solve(b, work); return; }
+  std::vector<double> rhs(b, b + n);
+  lu.solve(b, work);
+  tmp.resize(n);
+  for (int it = 0; it < steps; ++it) {
+    for (int i = 0; i < n; ++i) {
+      long double r = rhs[i];
+      for (int64_t e = ptr[i]; e < ptr[i + 1]; ++e) r -= (long double)val[e] * (long double)b[col[e]];
+      tmp[i] = (double)r;
+    }
+    lu.solve(tmp.data(), work);
+    for (int i = 0; i < n; ++i) b[i] += tmp[i];
+  }
+}
+
 // dense LU with partial pivoting (Ifpack_DenseContainer -> dgetrf / dgetrs), row major
 struct DenseLU {
   int n = 0;
@@ -240,6 +262,21 @@ struct DenseLU {
       }
     }
     return true;
+  }
+  std::vector<double> orig;  // kept when refinement is requested
+  void solveRefined(double* b, int steps) const {
+    if (steps <= 0 || orig.empty()) { solve(b); return; }
+    std::vector<double> rhs(b, b + n), r(n);
+    solve(b);
+    for (int it = 0; it < steps; ++it) {
+      for (int i = 0; i < n; ++i) {
+        long double t = rhs[i];
+        for (int j = 0; j < n; ++j) t -= (long double)orig[(size_t)i * n + j] * (long double)b[j];
+        r[i] = (double)t;
+      }
+      solve(r.data());
+      for (int i = 0; i < n; ++i) b[i] += r[i];
+    }
   }
   void solve(double* b) const {
     for (int k = 0; k < n; ++k)
@@ -418,6 +455,9 @@ class Level {
   // matrix blocks
   Csr A12, A21, A22;
   std::vector<SparseLU> sdLU;
+  std::vector<Csr> sdA;                  // the A11 blocks themselves (refinement only)
+  Csr coarseA;
+  int refineSteps = 0;
   // next level / coarse
   std::unique_ptr<Level> next;
   Csr reduced;                           // reduced Schur complement on the V-sums after dropping
@@ -563,7 +603,7 @@ void Level::a11Solve(const double* b, double* x) const {  // MatrixBlock::ApplyI
   const int nsd = part.nsd;
 #pragma omp parallel
   {
-    std::vector<double> work;
+    std::vector<double> work, tmp;
 #pragma omp for schedule(dynamic, 4)
     for (int sd = 0; sd < nsd; ++sd) {
       const int64_t p0 = part.intPtr[sd];
@@ -571,7 +611,8 @@ void Level::a11Solve(const double* b, double* x) const {  // MatrixBlock::ApplyI
       if (k == 0) continue;
       work.resize(k);
       std::memcpy(x + p0, b + p0, k * sizeof(double));
-      sdLU[sd].solve(x + p0, work.data());
+      if (refineSteps > 0) refinedSolve(sdLU[sd], sdA[sd].ptr, sdA[sd].col, sdA[sd].val, refineSteps, x + p0, work.data(), tmp);
+      else sdLU[sd].solve(x + p0, work.data());
     }
   }
 }
@@ -654,7 +695,10 @@ void Level::assemble(std::vector<double>& redVal, const std::vector<int64_t>& re
               if (cols[j].empty()) continue;
               std::fill(col.begin(), col.end(), 0.0);
               for (auto& pr : cols[j]) col[pr.first] = pr.second;
-              sdLU[sd].solve(col.data(), work.data());
+              if (refineSteps > 0)
+                refinedSolve(sdLU[sd], sdA[sd].ptr, sdA[sd].col, sdA[sd].val, refineSteps, col.data(), work.data(), vtmp);
+              else
+                sdLU[sd].solve(col.data(), work.data());
               for (int i = 0; i < m; ++i) {
                 double t = 0;
                 for (int64_t e = A21.ptr[s[i]]; e < A21.ptr[s[i] + 1]; ++e) {
@@ -727,6 +771,7 @@ void Level::assemble(std::vector<double>& redVal, const std::vector<int64_t>& re
   for (int64_t b = 0; b < (int64_t)blocks.size(); ++b) {
     if (blocks[b].empty()) continue;
     for (size_t e = 0; e < blkVal[b].size(); ++e) blkVal[b][e] += blkVal2[b][e];
+    if (refineSteps > 0) blockLU[b].orig = blkVal[b];
     if (!blockLU[b].factor((int)blocks[b].size(), blkVal[b].data())) {
 #pragma omp critical
       ok = false;
@@ -745,6 +790,7 @@ void Level::compute(std::vector<Partition>& parts, const std::vector<int64_t>& f
   // subdomain solvers (ComputeSubdomainSolvers :210-292): sparse LU of every A11(sd)
   auto t0 = now();
   sdLU.assign(nsd, SparseLU());
+  sdA.assign(refineSteps > 0 ? nsd : 0, Csr());
   std::vector<int> posInt(A.n, -1);
   for (int64_t p = 0; p < nI; ++p) posInt[intRow[p]] = (int)p;
   bool ok = true;
@@ -773,6 +819,7 @@ void Level::compute(std::vector<Partition>& parts, const std::vector<int64_t>& f
       ok = false;
     }
     nnzF += sdLU[sd].nnzFactors();
+    if (refineSteps > 0) sdA[sd] = std::move(B);
   }
   if (!ok) throw std::runtime_error("singular subdomain matrix");
   factorNnz = nnzF;
@@ -807,6 +854,7 @@ void Level::compute(std::vector<Partition>& parts, const std::vector<int64_t>& f
     next.reset(new Level());
     next->level = level + 1;
     next->maxLevel = maxLevel;
+    next->refineSteps = refineSteps;
     next->A = reduced;
     next->gids = vsumGids;
     std::vector<double> ttv(nS);
@@ -830,6 +878,7 @@ void Level::compute(std::vector<Partition>& parts, const std::vector<int64_t>& f
       putDirichlet(S, row);
     }
     if (nuniq > 0 && !factorCsr(S, coarseLU)) throw std::runtime_error("singular coarse matrix");
+    if (refineSteps > 0) coarseA = S;
   }
   tm.coarse = secs(t2, now());
 }
@@ -848,7 +897,7 @@ void Level::schurApplyInverse(const double* rhs, double* sol) const {
       if (rows.empty()) continue;
       tmp.resize(rows.size());
       for (size_t k = 0; k < rows.size(); ++k) tmp[k] = B[rows[k]];
-      blockLU[b].solve(tmp.data());
+      blockLU[b].solveRefined(tmp.data(), refineSteps);
       for (size_t k = 0; k < rows.size(); ++k) Y[rows[k]] = tmp[k];
     }
   }
@@ -860,9 +909,10 @@ void Level::schurApplyInverse(const double* rhs, double* sol) const {
   } else if (nuniq > 0) {
     for (int row : coarseFixRows)
       if (row > 0) vr[row] = 0.0;  // sic: 'lid > 0', src/HYMLS_CoarseSolver.cpp:289
-    std::vector<double> work(nuniq);
+    std::vector<double> work(nuniq), tmp;
     vs = vr;
-    coarseLU.solve(vs.data(), work.data());
+    if (refineSteps > 0) refinedSolve(coarseLU, coarseA.ptr, coarseA.col, coarseA.val, refineSteps, vs.data(), work.data(), tmp);
+    else coarseLU.solve(vs.data(), work.data());
   }
   for (int u = 0; u < nuniq; ++u) Y[uniqPtr[u]] = vs[u];
   applyOT(Y.data(), sol);
@@ -1112,6 +1162,13 @@ int ho_set_partition(void* hv, int level, int nsd, const int64_t* intPtr, const 
 int ho_set_fix_gids(void* hv, int count, const int64_t* gids) {
   Handle* h = (Handle*)hv;
   HO_TRY(h, h->fix.assign(gids, gids + count))
+}
+
+// steps > 0: every direct solve gets that many refinement steps with extended-precision residuals (checker use)
+int ho_set_refinement(void* hv, int steps) {
+  ((Handle*)hv)->L0.refineSteps = steps;
+  ((Handle*)hv)->computed = false;
+  return 0;
 }
 
 int ho_compute(void* hv, int threads) {

@@ -41,6 +41,7 @@ def load():
         lib.ho_set_partition.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp]
         lib.ho_set_fix_gids.argtypes = [vp, C.c_int, vp]
         lib.ho_compute.argtypes = [vp, C.c_int]
+        lib.ho_set_refinement.argtypes = [vp, C.c_int]
         lib.ho_apply_inverse.argtypes = [vp, vp, vp]
         lib.ho_solve.argtypes = [vp, C.c_int, vp, vp, C.c_double, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int),
                                  C.POINTER(C.c_int), C.POINTER(C.c_double), vp, C.c_int, C.POINTER(C.c_int)]
@@ -99,7 +100,7 @@ def maps_from_library(P):
 class Preconditioner:
     """HYMLS::Preconditioner(K, params, testVector) on the CPU (C++/OpenMP); same method names as oracle.hymls"""
 
-    def __init__(self, A, params, testvector, maps, threads=0):
+    def __init__(self, A, params, testvector, maps, threads=0, refine_steps=0):
         self.lib = load()
         A = sp.csr_matrix(A)
         A.sort_indices()
@@ -132,6 +133,9 @@ class Preconditioner:
             pos += 1
         fx = np.asarray(fix, dtype=np.int64)
         self._check(self.lib.ho_set_fix_gids(self.h, len(fix), fx.ctypes.data))
+        # refine_steps > 0: every direct solve is refined with extended-precision residuals (checker only: makes the
+        # oracle as accurate as the exact-arithmetic algorithm where plain FP64 LU solves are not)
+        self.lib.ho_set_refinement(self.h, int(refine_steps))
 
     def __del__(self):
         try:

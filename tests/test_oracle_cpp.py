@@ -99,3 +99,29 @@ def test_cpp_oracle_on_reference_fixture_target():
                                 max_iters=100, imp_scaling="Norm of Initial Residual")
     x, itc, convc, hc, _ = Cp.solve(b, tol=1e-8, max_iters=100)
     assert conv and convc and abs(its - itc) <= 1
+
+
+@pytest.mark.parametrize("eqn,dim,nx,sx,levels,cx,extra", [
+    ("Stokes-C", 2, 32, 4, 1, None, {}),
+    ("Stokes-C", 3, 16, 4, 2, 2, {"Partitioner": "Skew Cartesian"}),
+])
+def test_refined_cpp_oracle_reaches_the_extended_precision_truth(eqn, dim, nx, sx, levels, cx, extra):
+    """ho_set_refinement: one refinement step with extended-precision residuals on every direct solve brings the C++
+    oracle from the 1e-12 of plain FP64 LU solves to 1e-14 of the exact-arithmetic preconditioner (oracle/extended.py);
+    tests/test_gpu_baseline_sizes.py uses it as the ground truth at sizes the numpy code cannot reach."""
+    from oracle import extended as ox
+    p = make_params(eqn, dim, nx, sx, levels, cx, **extra)
+    A = sp.csr_matrix(-hb.galeri.create_matrix(eqn, dim, nx))
+    tv = hb.galeri.create_testvector(A)
+    T = ox.Preconditioner(A, p.copy(), tv)
+    T.initialize()
+    T.compute()
+    b = np.random.default_rng(1).uniform(-1, 1, A.shape[0])
+    xt = T.apply_inverse(b)
+    maps = oc.maps_from_python_oracle(A, p.copy(), tv)
+    err = []
+    for steps in (0, 1):
+        Cp = oc.Preconditioner(A, p.copy(), tv, maps, refine_steps=steps)
+        Cp.compute()
+        err.append(float(np.linalg.norm(Cp.apply_inverse(b) - xt) / np.linalg.norm(xt)))
+    assert err[1] <= 1e-14 and err[1] < err[0]

@@ -90,6 +90,101 @@ void batchedGemv(const GemvArgs& a, int numItems, int npMax, cudaStream_t s, int
 int gemvRowsPerItem() { return GEMV_ROWS; }
 
 // ---------------------------------------------------------------------------------------------
+// The same kernel for NV right-hand sides at once (Epetra_MultiVector with several columns: the reference resizes
+// its subdomain solvers to the number of columns, src/HYMLS_MatrixBlock.cpp:335-344): every row of A11^-1 is loaded
+// ONCE and multiplied with NV vectors staged in shared memory, so k columns cost one pass over the inverses instead
+// of k.  Vector v of xin / xsub / out starts at v * ldIn / ldSub / ldOut.  mode 0 only.
+// ---------------------------------------------------------------------------------------------
+template <int NV>
+__global__ void __launch_bounds__(GEMV_T)
+k_batched_gemv_multi(GemvArgs a, int64_t ldIn, int64_t ldSub, int64_t ldOut) {
+  const int item = blockIdx.x;
+  const int mat = a.itemMat[item];
+  const int r0 = a.itemRow0[item];
+  const int n = a.n[mat], np = a.np[mat];
+  const int nr = a.nrows ? a.nrows[mat] : n;
+  const int64_t v0 = a.vecOff[mat];
+  const double* __restrict__ A = a.A + a.matOff[mat];
+  extern __shared__ double sx[];  // NV x np
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  for (int q = tid; q < np; q += GEMV_T) {
+    const int64_t src = q < n ? (a.gather ? (int64_t)a.gather[v0 + q] : v0 + q) : 0;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      double x = 0.0;
+      if (q < n) {
+        x = a.xin[v * ldIn + src];
+        if (a.xsub) x -= a.xsub[v * ldSub + v0 + q];
+      }
+      sx[v * np + q] = x;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int rr = 0; rr < GEMV_ROWS / (GEMV_T / 32); ++rr) {
+    const int r = r0 + wid * (GEMV_ROWS / (GEMV_T / 32)) + rr;
+    if (r >= nr) break;
+    const double2* __restrict__ row = reinterpret_cast<const double2*>(A + (int64_t)r * np);
+    double acc[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) acc[v] = 0.0;
+    const int n2 = np >> 1;
+    int q = lane;
+    for (; q + 32 < n2; q += 64) {  // two independent 16-byte loads in flight per lane
+      const double2 m0 = __ldg(row + q), m1 = __ldg(row + q + 32);
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const double2 b0 = reinterpret_cast<const double2*>(sx + v * np)[q];
+        const double2 b1 = reinterpret_cast<const double2*>(sx + v * np)[q + 32];
+        acc[v] += m0.x * b0.x + m0.y * b0.y + m1.x * b1.x + m1.y * b1.y;
+      }
+    }
+    for (; q < n2; q += 32) {
+      const double2 m0 = __ldg(row + q);
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const double2 b0 = reinterpret_cast<const double2*>(sx + v * np)[q];
+        acc[v] += m0.x * b0.x + m0.y * b0.y;
+      }
+    }
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      double t = acc[v];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      acc[v] = t;
+    }
+    if (lane == 0) {
+      const int64_t o = (a.outOff ? a.outOff[mat] : v0) + r;
+      const int64_t dst = a.scatter ? (int64_t)a.scatter[o] : o;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) a.out[v * ldOut + dst] = acc[v];
+    }
+  }
+}
+
+// nv in 2..4; returns false when the kernel cannot hold nv vectors of npMax entries in shared memory
+bool batchedGemvMulti(const GemvArgs& a, int numItems, int npMax, int nv, int64_t ldIn, int64_t ldSub, int64_t ldOut,
+                      cudaStream_t s, int64_t* launches) {
+  if (numItems == 0) return true;
+  const size_t smem = (size_t)npMax * nv * sizeof(double);
+  if (smem > 200 * 1024 || nv < 2 || nv > 4) return false;
+  static PerDeviceLimit lim2, lim3, lim4;
+  if (nv == 2) {
+    if (lim2.raise(smem)) HY_CUDA(cudaFuncSetAttribute(k_batched_gemv_multi<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_batched_gemv_multi<2><<<numItems, GEMV_T, smem, s>>>(a, ldIn, ldSub, ldOut);
+  } else if (nv == 3) {
+    if (lim3.raise(smem)) HY_CUDA(cudaFuncSetAttribute(k_batched_gemv_multi<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_batched_gemv_multi<3><<<numItems, GEMV_T, smem, s>>>(a, ldIn, ldSub, ldOut);
+  } else {
+    if (lim4.raise(smem)) HY_CUDA(cudaFuncSetAttribute(k_batched_gemv_multi<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_batched_gemv_multi<4><<<numItems, GEMV_T, smem, s>>>(a, ldIn, ldSub, ldOut);
+  }
+  ++*launches;
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------
 // CSR SpMV variants (thread per row; rows have 1..~10 entries on level 0)
 //   y[r] = alpha * (b ? b[bidx ? bidx[r] : r] : 0) + beta * sum_e val[e] x[col[e]]
 // ---------------------------------------------------------------------------------------------

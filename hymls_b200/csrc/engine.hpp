@@ -225,6 +225,8 @@ class Engine {
   void solveDist(const double* b, double* x, int where, uint64_t seed, hymls_b200_solve_info* info, double* hist,
                  int histCap);
   void applyDevice(const double* dB, double* dX, const double* dT = nullptr, double* dS = nullptr);
+  bool applyDeviceMulti(const double* dB, int64_t ldb, double* dX, int64_t ldx, int nv);
+  DevBuf<double> x1m_, y1m_;  // interior work vectors of the multi-column apply
   // rows [r0, r1) of the (bordered) operator [K V; W' C] applied to the replicated vector `full`
   void operatorRows(const double* full, double* out, int64_t r0, int64_t r1);
 

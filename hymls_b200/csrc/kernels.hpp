@@ -111,6 +111,10 @@ struct GemvArgs {
   int mode;
 };
 void batchedGemv(const GemvArgs& a, int numItems, int npMax, cudaStream_t s, int64_t* launches);
+// nv = 2..4 vectors in one pass over the matrices (vector v of xin / xsub / out at v * ldIn / ldSub / ldOut; mode 0);
+// false: does not fit shared memory, the caller loops over the columns
+bool batchedGemvMulti(const GemvArgs& a, int numItems, int npMax, int nv, int64_t ldIn, int64_t ldSub, int64_t ldOut,
+                      cudaStream_t s, int64_t* launches);
 int gemvRowsPerItem();
 void spmv(const int64_t* ptr, const int* col, const double* val, const double* x, double* y, int64_t n, double alpha,
           const double* b, const int* bidx, double beta, cudaStream_t s, int64_t* launches);

@@ -276,3 +276,20 @@ def test_block_tridiagonal_coarse_solver(monkeypatch, eqn, dim, nx, sx, levels, 
     S = hb.Solver(Pb)
     x = S.ApplyInverse(A @ b)
     assert S.info["converged"]
+
+
+@pytest.mark.parametrize("nvec", [2, 3, 4, 5, 7])
+def test_multi_rhs_apply_matches_single_columns(nvec):
+    """Several right-hand sides share the passes over the subdomain inverses (k_batched_gemv_multi, up to 4 columns
+    per pass; the reference resizes its solvers to the number of columns, src/HYMLS_MatrixBlock.cpp:335-344): column
+    by column the result equals the single-vector ApplyInverse (different summation order inside a row only)."""
+    A, P, O = build("Stokes-C", 3, 16, 4, 2, 2, Partitioner="Skew Cartesian")
+    B = np.random.default_rng(9).uniform(-1, 1, (A.shape[0], nvec))
+    X = P.ApplyInverse(B)
+    for k in range(nvec):
+        xk = P.ApplyInverse(B[:, k].copy())
+        assert rel(X[:, k], xk) < 1e-13
+    import torch
+    Bd = torch.from_numpy(np.ascontiguousarray(B.T)).cuda()      # device: nvec x n, contiguous = column major
+    Xd = P.ApplyInverse(Bd).cpu().numpy().T
+    assert np.array_equal(Xd, X)

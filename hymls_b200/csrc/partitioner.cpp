@@ -470,6 +470,13 @@ void buildHierarchicalMap(const CartesianPartitioner& part, const std::vector<ch
     try {
       for (int64_t sd = s0; sd < s1; ++sd) {
         part.getGroups((int)sd, allInterior[sd], allGroups[sd]);
+        if (filter) {  // coarser levels keep ~1 % of the grid nodes: drop the others here, in parallel
+          auto gone = [&](gidx g) { return !present[g]; };
+          std::vector<gidx>& in = allInterior[sd];
+          in.erase(std::remove_if(in.begin(), in.end(), gone), in.end());
+          for (auto& grp : allGroups[sd])
+            grp.nodes.erase(std::remove_if(grp.nodes.begin(), grp.nodes.end(), gone), grp.nodes.end());
+        }
         std::sort(allInterior[sd].begin(), allInterior[sd].end());
         for (auto& grp : allGroups[sd]) std::sort(grp.nodes.begin(), grp.nodes.end());
       }

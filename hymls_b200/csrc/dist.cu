@@ -478,9 +478,23 @@ void Engine::solveDist(const double* b, double* x, int where, uint64_t seed, hym
       for (int k = 0; k < m && iters < maxIters; ++k) {
         double* vk = kV_.p + (size_t)k * ld;
         double* w = kV_.p + (size_t)(k + 1) * ld;
+        static const bool verboseSolve = getenv("HYMLS_B200_VERBOSE_SOLVE") != nullptr;
+        const bool lapIt = verboseSolve && comm_.rank() == 0 && (k % 50) == 20;
+        auto tl = std::chrono::steady_clock::now();
+        auto lapS = [&](const char* what) {
+          if (!lapIt) return;
+          cudaStreamSynchronize(s);
+          auto t1 = std::chrono::steady_clock::now();
+          fprintf(stderr, "[hymls_b200 solve dist] it %d %-28s %8.3f ms\n", k, what,
+                  std::chrono::duration<double, std::milli>(t1 - tl).count());
+          tl = t1;
+        };
+        if (lapIt) { cudaStreamSynchronize(s); tl = std::chrono::steady_clock::now(); }
         if (right) {
           Mglobal(vk, kX_.p);
+          lapS("ApplyInverse");
           Aglobal(kX_.p, w);
+          lapS("matrix halo + spmv");
         } else if (left) {
           A(vk, kW_.p);
           M(kW_.p, w);
@@ -496,8 +510,10 @@ void Engine::solveDist(const double* b, double* x, int where, uint64_t seed, hym
         multiDot(w, ld, 1, w, nOwn, kPartial_.p, dNrm, 0, s, &launches_);
         comm_.allReduceSum(dNrm, 1, s);
         scaleByInvNorm(w, dNrm, w, nOwn, s, &launches_);
+        lapS("CGS2 (4 sweeps, 3 allreduces)");
         HY_CUDA(cudaMemcpyAsync(hbuf.data(), kH_.p, (2 * m + 3) * sizeof(double), cudaMemcpyDeviceToHost, s));
         HY_CUDA(cudaStreamSynchronize(s));
+        lapS("Hessenberg column to host");
         for (int i = 0; i <= k; ++i) H[(size_t)i * m + k] = hbuf[i] + hbuf[m + 1 + i];
         const double hn = std::sqrt(hbuf[2 * m + 2]);
         double colNorm = 0.0;

@@ -303,12 +303,15 @@ void Engine::initialize() {
     // ownership: every level is sharded by the reference's subdomain -> rank map of that level
     // (BasePartitioner::CreatePIDMap); with fewer subdomains than ranks some ranks own nothing there
     L.ownSd.clear();
-    // Level 0 is distributed over the ranks.  The coarser levels are 100x smaller: their collectives (3 per level
-    // and ApplyInverse, each a few 10 us of latency) cost more than their whole replicated computation (0.65 GB of
-    // inverses at 128^3 = 0.1 ms), so they run replicated on every rank, bitwise identical everywhere
-    // (HYMLS_B200_SHARD_LEVELS=k distributes the first k levels instead).
-    static const int shardLevels = getenv("HYMLS_B200_SHARD_LEVELS") ? atoi(getenv("HYMLS_B200_SHARD_LEVELS")) : 1;
+    // Level 0 runs the owner-computes halo scheme (dist.cu).  The coarser levels are 100x smaller and latency bound:
+    // their subdomain solves (1 GB of inverses at 128^3) stay distributed, but everything on the separators
+    // (Householder, block solves, the next level / coarse solve) is REPLICATED -- bitwise identical on every rank --
+    // so that a coarse level costs two small collectives (separator right-hand side, interior result) instead of
+    // four (measured at 128^3 on 8 GPUs: 0.41 ms with four collectives, 0.60 ms fully replicated).
+    // HYMLS_B200_SHARD_LEVELS=k: only the first k levels are distributed at all.
+    static const int shardLevels = getenv("HYMLS_B200_SHARD_LEVELS") ? atoi(getenv("HYMLS_B200_SHARD_LEVELS")) : 1 << 20;
     L.sharded = comm_.size() > 1 && l < shardLevels;
+    L.repSep = L.sharded && l >= 1;
     if (L.sharded) {
       if (maxLevel_ == 0) throw Error(HYMLS_B200_ERR_UNSUPPORTED, "Number of Levels = 0 is single-GPU only");
       ParameterList pp = levelParams.deepCopy();
@@ -654,7 +657,7 @@ void Engine::uploadLevel(Level& L) {
   L.redCol.upload(S.redCol, s);
   // separator blocks
   std::vector<int64_t> blkVecOff(S.blkRowPtr.begin(), S.blkRowPtr.end() - 1);
-  if (L.sharded) {
+  if (L.sharded && !L.repSep) {
     // every rank holds (and inverts) all separator blocks, but applies only the ones whose owner
     // subdomain it owns; the block results are summed over the ranks in ApplyInverse
     std::vector<char> mask(S.nblk, 0);
@@ -1114,7 +1117,7 @@ void Engine::computeLevel(int l) {
       blkR_.alloc(blkW.n);
       HY_CUDA(cudaMemcpyAsync(blkA_.p, blkW.p, blkW.bytes(), cudaMemcpyDeviceToDevice, s));
     }
-    if (!L.sharded) {
+    if (!L.sharded || L.repSep) {
       int b0 = 0;
       while (b0 < S.nblk) {
         int b1 = std::min(S.nblk, b0 + 16384);
@@ -1502,9 +1505,10 @@ void Engine::applyLevel(int l, const double* B, double* X, const double* T) {
     b.out = L.Y.p;
     b.scatter = L.blkRows.p;
     b.mode = 0;
-    if (L.sharded) HY_CUDA(cudaMemsetAsync(L.Y.p, 0, (size_t)S.nS * sizeof(double), s));
+    const bool sumSep = L.sharded && !L.repSep;  // separator work distributed: results summed over the ranks
+    if (sumSep) HY_CUDA(cudaMemsetAsync(L.Y.p, 0, (size_t)S.nS * sizeof(double), s));
     batchedGemv(b, L.blk.numItems, L.blk.npMax, s, &launches_);
-    if (L.sharded) comm_.allReduceSum(L.Y.p, (size_t)S.nS, s);  // owned block rows from every rank
+    if (sumSep) comm_.allReduceSum(L.Y.p, (size_t)S.nS, s);  // owned block rows from every rank
     at.lap("householder + separator blocks");
     if (bm) {
       // Tc = q - bW' Y with zeros in the V-sum rows (SchurPreconditioner.cpp:1585-1590)
@@ -1516,7 +1520,7 @@ void Engine::applyLevel(int l, const double* B, double* X, const double* T) {
       applyLevel(l + 1, L.vsRhs.p, L.vsSol.p, bm ? L.bT.p : nullptr);
     } else if (bm) {
       coarseSolveBordered(L.vsRhs.p, L.bT.p, L.vsSol.p, S.nuniq);
-      if (L.sharded) {
+      if (sumSep) {
         comm_.broadcast(L.vsSol.p, (size_t)S.nuniq, 0, s);
         comm_.broadcast(bS_.p, (size_t)bm, 0, s);
       }
@@ -1525,7 +1529,7 @@ void Engine::applyLevel(int l, const double* B, double* X, const double* T) {
       // the coarse solve is replicated; rank 0's copy becomes the common one so that every rank
       // continues with bit-identical data (replicas may differ in the last bit, which a Krylov method
       // mixing per-rank partial results would amplify)
-      if (L.sharded) comm_.broadcast(L.vsSol.p, (size_t)S.nuniq, 0, s);
+      if (sumSep) comm_.broadcast(L.vsSol.p, (size_t)S.nuniq, 0, s);
     }
     at.lap("next level / coarse");
     // x2 = H [Y(non-V-sum); vsumSol], exported to X

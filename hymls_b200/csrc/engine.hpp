@@ -74,6 +74,7 @@ struct Level {
   std::vector<int64_t> a11ListPtr;  // per owned sd: range of the scatter list
   DevBuf<int64_t> a11ListPtrDev;
   bool sharded = false;
+  bool repSep = false;              // sharded coarser level: subdomain solves distributed, separator side replicated
   DevBuf<int> ownSdList;            // device copies of the owned lists for the pass-2 Schur kernels
   DevBuf<int64_t> ownRowList, ownLinkList;
   std::vector<int64_t> chunkOwnSd, chunkOwnRow, chunkOwnLink;  // per chunk: ranges in the lists (nchunks+1)

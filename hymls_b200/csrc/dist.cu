@@ -23,6 +23,7 @@
 #include <random>
 
 #include "engine.hpp"
+#include "hostpar.hpp"
 
 namespace hymls {
 
@@ -162,31 +163,46 @@ void Engine::buildDistPlan(Level& L) {
   }
   D.ready = true;
   D.matReady = false;
+  buildMatrixHalo();
 }
 
-// columns of my rows owned elsewhere (receive) and my rows that appear as columns of other ranks' rows (send)
+// columns of my rows owned elsewhere (receive) and my rows that appear as columns of other ranks' rows (send).
+// Part of Initialize (threaded over the rows): a rank that built this inside the first solve would make the others
+// wait in their first collective.
 void Engine::buildMatrixHalo() {
   Level& L = *levels_[0];
   DistPlan& D = L.dist;
   if (D.matReady) return;
   const int P = comm_.size(), me = comm_.rank();
-  std::vector<std::vector<int>> send(P), recv(P);
-  for (int64_t r = 0; r < n_; ++r) {
-    const int q = D.rowOwner[r];
-    for (int64_t e = hRowptr_[r]; e < hRowptr_[r + 1]; ++e) {
-      const int c = hColidx_[e];
-      const int qc = D.rowOwner[c];
-      if (q == qc) continue;
-      if (q == me) recv[qc].push_back(c);
-      else if (qc == me) send[q].push_back(c);
+  const int T = 64;
+  std::vector<std::vector<std::vector<int>>> sendT(T, std::vector<std::vector<int>>(P)),
+      recvT(T, std::vector<std::vector<int>>(P));
+  parallelFor(n_, [&](int64_t r0, int64_t r1, int t) {
+    auto& snd = sendT[t & (T - 1)];
+    auto& rcv = recvT[t & (T - 1)];
+    for (int64_t r = r0; r < r1; ++r) {
+      const int q = D.rowOwner[r];
+      for (int64_t e = hRowptr_[r]; e < hRowptr_[r + 1]; ++e) {
+        const int c = hColidx_[e];
+        const int qc = D.rowOwner[c];
+        if (q == qc) continue;
+        if (q == me) rcv[qc].push_back(c);
+        else if (qc == me) snd[q].push_back(c);
+      }
     }
-  }
+  });
+  std::vector<std::vector<int>> send(P), recv(P);
+  for (int t = 0; t < T; ++t)
+    for (int q = 0; q < P; ++q) {
+      send[q].insert(send[q].end(), sendT[t][q].begin(), sendT[t][q].end());
+      recv[q].insert(recv[q].end(), recvT[t][q].begin(), recvT[t][q].end());
+    }
   for (int q = 0; q < P; ++q) {
     sortUnique(send[q]);
     sortUnique(recv[q]);
   }
-  uploadHalo(D.mat, send, recv, stream_);
-  HY_CUDA(cudaStreamSynchronize(stream_));
+  uploadHalo(D.mat, send, recv, stream_, deviceOk_);
+  if (deviceOk_) HY_CUDA(cudaStreamSynchronize(stream_));
   D.matReady = true;
 }
 
@@ -367,6 +383,10 @@ void Engine::solveDist(const double* b, double* x, int where, uint64_t seed, hym
     HY_CUDA(cudaMemcpyAsync(kX_.p, x, n * sizeof(double), kind, s));
     packIdx(kX_.p, D.ownRows.p, xc.p, nOwn, s, &launches_);
   }
+  // the ranks start the timed region together (a late rank would otherwise bill its delay to the others' first
+  // collective)
+  comm_.allReduceSum(kH_.p, 1, s);
+  HY_CUDA(cudaStreamSynchronize(s));
   HY_CUDA(cudaEventRecord(ev0_, s));
   // operators: "global" vectors have length n with the owned entries valid
   auto Aglobal = [&](double* full, double* outC) {  // halo of `full` is filled in place

@@ -293,3 +293,46 @@ def test_multi_rhs_apply_matches_single_columns(nvec):
     Bd = torch.from_numpy(np.ascontiguousarray(B.T)).cuda()      # device: nvec x n, contiguous = column major
     Xd = P.ApplyInverse(Bd).cpu().numpy().T
     assert np.array_equal(Xd, X)
+
+
+def test_krylov_edge_cases_do_not_produce_nans():
+    """A zero right-hand side with a zero initial vector (zero initial residual, also with the explicit residual
+    test switched on) converges at once instead of normalising a zero vector; a solve that reaches the exact
+    solution in the Krylov space (Number of Levels = 0: one iteration) ends cleanly."""
+    import torch
+    for explicit in (False, True):
+        solver = {"Krylov Method": "GMRES", "Initial Vector": "Zero",
+                  "Iterative Solver": {"Maximum Iterations": 20, "Convergence Tolerance": 1e-10,
+                                       "Explicit Residual Test": explicit}}
+        A, P, O = build("Stokes-C", 2, 16, 4, 1, solver=solver)
+        S = hb.Solver(P)
+        x = S.ApplyInverse(np.zeros(A.shape[0]))
+        assert S.info["converged"] and S.num_iter == 0 and np.all(x == 0.0)
+    A, P, O = build("Stokes-C", 2, 16, 8, 0, solver={"Krylov Method": "GMRES", "Initial Vector": "Zero",
+                                                     "Iterative Solver": {"Maximum Iterations": 10,
+                                                                          "Convergence Tolerance": 1e-12}})
+    S = hb.Solver(P)
+    b = A @ np.random.default_rng(4).uniform(-1, 1, A.shape[0])
+    x = S.ApplyInverse(b)
+    assert np.all(np.isfinite(x)) and S.num_iter <= 3
+    assert np.linalg.norm(A @ x - b) <= 1e-9 * np.linalg.norm(b)
+
+
+def test_device_matrix_with_new_pattern_is_detected():
+    """hymls_b200_set_matrix_csr with device pointers compares the column indices too: equal row lengths with
+    different columns are a NEW pattern (the handle has to be initialized again), not a value update."""
+    import torch
+    A, P, O = build("Laplace", 2, 16, 4, 1)
+    A = sp.csr_matrix(A)
+    rp = torch.from_numpy(A.indptr.astype(np.int64)).cuda()
+    ci = torch.from_numpy(A.indices.astype(np.int32)).cuda()
+    v = torch.from_numpy(A.data.copy()).cuda()
+    P.SetMatrix((rp, ci, v))                 # same pattern: stays initialized
+    P.Compute()
+    ci2 = ci.clone()
+    row = 40                                  # swap two column indices of one row: same lengths, other pattern
+    a, b = int(A.indptr[row]), int(A.indptr[row + 1])
+    ci2[a:b] = torch.flip(ci2[a:b], dims=[0])
+    P.SetMatrix((rp, ci2, v))
+    with pytest.raises(hb.HymlsError):
+        P.ApplyInverse(np.ones(A.shape[0]))   # not computed any more: the pattern changed

@@ -103,6 +103,45 @@ def run_check(nx, sx, levels, cx, partitioner, rank, world, border=False, schur_
     return res
 
 
+def run_check_variants(rank, world):
+    """CG (Laplace) and left-preconditioned GMRES on the owner-distributed Krylov path vs the single-GPU solver"""
+    out = {}
+    for name, eqn, solver in [
+            ("cg_laplace", "Laplace", {"Krylov Method": "CG", "Initial Vector": "Zero",
+                                       "Iterative Solver": {"Maximum Iterations": 200, "Convergence Tolerance": 1e-10}}),
+            ("gmres_left_stokes", "Stokes-C", {"Krylov Method": "GMRES", "Initial Vector": "Random",
+                                              "Left or Right Preconditioning": "Left",
+                                              "Iterative Solver": {"Maximum Iterations": 300, "Num Blocks": 40,
+                                                                   "Convergence Tolerance": 1e-8}})]:
+        nx = 24 if eqn == "Laplace" else 16
+        params = {"Problem": {"Equations": eqn, "Dimension": 3, "nx": nx, "ny": nx, "nz": nx},
+                  "Preconditioner": {"Partitioner": "Skew Cartesian" if eqn != "Laplace" else "Cartesian",
+                                     "Separator Length": 4, "Number of Levels": 2, "Coarsening Factor": 2},
+                  "Solver": solver}
+        A = hb.galeri.create_matrix(eqn, 3, nx)
+        if eqn != "Laplace":
+            A = -A
+        tv = hb.galeri.create_testvector(A)
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(hb.Preconditioner.CommUniqueId()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        P = hb.Preconditioner(A, params, tv)
+        P.CommInit(bytes(idt.cpu().numpy().tobytes()), rank, world)
+        P.Initialize()
+        P.Compute()
+        Q = hb.Preconditioner(A, params, tv)
+        Q.Initialize()
+        Q.Compute()
+        b = A @ np.random.default_rng(3).uniform(-1, 1, A.shape[0])
+        S, T = hb.Solver(P), hb.Solver(Q)
+        x, y = S.ApplyInverse(b), T.ApplyInverse(b)
+        out[name] = {"iterations_sharded": int(S.num_iter), "iterations_single": int(T.num_iter),
+                     "converged": bool(S.info["converged"]),
+                     "solution_rel_diff": float(np.linalg.norm(x - y) / np.linalg.norm(y))}
+    return out
+
+
 def main():
     rank = int(os.environ["RANK"])
     world = int(os.environ["WORLD_SIZE"])
@@ -117,6 +156,8 @@ def main():
     part = a[4] if len(a) > 4 else "Skew Cartesian"
     res = run_check(nx, sx, levels, cx, part, rank, world, border="--border" in a,
                     schur_gemm=1 if "--schur-gemm" in a else None)
+    if "--variants" in a:
+        res["variants"] = run_check_variants(rank, world)
     if rank == 0:
         print("MGPU_CHECK " + json.dumps(res), flush=True)
     dist.barrier()

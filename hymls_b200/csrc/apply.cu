@@ -5,6 +5,7 @@
 // Krylov loop (Belos inside src/HYMLS_BaseSolver.cpp:347-356).  All of them are HBM-bandwidth bound.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdint>
 
 #include "device.cuh"
@@ -45,9 +46,11 @@ k_batched_gemv(GemvArgs a) {
     sx[q] = v;
   }
   __syncthreads();
-#pragma unroll
-  for (int rr = 0; rr < GEMV_ROWS / (GEMV_T / 32); ++rr) {
-    const int r = r0 + wid * (GEMV_ROWS / (GEMV_T / 32)) + rr;
+  // rows per warp: 4 (a 32-row slab per CTA) unless the work list was built with thinner slabs (a.rowsPerWarp:
+  // single large matrices such as the coarse inverse need more CTAs than n / 32 to fill 148 SMs)
+  const int rpw = a.rowsPerWarp > 0 ? a.rowsPerWarp : GEMV_ROWS / (GEMV_T / 32);
+  for (int rr = 0; rr < rpw; ++rr) {
+    const int r = r0 + wid * rpw + rr;
     if (r >= nr) break;
     const double2* __restrict__ row = reinterpret_cast<const double2*>(A + (int64_t)r * np);
     const double2* __restrict__ x2 = reinterpret_cast<const double2*>(sx);
@@ -88,6 +91,55 @@ void batchedGemv(const GemvArgs& a, int numItems, int npMax, cudaStream_t s, int
   ++*launches;
 }
 int gemvRowsPerItem() { return GEMV_ROWS; }
+
+// ---------------------------------------------------------------------------------------------
+// Small matrices (the separator blocks: 8 .. 192 rows, ~10^5 of them at 128^3): one WARP per matrix, grid-stride,
+// x in per-warp shared memory, min(32, np/2) lanes per row and several rows per pass for the tiny ones.
+// k_batched_gemv spends a 256-thread CTA per 32-row slab, which for these blocks is CTA-launch bound (ncu: 0.73 ms
+// for 0.83 GB = 14 % of the DRAM throughput, profiles/r02_ncu_gemv_traffic.json).  mode 0 only.
+// ---------------------------------------------------------------------------------------------
+static constexpr int SMALL_NP_MAX = 256;
+__global__ void __launch_bounds__(256)
+k_small_gemv(GemvArgs a, const int* __restrict__ matList, int numMats) {
+  __shared__ double sxAll[8 * SMALL_NP_MAX];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  double* sx = sxAll + wid * SMALL_NP_MAX;
+  for (int idx = blockIdx.x * 8 + wid; idx < numMats; idx += gridDim.x * 8) {
+    const int mat = matList ? matList[idx] : idx;
+    const int n = a.n[mat], np = a.np[mat];
+    const int64_t v0 = a.vecOff[mat];
+    const double* __restrict__ A = a.A + a.matOff[mat];
+    for (int q = lane; q < np; q += 32) sx[q] = q < n ? (a.gather ? a.xin[a.gather[v0 + q]] : a.xin[v0 + q]) : 0.0;
+    __syncwarp();
+    const int L = np >= 64 ? 32 : (np >= 32 ? 16 : (np >= 16 ? 8 : 4));  // lanes per row (np is a multiple of 8)
+    const int rowsPerPass = 32 / L, sub = lane % L, rsel = lane / L;
+    for (int r0 = 0; r0 < n; r0 += rowsPerPass) {
+      const int r = r0 + rsel;
+      double acc = 0.0;
+      if (r < n) {
+        const double* __restrict__ row = A + (int64_t)r * np;
+        for (int q = 2 * sub; q < np; q += 2 * L) {
+          const double2 m = __ldg(reinterpret_cast<const double2*>(row + q));
+          acc += m.x * sx[q] + m.y * sx[q + 1];
+        }
+      }
+      for (int o = L >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (sub == 0 && r < n) {
+        const int64_t o = (a.outOff ? a.outOff[mat] : v0) + r;
+        a.out[a.scatter ? a.scatter[o] : o] = acc;
+      }
+    }
+    __syncwarp();
+  }
+}
+bool smallGemv(const GemvArgs& a, const int* matList, int numMats, int npMax, cudaStream_t s, int64_t* launches) {
+  if (npMax > SMALL_NP_MAX) return false;
+  if (numMats == 0) return true;
+  const int blocks = std::min((numMats + 7) / 8, 148 * 8);
+  k_small_gemv<<<blocks, 256, 0, s>>>(a, matList, numMats);
+  ++*launches;
+  return true;
+}
 
 // ---------------------------------------------------------------------------------------------
 // The same kernel for NV right-hand sides at once (Epetra_MultiVector with several columns: the reference resizes

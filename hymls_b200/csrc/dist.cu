@@ -266,13 +266,7 @@ void Engine::applyLevel0Dist(const double* B, double* X) {
   householderList(L.uniqStart.p, D.ownUniq.p, (int)D.nOwnUniq, L.what.p, L.rhsS.p, L.Z.p, L.vsRhs.p, nullptr, nullptr,
                   nullptr, s, &launches_);
   comm_.allReduceSum(L.vsRhs.p, (size_t)S.nuniq, s);
-  GemvArgs b = L.blk.args();
-  b.xin = L.Z.p;
-  b.gather = L.blkRows.p;
-  b.out = L.Y.p;
-  b.scatter = L.blkRows.p;
-  b.mode = 0;
-  batchedGemv(b, L.blk.numItems, L.blk.npMax, s, &launches_);
+  blockSolves(L, L.Z.p, L.Y.p);
   mark("householder + blocks + vsum allreduce");
   if (levels_.size() > 1) {
     applyLevel(1, L.vsRhs.p, L.vsSol.p, nullptr);

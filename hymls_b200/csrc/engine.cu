@@ -196,17 +196,20 @@ void BatchedInverse::setup(const std::vector<int>& n_, const std::vector<int>& n
   hVecOff = vecOff_;
   count = (int)n_.size();
   npMax = 0;
-  std::vector<int> im, ir;
-  const int rows = gemvRowsPerItem();
+  std::vector<int> im, ir, ml;
+  const int rows = rowsPerWarp > 0 ? 8 * rowsPerWarp : gemvRowsPerItem();
   for (int m = 0; m < count; ++m) {
     npMax = std::max(npMax, np_[m]);
     if (applyMask && !(*applyMask)[m]) continue;
+    if (n_[m] > 0) ml.push_back(m);
     for (int r0 = 0; r0 < n_[m]; r0 += rows) {
       im.push_back(m);
       ir.push_back(r0);
     }
   }
   numItems = (int)im.size();
+  numMats = (int)ml.size();
+  matList.upload(ml, s);
   numItemsLead = 0;
   if (leadRows) {
     std::vector<int> lm, lr;
@@ -238,6 +241,7 @@ GemvArgs BatchedInverse::args() const {
   a.matOff = matOff.p;
   a.vecOff = vecOff.p;
   a.A = F.p;
+  a.rowsPerWarp = rowsPerWarp;
   return a;
 }
 
@@ -1240,6 +1244,7 @@ void Engine::augmentAndInvertCoarse(int n, int np, const double* bV, const doubl
   }
   std::vector<int> cn(1, n + bm), cnp(1, np);
   std::vector<int64_t> off{0, (int64_t)np * np}, voff(1, 0);
+  coarse_.rowsPerWarp = (n + bm) < 32 * 148 * 4 ? 1 : 0;  // one matrix: 8-row slabs give 4x the CTAs
   coarse_.setup(cn, cnp, off, voff, s);
   coarseN_ = n;
   coarseM_ = bm;
@@ -1430,6 +1435,18 @@ void Engine::coarseSolveBordered(const double* rhs, const double* T, double* sol
   HY_CUDA(cudaMemcpyAsync(bS_.p, coarseSol_.p + n, (size_t)bm * sizeof(double), cudaMemcpyDeviceToDevice, s));
 }
 
+// separator-block solves Y[blkRows] = blockinv * Z[blkRows] (ApplyBlockDiagonal, src/HYMLS_SchurPreconditioner.cpp:1311-1346)
+void Engine::blockSolves(Level& L, const double* Z, double* Y) {
+  GemvArgs b = L.blk.args();
+  b.xin = Z;
+  b.gather = L.blkRows.p;
+  b.out = Y;
+  b.scatter = L.blkRows.p;
+  b.mode = 0;
+  if (!smallGemv(b, L.blk.matList.p, L.blk.numMats, L.blk.npMax, stream_, &launches_))
+    batchedGemv(b, L.blk.numItems, L.blk.npMax, stream_, &launches_);
+}
+
 void Engine::applyLevel(int l, const double* B, double* X, const double* T) {
   Level& L = *levels_[l];
   const LevelSym& S = L.sym;
@@ -1499,15 +1516,9 @@ void Engine::applyLevel(int l, const double* B, double* X, const double* T) {
     householder(L.uniqStart.p, S.nuniq, L.what.p, L.rhsS.p, L.Z.p, L.vsRhs.p, nullptr, nullptr, nullptr, s,
                 &launches_);
     // non-V-sums: block diagonal solves (ApplyBlockDiagonal)
-    GemvArgs b = L.blk.args();
-    b.xin = L.Z.p;
-    b.gather = L.blkRows.p;
-    b.out = L.Y.p;
-    b.scatter = L.blkRows.p;
-    b.mode = 0;
     const bool sumSep = L.sharded && !L.repSep;  // separator work distributed: results summed over the ranks
     if (sumSep) HY_CUDA(cudaMemsetAsync(L.Y.p, 0, (size_t)S.nS * sizeof(double), s));
-    batchedGemv(b, L.blk.numItems, L.blk.npMax, s, &launches_);
+    blockSolves(L, L.Z.p, L.Y.p);
     if (sumSep) comm_.allReduceSum(L.Y.p, (size_t)S.nS, s);  // owned block rows from every rank
     at.lap("householder + separator blocks");
     if (bm) {
@@ -1595,13 +1606,7 @@ bool Engine::applyDeviceMulti(const double* dB, int64_t ldb, double* dX, int64_t
     double* X = dX + (int64_t)v * ldx;
     spmv(L.p21.p, L.c21.p, L.v21.p, x1m_.p + (int64_t)v * S.nI, L.rhsS.p, S.nS, 1.0, B, L.sepRow.p, -1.0, s, &launches_);
     householder(L.uniqStart.p, S.nuniq, L.what.p, L.rhsS.p, L.Z.p, L.vsRhs.p, nullptr, nullptr, nullptr, s, &launches_);
-    GemvArgs b = L.blk.args();
-    b.xin = L.Z.p;
-    b.gather = L.blkRows.p;
-    b.out = L.Y.p;
-    b.scatter = L.blkRows.p;
-    b.mode = 0;
-    batchedGemv(b, L.blk.numItems, L.blk.npMax, s, &launches_);
+    blockSolves(L, L.Z.p, L.Y.p);
     if (levels_.size() > 1) applyLevel(1, L.vsRhs.p, L.vsSol.p, nullptr);
     else coarseSolve(L.vsRhs.p, L.vsSol.p, S.nuniq);
     householder(L.uniqStart.p, S.nuniq, L.what.p, L.Y.p, L.Y.p, nullptr, L.vsSol.p, X, L.sepRow.p, s, &launches_);

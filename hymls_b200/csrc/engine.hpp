@@ -18,10 +18,13 @@ struct BatchedInverse {  // a set of dense inverses + the GEMV work list over th
   std::vector<int> hN, hNp;
   std::vector<int64_t> hMatOff, hVecOff;
   int count = 0, numItems = 0, npMax = 0;
+  DevBuf<int> matList;  // the matrices GEMV work exists for (all, or the flagged ones of applyMask)
+  int numMats = 0;
   // second work list over the leading `leadRows[m]` rows of every matrix (first solve of ApplyInverse)
   DevBuf<int> rowLimit, itemMatLead, itemRow0Lead;
   int numItemsLead = 0;
   // `applyMask` (optional, one flag per matrix): GEMV work items are created for flagged matrices only
+  int rowsPerWarp = 0;  // thinner GEMV slabs (see GemvArgs::rowsPerWarp); set before setup()
   void setup(const std::vector<int>& n_, const std::vector<int>& np_, const std::vector<int64_t>& matOff_,
              const std::vector<int64_t>& vecOff_, cudaStream_t s, const std::vector<char>* applyMask = nullptr,
              const std::vector<int>* leadRows = nullptr);
@@ -194,6 +197,7 @@ class Engine {
 
  private:
   void applyLevel(int l, const double* B, double* X, const double* T = nullptr);  // device pointers
+  void blockSolves(Level& L, const double* Z, double* Y);
   void computeLevel(int l);
   void computeBorder(int l);
   std::vector<std::pair<int, int>> a11Chunks(const Level& L) const;

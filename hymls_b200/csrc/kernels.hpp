@@ -109,12 +109,15 @@ struct GemvArgs {
   double* out;
   const int* scatter;
   int mode;
+  int rowsPerWarp;         // 0: default (4 rows per warp = 32-row slabs); otherwise the slab is 8 * rowsPerWarp rows
 };
 void batchedGemv(const GemvArgs& a, int numItems, int npMax, cudaStream_t s, int64_t* launches);
 // nv = 2..4 vectors in one pass over the matrices (vector v of xin / xsub / out at v * ldIn / ldSub / ldOut; mode 0);
 // false: does not fit shared memory, the caller loops over the columns
 bool batchedGemvMulti(const GemvArgs& a, int numItems, int npMax, int nv, int64_t ldIn, int64_t ldSub, int64_t ldOut,
                       cudaStream_t s, int64_t* launches);
+// many small matrices (np <= 256): one warp per matrix of matList[0..numMats) (nullptr: all); false = too large
+bool smallGemv(const GemvArgs& a, const int* matList, int numMats, int npMax, cudaStream_t s, int64_t* launches);
 int gemvRowsPerItem();
 void spmv(const int64_t* ptr, const int* col, const double* val, const double* x, double* y, int64_t n, double alpha,
           const double* b, const int* bidx, double beta, cudaStream_t s, int64_t* launches);

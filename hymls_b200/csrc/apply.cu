@@ -399,96 +399,6 @@ void multiDot(const double* V, int64_t ldv, int k, const double* w, int64_t n, d
 }
 int multiDotBlocks() { return DOT_BLOCKS; }
 
-// ---------------------------------------------------------------------------------------------
-// Fused sweep of the second half of a classical Gram-Schmidt pass:
-//     w <- w - V h        and, in the same pass over the basis,   out = V' w_new   (NORM = false)
-//                                                             or   out = w_new' w_new   (NORM = true).
-// The projection coefficients of pass 2 only need the UPDATED w row by row, so the axpy of pass 1 and the dots of
-// pass 2 share one read of V from HBM (tiles of 32 rows: the second touch of a tile hits L1/L2), and the axpy of
-// pass 2 is fused with the norm.  CGS2 costs 3 sweeps over the basis instead of 4 (+ the norm sweep).
-// A CTA owns tiles of 32 rows; warp c handles the vectors i = c, c+8, ...; sums in a fixed order (deterministic).
-// ---------------------------------------------------------------------------------------------
-template <bool NORM>
-__global__ void __launch_bounds__(256)
-k_multi_axpy_dot(const double* __restrict__ V, int64_t ldv, int k, const double* __restrict__ h,
-                 double* __restrict__ w, int64_t n, double* __restrict__ partial) {
-  extern __shared__ double sm[];
-  double* sh = sm;          // k coefficients
-  double* sAcc = sm + k;    // k dot accumulators
-  __shared__ double sRed[8][32];
-  __shared__ double sW[32];
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  for (int i = tid; i < k; i += 256) {
-    sh[i] = h[i];
-    sAcc[i] = 0.0;
-  }
-  double normAcc = 0.0;
-  __syncthreads();
-  const int64_t ntiles = (n + 31) >> 5;
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int64_t r = (tile << 5) + lane;
-    const bool valid = r < n;
-    double s0 = 0.0, s1 = 0.0;
-    if (valid) {
-      int i = wid;
-      for (; i + 8 < k; i += 16) {
-        s0 += sh[i] * V[(int64_t)i * ldv + r];
-        s1 += sh[i + 8] * V[(int64_t)(i + 8) * ldv + r];
-      }
-      if (i < k) s0 += sh[i] * V[(int64_t)i * ldv + r];
-    }
-    sRed[wid][lane] = s0 + s1;
-    __syncthreads();
-    if (wid == 0) {
-      double t = 0.0;
-      if (valid) {
-        double sum = 0.0;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) sum += sRed[c][lane];
-        t = w[r] - sum;
-        w[r] = t;
-      }
-      sW[lane] = t;
-      if (NORM) normAcc += t * t;
-    }
-    __syncthreads();
-    if (!NORM) {
-      const double wr = sW[lane];
-      for (int i = wid; i < k; i += 8) {
-        double p = valid ? V[(int64_t)i * ldv + r] * wr : 0.0;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
-        if (lane == 0) sAcc[i] += p;  // only warp (i mod 8) touches entry i
-      }
-    }
-  }
-  __syncthreads();
-  if (NORM) {
-    if (wid == 0) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) normAcc += __shfl_xor_sync(0xffffffffu, normAcc, o);
-      if (lane == 0) partial[blockIdx.x] = normAcc;
-    }
-  } else {
-    for (int i = tid; i < k; i += 256) partial[(int64_t)i * gridDim.x + blockIdx.x] = sAcc[i];
-  }
-}
-
-// w -= V h ; then hOut = V' w (k values) or, with hOut == nullptr, nrmOut = w' w
-void multiAxpyDot(const double* V, int64_t ldv, int k, const double* h, double* w, int64_t n, double* partial,
-                  double* hOut, double* nrmOut, cudaStream_t s, int64_t* launches) {
-  if (k == 0) return;
-  const size_t smem = (size_t)2 * k * sizeof(double);
-  if (hOut) {
-    k_multi_axpy_dot<false><<<DOT_BLOCKS, 256, smem, s>>>(V, ldv, k, h, w, n, partial);
-    k_reduce_partials<<<k, 256, 0, s>>>(partial, DOT_BLOCKS, k, hOut, 0);
-  } else {
-    k_multi_axpy_dot<true><<<DOT_BLOCKS, 256, smem, s>>>(V, ldv, k, h, w, n, partial);
-    k_reduce_partials<<<1, 256, 0, s>>>(partial, DOT_BLOCKS, 1, nrmOut, 0);
-  }
-  *launches += 2;
-}
-
 // w += sign * sum_i h[i] V_i : coefficients in shared memory; a thread owns two adjacent rows (16-byte loads,
 // eight of them in flight) when the basis is 16-byte aligned, one row otherwise
 template <bool PAIR>

@@ -515,12 +515,13 @@ void Engine::solveDist(const double* b, double* x, int where, uint64_t seed, hym
         } else {
           A(vk, w);
         }
-        // two passes of classical Gram-Schmidt in three sweeps over the basis (apply.cu: k_multi_axpy_dot)
         multiDot(kV_.p, ld, k + 1, w, nOwn, kPartial_.p, dH1, 0, s, &launches_);
         comm_.allReduceSum(dH1, (size_t)(k + 1), s);
-        multiAxpyDot(kV_.p, ld, k + 1, dH1, w, nOwn, kPartial_.p, dH2, nullptr, s, &launches_);
+        multiAxpy(kV_.p, ld, k + 1, dH1, w, nOwn, -1.0, s, &launches_);
+        multiDot(kV_.p, ld, k + 1, w, nOwn, kPartial_.p, dH2, 0, s, &launches_);
         comm_.allReduceSum(dH2, (size_t)(k + 1), s);
-        multiAxpyDot(kV_.p, ld, k + 1, dH2, w, nOwn, kPartial_.p, nullptr, dNrm, s, &launches_);
+        multiAxpy(kV_.p, ld, k + 1, dH2, w, nOwn, -1.0, s, &launches_);
+        multiDot(w, ld, 1, w, nOwn, kPartial_.p, dNrm, 0, s, &launches_);
         comm_.allReduceSum(dNrm, 1, s);
         scaleByInvNorm(w, dNrm, w, nOwn, s, &launches_);
         lapS("CGS2 (4 sweeps, 3 allreduces)");

@@ -2035,12 +2035,13 @@ void Engine::solve(const double* b, double* x, int where, uint64_t seed, hymls_b
           localRowsOfA(vfull, w);
         }
         // two passes of classical Gram-Schmidt (Belos ICGS/DGKS), fused multi-dot + multi-axpy
-        // (in three sweeps over the basis: the axpy of a pass is fused with the dots / norm that follow it)
         multiDot(kV_.p, chunk, k + 1, w, nloc, kPartial_.p, dH1, 0, s, &launches_);
         comm_.allReduceSum(dH1, (size_t)(k + 1), s);
-        multiAxpyDot(kV_.p, chunk, k + 1, dH1, w, nloc, kPartial_.p, dH2, nullptr, s, &launches_);
+        multiAxpy(kV_.p, chunk, k + 1, dH1, w, nloc, -1.0, s, &launches_);
+        multiDot(kV_.p, chunk, k + 1, w, nloc, kPartial_.p, dH2, 0, s, &launches_);
         comm_.allReduceSum(dH2, (size_t)(k + 1), s);
-        multiAxpyDot(kV_.p, chunk, k + 1, dH2, w, nloc, kPartial_.p, nullptr, dNrm, s, &launches_);
+        multiAxpy(kV_.p, chunk, k + 1, dH2, w, nloc, -1.0, s, &launches_);
+        multiDot(w, chunk, 1, w, nloc, kPartial_.p, dNrm, 0, s, &launches_);
         comm_.allReduceSum(dNrm, 1, s);
         scaleByInvNorm(w, dNrm, w, nloc, s, &launches_);
         HY_CUDA(cudaMemcpyAsync(hbuf.data(), kH_.p, (2 * m + 3) * sizeof(double), cudaMemcpyDeviceToHost, s));

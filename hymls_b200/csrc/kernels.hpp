@@ -129,9 +129,7 @@ void householder(const int* uniqStart, int nuniq, const double* w, const double*
 void multiDot(const double* V, int64_t ldv, int k, const double* w, int64_t n, double* partial, double* h,
               int accumulate, cudaStream_t s, int64_t* launches, const int* widx = nullptr);  // widx: w[widx[r]]
 int multiDotBlocks();
-// fused half pass of CGS2:  w -= V h, then hOut = V' w  (or nrmOut = w' w when hOut == nullptr) in the same sweep
-void multiAxpyDot(const double* V, int64_t ldv, int k, const double* h, double* w, int64_t n, double* partial,
-                  double* hOut, double* nrmOut, cudaStream_t s, int64_t* launches);
+
 void multiAxpy(const double* V, int64_t ldv, int k, const double* h, double* w, int64_t n, double sign,
                cudaStream_t s, int64_t* launches);
 void axpby(double a, const double* x, double b, double* y, int64_t n, cudaStream_t s, int64_t* launches);

@@ -93,17 +93,17 @@ void batchedGemv(const GemvArgs& a, int numItems, int npMax, cudaStream_t s, int
 int gemvRowsPerItem() { return GEMV_ROWS; }
 
 // ---------------------------------------------------------------------------------------------
-// Small matrices (the separator blocks: 8 .. 192 rows, ~10^5 of them at 128^3): one WARP per matrix, grid-stride,
+// Small matrices (the separator blocks: 8 .. a few hundred rows, ~10^5 of them at 128^3): one WARP per matrix, grid-stride,
 // x in per-warp shared memory, min(32, np/2) lanes per row and several rows per pass for the tiny ones.
 // k_batched_gemv spends a 256-thread CTA per 32-row slab, which for these blocks is CTA-launch bound (ncu: 0.73 ms
 // for 0.83 GB = 14 % of the DRAM throughput, profiles/r02_ncu_gemv_traffic.json).  mode 0 only.
 // ---------------------------------------------------------------------------------------------
-static constexpr int SMALL_NP_MAX = 256;
+static constexpr int SMALL_NP_MAX = 2048;  // 8 warps x 2048 doubles = 128 KB of shared memory at most
 __global__ void __launch_bounds__(256)
-k_small_gemv(GemvArgs a, const int* __restrict__ matList, int numMats) {
-  __shared__ double sxAll[8 * SMALL_NP_MAX];
+k_small_gemv(GemvArgs a, const int* __restrict__ matList, int numMats, int npMax) {
+  extern __shared__ double sxAll[];  // 8 x npMax
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  double* sx = sxAll + wid * SMALL_NP_MAX;
+  double* sx = sxAll + wid * npMax;
   for (int idx = blockIdx.x * 8 + wid; idx < numMats; idx += gridDim.x * 8) {
     const int mat = matList ? matList[idx] : idx;
     const int n = a.n[mat], np = a.np[mat];
@@ -135,8 +135,14 @@ k_small_gemv(GemvArgs a, const int* __restrict__ matList, int numMats) {
 bool smallGemv(const GemvArgs& a, const int* matList, int numMats, int npMax, cudaStream_t s, int64_t* launches) {
   if (npMax > SMALL_NP_MAX) return false;
   if (numMats == 0) return true;
-  const int blocks = std::min((numMats + 7) / 8, 148 * 8);
-  k_small_gemv<<<blocks, 256, 0, s>>>(a, matList, numMats);
+  const size_t smem = (size_t)8 * npMax * sizeof(double);
+  static PerDeviceLimit limit;
+  if (limit.raise(smem))
+    HY_CUDA(cudaFuncSetAttribute(k_small_gemv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // resident CTAs per SM follow from the shared memory; a few waves of warps keep the load balanced
+  const int perSm = std::max(1, std::min(8, (int)((200 * 1024) / std::max<size_t>(smem, 1))));
+  const int blocks = std::min((numMats + 7) / 8, 148 * perSm);
+  k_small_gemv<<<blocks, 256, smem, s>>>(a, matList, numMats, npMax);
   ++*launches;
   return true;
 }

@@ -334,12 +334,22 @@ void Engine::initialize() {
     // parameters of the next level (SetNextLevelParameters; sx *= cx)
     part.setNextLevelParameters(levelParams);
     L.dist.ready = false;
+    auto tu0 = std::chrono::steady_clock::now();
     if (L.sharded && l == 0 && !L.exact) buildDistPlan(L);  // host lists always, device copies with a device
+    auto tu1 = std::chrono::steady_clock::now();
     if (deviceOk_) uploadLevel(L);
+    if (getenv("HYMLS_B200_VERBOSE"))
+      fprintf(stderr, "[hymls_b200] level %d initialize: distributed plan %.3f s, device index arrays %.3f s\n", l,
+              std::chrono::duration<double>(tu1 - tu0).count(),
+              std::chrono::duration<double>(std::chrono::steady_clock::now() - tu1).count());
   }
   if (deviceOk_) {
+    auto tr0 = std::chrono::steady_clock::now();
     reserveComputeScratch();
     HY_CUDA(cudaStreamSynchronize(stream_));
+    if (getenv("HYMLS_B200_VERBOSE"))
+      fprintf(stderr, "[hymls_b200] initialize: scratch reservation %.3f s\n",
+              std::chrono::duration<double>(std::chrono::steady_clock::now() - tr0).count());
   }
   initialized_ = true;
   computed_ = false;

@@ -201,7 +201,10 @@ void BatchedInverse::setup(const std::vector<int>& n_, const std::vector<int>& n
   for (int m = 0; m < count; ++m) {
     npMax = std::max(npMax, np_[m]);
     if (applyMask && !(*applyMask)[m]) continue;
-    if (n_[m] > 0) ml.push_back(m);
+    if (smallSplit > 0 && np_[m] <= smallSplit) {  // tiny matrix: handled by the warp-per-matrix kernel
+      if (n_[m] > 0) ml.push_back(m);
+      continue;
+    }
     for (int r0 = 0; r0 < n_[m]; r0 += rows) {
       im.push_back(m);
       ir.push_back(r0);
@@ -676,8 +679,10 @@ void Engine::uploadLevel(Level& L) {
     // subdomain it owns; the block results are summed over the ranks in ApplyInverse
     std::vector<char> mask(S.nblk, 0);
     for (int b = 0; b < S.nblk; ++b) mask[b] = isOwn[S.blkOwnerSd[b]];
+    L.blk.smallSplit = 64;
     L.blk.setup(S.blkN, S.blkNp, S.blkOff, blkVecOff, s, &mask);
   } else {
+    L.blk.smallSplit = 64;
     L.blk.setup(S.blkN, S.blkNp, S.blkOff, blkVecOff, s);
   }
   L.blkRows.upload(S.blkRows, s);
@@ -1453,8 +1458,10 @@ void Engine::blockSolves(Level& L, const double* Z, double* Y) {
   b.out = Y;
   b.scatter = L.blkRows.p;
   b.mode = 0;
-  if (!smallGemv(b, L.blk.matList.p, L.blk.numMats, L.blk.npMax, stream_, &launches_))
-    batchedGemv(b, L.blk.numItems, L.blk.npMax, stream_, &launches_);
+  // blocks of up to 64 rows (the vast majority: edges, pressure tubes, ragged faces) go one per warp; the larger
+  // ones keep the CTA-per-slab kernel (a single warp per 500 x 500 block would serialise it)
+  smallGemv(b, L.blk.matList.p, L.blk.numMats, std::min(L.blk.npMax, L.blk.smallSplit), stream_, &launches_);
+  batchedGemv(b, L.blk.numItems, L.blk.npMax, stream_, &launches_);
 }
 
 void Engine::applyLevel(int l, const double* B, double* X, const double* T) {

@@ -18,7 +18,8 @@ struct BatchedInverse {  // a set of dense inverses + the GEMV work list over th
   std::vector<int> hN, hNp;
   std::vector<int64_t> hMatOff, hVecOff;
   int count = 0, numItems = 0, npMax = 0;
-  DevBuf<int> matList;  // the matrices GEMV work exists for (all, or the flagged ones of applyMask)
+  int smallSplit = 0;   // > 0: matrices with np <= smallSplit get no slab items but are listed in matList
+  DevBuf<int> matList;  // (flagged) matrices of at most smallSplit rows, for the warp-per-matrix kernel
   int numMats = 0;
   // second work list over the leading `leadRows[m]` rows of every matrix (first solve of ApplyInverse)
   DevBuf<int> rowLimit, itemMatLead, itemRow0Lead;

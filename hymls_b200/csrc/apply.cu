@@ -132,6 +132,55 @@ k_small_gemv(GemvArgs a, const int* __restrict__ matList, int numMats, int npMax
     __syncwarp();
   }
 }
+// Medium matrices (64 < np <= 512, e.g. the face blocks: a few hundred rows): one CTA per MATRIX, grid-stride; the 8
+// warps share x in shared memory and take the rows round-robin.  The slab kernel would spend one CTA (launch, x staging,
+// barrier) per 32 rows = per ~70 KB of such a block.
+__global__ void __launch_bounds__(256)
+k_cta_gemv(GemvArgs a, const int* __restrict__ matList, int numMats) {
+  extern __shared__ double sx[];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  for (int idx = blockIdx.x; idx < numMats; idx += gridDim.x) {
+    const int mat = matList[idx];
+    const int n = a.n[mat], np = a.np[mat];
+    const int64_t v0 = a.vecOff[mat];
+    const double* __restrict__ A = a.A + a.matOff[mat];
+    for (int q = tid; q < np; q += 256) sx[q] = q < n ? (a.gather ? a.xin[a.gather[v0 + q]] : a.xin[v0 + q]) : 0.0;
+    __syncthreads();
+    const double2* __restrict__ x2 = reinterpret_cast<const double2*>(sx);
+    const int n2 = np >> 1;
+    for (int r = wid; r < n; r += 8) {
+      const double2* __restrict__ row = reinterpret_cast<const double2*>(A + (int64_t)r * np);
+      double acc0 = 0.0, acc1 = 0.0;
+      int q = lane;
+      for (; q + 32 < n2; q += 64) {
+        const double2 m0 = __ldg(row + q), m1 = __ldg(row + q + 32);
+        const double2 b0 = x2[q], b1 = x2[q + 32];
+        acc0 += m0.x * b0.x + m0.y * b0.y;
+        acc1 += m1.x * b1.x + m1.y * b1.y;
+      }
+      if (q < n2) {
+        const double2 m0 = __ldg(row + q);
+        const double2 b0 = x2[q];
+        acc0 += m0.x * b0.x + m0.y * b0.y;
+      }
+      double acc = acc0 + acc1;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) {
+        const int64_t o = (a.outOff ? a.outOff[mat] : v0) + r;
+        a.out[a.scatter ? a.scatter[o] : o] = acc;
+      }
+    }
+    __syncthreads();
+  }
+}
+void ctaGemv(const GemvArgs& a, const int* matList, int numMats, int npMax, cudaStream_t s, int64_t* launches) {
+  if (numMats == 0) return;
+  const size_t smem = (size_t)npMax * sizeof(double);
+  k_cta_gemv<<<std::min(numMats, 148 * 8), 256, smem, s>>>(a, matList, numMats);
+  ++*launches;
+}
+
 bool smallGemv(const GemvArgs& a, const int* matList, int numMats, int npMax, cudaStream_t s, int64_t* launches) {
   if (npMax > SMALL_NP_MAX) return false;
   if (numMats == 0) return true;

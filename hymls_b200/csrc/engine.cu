@@ -196,13 +196,19 @@ void BatchedInverse::setup(const std::vector<int>& n_, const std::vector<int>& n
   hVecOff = vecOff_;
   count = (int)n_.size();
   npMax = 0;
-  std::vector<int> im, ir, ml;
+  std::vector<int> im, ir, ml, mid;
+  midNpMax = 0;
   const int rows = rowsPerWarp > 0 ? 8 * rowsPerWarp : gemvRowsPerItem();
   for (int m = 0; m < count; ++m) {
     npMax = std::max(npMax, np_[m]);
     if (applyMask && !(*applyMask)[m]) continue;
     if (smallSplit > 0 && np_[m] <= smallSplit) {  // tiny matrix: handled by the warp-per-matrix kernel
       if (n_[m] > 0) ml.push_back(m);
+      continue;
+    }
+    if (midSplit > 0 && np_[m] <= midSplit) {      // medium matrix: one CTA per matrix
+      mid.push_back(m);
+      midNpMax = std::max(midNpMax, np_[m]);
       continue;
     }
     for (int r0 = 0; r0 < n_[m]; r0 += rows) {
@@ -213,6 +219,8 @@ void BatchedInverse::setup(const std::vector<int>& n_, const std::vector<int>& n
   numItems = (int)im.size();
   numMats = (int)ml.size();
   matList.upload(ml, s);
+  numMid = (int)mid.size();
+  midList.upload(mid, s);
   numItemsLead = 0;
   if (leadRows) {
     std::vector<int> lm, lr;
@@ -680,9 +688,11 @@ void Engine::uploadLevel(Level& L) {
     std::vector<char> mask(S.nblk, 0);
     for (int b = 0; b < S.nblk; ++b) mask[b] = isOwn[S.blkOwnerSd[b]];
     L.blk.smallSplit = 64;
+    L.blk.midSplit = 512;
     L.blk.setup(S.blkN, S.blkNp, S.blkOff, blkVecOff, s, &mask);
   } else {
     L.blk.smallSplit = 64;
+    L.blk.midSplit = 512;
     L.blk.setup(S.blkN, S.blkNp, S.blkOff, blkVecOff, s);
   }
   L.blkRows.upload(S.blkRows, s);
@@ -1458,9 +1468,10 @@ void Engine::blockSolves(Level& L, const double* Z, double* Y) {
   b.out = Y;
   b.scatter = L.blkRows.p;
   b.mode = 0;
-  // blocks of up to 64 rows (the vast majority: edges, pressure tubes, ragged faces) go one per warp; the larger
-  // ones keep the CTA-per-slab kernel (a single warp per 500 x 500 block would serialise it)
+  // blocks of up to 64 rows (edges, pressure tubes, ragged faces) go one per warp, blocks of up to 512 rows (faces)
+  // one per CTA; only larger ones (coarser levels) use the CTA-per-32-row-slab kernel
   smallGemv(b, L.blk.matList.p, L.blk.numMats, std::min(L.blk.npMax, L.blk.smallSplit), stream_, &launches_);
+  ctaGemv(b, L.blk.midList.p, L.blk.numMid, L.blk.midNpMax, stream_, &launches_);
   batchedGemv(b, L.blk.numItems, L.blk.npMax, stream_, &launches_);
 }
 

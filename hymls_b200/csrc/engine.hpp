@@ -21,6 +21,9 @@ struct BatchedInverse {  // a set of dense inverses + the GEMV work list over th
   int smallSplit = 0;   // > 0: matrices with np <= smallSplit get no slab items but are listed in matList
   DevBuf<int> matList;  // (flagged) matrices of at most smallSplit rows, for the warp-per-matrix kernel
   int numMats = 0;
+  int midSplit = 0;     // > 0: matrices with smallSplit < np <= midSplit are listed in midList (CTA-per-matrix kernel)
+  DevBuf<int> midList;
+  int numMid = 0, midNpMax = 0;
   // second work list over the leading `leadRows[m]` rows of every matrix (first solve of ApplyInverse)
   DevBuf<int> rowLimit, itemMatLead, itemRow0Lead;
   int numItemsLead = 0;

@@ -117,6 +117,8 @@ void batchedGemv(const GemvArgs& a, int numItems, int npMax, cudaStream_t s, int
 bool batchedGemvMulti(const GemvArgs& a, int numItems, int npMax, int nv, int64_t ldIn, int64_t ldSub, int64_t ldOut,
                       cudaStream_t s, int64_t* launches);
 // many small matrices (np <= 256): one warp per matrix of matList[0..numMats) (nullptr: all); false = too large
+// medium matrices (np <= 512 here): one CTA per matrix of matList
+void ctaGemv(const GemvArgs& a, const int* matList, int numMats, int npMax, cudaStream_t s, int64_t* launches);
 bool smallGemv(const GemvArgs& a, const int* matList, int numMats, int npMax, cudaStream_t s, int64_t* launches);
 int gemvRowsPerItem();
 void spmv(const int64_t* ptr, const int* col, const double* val, const double* x, double* y, int64_t n, double alpha,

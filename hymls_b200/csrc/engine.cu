@@ -13,6 +13,7 @@
 namespace hymls {
 
 thread_local double g_devBytes = 0;
+thread_local DeviceArena* g_arena = nullptr;
 
 static const double SMALL_ENTRY = 1e-14;  // HYMLS_SMALL_ENTRY
 
@@ -376,6 +377,16 @@ static std::vector<int> toInt(const std::vector<T>& v) {
 void Engine::uploadLevel(Level& L) {
   LevelSym& S = L.sym;
   cudaStream_t s = stream_;
+  ArenaScope arenaScope(&L.arena);
+  const bool lapOn = getenv("HYMLS_B200_VERBOSE_SYM") != nullptr;
+  auto lapT = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!lapOn) return;
+    cudaStreamSynchronize(s);
+    auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[hymls_b200 upload] %-40s %.3f s\n", what, std::chrono::duration<double>(t1 - lapT).count());
+    lapT = t1;
+  };
   if (S.level > 0) {
     L.rowptr.upload(S.rowptr, s);
     L.colidx.upload(S.colidx, s);
@@ -399,28 +410,18 @@ void Engine::uploadLevel(Level& L) {
     a11OffG[sd] = L.ownOff[k];
     L.ownOff[k + 1] = L.ownOff[k] + (int64_t)onp[k] * onp[k];
   }
+  lap("row lists");
   L.a11.setup(on, onp, L.ownOff, ovec, s, nullptr, &onb);
+  lap("A11 batched-inverse setup");
   L.sdNG.upload(S.sdN, s);
   L.sdNpG.upload(S.sdNp, s);
   L.a11OffG.upload(a11OffG, s);
-  {
-    // dense-fill scatter list restricted to the owned subdomains, destinations in compact numbering
-    std::vector<int64_t> src, dst;
-    L.a11ListPtr.assign(nown + 1, 0);
-    for (int k = 0; k < nown; ++k) {
-      const int sd = L.ownSd[k];
-      const int64_t e0 = std::lower_bound(S.a11Dst.begin(), S.a11Dst.end(), S.a11Off[sd]) - S.a11Dst.begin();
-      const int64_t e1 = std::lower_bound(S.a11Dst.begin(), S.a11Dst.end(), S.a11Off[sd + 1]) - S.a11Dst.begin();
-      for (int64_t e = e0; e < e1; ++e) {
-        src.push_back(S.a11Src[e]);
-        dst.push_back(S.a11Dst[e] - S.a11Off[sd] + L.ownOff[k]);
-      }
-      L.a11ListPtr[k + 1] = (int64_t)src.size();
-    }
-    L.a11Src.upload(src, s);
-    L.a11Dst.upload(dst, s);
-    L.a11ListPtrDev.upload(L.a11ListPtr, s);
-  }
+  // dense-fill scatter list of the owned subdomains (destinations in compact numbering), built on the device
+  L.rowPos.alloc(S.n);
+  buildRowPos(L.intRow.p, S.nI, L.sepRow.p, S.nS, L.rowPos.p, s, &launches_);
+  buildA11List(L.rowptr.p, L.colidx.p, L.intRow.p, L.rowPos.p, S.nI, L.a11.n.p, L.a11.np.p, L.a11.matOff.p,
+               L.a11.vecOff.p, nown, L.a11Src, L.a11Dst, L.a11ListPtrDev, L.a11ListPtr, s, &launches_);
+  lap("A11 scatter list");
   // A12 / A21 / A22 (A21 restricted to the columns of owned interiors when sharded: partial products
   // are summed over the ranks)
   L.p12.upload(S.A12.ptr, s);
@@ -474,6 +475,7 @@ void Engine::uploadLevel(Level& L) {
     L.c22.upload(S.A22.col, s);
     L.src22.upload(S.A22.src, s);
   }
+  lap("A12 / A21 / A22");
   // Schur assembly data
   const int64_t totalRows = S.sdRowPtr[S.nsd];
   std::vector<int> rowSd(totalRows), rowInst(totalRows), rowLinkPos(totalRows);
@@ -509,6 +511,7 @@ void Engine::uploadLevel(Level& L) {
   L.dLen = maxN;
   L.rowSmem = (size_t)(maxN + maxM) * sizeof(double);
   L.blkSmem = maxBlkSmem;
+  lap("row -> instance lists");
   // chunks of subdomains whose workspace (C, SV: m*G each; S_LL: sum lsz^2) fits the budget
   const int64_t budget = (int64_t)96 << 20;  // doubles per array (768 MB)
   std::vector<int64_t> wsOffC(S.nsd, 0), wsOffD(S.nsd, 0), wsOffA(S.nsd, 0), wsOffS(S.nsd, 0), lnkOff(lnkSd.size(), 0);
@@ -596,6 +599,7 @@ void Engine::uploadLevel(Level& L) {
     L.ownRowList.upload(rows, s);
     L.ownLinkList.upload(links, s);
   }
+  lap("chunks");
   {
     // Colouring of the subdomains for the pass-2 assembly: greedy, in subdomain order, on the conflict graph
     // "share a separator group".  One colour is one launch, so contributions to an entry arrive in colour order.
@@ -640,6 +644,7 @@ void Engine::uploadLevel(Level& L) {
     L.colLk.upload(colLk, s);
     L.colRow.upload(colRow, s);
   }
+  lap("colouring");
   L.rowSd.upload(rowSd, s);
   L.rowInst.upload(rowInst, s);
   L.rowLinkPos.upload(rowLinkPos, s);
@@ -680,6 +685,7 @@ void Engine::uploadLevel(Level& L) {
   L.usign.upload(S.usign, s);
   L.redPtr.upload(S.redPtr, s);
   L.redCol.upload(S.redCol, s);
+  lap("Schur index uploads");
   // separator blocks
   std::vector<int64_t> blkVecOff(S.blkRowPtr.begin(), S.blkRowPtr.end() - 1);
   if (L.sharded && !L.repSep) {
@@ -696,6 +702,7 @@ void Engine::uploadLevel(Level& L) {
     L.blk.setup(S.blkN, S.blkNp, S.blkOff, blkVecOff, s);
   }
   L.blkRows.upload(S.blkRows, s);
+  lap("separator-block setup");
   // work vectors
   L.x1.alloc(S.nI);
   L.y1.alloc(S.nI);
@@ -709,6 +716,7 @@ void Engine::uploadLevel(Level& L) {
   if (L.x1.n) HY_CUDA(cudaMemsetAsync(L.x1.p, 0, L.x1.bytes(), s));
   if (L.Y.n) HY_CUDA(cudaMemsetAsync(L.Y.p, 0, L.Y.bytes(), s));
   HY_CUDA(cudaStreamSynchronize(s));
+  lap("work vectors");
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -938,7 +946,7 @@ void Engine::computeLevel(int l) {
       if (refine_) work2_.alloc((size_t)used);
       // Newton-Schulz step: with a sparse original (level 0: ~8 entries per row) the residual I - A X comes from
       // the dense-fill list directly (one GEMM per inverse instead of two); denser levels use two GEMMs
-      const double avgNnz = S.nI ? (double)S.a11Src.size() / (double)S.nI : 0.0;
+      const double avgNnz = S.nI ? (double)L.a11ListPtr.back() / (double)S.nI : 0.0;
       const bool sparseResidual = refine_ && avgNnz * 8.0 < (double)L.a11.npMax;
       invertRange(L.a11, k0, k1, work_.p, piv_, perm_, relOff, info_.p, s, &launches_,
                   (refine_ && !sparseResidual) ? std::function<void()>(fillChunk) : nullptr,

@@ -61,6 +61,7 @@ struct DistPlan {
 };
 
 struct Level {
+  DeviceArena arena;  // owns the index arrays uploaded by Initialize (declared first: destroyed last)
   LevelSym sym;
   DistPlan dist;
   bool exact = false;  // Number of Levels == 0: dense Schur complement instead of transform + drop
@@ -70,6 +71,7 @@ struct Level {
   DevBuf<double> val;
   // orderings
   DevBuf<int> intRow, sepRow;
+  DevBuf<int> rowPos;  // per row: interior position (>= 0) or -(separator position) - 1
   // A11: inverses of the subdomains this rank owns (all of them on one GPU), compact storage
   BatchedInverse a11;
   std::vector<int> ownSd;           // owned subdomains, ascending

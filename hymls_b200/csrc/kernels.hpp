@@ -3,6 +3,9 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <vector>
+
+#include "device.cuh"
 
 namespace hymls {
 
@@ -123,6 +126,13 @@ bool smallGemv(const GemvArgs& a, const int* matList, int numMats, int npMax, cu
 int gemvRowsPerItem();
 void spmv(const int64_t* ptr, const int* col, const double* val, const double* x, double* y, int64_t n, double alpha,
           const double* b, const int* bidx, double beta, cudaStream_t s, int64_t* launches);
+// indexing.cu: index arrays built on the device from the pattern
+void buildRowPos(const int* intRow, int64_t nI, const int* sepRow, int64_t nS, int* rowPos, cudaStream_t s,
+                 int64_t* launches);
+void buildA11List(const int64_t* rowptr, const int* colidx, const int* intRow, const int* rowPos, int64_t nI,
+                  const int* n, const int* np, const int64_t* matOff, const int64_t* vecOff, int count,
+                  DevBuf<int64_t>& src, DevBuf<int64_t>& dst, DevBuf<int64_t>& listPtrDev,
+                  std::vector<int64_t>& listPtr, cudaStream_t s, int64_t* launches);
 void gatherValues(const double* src, const int64_t* idx, double* dst, int64_t n, cudaStream_t s, int64_t* launches);
 void scatterValues(const double* src, const int64_t* srcIdx, const int64_t* dstIdx, int64_t dstBase, double* dst,
                    int64_t n, cudaStream_t s, int64_t* launches);

@@ -3,6 +3,9 @@
 #include "hostpar.hpp"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cmath>
 #include <unordered_map>
 
@@ -466,10 +469,14 @@ void buildHierarchicalMap(const CartesianPartitioner& part, const std::vector<ch
   std::vector<std::vector<gidx>> allInterior(nsd);
   std::vector<std::vector<SepGroup>> allGroups(nsd);
   std::vector<std::string> errors(64);
+  const auto tg0 = std::chrono::steady_clock::now();
+  std::vector<double> tGet(64, 0.0);
   parallelFor(nsd, [&](int64_t s0, int64_t s1, int t) {
     try {
       for (int64_t sd = s0; sd < s1; ++sd) {
+        auto q0 = std::chrono::steady_clock::now();
         part.getGroups((int)sd, allInterior[sd], allGroups[sd]);
+        tGet[t & 63] += std::chrono::duration<double>(std::chrono::steady_clock::now() - q0).count();
         if (filter) {  // coarser levels keep ~1 % of the grid nodes: drop the others here, in parallel
           auto gone = [&](gidx g) { return !present[g]; };
           std::vector<gidx>& in = allInterior[sd];
@@ -486,6 +493,10 @@ void buildHierarchicalMap(const CartesianPartitioner& part, const std::vector<ch
   }, 16);
   for (const std::string& e : errors)
     if (!e.empty()) throw Error(HYMLS_B200_ERR_ARG, e);
+  if (getenv("HYMLS_B200_VERBOSE_SYM")) { double m = 0; for (double v : tGet) m = std::max(m, v); fprintf(stderr, "TMP getGroups only max thread %.3f\n", m); }
+  if (getenv("HYMLS_B200_VERBOSE_SYM"))
+    fprintf(stderr, "[hymls_b200 sym] getGroups (parallel)                    %.3f s\n",
+            std::chrono::duration<double>(std::chrono::steady_clock::now() - tg0).count());
   for (int sd = 0; sd < nsd; ++sd) {
     std::vector<gidx>& interior = allInterior[sd];
     std::vector<SepGroup>& groups = allGroups[sd];
@@ -682,6 +693,9 @@ void SkewCartesianPartitioner::classifyTemplate() {
   std::vector<int64_t> fill(clsVarPtr_.begin(), clsVarPtr_.end() - 1);
   tmpl_.resize(scan.size());
   for (const TemplateNode& t : scan) tmpl_[fill[(size_t)t.cls * dof_ + t.var]++] = t;
+  innerScan_.clear();  // class 0 once more, all variables in one scan order (z, y, x, variable)
+  for (const TemplateNode& t : scan)
+    if (t.cls == 0) innerScan_.push_back(t);
 }
 
 void SkewCartesianPartitioner::partition() {
@@ -730,45 +744,40 @@ void SkewCartesianPartitioner::getGroups(int localSd, std::vector<gidx>& interio
            (vt == VT_W && nz_ > 1 && z == nz_ - 1 && !(perio_ & Z_PERIO));
   };
   // --- class 0: interior, in scan order over all variables
-  struct Placed { int x, y, z, var; };
-  std::vector<Placed> inner;
-  {
-    // the buckets of class 0 are per variable; merge them back into scan order (z, y, x, variable)
-    std::vector<const TemplateNode*> nodes;
-    for (int64_t q = clsVarPtr_[0]; q < clsVarPtr_[dof_]; ++q) nodes.push_back(&tmpl_[q]);
-    std::sort(nodes.begin(), nodes.end(), [](const TemplateNode* a, const TemplateNode* c) {
-      if (a->dz != c->dz) return a->dz < c->dz;
-      if (a->dy != c->dy) return a->dy < c->dy;
-      if (a->dx != c->dx) return a->dx < c->dx;
-      return a->var < c->var;
-    });
-    for (const TemplateNode* t : nodes) {
-      int x, y, z;
-      if (place(*t, x, y, z)) inner.push_back({x, y, z, t->var});
-    }
+  struct Placed { gidx gid; bool pressure; };
+  static thread_local std::vector<Placed> inner;
+  inner.clear();
+  for (const TemplateNode& t : innerScan_) {
+    int x, y, z;
+    if (place(t, x, y, z)) inner.push_back({gidOf(x, y, z, t.var), variableType_[t.var] == VT_PRESSURE});
   }
   std::vector<gidx> retained;
   {
     // The first pressure nodes of the interior are retained.  Reference quirk kept on purpose: it erases from
     // the list it iterates over, so the element right after a retained node is not examined.
-    std::vector<char> taken(inner.size(), 0);
-    for (size_t q = 0; q < inner.size() && (int)retained.size() < retainPressures_; ++q)
-      if (variableType_[inner[q].var] == VT_PRESSURE) {
-        taken[q] = 1;
-        retained.push_back(gidOf(inner[q].x, inner[q].y, inner[q].z, inner[q].var));
-        ++q;
+    size_t q = 0;
+    interior.reserve(inner.size() + 64);
+    for (; q < inner.size() && (int)retained.size() < retainPressures_; ++q) {
+      if (inner[q].pressure) {
+        retained.push_back(inner[q].gid);
+        if (++q < inner.size()) interior.push_back(inner[q].gid);
+      } else {
+        interior.push_back(inner[q].gid);
       }
-    for (size_t q = 0; q < inner.size(); ++q)
-      if (!taken[q]) interior.push_back(gidOf(inner[q].x, inner[q].y, inner[q].z, inner[q].var));
+    }
+    for (; q < inner.size(); ++q) interior.push_back(inner[q].gid);
   }
   // --- separator classes.  Far-wall velocities take part in the splitting (they count towards the length of a
   // part and keep its type number alive) and are removed from the emitted groups afterwards, like the reference.
   int type = 1;
   struct Part { int owner; std::vector<gidx> nodes; std::vector<char> wall; };
-  std::vector<Part> parts;
+  static thread_local std::vector<Part> parts;  // pool: the node vectors keep their capacity between calls
+  size_t nparts = 0;
   auto emitParts = [&]() {
-    std::stable_sort(parts.begin(), parts.end(), [](const Part& a, const Part& c) { return a.owner < c.owner; });
-    for (Part& p : parts) {
+    if (nparts > 1)
+      std::stable_sort(parts.begin(), parts.begin() + nparts, [](const Part& a, const Part& c) { return a.owner < c.owner; });
+    for (size_t pi = 0; pi < nparts; ++pi) {
+      Part& p = parts[pi];
       const int len = (int)p.nodes.size();
       int piece = len, groupType = linkVelocities_ ? type : -1;
       if (rx_ > 1) {
@@ -779,11 +788,21 @@ void SkewCartesianPartitioner::getGroups(int localSd, std::vector<gidx>& interio
       for (int lo = 0; lo < len; lo += piece) {
         out.emplace_back();  // (may stay empty: the caller drops empty groups)
         out.back().type = groupType;
-        for (int q = lo; q < std::min(len, lo + piece); ++q)
+        const int hi = std::min(len, lo + piece);
+        out.back().nodes.reserve(hi - lo);
+        for (int q = lo; q < hi; ++q)
           if (!p.wall[q]) out.back().nodes.push_back(p.nodes[q]);
       }
     }
-    parts.clear();
+    nparts = 0;
+  };
+  auto newPart = [&](int owner) -> Part& {
+    if (nparts == parts.size()) parts.emplace_back();
+    Part& p = parts[nparts++];
+    p.owner = owner;
+    p.nodes.clear();
+    p.wall.clear();
+    return p;
   };
   for (int cls = 1; cls < ncls_; ++cls) {
     ++type;
@@ -796,8 +815,8 @@ void SkewCartesianPartitioner::getGroups(int localSd, std::vector<gidx>& interio
         const bool wall = onFarWall(x, y, z, vt);
         if (wall && owner == me) interior.push_back(gidOf(x, y, z, v));
         size_t k = 0;
-        while (k < parts.size() && parts[k].owner != owner) ++k;
-        if (k == parts.size()) parts.push_back({owner, {}, {}});
+        while (k < nparts && parts[k].owner != owner) ++k;
+        if (k == nparts) newPart(owner);
         parts[k].nodes.push_back(gidOf(x, y, z, v));
         parts[k].wall.push_back(wall ? 1 : 0);
       }
@@ -806,7 +825,9 @@ void SkewCartesianPartitioner::getGroups(int localSd, std::vector<gidx>& interio
   }
   for (gidx g : retained) {  // retained pressures: one more class each, through the same splitting rules
     ++type;
-    parts.push_back({me, std::vector<gidx>(1, g), std::vector<char>(1, 0)});
+    Part& p = newPart(me);
+    p.nodes.push_back(g);
+    p.wall.push_back(0);
     emitParts();
   }
   std::sort(interior.begin(), interior.end());

@@ -94,6 +94,7 @@ class SkewCartesianPartitioner : public CartesianPartitioner {
   void classifyTemplate();
   std::vector<TemplateNode> tmpl_;      // sorted by (cls, var), scan order (z, y, x) inside
   std::vector<int64_t> clsVarPtr_;      // (ncls * dof + 1): ranges of tmpl_ per (class, variable)
+  std::vector<TemplateNode> innerScan_; // class 0 in scan order (z, y, x, variable)
   int ncls_ = 0;
 };
 

@@ -166,21 +166,14 @@ void buildLevelSym(LevelSym& L, const CartesianPartitioner& part, const std::vec
     L.A21.src.resize(L.A21.ptr[L.nS]);
     L.A22.col.resize(L.A22.ptr[L.nS]);
     L.A22.src.resize(L.A22.ptr[L.nS]);
-    L.a11Src.resize(a11Ptr[L.nI]);
-    L.a11Dst.resize(a11Ptr[L.nI]);
+    L.a11Nnz = a11Ptr[L.nI];  // (the dense-fill scatter list itself is built on the device, indexing.cu)
     parallelFor(L.nI, [&](int64_t p0, int64_t p1, int) {
       for (int64_t p = p0; p < p1; ++p) {
-        const int r = L.intRow[p], sd = sdOfInt[p];
-        int64_t f11 = a11Ptr[p], f12 = L.A12.ptr[p];
+        const int r = L.intRow[p];
+        int64_t f12 = L.A12.ptr[p];
         for (int64_t e = L.rowptr[r]; e < L.rowptr[r + 1]; ++e) {
           const int cp = L.rowPos[L.colidx[e]];
-          if (cp >= 0) {
-            if (sdOfInt[cp] == sd) {
-              const int64_t li = p - H.intPtr[sd], lj = cp - H.intPtr[sd];
-              L.a11Src[f11] = e;
-              L.a11Dst[f11++] = L.a11Off[sd] + li * L.sdNp[sd] + lj;
-            }
-          } else {
+          if (cp < 0) {
             L.A12.col[f12] = -cp - 1;
             L.A12.src[f12++] = e;
           }

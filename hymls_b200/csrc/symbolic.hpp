@@ -36,7 +36,7 @@ struct LevelSym {
   std::vector<int> sdNb;        // leading interior nodes of sd that separator rows couple to (columns of A21)
   double sumNNb = 0;            // sum n_sd * nb_sd
   std::vector<int64_t> a11Off;  // nsd+1, in doubles
-  std::vector<int64_t> a11Src, a11Dst;
+  int64_t a11Nnz = 0;  // nonzeros inside the subdomain matrices
   int64_t ignoredInteriorCouplings = 0;  // entries between interiors of different subdomains
 
   CsrPattern A12, A21, A22;  // indices are positions in the interior / separator orderings

@@ -24,11 +24,11 @@ namespace hymls {
 // sparsity pattern; cudaMalloc costs 3-10 ms a call on a 180 GB device (measured: 7 small allocations = 68 ms), so
 // Initialize takes them from 256 MB slabs instead.  Memory goes back when the level is destroyed.
 struct DeviceArena {
-  static constexpr size_t SLAB = (size_t)256 << 20, DIRECT = (size_t)64 << 20;
+  size_t SLAB, DIRECT;  // slab size; requests of at least DIRECT bytes get an allocation of their own
   std::vector<void*> slabs;
   char* cur = nullptr;
   size_t left = 0;
-  DeviceArena() {}
+  explicit DeviceArena(size_t slab = (size_t)256 << 20, size_t direct = (size_t)64 << 20) : SLAB(slab), DIRECT(direct) {}
   DeviceArena(const DeviceArena&) = delete;
   DeviceArena& operator=(const DeviceArena&) = delete;
   ~DeviceArena() {
@@ -43,15 +43,21 @@ struct DeviceArena {
       return p;
     }
     if (bytes > left) {
-      HY_CUDA(cudaMalloc(&p, SLAB));
+      const size_t slab = bytes > SLAB ? bytes : SLAB;
+      HY_CUDA(cudaMalloc(&p, slab));
       slabs.push_back(p);
       cur = (char*)p;
-      left = SLAB;
+      left = slab;
     }
     p = cur;
     cur += bytes;
     left -= bytes;
     return p;
+  }
+  // bump-allocate from memory somebody else owns first (e.g. the Compute workspace, idle during Initialize)
+  void adopt(void* p, size_t bytes) {
+    cur = (char*)p;
+    left = bytes;
   }
   // a buffer that is re-allocated (grown) returns its memory: direct allocations are freed, slab pieces stay
   void giveBack(void* p, size_t bytes) {

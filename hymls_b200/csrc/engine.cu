@@ -277,7 +277,6 @@ void Engine::initialize() {
     Level& L = *levels_[l];
     L.sym = LevelSym();  // a re-Initialize starts from scratch
     coarseBT_.planned = coarseBT_.active = false;
-    L.t12Ptr.release();
     LevelSym& S = L.sym;
     S.level = l;
     L.exact = (maxLevel_ == 0);
@@ -293,8 +292,9 @@ void Engine::initialize() {
       S.n = n_;
       S.rowGid.resize(n_);
       for (int64_t i = 0; i < n_; ++i) S.rowGid[i] = i;
-      S.rowptr = hRowptr_;
-      S.colidx = hColidx_;
+      S.rowptr = hRowptr_.data();
+      S.colidx = hColidx_.data();
+      S.nnz = (int64_t)hColidx_.size();
       S.testVector = hTestVector_;
       gid2row.assign(n_, -1);
     } else {
@@ -302,8 +302,9 @@ void Engine::initialize() {
       S.n = P.nuniq;
       S.rowGid.resize(S.n);
       for (int u = 0; u < P.nuniq; ++u) S.rowGid[u] = P.H.sepGid[P.H.uniqPtr[u]];
-      S.rowptr = P.redPtr;
-      S.colidx = P.redCol;
+      S.rowptr = P.redPtr.data();
+      S.colidx = P.redCol.data();
+      S.nnz = (int64_t)P.redCol.size();
       S.testVector = P.nextTestVector;
       std::fill(gid2row.begin(), gid2row.end(), -1);
     }
@@ -346,6 +347,19 @@ void Engine::initialize() {
     // parameters of the next level (SetNextLevelParameters; sx *= cx)
     part.setNextLevelParameters(levelParams);
     L.dist.ready = false;
+    if (!deviceOk_) S.ignoredInteriorCouplings = countInteriorCouplings(S);
+  }
+  // The inversion workspace of Compute is allocated now (its size follows from the symbolic phase alone): the device
+  // side of Initialize below uses it as scratch
+  if (deviceOk_) {
+    auto tw0 = std::chrono::steady_clock::now();
+    work_.alloc(inversionWorkspace());
+    if (getenv("HYMLS_B200_VERBOSE"))
+      fprintf(stderr, "[hymls_b200] initialize: inversion workspace (%.2f GB) %.3f s\n", work_.bytes() / 1e9,
+              std::chrono::duration<double>(std::chrono::steady_clock::now() - tw0).count());
+  }
+  for (int l = 0; l < nlev; ++l) {
+    Level& L = *levels_[l];
     auto tu0 = std::chrono::steady_clock::now();
     if (L.sharded && l == 0 && !L.exact) buildDistPlan(L);  // host lists always, device copies with a device
     auto tu1 = std::chrono::steady_clock::now();
@@ -378,6 +392,9 @@ void Engine::uploadLevel(Level& L) {
   LevelSym& S = L.sym;
   cudaStream_t s = stream_;
   ArenaScope arenaScope(&L.arena);
+  // scratch of the device-side index construction: one or two slabs, released together at the end
+  DeviceArena scratch((size_t)512 << 20, ~(size_t)0 >> 1);
+  scratch.adopt(work_.p, work_.bytes());  // the Compute workspace is idle now: no extra cudaMalloc / cudaFree
   const bool lapOn = getenv("HYMLS_B200_VERBOSE_SYM") != nullptr;
   auto lapT = std::chrono::steady_clock::now();
   auto lap = [&](const char* what) {
@@ -388,9 +405,10 @@ void Engine::uploadLevel(Level& L) {
     lapT = t1;
   };
   if (S.level > 0) {
-    L.rowptr.upload(S.rowptr, s);
-    L.colidx.upload(S.colidx, s);
-    L.val.alloc(S.colidx.size());
+    const LevelSym& P = levels_[S.level - 1]->sym;
+    L.rowptr.upload(P.redPtr, s);
+    L.colidx.upload(P.redCol, s);
+    L.val.alloc(P.redCol.size());
   }
   L.intRow.upload(S.intRow, s);
   L.sepRow.upload(S.sepRow, s);
@@ -416,41 +434,41 @@ void Engine::uploadLevel(Level& L) {
   L.sdNG.upload(S.sdN, s);
   L.sdNpG.upload(S.sdNp, s);
   L.a11OffG.upload(a11OffG, s);
-  // dense-fill scatter list of the owned subdomains (destinations in compact numbering), built on the device
+  L.intPtrG.upload(S.H.intPtr, s);
+  // Index arrays derived from the pattern are built on the device (indexing.cu): row -> position map, the dense-fill
+  // scatter list of the owned subdomains (destinations in compact numbering), the A12 / A21 / A22 split with the
+  // transposed index of A12 (A21 restricted to the columns of owned interiors when sharded: partial products are
+  // summed over the ranks)
   L.rowPos.alloc(S.n);
   buildRowPos(L.intRow.p, S.nI, L.sepRow.p, S.nS, L.rowPos.p, s, &launches_);
-  buildA11List(L.rowptr.p, L.colidx.p, L.intRow.p, L.rowPos.p, S.nI, L.a11.n.p, L.a11.np.p, L.a11.matOff.p,
-               L.a11.vecOff.p, nown, L.a11Src, L.a11Dst, L.a11ListPtrDev, L.a11ListPtr, s, &launches_);
-  lap("A11 scatter list");
-  // A12 / A21 / A22 (A21 restricted to the columns of owned interiors when sharded: partial products
-  // are summed over the ranks)
-  L.p12.upload(S.A12.ptr, s);
-  L.c12.upload(S.A12.col, s);
-  L.src12.upload(S.A12.src, s);
-  L.v12.alloc(S.A12.col.size());
-  if (!L.sharded) {
-    L.p21.upload(S.A21.ptr, s);
-    L.c21.upload(S.A21.col, s);
-    L.src21.upload(S.A21.src, s);
-    L.v21.alloc(S.A21.col.size());
-  } else {
-    std::vector<char> ownInt(S.nI, 0);
-    for (int sd : L.ownSd)
-      for (int64_t p = S.H.intPtr[sd]; p < S.H.intPtr[sd + 1]; ++p) ownInt[p] = 1;
-    std::vector<int64_t> ptr(S.nS + 1, 0), src;
-    std::vector<int> col;
-    for (int64_t p = 0; p < S.nS; ++p) {
-      for (int64_t e = S.A21.ptr[p]; e < S.A21.ptr[p + 1]; ++e)
-        if (ownInt[S.A21.col[e]]) {
-          col.push_back(S.A21.col[e]);
-          src.push_back(S.A21.src[e]);
-        }
-      ptr[p + 1] = (int64_t)col.size();
+  L.posMat.alloc(S.nI);
+  buildPosMat(L.a11.n.p, L.a11.vecOff.p, nown, S.nI, L.posMat.p, s, &launches_);
+  {
+    DevBuf<int> posSdBuf;  // interior position -> subdomain; equals posMat when every subdomain is owned
+    const int* posSd = L.posMat.p;
+    if (nown != S.nsd) {
+      ArenaScope tmpScope(&scratch);
+      posSdBuf.alloc(S.nI);
+      buildPosMat(L.sdNG.p, L.intPtrG.p, S.nsd, S.nI, posSdBuf.p, s, &launches_);
+      posSd = posSdBuf.p;
     }
-    L.p21.upload(ptr, s);
-    L.c21.upload(col, s);
-    L.src21.upload(src, s);
-    L.v21.alloc(col.size());
+    S.ignoredInteriorCouplings =
+        buildA11List(L.rowptr.p, L.colidx.p, L.intRow.p, L.rowPos.p, L.posMat.p, posSd, S.nI, L.a11.np.p,
+                     L.a11.matOff.p, L.a11.vecOff.p, nown, L.a11Src, L.a11Dst, L.a11ListPtrDev, L.a11ListPtr, &scratch, s,
+                     &launches_);
+  }
+  lap("A11 scatter list");
+  {
+    SplitOut so{&L.p12, &L.c12, &L.src12, &L.p21, &L.c21, &L.src21, &L.p22, &L.c22, &L.src22, &L.t12Ptr, &L.t12Col, &L.t12Idx};
+    buildSplit(L.rowptr.p, L.colidx.p, L.intRow.p, L.sepRow.p, L.rowPos.p, L.posMat.p, L.sharded, L.exact, S.nI, S.nS,
+               so, &scratch, s, &launches_);
+    L.nnz12 = so.nnz12;
+    L.nnz21 = so.nnz21;
+    L.nnz22 = so.nnz22;
+    L.v12.alloc(L.nnz12);
+    L.v21.alloc(L.nnz21);
+  }
+  if (L.sharded) {
     // interior results: every rank packs its owned segments, the packs are all-gathered
     const int P = comm_.size();
     std::vector<int64_t> cnt(P, 0);
@@ -469,11 +487,6 @@ void Engine::uploadLevel(Level& L) {
     L.packedRow.upload(packedRow, s);
     L.gatherOutOff.upload(outOff, s);
     L.xI.alloc((size_t)P * L.maxOwnI);
-  }
-  if (L.exact) {
-    L.p22.upload(S.A22.ptr, s);
-    L.c22.upload(S.A22.col, s);
-    L.src22.upload(S.A22.src, s);
   }
   lap("A12 / A21 / A22");
   // Schur assembly data
@@ -511,7 +524,39 @@ void Engine::uploadLevel(Level& L) {
   L.dLen = maxN;
   L.rowSmem = (size_t)(maxN + maxM) * sizeof(double);
   L.blkSmem = maxBlkSmem;
-  lap("row -> instance lists");
+  // per-subdomain local pieces of A21 / A22 / A12 for the Schur assembly, built on the device
+  L.rowSd.upload(rowSd, s);
+  L.sdSep.upload(S.sdSep, s);
+  L.uniqStart.upload(toInt(S.H.uniqPtr), s);
+  {
+    // occurrences of every unique group: (subdomain, local offset of the group in that subdomain)
+    std::vector<int64_t> occPtr(S.nuniq + 1, 0);
+    const int64_t ninst = S.sdInstPtr[S.nsd];
+    for (int64_t g = 0; g < ninst; ++g) occPtr[S.instUniq[g] + 1]++;
+    for (int u = 0; u < S.nuniq; ++u) occPtr[u + 1] += occPtr[u];
+    std::vector<int> occSd(ninst), occLoc(ninst);
+    std::vector<int64_t> f(occPtr.begin(), occPtr.end() - 1);
+    for (int sd = 0; sd < S.nsd; ++sd)
+      for (int64_t g = S.sdInstPtr[sd]; g < S.sdInstPtr[sd + 1]; ++g) {
+        const int64_t o = f[S.instUniq[g]]++;
+        occSd[o] = sd;
+        occLoc[o] = S.instLoc[g];
+      }
+    DevBuf<int64_t> dOccPtr;
+    DevBuf<int> dOccSd, dOccLoc;
+    {
+      ArenaScope tmpScope(&scratch);
+      dOccPtr.upload(occPtr, s);
+      dOccSd.upload(occSd, s);
+      dOccLoc.upload(occLoc, s);
+    }
+    LocalOut lo{&L.s21Ptr, &L.s21Col, &L.s21Src, &L.s22Ptr, &L.s22Col, &L.s22Src, &L.s12Ptr, &L.s12Row, &L.s12Src};
+    buildLocalPieces(L.rowptr.p, L.colidx.p, L.sepRow.p, L.rowPos.p, L.rowSd.p, L.sdSep.p, L.intPtrG.p, L.uniqStart.p,
+                     S.nuniq, S.nS, dOccPtr.p, dOccSd.p, dOccLoc.p, L.t12Ptr.p, L.t12Col.p, L.t12Idx.p, L.src12.p,
+                     totalRows, lo, &scratch, s, &launches_);
+    L.nnzS21 = lo.nnz21;
+  }
+  lap("row -> instance lists, local pieces");
   // chunks of subdomains whose workspace (C, SV: m*G each; S_LL: sum lsz^2) fits the budget
   const int64_t budget = (int64_t)96 << 20;  // doubles per array (768 MB)
   std::vector<int64_t> wsOffC(S.nsd, 0), wsOffD(S.nsd, 0), wsOffA(S.nsd, 0), wsOffS(S.nsd, 0), lnkOff(lnkSd.size(), 0);
@@ -565,7 +610,7 @@ void Engine::uploadLevel(Level& L) {
   // interior nodes, and streaming that many rows of A11^-1 per separator row costs more than one DMMA GEMM
   // per subdomain.  Level 0 (a few entries per row) keeps the sparse accumulation.
   {
-    const double avgNnz = totalRows ? (double)S.s21Col.size() / (double)totalRows : 0.0;
+    const double avgNnz = totalRows ? (double)L.nnzS21 / (double)totalRows : 0.0;
     // Measured at 128^3 (level 1: 200 subdomains, n ~ 700, m ~ 830, ~100 entries per A21 row): sparse path 113 ms,
     // dense D = A21 A11^-1 only 123 ms (the sparse product with A12 dominates), both products as GEMMs 25 ms.
     // HYMLS_B200_SCHUR_GEMM overrides: 0 = sparse everywhere, 1 = dense on every level that fits, 2 = first GEMM only.
@@ -645,21 +690,10 @@ void Engine::uploadLevel(Level& L) {
     L.colRow.upload(colRow, s);
   }
   lap("colouring");
-  L.rowSd.upload(rowSd, s);
   L.rowInst.upload(rowInst, s);
   L.rowLinkPos.upload(rowLinkPos, s);
-  L.sdSep.upload(S.sdSep, s);
   L.sdM.upload(S.sdM, s);
   L.sdRowPtr.upload(S.sdRowPtr, s);
-  L.s21Ptr.upload(S.s21Ptr, s);
-  L.s21Col.upload(S.s21Col, s);
-  L.s21Src.upload(S.s21Src, s);
-  L.s12Ptr.upload(S.s12Ptr, s);
-  L.s12Row.upload(S.s12Row, s);
-  L.s12Src.upload(S.s12Src, s);
-  L.s22Ptr.upload(S.s22Ptr, s);
-  L.s22Col.upload(S.s22Col, s);
-  L.s22Src.upload(S.s22Src, s);
   L.sdInstPtr.upload(S.sdInstPtr, s);
   L.instLoc.upload(S.instLoc, s);
   L.instLen.upload(S.instLen, s);
@@ -673,7 +707,6 @@ void Engine::uploadLevel(Level& L) {
   L.wsOffD.upload(wsOffD, s);
   L.wsOffA.upload(wsOffA, s);
   L.wsOffS.upload(wsOffS, s);
-  L.uniqStart.upload(toInt(S.H.uniqPtr), s);
   L.uniqBlk.upload(S.uniqBlk, s);
   L.uniqBlkOff.upload(S.uniqBlkOff, s);
   L.what.upload(S.what, s);
@@ -870,10 +903,37 @@ std::vector<std::pair<int, int>> Engine::a11Chunks(const Level& L) const {
   return out;
 }
 
+// doubles of the inversion workspace: the largest chunk of dense subdomain matrices over the levels, or the dense
+// coarse matrix.  Needs the symbolic phase only.
+size_t Engine::inversionWorkspace() const {
+  size_t work = 0;
+  const int64_t budget = (int64_t)1 << 29;  // as in a11Chunks
+  for (auto& lp : levels_) {
+    const Level& L = *lp;
+    const LevelSym& S = L.sym;
+    int64_t used = 0;
+    int cnt = 0;
+    for (int sd : L.ownSd) {
+      const int64_t need = (int64_t)S.sdNp[sd] * S.sdNp[sd];
+      if (cnt > 0 && (used + need > budget || cnt >= 16384)) {
+        used = 0;
+        cnt = 0;
+      }
+      used += need;
+      ++cnt;
+      work = std::max(work, (size_t)used);
+    }
+  }
+  const LevelSym& T = levels_.back()->sym;
+  const int64_t nc = ((levels_.back()->exact ? T.nS : (int64_t)T.nuniq) + 8 + 7) & ~(int64_t)7;
+  return std::max(work, (size_t)(nc * nc));
+}
+
 // Allocates the scratch of Compute once, at the end of Initialize, so that the first Compute does not pay
-// for cudaMalloc of multi-GB buffers (the buffers only grow afterwards)
+// for cudaMalloc of multi-GB buffers (the buffers only grow afterwards).  All of it comes from ONE allocation:
+// cudaMalloc / cudaFree cost 10-100 ms a call next to a 17 GB resident factor store.
 void Engine::reserveComputeScratch() {
-  size_t work = 0, piv = 0, perm = 0, blkW = 0, wsC = 0, wsSLL = 0, red = 0;
+  size_t work = 0, piv = 0, perm = 0, blkW = 0, wsC = 0, wsSLL = 0, red = 0, dD = 0, dA = 0, dS = 0;
   auto batch = [&](int cnt, int npMax) {
     piv = std::max(piv, (size_t)cnt * (npMax + 128));
     perm = std::max(perm, (size_t)cnt * npMax);
@@ -892,6 +952,11 @@ void Engine::reserveComputeScratch() {
       red = std::max(red, S.redCol.size());
       wsC = std::max(wsC, (size_t)L.wsCLen);
       wsSLL = std::max(wsSLL, (size_t)L.wsSLLLen);
+      if (L.schurGemm) dD = std::max(dD, (size_t)L.wsDLen);
+      if (L.schurGemm == 1) {
+        dA = std::max(dA, (size_t)L.wsALen);
+        dS = std::max(dS, (size_t)L.wsSLen);
+      }
       int npMax = 0;
       for (int b = 0; b < S.nblk; ++b) npMax = std::max(npMax, S.blkNp[b]);
       batch(std::min(S.nblk, 16384), npMax);
@@ -902,21 +967,48 @@ void Engine::reserveComputeScratch() {
   const int64_t nc = ((levels_.back()->exact ? T.nS : (int64_t)T.nuniq) + 8 + 7) & ~(int64_t)7;
   work = std::max(work, (size_t)(nc * nc));
   batch(1, (int)nc);
-  work_.alloc(work);
+  work_.alloc(work);  // (already there: sized by inversionWorkspace() before the uploads)
+  const bool multi = comm_.size() > 1;
+  struct Want { std::function<bool()> fits; std::function<void()> release, alloc; size_t bytes; };
+  std::vector<Want> wants;
+  auto want = [&](auto& buf, size_t cnt) {
+    if (cnt == 0) return;
+    auto* b = &buf;
+    wants.push_back({[b, cnt] { return b->p && cnt <= b->cap; }, [b] { b->release(); }, [b, cnt] { b->alloc(cnt); },
+                     (cnt * sizeof(*b->p) + 255) & ~(size_t)255});
+  };
   if (refine_) {
-    work2_.alloc(work);
-    blkA_.alloc(std::max(blkW, (size_t)(nc * nc)));
-    blkR_.alloc(blkW);
+    want(work2_, work);
+    want(blkA_, std::max(blkW, (size_t)(nc * nc)));
+    want(blkR_, blkW);
   }
-  piv_.alloc(piv);
-  perm_.alloc(perm);
-  blkW_.alloc(blkW);
-  wsC_.alloc(wsC);
-  wsSV_.alloc(wsC);
-  wsSLL_.alloc(wsSLL);
-  if (comm_.size() > 1) {
-    red2_.alloc(red);
-    blk2_.alloc(blkW);
+  want(piv_, piv);
+  want(perm_, perm);
+  want(blkW_, blkW);
+  want(wsC_, wsC);
+  want(wsSV_, wsC);
+  want(wsSLL_, wsSLL);
+  want(a21d_, dD);  // dense Schur path (coarser levels)
+  want(dmat_, dD);
+  want(a12d_, dA);
+  want(skd_, dS);
+  if (multi) {
+    want(red2_, red);
+    want(blk2_, blkW);
+  }
+  bool allFit = true;
+  size_t total = 0;
+  for (const Want& w : wants) {
+    allFit = allFit && w.fits();
+    total += w.bytes;
+  }
+  if (!allFit) {  // (re-Initialize with larger needs: everything moves to a new block)
+    for (const Want& w : wants) w.release();
+    computeArena_.reset(new DeviceArena(total + 4096, ~(size_t)0 >> 1));
+    ArenaScope scope(computeArena_.get());
+    for (const Want& w : wants) w.alloc();
+  } else {
+    for (const Want& w : wants) w.alloc();  // sets the sizes in use
   }
 }
 
@@ -926,7 +1018,7 @@ void Engine::computeLevel(int l) {
   cudaStream_t s = stream_;
   PhaseTimer pt(s, l);
   // (1) off-diagonal blocks: value gathers (MatrixBlock::Compute)
-  gatherValues(L.val.p, L.src12.p, L.v12.p, (int64_t)S.A12.col.size(), s, &launches_);
+  gatherValues(L.val.p, L.src12.p, L.v12.p, L.nnz12, s, &launches_);
   gatherValues(L.val.p, L.src21.p, L.v21.p, (int64_t)L.v21.n, s, &launches_);
   // (2) A11 blocks: dense fill + batched inversion, in chunks of (owned) subdomains (ComputeSubdomainSolvers)
   {
@@ -1023,8 +1115,8 @@ void Engine::computeLevel(int l) {
     HY_CUDA(cudaMemsetAsync(work_.p, 0, (size_t)np * np * sizeof(double), s));
     // A22 part: gather the values of the A22 block into a temporary and densify
     DevBuf<double> v22;
-    v22.alloc(S.A22.col.size());
-    gatherValues(L.val.p, L.src22.p, v22.p, (int64_t)S.A22.col.size(), s, &launches_);
+    v22.alloc(L.nnz22);
+    gatherValues(L.val.p, L.src22.p, v22.p, L.nnz22, s, &launches_);
     csrToDense(L.p22.p, L.c22.p, v22.p, work_.p, nS, np, s, &launches_);
     for (size_t q = 0; q + 1 < L.colRowPtr.size(); ++q)  // one colour of subdomains per launch: plain adds
       schurDense(a, L.colRowPtr[q], L.colRowPtr[q + 1], work_.p, np, L.rowSmem, s, &launches_, L.colRow.p);
@@ -1342,23 +1434,6 @@ void Engine::computeBorder(int l) {
   bPartial_.alloc((size_t)(bm + 2) * multiDotBlocks());
   bDots_.alloc((size_t)bm * bm + bm);
   if (L.Q1.n) HY_CUDA(cudaMemsetAsync(L.Q1.p, 0, L.Q1.bytes(), s));
-  if (L.t12Ptr.n == 0) {  // transposed index of A12 (counting sort by column), once per pattern
-    std::vector<int64_t> tp(nS + 1, 0), ti(S.A12.col.size());
-    std::vector<int> tc(S.A12.col.size());
-    for (int c : S.A12.col) tp[c + 1]++;
-    for (int64_t p = 0; p < nS; ++p) tp[p + 1] += tp[p];
-    std::vector<int64_t> fill(tp.begin(), tp.end() - 1);
-    for (int64_t r = 0; r < nI; ++r)
-      for (int64_t e = S.A12.ptr[r]; e < S.A12.ptr[r + 1]; ++e) {
-        const int64_t q = fill[S.A12.col[e]]++;
-        tc[q] = (int)r;
-        ti[q] = e;
-      }
-    L.t12Ptr.upload(tp, s);
-    L.t12Col.upload(tc, s);
-    L.t12Idx.upload(ti, s);
-    HY_CUDA(cudaStreamSynchronize(s));
-  }
   for (int j = 0; j < bm; ++j) {
     const double* Vj = L.bV.p + (int64_t)j * n;
     const double* Wj = L.bW.p + (int64_t)j * n;
@@ -2246,7 +2321,7 @@ void Engine::getStats(hymls_b200_stats* st) {
       const LevelSym& T = lp->sym;
       double sb = 0;
       for (int b = 0; b < T.nblk; ++b) sb += 8.0 * (double)T.blkN[b] * T.blkN[b];
-      bytes += 8.0 * (T.sumNsq + T.sumNNb) + 12.0 * (double)(T.A12.nnz() + T.A21.nnz()) +
+      bytes += 8.0 * (T.sumNsq + T.sumNNb) + 12.0 * (double)(lp->nnz12 + lp->nnz21) +
                4.0 * (double)(T.nI + T.nS + 2) + sb + 2.0 * 12.0 * (double)T.nS * 2.0 + 8.0 * (10.0 * T.nI + 14.0 * T.nS);
     }
     if (coarseBT_.active) {

@@ -72,6 +72,9 @@ struct Level {
   // orderings
   DevBuf<int> intRow, sepRow;
   DevBuf<int> rowPos;  // per row: interior position (>= 0) or -(separator position) - 1
+  DevBuf<int> posMat;  // per interior position: owned matrix (index into a11) or -1
+  DevBuf<int64_t> intPtrG;  // per (global) subdomain: first interior position, nsd+1
+  int64_t nnz12 = 0, nnz21 = 0, nnz22 = 0, nnzS21 = 0;  // entries of the device-built index arrays
   // A11: inverses of the subdomains this rank owns (all of them on one GPU), compact storage
   BatchedInverse a11;
   std::vector<int> ownSd;           // owned subdomains, ascending
@@ -208,6 +211,7 @@ class Engine {
   void computeBorder(int l);
   std::vector<std::pair<int, int>> a11Chunks(const Level& L) const;
   void reserveComputeScratch();
+  size_t inversionWorkspace() const;
   void checkInfo(const std::string& what);
   void computeCoarse(const int64_t* ptr, const int* col, double* val, int n, const std::vector<gidx>& rowGid,
                      const std::vector<int64_t>& hPtr, const std::vector<int>& hCol, const double* bV = nullptr,
@@ -263,6 +267,7 @@ class Engine {
   std::vector<double> hV_, hW_, hC_;
   DevBuf<double> bS_, bTin_, bPartial_, bDots_, bC_, bC0_;
   // scratch
+  std::unique_ptr<DeviceArena> computeArena_;  // one block for the scratch of Compute (declared before its users)
   DevBuf<double> work_;      // inversion workspace
   DevBuf<double> work2_, blkA_, blkR_;  // Newton-Schulz refinement: residuals, copies of the dense originals
   bool refine_ = true;

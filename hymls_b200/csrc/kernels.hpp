@@ -129,10 +129,34 @@ void spmv(const int64_t* ptr, const int* col, const double* val, const double* x
 // indexing.cu: index arrays built on the device from the pattern
 void buildRowPos(const int* intRow, int64_t nI, const int* sepRow, int64_t nS, int* rowPos, cudaStream_t s,
                  int64_t* launches);
-void buildA11List(const int64_t* rowptr, const int* colidx, const int* intRow, const int* rowPos, int64_t nI,
-                  const int* n, const int* np, const int64_t* matOff, const int64_t* vecOff, int count,
-                  DevBuf<int64_t>& src, DevBuf<int64_t>& dst, DevBuf<int64_t>& listPtrDev,
-                  std::vector<int64_t>& listPtr, cudaStream_t s, int64_t* launches);
+void buildPosMat(const int* n, const int64_t* vecOff, int count, int64_t nI, int* posMat, cudaStream_t s,
+                 int64_t* launches);
+int64_t buildA11List(const int64_t* rowptr, const int* colidx, const int* intRow, const int* rowPos,
+                     const int* posMat, const int* posSd, int64_t nI, const int* np, const int64_t* matOff,
+                     const int64_t* vecOff, int count, DevBuf<int64_t>& src, DevBuf<int64_t>& dst,
+                     DevBuf<int64_t>& listPtrDev, std::vector<int64_t>& listPtr, DeviceArena* scratch, cudaStream_t s,
+                     int64_t* launches);
+struct SplitOut {
+  DevBuf<int64_t>* p12; DevBuf<int>* c12; DevBuf<int64_t>* src12;
+  DevBuf<int64_t>* p21; DevBuf<int>* c21; DevBuf<int64_t>* src21;
+  DevBuf<int64_t>* p22; DevBuf<int>* c22; DevBuf<int64_t>* src22;
+  DevBuf<int64_t>* t12Ptr; DevBuf<int>* t12Col; DevBuf<int64_t>* t12Idx;
+  int64_t nnz12 = 0, nnz21 = 0, nnz22 = 0;
+};
+void buildSplit(const int64_t* rowptr, const int* colidx, const int* intRow, const int* sepRow, const int* rowPos,
+                const int* posMat, bool ownedOnly, bool want22, int64_t nI, int64_t nS, SplitOut& o,
+                DeviceArena* scratch, cudaStream_t s, int64_t* launches);
+struct LocalOut {
+  DevBuf<int64_t>* s21Ptr; DevBuf<int>* s21Col; DevBuf<int64_t>* s21Src;
+  DevBuf<int64_t>* s22Ptr; DevBuf<int>* s22Col; DevBuf<int64_t>* s22Src;
+  DevBuf<int64_t>* s12Ptr; DevBuf<int>* s12Row; DevBuf<int64_t>* s12Src;
+  int64_t nnz21 = 0, nnz22 = 0, nnz12 = 0;
+};
+void buildLocalPieces(const int64_t* rowptr, const int* colidx, const int* sepRow, const int* rowPos, const int* rowSd,
+                      const int* sdSep, const int64_t* intPtr, const int* uniqStart, int nuniq, int64_t nS,
+                      const int64_t* occPtr, const int* occSd, const int* occLoc, const int64_t* t12Ptr,
+                      const int* t12Col, const int64_t* t12Idx, const int64_t* src12, int64_t totalRows, LocalOut& o,
+                      DeviceArena* scratch, cudaStream_t s, int64_t* launches);
 void gatherValues(const double* src, const int64_t* idx, double* dst, int64_t n, cudaStream_t s, int64_t* launches);
 void scatterValues(const double* src, const int64_t* srcIdx, const int64_t* dstIdx, int64_t dstBase, double* dst,
                    int64_t n, cudaStream_t s, int64_t* launches);

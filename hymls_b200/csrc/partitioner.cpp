@@ -462,21 +462,16 @@ void buildHierarchicalMap(const CartesianPartitioner& part, const std::vector<ch
   H.grpPtr.assign(1, 0);
   H.uniqPtr.assign(1, 0);
   const bool filter = !present.empty();
-  std::unordered_map<gidx, int> uniqueByFirst;
-  uniqueByFirst.reserve((size_t)nsd * 32);
   // the per-subdomain group lists are independent (GetGroups is const): build and sort them in parallel, then
   // merge sequentially in subdomain order (the order decides which subdomain owns a shared group)
   std::vector<std::vector<gidx>> allInterior(nsd);
   std::vector<std::vector<SepGroup>> allGroups(nsd);
   std::vector<std::string> errors(64);
   const auto tg0 = std::chrono::steady_clock::now();
-  std::vector<double> tGet(64, 0.0);
   parallelFor(nsd, [&](int64_t s0, int64_t s1, int t) {
     try {
       for (int64_t sd = s0; sd < s1; ++sd) {
-        auto q0 = std::chrono::steady_clock::now();
         part.getGroups((int)sd, allInterior[sd], allGroups[sd]);
-        tGet[t & 63] += std::chrono::duration<double>(std::chrono::steady_clock::now() - q0).count();
         if (filter) {  // coarser levels keep ~1 % of the grid nodes: drop the others here, in parallel
           auto gone = [&](gidx g) { return !present[g]; };
           std::vector<gidx>& in = allInterior[sd];
@@ -493,53 +488,89 @@ void buildHierarchicalMap(const CartesianPartitioner& part, const std::vector<ch
   }, 16);
   for (const std::string& e : errors)
     if (!e.empty()) throw Error(HYMLS_B200_ERR_ARG, e);
-  if (getenv("HYMLS_B200_VERBOSE_SYM")) { double m = 0; for (double v : tGet) m = std::max(m, v); fprintf(stderr, "TMP getGroups only max thread %.3f\n", m); }
   if (getenv("HYMLS_B200_VERBOSE_SYM"))
     fprintf(stderr, "[hymls_b200 sym] getGroups (parallel)                    %.3f s\n",
             std::chrono::duration<double>(std::chrono::steady_clock::now() - tg0).count());
+  // Merge.  Which subdomain owns a shared group is decided in subdomain order, but only the GROUP bookkeeping is
+  // sequential (~10^5 groups); the node lists (~10^7 GIDs) are copied in parallel once every offset is known.
+  // (the parallel phase above already removed the nodes that do not exist on this level)
+  gidx maxGid = -1;
+  {
+    std::vector<gidx> tmax(64, -1);
+    parallelFor(nsd, [&](int64_t s0, int64_t s1, int t) {
+      gidx m = -1;
+      for (int64_t sd = s0; sd < s1; ++sd)
+        for (const auto& grp : allGroups[sd])
+          if (!grp.nodes.empty()) m = std::max(m, grp.nodes.front());
+      tmax[t & 63] = std::max(tmax[t & 63], m);
+    }, 16);
+    for (gidx m : tmax) maxGid = std::max(maxGid, m);
+  }
+  std::vector<int> uniqueByFirst((size_t)(maxGid + 1), -1);  // first GID of a group -> unique id
+  std::vector<int> uniqSrcSd, uniqSrcGrp;                     // where the node list of a unique group comes from
+  std::vector<int64_t> ovlPtr(nsd + 1, 0);
+  std::vector<int64_t> sdFirstUniq(nsd + 1, 0);
+  H.intPtr.resize(nsd + 1);
+  H.sdGrpPtr.resize(nsd + 1);
   for (int sd = 0; sd < nsd; ++sd) {
-    std::vector<gidx>& interior = allInterior[sd];
-    std::vector<SepGroup>& groups = allGroups[sd];
-    for (gidx g : interior)
-      if (!filter || present[g]) {
-        H.intGid.push_back(g);
-        H.overlappingGid.push_back(g);
-      }
-    H.intPtr.push_back((int64_t)H.intGid.size());
-    for (auto& grp : groups) {
-      size_t before = H.grpGid.size();
-      for (gidx g : grp.nodes)
-        if (!filter || present[g]) H.grpGid.push_back(g);
-      if (H.grpGid.size() == before) continue;  // empty after filtering: removed (:241-244)
-      H.grpPtr.push_back((int64_t)H.grpGid.size());
+    H.intPtr[sd + 1] = H.intPtr[sd] + (int64_t)allInterior[sd].size();
+    int64_t newSep = 0;
+    const std::vector<SepGroup>& groups = allGroups[sd];
+    for (size_t gi = 0; gi < groups.size(); ++gi) {
+      const SepGroup& grp = groups[gi];
+      if (grp.nodes.empty()) continue;  // empty after filtering: removed (:241-244)
+      const int64_t len = (int64_t)grp.nodes.size();
+      H.grpPtr.push_back(H.grpPtr.back() + len);
       H.grpType.push_back(grp.type);
-      gidx first = H.grpGid[before];
-      auto it = uniqueByFirst.find(first);
-      int u;
-      if (it == uniqueByFirst.end()) {
-        u = (int)H.uniqOwnerSd.size();
-        uniqueByFirst.emplace(first, u);
+      int& slot = uniqueByFirst[grp.nodes.front()];
+      if (slot < 0) {
+        slot = (int)H.uniqOwnerSd.size();
         H.uniqOwnerSd.push_back(sd);
         H.uniqType.push_back(grp.type);
-        for (size_t q = before; q < H.grpGid.size(); ++q) {
-          H.sepGid.push_back(H.grpGid[q]);
-          H.overlappingGid.push_back(H.grpGid[q]);
-        }
-        H.uniqPtr.push_back((int64_t)H.sepGid.size());
-      } else {
-        u = it->second;
+        H.uniqPtr.push_back(H.uniqPtr.back() + len);
+        uniqSrcSd.push_back(sd);
+        uniqSrcGrp.push_back((int)gi);
+        newSep += len;
+      } else if (H.uniqPtr[slot + 1] - H.uniqPtr[slot] != len) {
         // the reference identifies groups by their first GID only (:261-271); a mismatch in the
         // node list would make its maps inconsistent, so we refuse it.
-        int64_t len = H.uniqPtr[u + 1] - H.uniqPtr[u];
-        if (len != (int64_t)(H.grpGid.size() - before))
-          throw Error(HYMLS_B200_ERR_ARG, "separator group seen with two different node lists");
+        throw Error(HYMLS_B200_ERR_ARG, "separator group seen with two different node lists");
       }
-      H.grpUnique.push_back(u);
+      H.grpUnique.push_back(slot);
     }
-    H.sdGrpPtr.push_back((int64_t)H.grpType.size());
-    std::vector<gidx>().swap(interior);   // release as we go
-    std::vector<SepGroup>().swap(groups);
+    H.sdGrpPtr[sd + 1] = (int64_t)H.grpType.size();
+    sdFirstUniq[sd + 1] = (int64_t)H.uniqOwnerSd.size();
+    ovlPtr[sd + 1] = ovlPtr[sd] + (int64_t)allInterior[sd].size() + newSep;
   }
+  H.intGid.resize(H.intPtr[nsd]);
+  H.grpGid.resize(H.grpPtr.back());
+  H.sepGid.resize(H.uniqPtr.back());
+  H.overlappingGid.resize(ovlPtr[nsd]);
+  parallelFor(nsd, [&](int64_t s0, int64_t s1, int) {
+    for (int64_t sd = s0; sd < s1; ++sd) {
+      std::vector<gidx>& interior = allInterior[sd];
+      std::copy(interior.begin(), interior.end(), H.intGid.begin() + H.intPtr[sd]);
+      gidx* ovl = H.overlappingGid.data() + ovlPtr[sd];
+      ovl = std::copy(interior.begin(), interior.end(), ovl);
+      int64_t g = H.sdGrpPtr[sd];
+      for (const SepGroup& grp : allGroups[sd]) {
+        if (grp.nodes.empty()) continue;
+        std::copy(grp.nodes.begin(), grp.nodes.end(), H.grpGid.begin() + H.grpPtr[g]);
+        ++g;
+      }
+      for (int64_t u = sdFirstUniq[sd]; u < sdFirstUniq[sd + 1]; ++u) {  // the unique groups this subdomain owns
+        const std::vector<gidx>& nodes = allGroups[uniqSrcSd[u]][uniqSrcGrp[u]].nodes;
+        std::copy(nodes.begin(), nodes.end(), H.sepGid.begin() + H.uniqPtr[u]);
+        ovl = std::copy(nodes.begin(), nodes.end(), ovl);
+      }
+    }
+  }, 16);
+  parallelFor(nsd, [&](int64_t s0, int64_t s1, int) {  // release the per-subdomain lists (in parallel: ~10^6 frees)
+    for (int64_t sd = s0; sd < s1; ++sd) {
+      std::vector<gidx>().swap(allInterior[sd]);
+      std::vector<SepGroup>().swap(allGroups[sd]);
+    }
+  }, 16);
 }
 
 }  // namespace hymls

@@ -35,6 +35,29 @@ struct SymTimer {
     t0 = t1;
   }
 };
+// Host version of the Tester::isDDcorrect count (src/HYMLS_Tester.cpp:253-455) for runs without a device (index maps
+// only); with a device the count falls out of the A11 list construction (indexing.cu)
+int64_t countInteriorCouplings(const LevelSym& L) {
+  std::vector<int> sdOfInt(L.nI);
+  for (int sd = 0; sd < L.nsd; ++sd)
+    for (int64_t p = L.H.intPtr[sd]; p < L.H.intPtr[sd + 1]; ++p) sdOfInt[p] = sd;
+  std::vector<int64_t> perThread(64, 0);
+  parallelFor(L.nI, [&](int64_t p0, int64_t p1, int t) {
+    int64_t ignored = 0;
+    for (int64_t p = p0; p < p1; ++p) {
+      const int r = L.intRow[p], sd = sdOfInt[p];
+      for (int64_t e = L.rowptr[r]; e < L.rowptr[r + 1]; ++e) {
+        const int cp = L.rowPos[L.colidx[e]];
+        if (cp >= 0 && sdOfInt[cp] != sd) ++ignored;
+      }
+    }
+    perThread[t & 63] += ignored;
+  });
+  int64_t total = 0;
+  for (int64_t v : perThread) total += v;
+  return total;
+}
+
 void buildLevelSym(LevelSym& L, const CartesianPartitioner& part, const std::vector<int>& gid2row) {
   SymTimer st;
   std::vector<char> present;
@@ -62,39 +85,70 @@ void buildLevelSym(LevelSym& L, const CartesianPartitioner& part, const std::vec
   // needs just this leading block of rows of A11^-1 (engine.cu:applyLevel).
   {
     std::vector<char> isInt(L.n, 0), hit(L.n, 0);
-    for (int64_t p = 0; p < L.nI; ++p) {
-      int r = gid2row[H.intGid[p]];
-      if (r < 0 || isInt[r]) throw Error(HYMLS_B200_ERR_ARG, "interior node not in map / listed twice");
-      isInt[r] = 1;
-    }
-    for (int64_t p = 0; p < L.nS; ++p) {
-      int r = gid2row[H.sepGid[p]];
-      if (r < 0) throw Error(HYMLS_B200_ERR_ARG, "separator node not in map / listed twice");
-      for (int64_t e = L.rowptr[r]; e < L.rowptr[r + 1]; ++e)
-        if (isInt[L.colidx[e]]) hit[L.colidx[e]] = 1;
-    }
-    L.sdNb.assign(H.nsd, 0);
-    L.sumNNb = 0;
-    for (int sd = 0; sd < H.nsd; ++sd) {
-      int64_t q = H.intPtr[sd];
-      for (int pass = 0; pass < 2; ++pass)
-        for (int64_t p = H.intPtr[sd]; p < H.intPtr[sd + 1]; ++p) {
-          int r = gid2row[H.intGid[p]];
-          if ((hit[r] != 0) == (pass == 0)) {
-            L.intRow[q] = r;
-            L.rowPos[r] = (int)q;
-            ++q;
-          }
+    std::vector<int> bad(64, 0);
+    parallelFor(L.nI, [&](int64_t p0, int64_t p1, int t) {
+      for (int64_t p = p0; p < p1; ++p) {
+        const int r = gid2row[H.intGid[p]];
+        if (r < 0) bad[t & 63] = 1; else isInt[r] = 1;
+      }
+    });
+    for (int b : bad)
+      if (b) throw Error(HYMLS_B200_ERR_ARG, "interior node not in map / listed twice");
+    // (several threads may store the same 1 into hit[]: relaxed atomic stores keep that well defined)
+    parallelFor(L.nS, [&](int64_t p0, int64_t p1, int t) {
+      for (int64_t p = p0; p < p1; ++p) {
+        const int r = gid2row[H.sepGid[p]];
+        if (r < 0) {
+          bad[t & 63] = 1;
+          continue;
         }
-      for (int64_t p = H.intPtr[sd]; p < H.intPtr[sd + 1]; ++p) L.sdNb[sd] += hit[L.intRow[p]] ? 1 : 0;
-      L.sumNNb += (double)L.sdNb[sd] * (double)(H.intPtr[sd + 1] - H.intPtr[sd]);
-    }
+        for (int64_t e = L.rowptr[r]; e < L.rowptr[r + 1]; ++e)
+          if (isInt[L.colidx[e]]) __atomic_store_n(&hit[L.colidx[e]], (char)1, __ATOMIC_RELAXED);
+      }
+    });
+    for (int b : bad)
+      if (b) throw Error(HYMLS_B200_ERR_ARG, "separator node not in map / listed twice");
+    L.sdNb.assign(H.nsd, 0);
+    std::vector<double> sumPerThread(64, 0.0);
+    parallelFor(H.nsd, [&](int64_t s0, int64_t s1, int t) {
+      for (int64_t sd = s0; sd < s1; ++sd) {
+        int64_t q = H.intPtr[sd];
+        for (int pass = 0; pass < 2; ++pass)
+          for (int64_t p = H.intPtr[sd]; p < H.intPtr[sd + 1]; ++p) {
+            int r = gid2row[H.intGid[p]];
+            if ((hit[r] != 0) == (pass == 0)) {
+              L.intRow[q] = r;
+              L.rowPos[r] = (int)q;
+              ++q;
+            }
+          }
+        for (int64_t p = H.intPtr[sd]; p < H.intPtr[sd + 1]; ++p) L.sdNb[sd] += hit[L.intRow[p]] ? 1 : 0;
+      }
+    }, 16);
+    // (summed in subdomain order: the statistic must not depend on the thread count)
+    L.sumNNb = 0;
+    for (int sd = 0; sd < H.nsd; ++sd) L.sumNNb += (double)L.sdNb[sd] * (double)(H.intPtr[sd + 1] - H.intPtr[sd]);
   }
-  for (int64_t p = 0; p < L.nS; ++p) {
-    int r = gid2row[H.sepGid[p]];
-    if (r < 0 || L.rowPos[r] != INT32_MIN) throw Error(HYMLS_B200_ERR_ARG, "separator node not in map / listed twice");
-    L.sepRow[p] = r;
-    L.rowPos[r] = -(int)p - 1;
+  {
+    std::vector<int> bad(64, 0);
+    parallelFor(L.nS, [&](int64_t p0, int64_t p1, int t) {
+      for (int64_t p = p0; p < p1; ++p) {
+        const int r = gid2row[H.sepGid[p]];
+        if (r < 0 || L.rowPos[r] >= 0) {  // not in the map, or also an interior node
+          bad[t & 63] = 1;
+          continue;
+        }
+        L.sepRow[p] = r;
+        L.rowPos[r] = -(int)p - 1;
+      }
+    });
+    // interior + separator counts equal the map size (checked above), so a node listed twice leaves a row uncovered
+    parallelFor(L.n, [&](int64_t r0, int64_t r1, int t) {
+      for (int64_t r = r0; r < r1; ++r)
+        if (L.rowPos[r] == INT32_MIN) bad[t & 63] = 1;
+    });
+    for (int b : bad)
+      if (b) throw Error(HYMLS_B200_ERR_ARG, "separator node not in map / listed twice");
   }
   st.lap("before: A11 blocks");
   // ---- A11 blocks ----
@@ -102,101 +156,15 @@ void buildLevelSym(LevelSym& L, const CartesianPartitioner& part, const std::vec
   L.sdNp.resize(L.nsd);
   L.a11Off.assign(L.nsd + 1, 0);
   L.sumNsq = 0;
-  std::vector<int> sdOfInt(L.nI);
   for (int sd = 0; sd < L.nsd; ++sd) {
     int n = (int)(H.intPtr[sd + 1] - H.intPtr[sd]);
     L.sdN[sd] = n;
     L.sdNp[sd] = roundUp8(n);
     L.a11Off[sd + 1] = L.a11Off[sd] + (int64_t)L.sdNp[sd] * L.sdNp[sd];
     L.sumNsq += (double)n * n;
-    for (int64_t p = H.intPtr[sd]; p < H.intPtr[sd + 1]; ++p) sdOfInt[p] = sd;
   }
-  st.lap("before: split the matrix into A11");
-  // ---- split the matrix into A11 (dense scatter list), A12, A21, A22 ----
-  L.A12.ptr.assign(L.nI + 1, 0);
-  L.A21.ptr.assign(L.nS + 1, 0);
-  L.A22.ptr.assign(L.nS + 1, 0);
-  L.ignoredInteriorCouplings = 0;
-  {
-    // counting pass (parallel over rows), prefix sums, fill pass (every row writes its own slots, so the
-    // arrays are identical to a sequential sweep whatever the thread count)
-    std::vector<int64_t> a11Ptr(L.nI + 1, 0);
-    std::vector<int64_t> ignoredPerThread(64, 0);
-    parallelFor(L.nI, [&](int64_t p0, int64_t p1, int t) {
-      int64_t ignored = 0;
-      for (int64_t p = p0; p < p1; ++p) {
-        const int r = L.intRow[p], sd = sdOfInt[p];
-        int64_t c11 = 0, c12 = 0;
-        for (int64_t e = L.rowptr[r]; e < L.rowptr[r + 1]; ++e) {
-          const int cp = L.rowPos[L.colidx[e]];
-          if (cp >= 0) {
-            if (sdOfInt[cp] == sd) ++c11; else ++ignored;
-          } else {
-            ++c12;
-          }
-        }
-        a11Ptr[p + 1] = c11;
-        L.A12.ptr[p + 1] = c12;
-      }
-      ignoredPerThread[t & 63] += ignored;
-    });
-    for (int64_t v : ignoredPerThread) L.ignoredInteriorCouplings += v;
-    parallelFor(L.nS, [&](int64_t p0, int64_t p1, int) {
-      for (int64_t p = p0; p < p1; ++p) {
-        const int r = L.sepRow[p];
-        int64_t c21 = 0, c22 = 0;
-        for (int64_t e = L.rowptr[r]; e < L.rowptr[r + 1]; ++e) {
-          if (L.rowPos[L.colidx[e]] >= 0) ++c21; else ++c22;
-        }
-        L.A21.ptr[p + 1] = c21;
-        L.A22.ptr[p + 1] = c22;
-      }
-    });
-    for (int64_t p = 0; p < L.nI; ++p) {
-      L.A12.ptr[p + 1] += L.A12.ptr[p];
-      a11Ptr[p + 1] += a11Ptr[p];
-    }
-    for (int64_t p = 0; p < L.nS; ++p) {
-      L.A21.ptr[p + 1] += L.A21.ptr[p];
-      L.A22.ptr[p + 1] += L.A22.ptr[p];
-    }
-    L.A12.col.resize(L.A12.ptr[L.nI]);
-    L.A12.src.resize(L.A12.ptr[L.nI]);
-    L.A21.col.resize(L.A21.ptr[L.nS]);
-    L.A21.src.resize(L.A21.ptr[L.nS]);
-    L.A22.col.resize(L.A22.ptr[L.nS]);
-    L.A22.src.resize(L.A22.ptr[L.nS]);
-    L.a11Nnz = a11Ptr[L.nI];  // (the dense-fill scatter list itself is built on the device, indexing.cu)
-    parallelFor(L.nI, [&](int64_t p0, int64_t p1, int) {
-      for (int64_t p = p0; p < p1; ++p) {
-        const int r = L.intRow[p];
-        int64_t f12 = L.A12.ptr[p];
-        for (int64_t e = L.rowptr[r]; e < L.rowptr[r + 1]; ++e) {
-          const int cp = L.rowPos[L.colidx[e]];
-          if (cp < 0) {
-            L.A12.col[f12] = -cp - 1;
-            L.A12.src[f12++] = e;
-          }
-        }
-      }
-    });
-    parallelFor(L.nS, [&](int64_t p0, int64_t p1, int) {
-      for (int64_t p = p0; p < p1; ++p) {
-        const int r = L.sepRow[p];
-        int64_t f21 = L.A21.ptr[p], f22 = L.A22.ptr[p];
-        for (int64_t e = L.rowptr[r]; e < L.rowptr[r + 1]; ++e) {
-          const int cp = L.rowPos[L.colidx[e]];
-          if (cp >= 0) {
-            L.A21.col[f21] = cp;
-            L.A21.src[f21++] = e;
-          } else {
-            L.A22.col[f22] = -cp - 1;
-            L.A22.src[f22++] = e;
-          }
-        }
-      }
-    });
-  }
+  // (the split of the matrix into A11 / A12 / A21 / A22 and the per-subdomain local pieces of the Schur assembly are
+  // built on the device from the pattern: indexing.cu)
   st.lap("before: group instances, per-subdomain separator lists");
   // ---- group instances, per-subdomain separator lists ----
   L.sdM.resize(L.nsd);
@@ -266,83 +234,6 @@ void buildLevelSym(LevelSym& L, const CartesianPartitioner& part, const std::vec
     }
   }
   L.nblk = (int)L.blkN.size();
-  st.lap("before: per-subdomain local sparse pieces");
-  // ---- per-subdomain local sparse pieces (Construct11 / Construct22 index work) ----
-  {
-    const int64_t totalRows = L.sdRowPtr[L.nsd];
-    L.s21Ptr.assign(totalRows + 1, 0);
-    L.s22Ptr.assign(totalRows + 1, 0);
-    L.s12Ptr.assign(totalRows + 1, 0);
-    // counting pass then fill pass, both parallel over the subdomains (disjoint row ranges)
-    for (int pass = 0; pass < 2; ++pass) {
-      if (pass == 1) {
-        for (int64_t i = 0; i < totalRows; ++i) {
-          L.s21Ptr[i + 1] += L.s21Ptr[i];
-          L.s22Ptr[i + 1] += L.s22Ptr[i];
-          L.s12Ptr[i + 1] += L.s12Ptr[i];
-        }
-        L.s21Col.resize(L.s21Ptr[totalRows]);
-        L.s21Src.resize(L.s21Ptr[totalRows]);
-        L.s22Col.resize(L.s22Ptr[totalRows]);
-        L.s22Src.resize(L.s22Ptr[totalRows]);
-        L.s12Row.resize(L.s12Ptr[totalRows]);
-        L.s12Src.resize(L.s12Ptr[totalRows]);
-      }
-      parallelFor(L.nsd, [&](int64_t sd0, int64_t sd1, int) {
-        std::vector<int> loc(L.nS, -1);
-        std::vector<int64_t> f21, f22, f12;
-        for (int64_t sd = sd0; sd < sd1; ++sd) {
-          const int64_t base = L.sdRowPtr[sd];
-          const int m = L.sdM[sd];
-          const int64_t i0 = H.intPtr[sd], i1 = H.intPtr[sd + 1];
-          if (pass == 1) {
-            f21.assign(L.s21Ptr.begin() + base, L.s21Ptr.begin() + base + m);
-            f22.assign(L.s22Ptr.begin() + base, L.s22Ptr.begin() + base + m);
-            f12.assign(L.s12Ptr.begin() + base, L.s12Ptr.begin() + base + m);
-          }
-          for (int i = 0; i < m; ++i) loc[L.sdSep[base + i]] = i;
-          for (int i = 0; i < m; ++i) {
-            int ps = L.sdSep[base + i];
-            for (int64_t e = L.A21.ptr[ps]; e < L.A21.ptr[ps + 1]; ++e) {
-              int c = L.A21.col[e];
-              if (c >= i0 && c < i1) {
-                if (pass == 0) {
-                  L.s21Ptr[base + i + 1]++;
-                } else {
-                  L.s21Col[f21[i]] = (int)(c - i0);
-                  L.s21Src[f21[i]++] = L.A21.src[e];
-                }
-              }
-            }
-            for (int64_t e = L.A22.ptr[ps]; e < L.A22.ptr[ps + 1]; ++e) {
-              int j = loc[L.A22.col[e]];
-              if (j >= 0) {
-                if (pass == 0) {
-                  L.s22Ptr[base + i + 1]++;
-                } else {
-                  L.s22Col[f22[i]] = j;
-                  L.s22Src[f22[i]++] = L.A22.src[e];
-                }
-              }
-            }
-          }
-          for (int64_t p = i0; p < i1; ++p) {
-            for (int64_t e = L.A12.ptr[p]; e < L.A12.ptr[p + 1]; ++e) {
-              int j = loc[L.A12.col[e]];
-              if (j < 0) continue;  // coupling to a separator that does not surround this subdomain
-              if (pass == 0) {
-                L.s12Ptr[base + j + 1]++;
-              } else {
-                L.s12Row[f12[j]] = (int)(p - i0);
-                L.s12Src[f12[j]++] = L.A12.src[e];
-              }
-            }
-          }
-          for (int i = 0; i < m; ++i) loc[L.sdSep[base + i]] = -1;
-        }
-      }, 8);
-    }
-  }
   st.lap("before: reduced Schur pattern on the V-sums");
   // ---- reduced Schur pattern on the V-sums: union of per-subdomain cliques (:737-787) ----
   {
@@ -359,14 +250,22 @@ void buildLevelSym(LevelSym& L, const CartesianPartitioner& part, const std::vec
     }
     std::vector<std::vector<int>> rows(L.nuniq);
     parallelFor(L.nuniq, [&](int64_t u0, int64_t u1, int) {
+      std::vector<int64_t> stamp(L.nuniq, -1);  // duplicates are dropped before sorting (a group is seen by up to
+      std::vector<int> r;                        // 8 subdomains that share most of their groups)
       for (int64_t u = u0; u < u1; ++u) {
-        std::vector<int>& r = rows[u];
+        r.clear();
         for (int64_t o = occPtr[u]; o < occPtr[u + 1]; ++o) {
           const int sd = occSd[o];
-          for (int64_t h = L.sdInstPtr[sd]; h < L.sdInstPtr[sd + 1]; ++h) r.push_back(L.instUniq[h]);
+          for (int64_t h = L.sdInstPtr[sd]; h < L.sdInstPtr[sd + 1]; ++h) {
+            const int v = L.instUniq[h];
+            if (stamp[v] != u) {
+              stamp[v] = u;
+              r.push_back(v);
+            }
+          }
         }
         std::sort(r.begin(), r.end());
-        r.erase(std::unique(r.begin(), r.end()), r.end());
+        rows[u] = r;
       }
     }, 256);
     L.redPtr.assign(L.nuniq + 1, 0);

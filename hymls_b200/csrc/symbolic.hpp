@@ -22,8 +22,11 @@ struct LevelSym {
   int level = 0;
   int64_t n = 0;
   std::vector<gidx> rowGid;  // GID of every row of this level's matrix
-  std::vector<int64_t> rowptr;
-  std::vector<int> colidx;
+  // pattern of this level's matrix: a VIEW of the caller's arrays (level 0: the engine's copy of the Jacobian pattern,
+  // level l: redPtr / redCol of level l-1), valid as long as those live
+  const int64_t* rowptr = nullptr;
+  const int* colidx = nullptr;
+  int64_t nnz = 0;
 
   HierarchicalMap H;
   int nsd = 0, nuniq = 0, nblk = 0;
@@ -36,18 +39,13 @@ struct LevelSym {
   std::vector<int> sdNb;        // leading interior nodes of sd that separator rows couple to (columns of A21)
   double sumNNb = 0;            // sum n_sd * nb_sd
   std::vector<int64_t> a11Off;  // nsd+1, in doubles
-  int64_t a11Nnz = 0;  // nonzeros inside the subdomain matrices
   int64_t ignoredInteriorCouplings = 0;  // entries between interiors of different subdomains
 
-  CsrPattern A12, A21, A22;  // indices are positions in the interior / separator orderings
 
   // ---- Schur-complement assembly (SchurComplement::Construct11/22, ConstructSCPart) ----
   std::vector<int> sdM;              // separator nodes around sd
   std::vector<int64_t> sdRowPtr;     // nsd+1: offset of sd's first local separator row in the s* arrays
   std::vector<int> sdSep;            // [sdRowPtr[sd] + i] -> separator position of local node i
-  std::vector<int64_t> s21Ptr, s12Ptr, s22Ptr;  // (total local rows)+1
-  std::vector<int> s21Col, s12Row, s22Col;
-  std::vector<int64_t> s21Src, s12Src, s22Src;
   // group instances (a separator group as seen from one subdomain)
   std::vector<int64_t> sdInstPtr;    // nsd+1
   std::vector<int> instLoc, instLen, instUniq, instLink;  // local offset, length, unique id, linked-set id (per sd)
@@ -76,6 +74,7 @@ struct LevelSym {
 
 // Builds everything above from the matrix pattern and the partitioner of this level.
 // `gid2row`: dense map GID -> row (or -1) over the fine-grid GID space.
+int64_t countInteriorCouplings(const LevelSym& L);
 void buildLevelSym(LevelSym& L, const CartesianPartitioner& part, const std::vector<int>& gid2row);
 
 }  // namespace hymls

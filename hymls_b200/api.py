@@ -36,7 +36,8 @@ class _Stats(C.Structure):
                 ("num_subdomains", C.c_int64), ("num_blocks", C.c_int64), ("sum_nsd_sq", C.c_double),
                 ("bytes_apply", C.c_double), ("flops_compute", C.c_double), ("bytes_a11_level0", C.c_double),
                 ("kernel_launches", C.c_int64), ("device_bytes", C.c_double), ("sum_nsd_nb", C.c_double),
-                ("bytes_a11_full_pass", C.c_double), ("ms_a11_lead", C.c_double), ("interior_couplings", C.c_int64)]
+                ("bytes_a11_full_pass", C.c_double), ("ms_a11_lead", C.c_double), ("interior_couplings", C.c_int64),
+                ("a11_split", C.c_int64)]
 
 
 def lib_path():

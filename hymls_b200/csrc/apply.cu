@@ -22,6 +22,8 @@ namespace hymls {
 //   rows [0, nrows[mat]) only when nrows is given (the first solve of ApplyInverse needs a leading block)
 //   mode 0:  out[scatter ? scatter[p] : p] = acc
 //   mode 1:  out[scatter ? scatter[p] : p] = xprev[p] - acc   (second A11 solve of ApplyInverse: fused update + export)
+// (Tried in round 2 and dropped: two rows per warp at a time -- 8 loads in flight per lane, x read once for both rows --
+//  needs 78 registers, 3 CTAs per SM instead of 4, and ran the full pass at 5.6 TB/s instead of 6.1 TB/s.)
 // ---------------------------------------------------------------------------------------------
 static constexpr int GEMV_ROWS = 32;   // rows per CTA
 static constexpr int GEMV_T = 256;     // 8 warps, 4 rows each
@@ -37,7 +39,9 @@ k_batched_gemv(GemvArgs a) {
   const double* __restrict__ A = a.A + a.matOff[mat];
   extern __shared__ double sx[];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  for (int q = tid; q < np; q += GEMV_T) {
+  // columns read: all (padded) np, or the leading ncols[mat] rounded up to a 16-byte pair
+  const int nc = a.ncols ? min(np, (a.ncols[mat] + 1) & ~1) : np;
+  for (int q = tid; q < nc; q += GEMV_T) {
     double v = 0.0;
     if (q < n) {
       v = a.gather ? a.xin[a.gather[v0 + q]] : a.xin[v0 + q];
@@ -55,7 +59,7 @@ k_batched_gemv(GemvArgs a) {
     const double2* __restrict__ row = reinterpret_cast<const double2*>(A + (int64_t)r * np);
     const double2* __restrict__ x2 = reinterpret_cast<const double2*>(sx);
     double acc0 = 0.0, acc1 = 0.0;
-    const int n2 = np >> 1;
+    const int n2 = nc >> 1;
     int q = lane;
     for (; q + 96 < n2; q += 128) {  // 4 independent 16-byte loads in flight per lane
       double2 m0 = __ldg(row + q), m1 = __ldg(row + q + 32), m2 = __ldg(row + q + 64), m3 = __ldg(row + q + 96);

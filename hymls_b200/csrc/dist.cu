@@ -253,6 +253,17 @@ void Engine::applyLevel0Dist(const double* B, double* X) {
     HY_CUDA(cudaEventElapsedTime(&ms, evA_, evB_));
     a11LeadMs_ += ms;
   }
+  const bool split = splitActive(L, 0);  // see Engine::applyLevel
+  if (split) {
+    HY_CUDA(cudaEventRecord(evFork_, s));
+    HY_CUDA(cudaStreamWaitEvent(side_, evFork_, 0));
+    GemvArgs t = g;
+    t.itemMat = L.a11.itemMatTrail.p;
+    t.itemRow0 = L.a11.itemRow0Trail.p;
+    t.nrows = nullptr;
+    batchedGemv(t, L.a11.numItemsTrail, L.a11.npMax, side_, &launches_);
+    HY_CUDA(cudaEventRecord(evJoin_, side_));
+  }
   mark("A11 gemv 1 (leading rows)");
   // Z = -A21[:, owned interiors] x1 at the separators my subdomains touch; ghost parts go to their owners
   spmvRows(L.p21.p, L.c21.p, L.v21.p, L.x1.p, L.Z.p, D.rows21.p, D.nRows21, 0.0, nullptr, nullptr, -1.0, 0, s,
@@ -288,6 +299,15 @@ void Engine::applyLevel0Dist(const double* B, double* X) {
   g.out = X;
   g.scatter = L.intRow.p;
   g.mode = 0;
+  if (split) {  // X[interior] = x1 - A11^-1[:, :nb] y1
+    HY_CUDA(cudaStreamWaitEvent(s, evJoin_, 0));
+    g.xin = L.y1.p;
+    g.gather = nullptr;
+    g.xsub = nullptr;
+    g.xprev = L.x1.p;
+    g.ncols = L.a11.rowLimit.p;
+    g.mode = 1;
+  }
   if (timeIt) HY_CUDA(cudaEventRecord(evA_, s));
   batchedGemv(g, L.a11.numItems, L.a11.npMax, s, &launches_);
   if (timeIt) {

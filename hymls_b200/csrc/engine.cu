@@ -55,6 +55,12 @@ Engine::Engine(const std::string& xml) {
     HY_CUDA(cudaEventCreate(&ev1_));
     HY_CUDA(cudaEventCreate(&evA_));
     HY_CUDA(cudaEventCreate(&evB_));
+    if (const char* e = getenv("HYMLS_B200_SPLIT_SOLVE")) splitSolve_ = atoi(e) != 0;
+    int lo = 0, hi = 0;
+    HY_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));  // lo = least priority
+    HY_CUDA(cudaStreamCreateWithPriority(&side_, cudaStreamNonBlocking, lo));
+    HY_CUDA(cudaEventCreateWithFlags(&evFork_, cudaEventDisableTiming));
+    HY_CUDA(cudaEventCreateWithFlags(&evJoin_, cudaEventDisableTiming));
   }
 }
 
@@ -133,6 +139,9 @@ Engine::~Engine() {
   if (ev1_) cudaEventDestroy(ev1_);
   if (evA_) cudaEventDestroy(evA_);
   if (evB_) cudaEventDestroy(evB_);
+  if (evFork_) cudaEventDestroy(evFork_);
+  if (evJoin_) cudaEventDestroy(evJoin_);
+  if (side_) cudaStreamDestroy(side_);
 }
 
 void Engine::setMatrix(int64_t n, const int64_t* rowptr, const int32_t* colidx, const double* values, int where) {
@@ -234,6 +243,15 @@ void BatchedInverse::setup(const std::vector<int>& n_, const std::vector<int>& n
     rowLimit.upload(*leadRows, s);
     itemMatLead.upload(lm, s);
     itemRow0Lead.upload(lr, s);
+    std::vector<int> tm, tr;
+    for (int m = 0; m < count; ++m)
+      for (int r0 = (*leadRows)[m]; r0 < n_[m]; r0 += rows) {
+        tm.push_back(m);
+        tr.push_back(r0);
+      }
+    numItemsTrail = (int)tm.size();
+    itemMatTrail.upload(tm, s);
+    itemRow0Trail.upload(tr, s);
   }
   n.upload(hN, s);
   np.upload(hNp, s);
@@ -1586,6 +1604,22 @@ void Engine::applyLevel(int l, const double* B, double* X, const double* T) {
     HY_CUDA(cudaEventElapsedTime(&ms, evA_, evB_));
     a11LeadMs_ += ms;
   }
+  // Split second solve (level 0):  x1 = A11^-1 b1 - A11^-1[:, :nb] (A12 x2)[:nb].  The leading rows of A11^-1 b1 are
+  // in x1 already; the remaining rows [nb, n) are computed NOW on the low-priority side stream, concurrently with
+  // the latency-bound separator phase below, and the pass that has to wait for x2 reads the leading nb columns only
+  // (A12 x2 is zero outside the leading interior nodes, symbolic.cpp).  Same bytes as one full pass, (n - nb) n of
+  // them off the critical path.
+  const bool split = splitActive(L, l);
+  if (split) {
+    HY_CUDA(cudaEventRecord(evFork_, s));
+    HY_CUDA(cudaStreamWaitEvent(side_, evFork_, 0));
+    GemvArgs t = g;
+    t.itemMat = L.a11.itemMatTrail.p;
+    t.itemRow0 = L.a11.itemRow0Trail.p;
+    t.nrows = nullptr;
+    batchedGemv(t, L.a11.numItemsTrail, L.a11.npMax, side_, &launches_);
+    HY_CUDA(cudaEventRecord(evJoin_, side_));
+  }
   at.lap("A11 gemv 1 (leading rows)");
   const int bm = borderM_;
   if (bm) {
@@ -1667,6 +1701,15 @@ void Engine::applyLevel(int l, const double* B, double* X, const double* T) {
   g.out = X;
   g.scatter = L.intRow.p;
   g.mode = 0;
+  if (split) {  // X[interior] = x1 - A11^-1[:, :nb] y1
+    HY_CUDA(cudaStreamWaitEvent(s, evJoin_, 0));
+    g.xin = L.y1.p;
+    g.gather = nullptr;
+    g.xsub = nullptr;
+    g.xprev = L.x1.p;
+    g.ncols = L.a11.rowLimit.p;
+    g.mode = 1;
+  }
   if (L.sharded) {  // owned interiors packed per rank, all-gathered, then exported
     g.out = L.xI.p;
     g.outOff = L.gatherOutOff.p;
@@ -2311,7 +2354,8 @@ void Engine::getStats(hymls_b200_stats* st) {
         own += (double)S.sdN[sd] * S.sdN[sd];
         ownLead += (double)S.sdN[sd] * S.sdNb[sd];
       }
-      st->bytes_a11_full_pass = 8.0 * own;             // this rank's share when sharded
+      st->a11_split = splitActive(*levels_[0], 0) ? 1 : 0;
+      st->bytes_a11_full_pass = 8.0 * (st->a11_split ? ownLead : own);  // this rank's share when sharded
       st->bytes_a11_level0 = 8.0 * (own + ownLead);
     }
     // algorithmic bytes of one ApplyInverse, summed over the levels; the A11 term is

@@ -27,6 +27,9 @@ struct BatchedInverse {  // a set of dense inverses + the GEMV work list over th
   // second work list over the leading `leadRows[m]` rows of every matrix (first solve of ApplyInverse)
   DevBuf<int> rowLimit, itemMatLead, itemRow0Lead;
   int numItemsLead = 0;
+  // third work list: the remaining rows [leadRows[m], n) (computed off the critical path, see Engine::applyLevel)
+  DevBuf<int> itemMatTrail, itemRow0Trail;
+  int numItemsTrail = 0;
   // `applyMask` (optional, one flag per matrix): GEMV work items are created for flagged matrices only
   int rowsPerWarp = 0;  // thinner GEMV slabs (see GemvArgs::rowsPerWarp); set before setup()
   void setup(const std::vector<int>& n_, const std::vector<int>& np_, const std::vector<int64_t>& matOff_,
@@ -285,6 +288,11 @@ class Engine {
   hymls_b200_stats stats_{};
   int64_t launches_ = 0;
   cudaEvent_t ev0_ = nullptr, ev1_ = nullptr, evA_ = nullptr, evB_ = nullptr;
+  // split second subdomain solve (applyLevel): low-priority side stream + fork / join events
+  cudaStream_t side_ = nullptr;
+  cudaEvent_t evFork_ = nullptr, evJoin_ = nullptr;
+  bool splitSolve_ = false;  // HYMLS_B200_SPLIT_SOLVE=1 enables (measured slower on 1 GPU)
+  bool splitActive(const Level& L, int l) const { return splitSolve_ && l == 0 && !L.exact && side_ != nullptr; }
   bool timeA11_ = false;
   double a11Ms_ = 0, a11LeadMs_ = 0;
   int a11Launches_ = 0;

@@ -104,6 +104,7 @@ struct GemvArgs {
   const int64_t* vecOff;   // offset of each matrix' segment in the packed vectors
   const int64_t* outOff;   // optional: offset of each matrix' segment in `out` (default: vecOff)
   const int* nrows;        // optional: only rows [0, nrows[mat]) are computed (default: all n)
+  const int* ncols;        // optional: x is zero beyond its first ncols[mat] entries, the rows are read that far only
   const double* A;
   const double* xin;
   const int* gather;

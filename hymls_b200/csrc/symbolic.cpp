@@ -108,6 +108,20 @@ void buildLevelSym(LevelSym& L, const CartesianPartitioner& part, const std::vec
     });
     for (int b : bad)
       if (b) throw Error(HYMLS_B200_ERR_ARG, "separator node not in map / listed twice");
+    // ... and the interior rows that couple to separators (the rows of A12 with entries): A12 x2 is zero outside
+    // them, so the correction A11^-1 (A12 x2) of the second solve needs the same leading COLUMNS only.  For a
+    // structurally symmetric matrix both sets coincide.
+    parallelFor(L.nI, [&](int64_t p0, int64_t p1, int) {
+      for (int64_t p = p0; p < p1; ++p) {
+        const int r = gid2row[H.intGid[p]];
+        if (hit[r]) continue;
+        for (int64_t e = L.rowptr[r]; e < L.rowptr[r + 1]; ++e)
+          if (!isInt[L.colidx[e]]) {
+            __atomic_store_n(&hit[r], (char)1, __ATOMIC_RELAXED);
+            break;
+          }
+      }
+    });
     L.sdNb.assign(H.nsd, 0);
     std::vector<double> sumPerThread(64, 0.0);
     parallelFor(H.nsd, [&](int64_t s0, int64_t s1, int t) {

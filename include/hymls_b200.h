@@ -222,6 +222,11 @@ typedef struct {
   int64_t interior_couplings;   /* matrix entries between interiors of DIFFERENT subdomains, all levels: must be 0
                                    for a correct domain decomposition (Tester::isDDcorrect, src/HYMLS_Tester.cpp:253-455);
                                    such entries would be ignored by the subdomain solvers */
+  int64_t a11_split;            /* 1: the second level-0 subdomain solve is split (HYMLS_B200_SPLIT_SOLVE=1, off by default): rows [nb, n) of A11^-1 b1
+                                   run on a low-priority stream beside the separator phase, and the pass on the critical
+                                   path reads only the leading nb COLUMNS (x1 = A11^-1 b1 - A11^-1[:, :nb] (A12 x2)); the
+                                   bytes per ApplyInverse are unchanged.  bytes_a11_full_pass / ms_a11_kernel_per_launch
+                                   then describe that leading-columns pass (8 * sum n_sd nb_sd bytes).  0: one full pass */
 } hymls_b200_stats;
 int hymls_b200_get_stats(hymls_b200_t* h, hymls_b200_stats* st);
 

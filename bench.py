@@ -363,11 +363,17 @@ def main():
     gm = None
     if not args.no_solve:
         S = hb.Solver(P)
-        xs = S.ApplyInverse(torch.from_numpy(bh).cuda(), x=torch.from_numpy(x0h).cuda())
+        bd, xd = torch.from_numpy(bh).cuda(), torch.from_numpy(x0h).cuda()
         torch.cuda.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        xs = S.ApplyInverse(bd, x=xd)
+        torch.cuda.synchronize()
+        solve_wall = time.perf_counter() - t0   # first call: includes the one-off allocation of the Krylov basis
         err = float(np.linalg.norm(xs.cpu().numpy() - xex) / np.linalg.norm(bh))
         gm = {"iterations": S.num_iter, "converged": bool(S.info["converged"]),
-              "solve_s": S.info["solve_seconds"], "explicit_rel_residual": S.info["explicit_rel_residual"],
+              "solve_s": S.info["solve_seconds"], "solve_wall_first_call_s": solve_wall,
+              "explicit_rel_residual": S.info["explicit_rel_residual"],
               "rel_error": err, "tol": 1e-8, "restart": "none (Num Blocks 600)",
               "history_first15": [float(v) for v in S.history[:15]]}
     # ---- multi-GPU: sharded vs single-GPU results on a small problem, inside the same job ----

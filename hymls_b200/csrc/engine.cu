@@ -142,6 +142,9 @@ Engine::~Engine() {
   if (evFork_) cudaEventDestroy(evFork_);
   if (evJoin_) cudaEventDestroy(evJoin_);
   if (side_) cudaStreamDestroy(side_);
+  destroyPipeEvents();
+  if (pipeStart_) cudaEventDestroy(pipeStart_);
+  if (pipeCopy_) cudaStreamDestroy(pipeCopy_);
 }
 
 void Engine::setMatrix(int64_t n, const int64_t* rowptr, const int32_t* colidx, const double* values, int where) {
@@ -226,6 +229,14 @@ void BatchedInverse::setup(const std::vector<int>& n_, const std::vector<int>& n
       ir.push_back(r0);
     }
   }
+  hItemPtr.assign(1, 0);  // first item of every matrix (exact when no matrix is masked or split off, see uses)
+  {
+    size_t i = 0;
+    for (int m = 0; m < count; ++m) {
+      while (i < im.size() && im[i] == m) ++i;
+      hItemPtr.push_back((int)i);
+    }
+  }
   numItems = (int)im.size();
   numMats = (int)ml.size();
   matList.upload(ml, s);
@@ -240,6 +251,14 @@ void BatchedInverse::setup(const std::vector<int>& n_, const std::vector<int>& n
         lr.push_back(r0);
       }
     numItemsLead = (int)lm.size();
+    hItemPtrLead.assign(1, 0);
+    {
+      size_t i = 0;
+      for (int m = 0; m < count; ++m) {
+        while (i < lm.size() && lm[i] == m) ++i;
+        hItemPtrLead.push_back((int)i);
+      }
+    }
     rowLimit.upload(*leadRows, s);
     itemMatLead.upload(lm, s);
     itemRow0Lead.upload(lr, s);
@@ -387,6 +406,7 @@ void Engine::initialize() {
               std::chrono::duration<double>(tu1 - tu0).count(),
               std::chrono::duration<double>(std::chrono::steady_clock::now() - tu1).count());
   }
+  planHostPipeline();
   if (deviceOk_) {
     auto tr0 = std::chrono::steady_clock::now();
     reserveComputeScratch();
@@ -1595,8 +1615,21 @@ void Engine::applyLevel(int l, const double* B, double* X, const double* T) {
   g.itemRow0 = L.a11.itemRow0Lead.p;
   g.nrows = L.a11.rowLimit.p;
   const bool timeIt = timeA11_ && l == 0;
+  // host-buffer call with the copies overlapped (applyHostPiped): b arrives in chunks on the copy stream
+  const bool piped = l == 0 && pipeHostX_ != nullptr && !timeIt;
   if (timeIt) HY_CUDA(cudaEventRecord(evA_, s));
-  batchedGemv(g, L.a11.numItemsLead, L.a11.npMax, s, &launches_);
+  if (piped) {
+    const HostPipePlan& P = pipePlan_;
+    for (int c = 0; c < P.K; ++c) {
+      HY_CUDA(cudaStreamWaitEvent(s, pipeIn_[c], 0));  // rows [0, inRows[c+1]) of b are on the device
+      GemvArgs gc = g;
+      gc.itemMat += P.leadItem[c];
+      gc.itemRow0 += P.leadItem[c];
+      batchedGemv(gc, P.leadItem[c + 1] - P.leadItem[c], L.a11.npMax, s, &launches_);
+    }
+  } else {
+    batchedGemv(g, L.a11.numItemsLead, L.a11.npMax, s, &launches_);
+  }
   if (timeIt) {
     HY_CUDA(cudaEventRecord(evB_, s));
     HY_CUDA(cudaEventSynchronize(evB_));
@@ -1716,7 +1749,25 @@ void Engine::applyLevel(int l, const double* B, double* X, const double* T) {
     g.scatter = nullptr;
   }
   if (timeIt) HY_CUDA(cudaEventRecord(evA_, s));
-  batchedGemv(g, L.a11.numItems, L.a11.npMax, s, &launches_);
+  if (piped && !L.sharded && !split) {
+    // the separator rows of X are final already (Householder above); after chunk c so are the interior rows below
+    // the first row of the later chunks: they leave on the copy stream while the next chunk runs
+    const HostPipePlan& P = pipePlan_;
+    for (int c = 0; c < P.K; ++c) {
+      GemvArgs gc = g;
+      gc.itemMat += P.fullItem[c];
+      gc.itemRow0 += P.fullItem[c];
+      batchedGemv(gc, P.fullItem[c + 1] - P.fullItem[c], L.a11.npMax, s, &launches_);
+      HY_CUDA(cudaEventRecord(pipeOut_[c], s));
+      HY_CUDA(cudaStreamWaitEvent(pipeCopy_, pipeOut_[c], 0));
+      const int64_t r0 = P.outRows[c], r1 = P.outRows[c + 1];
+      if (r1 > r0)
+        HY_CUDA(cudaMemcpyAsync(pipeHostX_ + r0, X + r0, (size_t)(r1 - r0) * sizeof(double), cudaMemcpyDeviceToHost,
+                                pipeCopy_));
+    }
+  } else {
+    batchedGemv(g, L.a11.numItems, L.a11.npMax, s, &launches_);
+  }
   if (timeIt) {
     HY_CUDA(cudaEventRecord(evB_, s));
     HY_CUDA(cudaEventSynchronize(evB_));
@@ -1841,6 +1892,8 @@ void Engine::applyInverse(const double* B, int64_t ldb, double* X, int64_t ldx, 
     if (where == HYMLS_B200_DEVICE) {
       if (nv > 1) done = applyDeviceMulti(b, ldb, x, ldx, nv);
       if (!done) applyDevice(b, x);
+    } else if (nv == 1 && hostPipeUsable(b, x)) {
+      applyHostPiped(b, x);  // copies overlapped with the two passes over the level-0 inverses
     } else {
       bufB_.alloc((size_t)n_ * nv);
       bufX_.alloc((size_t)n_ * nv);
@@ -1856,6 +1909,137 @@ void Engine::applyInverse(const double* B, int64_t ldb, double* X, int64_t ldx, 
       HY_CUDA(cudaStreamSynchronize(stream_));
     }
     k += done ? nv : 1;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host-buffer ApplyInverse with the copies overlapped (one GPU, pinned buffers)
+// ---------------------------------------------------------------------------------------------
+void Engine::destroyPipeEvents() {
+  for (cudaEvent_t e : pipeIn_) cudaEventDestroy(e);
+  for (cudaEvent_t e : pipeOut_) cudaEventDestroy(e);
+  pipeIn_.clear();
+  pipeOut_.clear();
+}
+
+// Part of Initialize: the chunk schedule follows from the orderings alone (host work: also done without a device, so
+// that the CPU tests see it).  HYMLS_B200_HOST_PIPELINE=0 switches the pipeline off, .._CHUNKS sets K (default 8),
+// .._MIN_ROWS the smallest problem it is used for (default 2^20 rows: below, the event traffic costs more than the
+// copies).
+void Engine::planHostPipeline() {
+  pipePlan_ = HostPipePlan();
+  pipeState_ = 0;
+  pipeHostX_ = nullptr;
+  destroyPipeEvents();
+  const char* e = getenv("HYMLS_B200_HOST_PIPELINE");
+  pipeEnabled_ = e ? atoi(e) != 0 : true;  // (read again at every host-buffer call: the switch works at run time)
+  e = getenv("HYMLS_B200_HOST_PIPELINE_CHUNKS");
+  const int K = e ? atoi(e) : 8;
+  e = getenv("HYMLS_B200_HOST_PIPELINE_MIN_ROWS");
+  const int64_t minRows = e ? atoll(e) : ((int64_t)1 << 20);
+  if (comm_.size() > 1 || levels_.empty() || levels_[0]->exact || n_ < minRows || K < 2 || K > 64) return;
+  const Level& L = *levels_[0];
+  const LevelSym& S = L.sym;
+  if ((int)L.ownSd.size() != S.nsd) return;
+  const std::vector<int64_t> vecOff(S.H.intPtr.begin(), S.H.intPtr.begin() + S.nsd);
+  const int rows = gemvRowsPerItem();
+  HostPipePlan P = planHostPipe(S.sdN, S.sdNb, vecOff, S.intRow, S.n, rows, K);
+  if (P.K < 2 || !checkHostPipe(P, S.sdN, S.sdNb, vecOff, S.intRow, S.n, rows)) return;
+  if (deviceOk_) {
+    // the work lists on the device must be cut exactly where the plan says
+    const BatchedInverse& a = L.a11;
+    if ((int)a.hItemPtr.size() != S.nsd + 1 || (int)a.hItemPtrLead.size() != S.nsd + 1) return;
+    for (int c = 0; c <= P.K; ++c)
+      if (a.hItemPtr[P.matStart[c]] != P.fullItem[c] || a.hItemPtrLead[P.matStart[c]] != P.leadItem[c]) return;
+    if (a.numItems != P.fullItem[P.K] || a.numItemsLead != P.leadItem[P.K]) return;
+    if (!pipeCopy_) HY_CUDA(cudaStreamCreateWithFlags(&pipeCopy_, cudaStreamNonBlocking));
+    if (!pipeStart_) HY_CUDA(cudaEventCreateWithFlags(&pipeStart_, cudaEventDisableTiming));
+    pipeIn_.assign(P.K, nullptr);
+    pipeOut_.assign(P.K, nullptr);
+    for (int c = 0; c < P.K; ++c) {
+      HY_CUDA(cudaEventCreateWithFlags(&pipeIn_[c], cudaEventDisableTiming));
+      HY_CUDA(cudaEventCreateWithFlags(&pipeOut_[c], cudaEventDisableTiming));
+    }
+  }
+  pipePlan_ = P;
+}
+
+bool Engine::hostPipeUsable(const double* b, const double* x) {
+  if (const char* e = getenv("HYMLS_B200_HOST_PIPELINE")) pipeEnabled_ = atoi(e) != 0;
+  if (!pipeEnabled_ || pipeState_ < 0 || pipePlan_.K < 2 || !pipeCopy_ || (int)pipeIn_.size() != pipePlan_.K) return false;
+  if (comm_.size() > 1 || borderM_ > 0 || levels_.empty() || levels_[0]->exact || levels_[0]->sharded || splitSolve_ ||
+      timeA11_)
+    return false;
+  if (b < x + n_ && x < b + n_) return false;  // in-place call: the self-check of the first call needs b intact
+  // pageable memory gains nothing (its copies are staged synchronously): pinned / registered buffers only
+  cudaPointerAttributes ab{}, ax{};
+  if (cudaPointerGetAttributes(&ab, b) != cudaSuccess || cudaPointerGetAttributes(&ax, x) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return ab.type == cudaMemoryTypeHost && ax.type == cudaMemoryTypeHost;
+}
+
+void Engine::applyHostPiped(const double* b, double* x) {
+  cudaStream_t s = stream_;
+  const size_t bytes = (size_t)n_ * sizeof(double);
+  bufB_.alloc(n_);
+  bufX_.alloc(n_);
+  auto piped = [&]() {
+    const HostPipePlan& P = pipePlan_;
+    HY_CUDA(cudaEventRecord(pipeStart_, s));  // the staging buffers may still be in use by earlier work on s
+    HY_CUDA(cudaStreamWaitEvent(pipeCopy_, pipeStart_, 0));
+    for (int c = 0; c < P.K; ++c) {
+      const int64_t r0 = P.inRows[c], r1 = P.inRows[c + 1];
+      if (r1 > r0)
+        HY_CUDA(cudaMemcpyAsync(bufB_.p + r0, b + r0, (size_t)(r1 - r0) * sizeof(double), cudaMemcpyHostToDevice,
+                                pipeCopy_));
+      HY_CUDA(cudaEventRecord(pipeIn_[c], pipeCopy_));
+    }
+    pipeHostX_ = x;
+    try {
+      applyDevice(bufB_.p, bufX_.p);  // applyLevel(0) waits for / hands over the chunks
+    } catch (...) {
+      pipeHostX_ = nullptr;
+      cudaStreamSynchronize(pipeCopy_);
+      cudaStreamSynchronize(s);
+      throw;
+    }
+    pipeHostX_ = nullptr;
+    HY_CUDA(cudaStreamSynchronize(pipeCopy_));
+    HY_CUDA(cudaStreamSynchronize(s));
+  };
+  if (pipeState_ == 1) {
+    piped();
+    return;
+  }
+  // first use: the serial path gives the expected result; the pipelined call then starts from poisoned buffers and
+  // has to reproduce it bit for bit (same kernels on the same data, only cut into chunks)
+  const int callsBefore = stats_.num_apply_inverse;
+  HY_CUDA(cudaMemcpyAsync(bufB_.p, b, bytes, cudaMemcpyHostToDevice, s));
+  applyDevice(bufB_.p, bufX_.p);
+  HY_CUDA(cudaMemcpyAsync(x, bufX_.p, bytes, cudaMemcpyDeviceToHost, s));
+  HY_CUDA(cudaStreamSynchronize(s));
+  std::vector<double> expect(x, x + n_);
+  HY_CUDA(cudaMemsetAsync(bufB_.p, 0xff, bytes, s));
+  HY_CUDA(cudaMemsetAsync(bufX_.p, 0xff, bytes, s));
+  memset(x, 0xff, bytes);
+  bool same = false;
+  std::string why = "results differ";
+  try {
+    piped();
+    same = memcmp(x, expect.data(), bytes) == 0;
+  } catch (const Error& err) {
+    why = err.what();
+  }
+  stats_.num_apply_inverse = callsBefore + 1;  // one call of the user
+  if (same) {
+    pipeState_ = 1;
+  } else {
+    pipeState_ = -1;
+    memcpy(x, expect.data(), bytes);
+    fprintf(stderr, "[hymls_b200] host-buffer pipeline failed its self-check (%s): serial copies from now on\n",
+            why.c_str());
   }
 }
 
@@ -2303,6 +2487,18 @@ void Engine::solve(const double* b, double* x, int where, uint64_t seed, hymls_b
 
 // test hook: copies a device array to the host (doubles). Returns its length.
 int64_t Engine::debugCopy(int level, const std::string& name, double* out, int64_t cap) {
+  if (name.rfind("pipe_", 0) == 0) {  // schedule of the pipelined host-buffer ApplyInverse (host data, no device needed)
+    const HostPipePlan& P = pipePlan_;
+    std::vector<double> v;
+    if (name == "pipe_matstart") v.assign(P.matStart.begin(), P.matStart.end());
+    else if (name == "pipe_leaditem") v.assign(P.leadItem.begin(), P.leadItem.end());
+    else if (name == "pipe_fullitem") v.assign(P.fullItem.begin(), P.fullItem.end());
+    else if (name == "pipe_inrows") v.assign(P.inRows.begin(), P.inRows.end());
+    else if (name == "pipe_outrows") v.assign(P.outRows.begin(), P.outRows.end());
+    else throw Error(HYMLS_B200_ERR_ARG, "debug_copy: unknown array '" + name + "'");
+    if (out && cap >= (int64_t)v.size()) std::copy(v.begin(), v.end(), out);
+    return (int64_t)v.size();
+  }
   needDevice();
   Level& L = *levels_.at(level);
   const double* p = nullptr;
@@ -2361,6 +2557,8 @@ void Engine::getStats(hymls_b200_stats* st) {
         ownLead += (double)S.sdN[sd] * S.sdNb[sd];
       }
       st->a11_split = splitActive(*levels_[0], 0) ? 1 : 0;
+      st->host_pipeline_chunks = pipePlan_.K;
+      st->host_pipeline_state = pipeEnabled_ ? pipeState_ : -2;
       st->bytes_a11_full_pass = 8.0 * (st->a11_split ? ownLead : own);  // this rank's share when sharded
       st->bytes_a11_level0 = 8.0 * (own + ownLead);
     }

@@ -27,6 +27,7 @@ struct BatchedInverse {  // a set of dense inverses + the GEMV work list over th
   // second work list over the leading `leadRows[m]` rows of every matrix (first solve of ApplyInverse)
   DevBuf<int> rowLimit, itemMatLead, itemRow0Lead;
   int numItemsLead = 0;
+  std::vector<int> hItemPtr, hItemPtrLead;  // count+1: first work item of every matrix in itemMat / itemMatLead
   // third work list: the remaining rows [leadRows[m], n) (computed off the critical path, see Engine::applyLevel)
   DevBuf<int> itemMatTrail, itemRow0Trail;
   int numItemsTrail = 0;
@@ -293,6 +294,20 @@ class Engine {
   cudaEvent_t evFork_ = nullptr, evJoin_ = nullptr;
   bool splitSolve_ = false;  // HYMLS_B200_SPLIT_SOLVE=1 enables (measured slower on 1 GPU)
   bool splitActive(const Level& L, int l) const { return splitSolve_ && l == 0 && !L.exact && side_ != nullptr; }
+  // Host-buffer ApplyInverse on one GPU (pinned buffers): the H2D copy of b runs beside the leading-rows pass over the
+  // level-0 inverses, the D2H copy of x beside the full pass (HostPipePlan, symbolic.hpp).  The first pipelined call
+  // is checked bitwise against the serial path and the pipeline is switched off for the handle if they differ.
+  HostPipePlan pipePlan_;        // K == 0: none (several ranks, exact level 0, small problem)
+  bool pipeEnabled_ = true;      // HYMLS_B200_HOST_PIPELINE=0 switches it off
+  int pipeState_ = 0;            // 0: not used yet, 1: verified and in use, -1: self-check failed, serial path from now on
+  cudaStream_t pipeCopy_ = nullptr;
+  cudaEvent_t pipeStart_ = nullptr;
+  std::vector<cudaEvent_t> pipeIn_, pipeOut_;
+  double* pipeHostX_ = nullptr;  // host destination of the pipelined call in flight (nullptr: none)
+  void planHostPipeline();
+  void destroyPipeEvents();
+  bool hostPipeUsable(const double* b, const double* x);
+  void applyHostPiped(const double* b, double* x);
   bool timeA11_ = false;
   double a11Ms_ = 0, a11LeadMs_ = 0;
   int a11Launches_ = 0;

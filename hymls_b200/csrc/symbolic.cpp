@@ -333,4 +333,89 @@ void buildLevelSym(LevelSym& L, const CartesianPartitioner& part, const std::vec
   st.lap("reflectors");
 }
 
+// ---------------------------------------------------------------------------------------------
+// Copy / compute schedule of the host-buffer ApplyInverse (see HostPipePlan)
+// ---------------------------------------------------------------------------------------------
+HostPipePlan planHostPipe(const std::vector<int>& n, const std::vector<int>& nb, const std::vector<int64_t>& vecOff,
+                          const std::vector<int>& intRow, int64_t nRows, int rowsPerItem, int K) {
+  HostPipePlan P;
+  const int M = (int)n.size();
+  if (M == 0 || K < 2 || rowsPerItem <= 0 || nRows <= 0) return P;
+  // smallest / largest matrix row of every matrix, work = bytes of its inverse
+  std::vector<int64_t> lo(M, nRows), hi(M, -1);
+  std::vector<double> cum(M + 1, 0.0);
+  for (int m = 0; m < M; ++m) {
+    for (int q = 0; q < n[m]; ++q) {
+      const int64_t r = intRow[vecOff[m] + q];
+      lo[m] = std::min(lo[m], r);
+      hi[m] = std::max(hi[m], r);
+    }
+    cum[m + 1] = cum[m] + (double)n[m] * (double)n[m];
+  }
+  if (cum[M] <= 0.0) return P;
+  P.matStart.push_back(0);
+  for (int c = 1; c < K; ++c) {
+    const double target = cum[M] * (double)c / (double)K;
+    int m = (int)(std::lower_bound(cum.begin(), cum.end(), target) - cum.begin());
+    m = std::min(m, M);
+    if (m > P.matStart.back() && m < M) P.matStart.push_back(m);
+  }
+  P.matStart.push_back(M);
+  P.K = (int)P.matStart.size() - 1;
+  if (P.K < 2) return HostPipePlan();
+  std::vector<int64_t> sufLo(M + 1, nRows);
+  for (int m = M - 1; m >= 0; --m) sufLo[m] = std::min(sufLo[m + 1], lo[m]);
+  P.leadItem.assign(P.K + 1, 0);
+  P.fullItem.assign(P.K + 1, 0);
+  P.inRows.assign(P.K + 1, 0);
+  P.outRows.assign(P.K + 1, 0);
+  for (int c = 0; c < P.K; ++c) {
+    int lead = 0, full = 0;
+    int64_t need = P.inRows[c];
+    for (int m = P.matStart[c]; m < P.matStart[c + 1]; ++m) {
+      lead += (nb[m] + rowsPerItem - 1) / rowsPerItem;
+      full += (n[m] + rowsPerItem - 1) / rowsPerItem;
+      need = std::max(need, hi[m] + 1);
+    }
+    P.leadItem[c + 1] = P.leadItem[c] + lead;
+    P.fullItem[c + 1] = P.fullItem[c] + full;
+    P.inRows[c + 1] = c + 1 == P.K ? nRows : need;
+    P.outRows[c + 1] = c + 1 == P.K ? nRows : std::max(P.outRows[c], sufLo[P.matStart[c + 1]]);
+  }
+  return P;
+}
+
+bool checkHostPipe(const HostPipePlan& P, const std::vector<int>& n, const std::vector<int>& nb,
+                   const std::vector<int64_t>& vecOff, const std::vector<int>& intRow, int64_t nRows,
+                   int rowsPerItem) {
+  const int M = (int)n.size(), K = P.K;
+  if (K < 2 || (int)P.matStart.size() != K + 1 || (int)P.leadItem.size() != K + 1 ||
+      (int)P.fullItem.size() != K + 1 || (int)P.inRows.size() != K + 1 || (int)P.outRows.size() != K + 1)
+    return false;
+  if (P.matStart[0] != 0 || P.matStart[K] != M || P.leadItem[0] != 0 || P.fullItem[0] != 0 || P.inRows[0] != 0 ||
+      P.outRows[0] != 0 || P.inRows[K] != nRows || P.outRows[K] != nRows)
+    return false;
+  int64_t lead = 0, full = 0;
+  int c = 0;
+  for (int m = 0; m < M; ++m) {
+    while (c < K && m >= P.matStart[c + 1]) {  // chunk boundary: the work lists must be cut exactly here
+      if (P.matStart[c + 1] <= P.matStart[c] || P.leadItem[c + 1] != lead || P.fullItem[c + 1] != full ||
+          P.inRows[c + 1] < P.inRows[c] || P.outRows[c + 1] < P.outRows[c])
+        return false;
+      ++c;
+    }
+    if (c >= K) return false;
+    for (int r0 = 0; r0 < nb[m]; r0 += rowsPerItem) ++lead;   // the loops of BatchedInverse::setup
+    for (int r0 = 0; r0 < n[m]; r0 += rowsPerItem) ++full;
+    for (int q = 0; q < n[m]; ++q) {
+      const int64_t r = intRow[vecOff[m] + q];
+      if (r < 0 || r >= nRows) return false;
+      if (r >= P.inRows[c + 1]) return false;  // b[r] on the device before chunk c of the first pass starts
+      if (r < P.outRows[c]) return false;      // x[r] not copied out before chunk c of the last pass has written it
+    }
+  }
+  return c == K - 1 && P.leadItem[K] == lead && P.fullItem[K] == full;
+}
+
+
 }  // namespace hymls

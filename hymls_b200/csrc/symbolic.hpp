@@ -72,6 +72,26 @@ struct LevelSym {
   double sumNsq = 0;  // sum n_sd^2
 };
 
+// Schedule that overlaps the host <-> device copies of a host-buffer ApplyInverse (one GPU) with the two passes over
+// the level-0 subdomain inverses.  The subdomains (= matrices of the batched GEMV, in storage order) are cut into K
+// consecutive chunks of about equal bytes.  Chunk c of the first pass needs b only on the rows its interiors occupy, so
+// it may start once rows [0, inRows[c+1]) have arrived; after chunk c of the last pass every row below the smallest
+// interior row of the later chunks is final, so rows [outRows[c], outRows[c+1]) can leave while chunk c+1 runs.
+// (Subdomains are numbered along z, matrix rows likewise: a subdomain spans ~10 % of the row range at 128^3.)
+struct HostPipePlan {
+  int K = 0;                             // 0: no plan
+  std::vector<int> matStart;             // K+1: chunk c = matrices [matStart[c], matStart[c+1])
+  std::vector<int> leadItem, fullItem;   // K+1: the chunks' ranges in the leading-rows / full GEMV work lists
+  std::vector<int64_t> inRows, outRows;  // K+1, nondecreasing, first 0, last nRows
+};
+// n / nb / vecOff: per matrix its order, its leading rows and the offset of its segment in the interior ordering;
+// intRow: interior position -> matrix row; rowsPerItem: rows of one GEMV work item
+HostPipePlan planHostPipe(const std::vector<int>& n, const std::vector<int>& nb, const std::vector<int64_t>& vecOff,
+                          const std::vector<int>& intRow, int64_t nRows, int rowsPerItem, int K);
+// row-by-row verification of a plan against its definition (independent formulation; cheap: one pass over intRow)
+bool checkHostPipe(const HostPipePlan& P, const std::vector<int>& n, const std::vector<int>& nb,
+                   const std::vector<int64_t>& vecOff, const std::vector<int>& intRow, int64_t nRows, int rowsPerItem);
+
 // Builds everything above from the matrix pattern and the partitioner of this level.
 // `gid2row`: dense map GID -> row (or -1) over the fine-grid GID space.
 int64_t countInteriorCouplings(const LevelSym& L);

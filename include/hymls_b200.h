@@ -227,6 +227,12 @@ typedef struct {
                                    path reads only the leading nb COLUMNS (x1 = A11^-1 b1 - A11^-1[:, :nb] (A12 x2)); the
                                    bytes per ApplyInverse are unchanged.  bytes_a11_full_pass / ms_a11_kernel_per_launch
                                    then describe that leading-columns pass (8 * sum n_sd nb_sd bytes).  0: one full pass */
+  int64_t host_pipeline_chunks; /* ApplyInverse with HOST buffers on one GPU: number of chunks in which the copy of b is
+                                   overlapped with the leading-rows pass and the copy of x with the full pass over the
+                                   level-0 inverses (0: no schedule -- several ranks, Number of Levels = 0, or fewer rows
+                                   than HYMLS_B200_HOST_PIPELINE_MIN_ROWS, default 2^20).  Used for pinned buffers only */
+  int64_t host_pipeline_state;  /* 0: not used yet, 1: in use (its first call reproduced the serial path bit for bit),
+                                   -1: that check failed, serial copies are used, -2: switched off (HYMLS_B200_HOST_PIPELINE=0) */
 } hymls_b200_stats;
 int hymls_b200_get_stats(hymls_b200_t* h, hymls_b200_stats* st);
 

@@ -430,6 +430,10 @@ def main():
         "e2e": {"value": args.steps / (e2e_ms * 1e-3), "unit": "1/s", "h2d_bytes_per_step": 8 * n,
                 "d2h_bytes_per_step": 8 * n, "per_rank_bytes_each_way": 8 * len(rows),
                 "matches_device_result": e2e_ok,
+                # one GPU: the copies are overlapped with the two passes over the level-0 inverses in `chunks` pieces
+                # (state 1 = the first such call reproduced the serial path bit for bit)
+                "host_pipeline": {"chunks": int(st2.get("host_pipeline_chunks", 0)),
+                                  "state": int(st2.get("host_pipeline_state", 0))},
                 "call": "hymls_b200_apply_inverse_dist (pinned host rows this rank owns in / out)"},
         "gpu_launches": int(launches),
         "clocks": clocks,

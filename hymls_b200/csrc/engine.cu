@@ -1923,9 +1923,11 @@ void Engine::destroyPipeEvents() {
 }
 
 // Part of Initialize: the chunk schedule follows from the orderings alone (host work: also done without a device, so
-// that the CPU tests see it).  HYMLS_B200_HOST_PIPELINE=0 switches the pipeline off, .._CHUNKS sets K (default 8),
-// .._MIN_ROWS the smallest problem it is used for (default 2^20 rows: below, the event traffic costs more than the
-// copies).
+// that the CPU tests see it).  HYMLS_B200_HOST_PIPELINE=0 switches the pipeline off, .._CHUNKS sets K, .._TAPER=0
+// makes the chunks equal, .._MIN_ROWS is the smallest problem it is used for (default 2^20 rows: at 64^3 the copies
+// are 0.15 ms each and nothing is gained).  Defaults from profiles/r02_host_pipeline_variants_1gpu.log (128^3, one
+// B200, serial copies 13.7 ms): 6 tapered chunks 11.87 ms, 8 tapered 11.95, 8 equal 12.10, 12 tapered 12.02,
+// 16 equal 12.35 -- every chunk boundary costs about 30 us of kernel tails and event waits.
 void Engine::planHostPipeline() {
   pipePlan_ = HostPipePlan();
   pipeState_ = 0;
@@ -1934,7 +1936,7 @@ void Engine::planHostPipeline() {
   const char* e = getenv("HYMLS_B200_HOST_PIPELINE");
   pipeEnabled_ = e ? atoi(e) != 0 : true;  // (read again at every host-buffer call: the switch works at run time)
   e = getenv("HYMLS_B200_HOST_PIPELINE_CHUNKS");
-  const int K = e ? atoi(e) : 8;
+  const int K = e ? atoi(e) : 6;
   e = getenv("HYMLS_B200_HOST_PIPELINE_MIN_ROWS");
   const int64_t minRows = e ? atoll(e) : ((int64_t)1 << 20);
   if (comm_.size() > 1 || levels_.empty() || levels_[0]->exact || n_ < minRows || K < 2 || K > 64) return;
@@ -1943,7 +1945,9 @@ void Engine::planHostPipeline() {
   if ((int)L.ownSd.size() != S.nsd) return;
   const std::vector<int64_t> vecOff(S.H.intPtr.begin(), S.H.intPtr.begin() + S.nsd);
   const int rows = gemvRowsPerItem();
-  HostPipePlan P = planHostPipe(S.sdN, S.sdNb, vecOff, S.intRow, S.n, rows, K);
+  e = getenv("HYMLS_B200_HOST_PIPELINE_TAPER");
+  const bool taper = e ? atoi(e) != 0 : true;
+  HostPipePlan P = planHostPipe(S.sdN, S.sdNb, vecOff, S.intRow, S.n, rows, K, taper);
   if (P.K < 2 || !checkHostPipe(P, S.sdN, S.sdNb, vecOff, S.intRow, S.n, rows)) return;
   if (deviceOk_) {
     // the work lists on the device must be cut exactly where the plan says

@@ -337,7 +337,7 @@ void buildLevelSym(LevelSym& L, const CartesianPartitioner& part, const std::vec
 // Copy / compute schedule of the host-buffer ApplyInverse (see HostPipePlan)
 // ---------------------------------------------------------------------------------------------
 HostPipePlan planHostPipe(const std::vector<int>& n, const std::vector<int>& nb, const std::vector<int64_t>& vecOff,
-                          const std::vector<int>& intRow, int64_t nRows, int rowsPerItem, int K) {
+                          const std::vector<int>& intRow, int64_t nRows, int rowsPerItem, int K, bool taper) {
   HostPipePlan P;
   const int M = (int)n.size();
   if (M == 0 || K < 2 || rowsPerItem <= 0 || nRows <= 0) return P;
@@ -353,9 +353,17 @@ HostPipePlan planHostPipe(const std::vector<int>& n, const std::vector<int>& nb,
     cum[m + 1] = cum[m] + (double)n[m] * (double)n[m];
   }
   if (cum[M] <= 0.0) return P;
+  // share of the work per chunk: equal, or tapered towards both ends (1 2 4 8 8 .. 8 4 2 1): the copy of b that the
+  // FIRST chunk waits for and the copy of x that follows the LAST chunk are the parts that cannot be hidden
+  std::vector<double> share(K, 1.0);
+  if (taper)
+    for (int c = 0; c < K; ++c) share[c] = (double)(1 << std::min(std::min(c, K - 1 - c), 3));
+  double total = 0.0, acc = 0.0;
+  for (double v : share) total += v;
   P.matStart.push_back(0);
   for (int c = 1; c < K; ++c) {
-    const double target = cum[M] * (double)c / (double)K;
+    acc += share[c - 1];
+    const double target = cum[M] * acc / total;
     int m = (int)(std::lower_bound(cum.begin(), cum.end(), target) - cum.begin());
     m = std::min(m, M);
     if (m > P.matStart.back() && m < M) P.matStart.push_back(m);

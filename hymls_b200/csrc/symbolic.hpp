@@ -87,7 +87,7 @@ struct HostPipePlan {
 // n / nb / vecOff: per matrix its order, its leading rows and the offset of its segment in the interior ordering;
 // intRow: interior position -> matrix row; rowsPerItem: rows of one GEMV work item
 HostPipePlan planHostPipe(const std::vector<int>& n, const std::vector<int>& nb, const std::vector<int64_t>& vecOff,
-                          const std::vector<int>& intRow, int64_t nRows, int rowsPerItem, int K);
+                          const std::vector<int>& intRow, int64_t nRows, int rowsPerItem, int K, bool taper = false);
 // row-by-row verification of a plan against its definition (independent formulation; cheap: one pass over intRow)
 bool checkHostPipe(const HostPipePlan& P, const std::vector<int>& n, const std::vector<int>& nb,
                    const std::vector<int64_t>& vecOff, const std::vector<int>& intRow, int64_t nRows, int rowsPerItem);

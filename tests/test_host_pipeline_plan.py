@@ -16,10 +16,12 @@ def _plan(P):
     return {k: P.DebugArray("pipe_" + k).astype(np.int64) for k in ("matstart", "leaditem", "fullitem", "inrows", "outrows")}
 
 
-@pytest.mark.parametrize("partitioner,nx,sx,chunks", [("Skew Cartesian", 16, 4, 8), ("Cartesian", 16, 4, 5),
-                                                      ("Skew Cartesian", 32, 8, 16)])
-def test_schedule_follows_its_definition(partitioner, nx, sx, chunks, monkeypatch):
+@pytest.mark.parametrize("partitioner,nx,sx,chunks,taper", [("Skew Cartesian", 16, 4, 8, 0), ("Cartesian", 16, 4, 5, 0),
+                                                            ("Skew Cartesian", 32, 8, 16, 0),
+                                                            ("Skew Cartesian", 32, 4, 8, 1)])
+def test_schedule_follows_its_definition(partitioner, nx, sx, chunks, taper, monkeypatch):
     monkeypatch.setenv("HYMLS_B200_HOST_PIPELINE_MIN_ROWS", "0")
+    monkeypatch.setenv("HYMLS_B200_HOST_PIPELINE_TAPER", str(taper))
     monkeypatch.setenv("HYMLS_B200_HOST_PIPELINE_CHUNKS", str(chunks))
     prec = {"Partitioner": partitioner, "Separator Length": sx, "Number of Levels": 2, "Coarsening Factor": 2}
     if partitioner == "Cartesian":
@@ -59,7 +61,10 @@ def test_schedule_follows_its_definition(partitioner, nx, sx, chunks, monkeypatc
         w = written_by[pl["outrows"][c]:pl["outrows"][c + 1]]
         assert np.all(w <= c)
     # chunks of comparable work, and a schedule that actually overlaps: half of b is not needed by the first chunk
-    assert sizes.max() <= 2.5 * sizes.mean()
+    if taper:   # shares 1 2 4 8 8 4 2 1: the end chunks are the small ones
+        assert sizes[0] < 0.5 * sizes.mean() and sizes[-1] < 0.5 * sizes.mean() and sizes.max() <= 3.5 * sizes.mean()
+    else:
+        assert sizes.max() <= 2.5 * sizes.mean()
     assert pl["inrows"][1] <= 0.75 * n and pl["outrows"][K - 1] >= 0.25 * n
 
 

@@ -3,6 +3,7 @@ serial copies (HYMLS_B200_HOST_PIPELINE=0) vs overlapped copies on the same hand
 and the time per call of both, for a few chunk counts.  Appends one JSON object per grid to the output file as it goes.
 
     python tools/host_pipeline_check.py gpurun_out/host_pipeline.jsonl 64 128
+    python tools/host_pipeline_check.py gpurun_out/host_pipeline.jsonl 128:8,8t,6t,10t
 """
 import ctypes as C
 import json
@@ -58,15 +59,16 @@ def run(nx, out, chunk_list, reps):
     b[:] = np.random.default_rng(0).uniform(-1, 1, n)
     rec = {"nx": nx, "n": int(n), "chunks": {}}
     P = None
-    for K in chunk_list:
-        os.environ["HYMLS_B200_HOST_PIPELINE_CHUNKS"] = str(K)
+    for K in chunk_list:   # "8": equal chunks, "8t": tapered towards both ends
+        os.environ["HYMLS_B200_HOST_PIPELINE_TAPER"] = "1" if str(K).endswith("t") else "0"
+        os.environ["HYMLS_B200_HOST_PIPELINE_CHUNKS"] = str(K).rstrip("t")
         if P is not None:
             P.__del__()   # one handle at a time: 37.6 GB of inverses at 128^3
         P = hb.Preconditioner(A, params(nx), tv)
         P.Initialize()
         P.Compute()
         lib, h = P._lib, P._h
-        log("K=%d initialized + computed" % K)
+        log("K=%s initialized + computed" % K)
         os.environ["HYMLS_B200_HOST_PIPELINE"] = "0"
         xs[:] = 0
         ms_serial = timed(lib, h, b, xs, reps)
@@ -83,7 +85,7 @@ def run(nx, out, chunk_list, reps):
              "finite": bool(np.isfinite(xp).all()), "calls_counted": int(st["num_apply_inverse"] - calls0),
              "calls_made": reps + 2, "ms_serial": ms_serial, "ms_pipelined": ms_piped}
         rec["chunks"][str(K)] = r
-        log("K=%d %s" % (K, json.dumps(r)))
+        log("K=%s %s" % (K, json.dumps(r)))
         with open(out, "a") as f:
             f.write(json.dumps({"nx": nx, "K": K, **r}) + "\n")
     return rec
@@ -92,7 +94,9 @@ def run(nx, out, chunk_list, reps):
 if __name__ == "__main__":
     out = sys.argv[1]
     os.makedirs(os.path.dirname(os.path.abspath(out)), exist_ok=True)
-    grids = [int(v) for v in sys.argv[2:]] or [64]
-    for nx in grids:
-        run(nx, out, [8] if nx < 128 else [8, 16, 4], 20)
+    grids = [v for v in sys.argv[2:]] or ["64"]     # "128" or "128:8,8t,6t" (grid : chunk variants)
+    for g in grids:
+        nx = int(g.split(":")[0])
+        variants = g.split(":")[1].split(",") if ":" in g else (["8"] if nx < 128 else ["8", "16", "4"])
+        run(nx, out, variants, 20)
     log("done")

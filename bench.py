@@ -17,7 +17,7 @@ Timing is the max over ranks.  With N > 1 the line also carries `mgpu_check`: sh
 GMRES on a small problem run inside the same job.
 
 The CPU arm runs the SAME parameter list (levels, cx, partitioner) on the same workload when the host can hold it
-(--cpu-nx, default: the workload's nx for --gpus 1 with >= 12 cores and >= 96 GB of free RAM, else 64) for K real ApplyInverse
+(--cpu-nx, default: the workload's nx for --gpus 1 with >= 16 cores and >= 96 GB of free RAM, else 64) for K real ApplyInverse
 calls and the GMRES solve; on a smaller grid the rate is scaled by the subdomain ratio and flagged.
 """
 import argparse
@@ -231,7 +231,8 @@ def reference_arm(args, workload):
     if nx_cpu <= 0:
         # the full workload takes ~4 minutes on 16 cores (Compute ~45 s, GMRES ~3 min): run it for the N=1 line; the
         # lines of a scaling run (N > 1, same CPU quantity every time) use the 64^3 grid scaled by the subdomain ratio
-        full = cores >= 12 and mem_available_gb() >= 96.0 and args.gpus == 1
+        # (fewer than 16 cores would push the full-size run beyond ~5 minutes)
+        full = cores >= 16 and mem_available_gb() >= 96.0 and args.gpus == 1
         nx_cpu = args.nx if full else min(args.nx, 64)
     r = cpu_oracle_run(nx_cpu, args.sx, args.levels, args.cx, args.steps, args.warmup, threads, not args.no_solve)
     same = nx_cpu == args.nx

@@ -23,6 +23,7 @@
 #include <omp.h>
 
 #include <algorithm>
+#include <array>
 #include <chrono>
 #include <cmath>
 #include <cstdint>
@@ -59,6 +60,7 @@ struct Csr {
 // Sparse LU, left looking (Gilbert-Peierls), partial pivoting with a preference for the diagonal
 // (threshold 0.001 like KLU's default), column ordering = minimum degree on A + A'.
 // ---------------------------------------------------------------------------------------------
+static std::vector<int> minimumDegreeOrderAdj(std::vector<std::vector<int>>& adj);
 static std::vector<int> minimumDegreeOrder(int n, const std::vector<int>& Ap, const std::vector<int>& Ai) {
   std::vector<std::vector<int>> adj(n);
   for (int j = 0; j < n; ++j)
@@ -69,6 +71,11 @@ static std::vector<int> minimumDegreeOrder(int n, const std::vector<int>& Ap, co
         adj[j].push_back(i);
       }
     }
+  return minimumDegreeOrderAdj(adj);
+}
+// adj: undirected graph as (possibly unsorted, repeated) neighbour lists without self loops; consumed
+static std::vector<int> minimumDegreeOrderAdj(std::vector<std::vector<int>>& adj) {
+  const int n = (int)adj.size();
   for (auto& a : adj) {
     std::sort(a.begin(), a.end());
     a.erase(std::unique(a.begin(), a.end()), a.end());
@@ -99,14 +106,151 @@ static std::vector<int> minimumDegreeOrder(int n, const std::vector<int>& Ap, co
   return order;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Ordering and scaling of the reference's subdomain solver ("Custom Ordering" / "Custom Scaling", both default true,
+// src/HYMLS_SparseDirectSolver.cpp:238-239): MatrixUtils::FillReducingOrdering (src/HYMLS_MatrixUtils.cpp:1311-1740)
+// and SparseDirectSolver::ComputeScaling (src/HYMLS_SparseDirectSolver.cpp:632-664).
+//   * nodes with a zero diagonal are P-nodes, the others V-nodes (:1338-1363); the matrix must be an F-matrix: every
+//     V-row has at most two P-entries (:1414);
+//   * a fill-reducing ordering q of the V-nodes on the graph of A_VV + B B' (:1428-1432, AMD in the reference, exact
+//     minimum degree here);
+//   * walking through q, a V-node that still couples to two different (merged) P-nodes takes one of them along right
+//     behind it -- the one with fewer couplings; merged P-nodes are tracked with a union-find (:1644-1694) -- and the two
+//     ROWS are interchanged so that the pivots are  b 0 / a b  (:1690-1692); P-nodes never picked come last (:1706-1717);
+//   * rows and columns of P-nodes are scaled by the largest diagonal entry.
+// KLU then factors in exactly this order (ordering = 2: given, pivot tolerance 0: the diagonal whenever it is non-zero,
+// :244-254).  Returns false when the matrix is not of that form (the caller orders it like a general matrix).
+// ---------------------------------------------------------------------------------------------
+static bool fmatrixOrdering(int N, const std::vector<int>& Ap, const std::vector<int>& Ai, const std::vector<double>& Ax,
+                            std::vector<int>& rowperm, std::vector<int>& colperm, std::vector<double>& scale) {
+  std::vector<double> diag(N, 0.0);
+  // row-wise pattern (columns ascending)
+  std::vector<int> Rp(N + 1, 0), Rc(Ai.size());
+  for (int i : Ai) Rp[i + 1]++;
+  for (int i = 0; i < N; ++i) Rp[i + 1] += Rp[i];
+  {
+    std::vector<int> fill(Rp.begin(), Rp.end() - 1);
+    for (int j = 0; j < N; ++j)
+      for (int p = Ap[j]; p < Ap[j + 1]; ++p) {
+        Rc[fill[Ai[p]]++] = j;
+        if (Ai[p] == j) diag[j] = Ax[p];
+      }
+  }
+  std::vector<int> vIdx(N, -1), pIdx(N, -1), V, P;
+  double dmax = 0.0;
+  for (int i = 0; i < N; ++i) {
+    dmax = std::max(dmax, std::fabs(diag[i]));
+    if (diag[i] == 0.0) { pIdx[i] = (int)P.size(); P.push_back(i); }
+    else { vIdx[i] = (int)V.size(); V.push_back(i); }
+  }
+  const int n = (int)V.size(), m = (int)P.size();
+  scale.assign(N, 1.0);
+  for (int i = 0; i < N; ++i)
+    if (std::fabs(diag[i]) <= SMALL * dmax) scale[i] = dmax;
+  rowperm.assign(N, 0);
+  colperm.assign(N, 0);
+  if (m == 0) {
+    std::vector<int> q = minimumDegreeOrder(N, Ap, Ai);
+    rowperm = q;
+    colperm = q;
+    return true;
+  }
+  // Gr: the (at most two) P-nodes of every V-row; cont: V-couplings of every P-row
+  std::vector<std::array<int, 2>> Gr(n, std::array<int, 2>{m, m});
+  std::vector<int> cont(m, 0);
+  int maxB = 0;
+  for (int i = 0; i < n; ++i) {
+    int cnt = 0;
+    for (int e = Rp[V[i]]; e < Rp[V[i] + 1]; ++e) {
+      const int j = pIdx[Rc[e]];
+      if (j < 0) continue;
+      if (Gr[i][0] == m) Gr[i][0] = j; else Gr[i][1] = j;
+      ++cnt;
+    }
+    maxB = std::max(maxB, cnt);
+  }
+  if (maxB != 1 && maxB != 2) return false;
+  for (int j = 0; j < m; ++j)
+    for (int e = Rp[P[j]]; e < Rp[P[j] + 1]; ++e)
+      if (vIdx[Rc[e]] >= 0) cont[j]++;
+  // graph of A_VV + B Bt, Bt = A_PV
+  std::vector<std::vector<int>> adj(n);
+  for (int i = 0; i < n; ++i)
+    for (int e = Rp[V[i]]; e < Rp[V[i] + 1]; ++e) {
+      const int c = Rc[e];
+      if (vIdx[c] >= 0) {
+        if (vIdx[c] != i) { adj[i].push_back(vIdx[c]); adj[vIdx[c]].push_back(i); }
+      } else {
+        for (int f = Rp[c]; f < Rp[c + 1]; ++f) {
+          const int k = vIdx[Rc[f]];
+          if (k >= 0 && k != i) { adj[i].push_back(k); adj[k].push_back(i); }
+        }
+      }
+    }
+  const std::vector<int> q = minimumDegreeOrderAdj(adj);
+  std::vector<int> pid(m + 1), symperm(N, -1), perm(N);
+  for (int i = 0; i <= m; ++i) pid[i] = i;
+  for (int i = 0; i < N; ++i) perm[i] = i;
+  int jj = 0;
+  for (int i = 0; i < n; ++i) {
+    const int qi = q[i];
+    symperm[jj] = V[qi];
+    int g1 = Gr[qi][0], g2 = Gr[qi][1];
+    while (pid[g1] != g1) g1 = pid[g1];
+    while (pid[g2] != g2) g2 = pid[g2];
+    if (g1 == g2) { jj += 1; continue; }  // no P-coupling (left)
+    int take;
+    if (g1 == m) { pid[g2] = pid[g1]; take = g2; }
+    else if (g2 == m) { pid[g1] = pid[g2]; take = g1; }
+    else if (cont[g2] > cont[g1]) { pid[g1] = pid[g2]; take = g1; cont[g2] = cont[g1] + cont[g2] - 2; }
+    else { pid[g2] = pid[g1]; take = g2; cont[g1] = cont[g1] + cont[g2] - 2; }
+    symperm[jj + 1] = P[take];
+    perm[jj] = jj + 1;
+    perm[jj + 1] = jj;
+    jj += 2;
+  }
+  std::vector<char> placed(N, 0);
+  for (int i = 0; i < jj; ++i) placed[symperm[i]] = 1;
+  for (int i = 0; i < N; ++i)
+    if (!placed[i]) symperm[jj++] = i;
+  if (jj != N) return false;
+  for (int i = 0; i < N; ++i) {
+    colperm[i] = symperm[i];
+    rowperm[i] = symperm[perm[i]];
+  }
+  return true;
+}
+
 struct SparseLU {
   int n = 0;
   std::vector<int> Lp, Li, Up, Ui, pinv, q;  // L unit lower (diagonal first in every column), U (diagonal last)
   std::vector<double> Lx, Ux;
+  std::vector<double> scale;  // F-matrix path: rows and columns of the P-nodes scaled (empty: none)
+  bool fOrdered = false;      // factored in the reference's F-matrix order with static pivots
   // A in CSC (Ap, Ai, Ax).  Returns false when a pivot column is exactly zero.
-  bool factor(int n_, const std::vector<int>& Ap, const std::vector<int>& Ai, const std::vector<double>& Ax) {
+  // fmatrix: order, scale and pivot like the reference's subdomain solver when the matrix has that form
+  bool factor(int n_, const std::vector<int>& Ap, const std::vector<int>& Ai, const std::vector<double>& AxIn,
+              bool fmatrix = false) {
     n = n_;
-    q = minimumDegreeOrder(n, Ap, Ai);
+    std::vector<int> prefRow;  // preferred pivot row of elimination step k (the diagonal of the permuted matrix)
+    std::vector<double> AxScaled;
+    scale.clear();
+    fOrdered = false;
+    if (fmatrix) {
+      std::vector<int> rp, cp;
+      if (fmatrixOrdering(n, Ap, Ai, AxIn, rp, cp, scale)) {
+        q = cp;
+        prefRow = rp;
+        fOrdered = true;
+        AxScaled = AxIn;
+        for (int j = 0; j < n; ++j)
+          for (int p = Ap[j]; p < Ap[j + 1]; ++p) AxScaled[p] *= scale[Ai[p]] * scale[j];
+      } else {
+        scale.clear();
+      }
+    }
+    const std::vector<double>& Ax = fOrdered ? AxScaled : AxIn;
+    if (!fOrdered) q = minimumDegreeOrder(n, Ap, Ai);
     pinv.assign(n, -1);
     Lp.assign(n + 1, 0);
     Up.assign(n + 1, 0);
@@ -173,7 +317,12 @@ struct SparseLU {
         }
       }
       if (ipiv < 0 || a <= 0.0) return false;
-      if (pinv[col] < 0 && mark[col] == k && std::fabs(x[col]) >= 0.001 * a) ipiv = col;
+      if (fOrdered) {  // given order, pivot tolerance 0: the diagonal of the permuted matrix whenever it is non-zero
+        const int pr = prefRow[k];
+        if (pinv[pr] < 0 && mark[pr] == k && x[pr] != 0.0) ipiv = pr;
+      } else if (pinv[col] < 0 && mark[col] == k && std::fabs(x[col]) >= 0.001 * a) {
+        ipiv = col;
+      }
       const double pivot = x[ipiv];
       Ui.push_back(k);
       Ux.push_back(pivot);
@@ -196,6 +345,8 @@ struct SparseLU {
   }
   // b <- A^-1 b  (work: n doubles)
   void solve(double* b, double* work) const {
+    if (!scale.empty())
+      for (int i = 0; i < n; ++i) b[i] *= scale[i];
     for (int i = 0; i < n; ++i) work[pinv[i]] = b[i];
     for (int j = 0; j < n; ++j) {
       const double xj = work[j];
@@ -209,6 +360,8 @@ struct SparseLU {
         for (int p = Up[j]; p < Up[j + 1] - 1; ++p) work[Ui[p]] -= Ux[p] * xj;
     }
     for (int k = 0; k < n; ++k) b[q[k]] = work[k];
+    if (!scale.empty())
+      for (int i = 0; i < n; ++i) b[i] *= scale[i];
   }
   int64_t nnzFactors() const { return (int64_t)Li.size() + (int64_t)Ui.size(); }
 };
@@ -398,7 +551,7 @@ static void putDirichlet(Csr& A, int row) {
         if (A.col[e] == row) A.val[e] = 0.0;
 }
 
-static bool factorCsr(const Csr& A, SparseLU& lu) {  // CSR -> CSC -> LU
+static bool factorCsr(const Csr& A, SparseLU& lu, bool fmatrix = false) {  // CSR -> CSC -> LU
   const int n = (int)A.n;
   std::vector<int> Ap(n + 1, 0), Ai(A.col.size());
   std::vector<double> Ax(A.col.size());
@@ -411,7 +564,7 @@ static bool factorCsr(const Csr& A, SparseLU& lu) {  // CSR -> CSC -> LU
       Ai[p] = r;
       Ax[p] = A.val[e];
     }
-  return lu.factor(n, Ap, Ai, Ax);
+  return lu.factor(n, Ap, Ai, Ax, fmatrix);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -458,6 +611,9 @@ class Level {
   std::vector<Csr> sdA;                  // the A11 blocks themselves (refinement only)
   Csr coarseA;
   int refineSteps = 0;
+  // subdomain solvers ordered / scaled / pivoted like the reference's ("Custom Ordering", "Custom Scaling" = true);
+  // false: general minimum-degree ordering with threshold partial pivoting (ho_set_subdomain_ordering)
+  bool fmatrixSolver = true;
   // next level / coarse
   std::unique_ptr<Level> next;
   Csr reduced;                           // reduced Schur complement on the V-sums after dropping
@@ -814,7 +970,7 @@ void Level::compute(std::vector<Partition>& parts, const std::vector<int64_t>& f
       for (auto& pr : ent) { B.col.push_back(pr.first); B.val.push_back(pr.second); }
       B.ptr[i + 1] = (int64_t)B.col.size();
     }
-    if (!factorCsr(B, sdLU[sd])) {
+    if (!factorCsr(B, sdLU[sd], fmatrixSolver)) {
 #pragma omp critical
       ok = false;
     }
@@ -855,6 +1011,7 @@ void Level::compute(std::vector<Partition>& parts, const std::vector<int64_t>& f
     next->level = level + 1;
     next->maxLevel = maxLevel;
     next->refineSteps = refineSteps;
+    next->fmatrixSolver = fmatrixSolver;
     next->A = reduced;
     next->gids = vsumGids;
     std::vector<double> ttv(nS);
@@ -1171,6 +1328,12 @@ int ho_set_refinement(void* hv, int steps) {
   return 0;
 }
 
+// 1 (default): the reference's F-matrix ordering + scaling + static pivots in the subdomain solvers; 0: general path
+int ho_set_subdomain_ordering(void* hv, int fmatrix) {
+  ((Handle*)hv)->L0.fmatrixSolver = fmatrix != 0;
+  return 0;
+}
+
 int ho_compute(void* hv, int threads) {
   Handle* h = (Handle*)hv;
   HO_TRY(h, {
@@ -1240,6 +1403,30 @@ int ho_get_reduced(void* hv, int level, int64_t* n, int64_t* nnz, int64_t* ptr, 
     if (col) std::copy(L->reduced.col.begin(), L->reduced.col.end(), col);
     if (val) std::copy(L->reduced.val.begin(), L->reduced.val.end(), val);
   })
+}
+
+// Fill of the sparse LU on its own (CSC input): nnz(L) incl. the unit diagonal and nnz(U) incl. the diagonal, and the
+// solution of A x = b as a check.  Lets the tests compare the fill of the CPU baseline's factorization with the
+// reference's known-answer counts for KLU (testSuite/unit_tests/HYMLS_SparseDirectSolver.cpp:62-152).
+int ho_lu_fill(int n, const int32_t* Ap, const int32_t* Ai, const double* Ax, int fmatrix, const double* b, double* x,
+               int64_t* nnzL, int64_t* nnzU) {
+  try {
+    std::vector<int> ap(Ap, Ap + n + 1), ai(Ai, Ai + Ap[n]);
+    std::vector<double> ax(Ax, Ax + Ap[n]);
+    SparseLU lu;
+    if (!lu.factor(n, ap, ai, ax, fmatrix != 0)) return -2;
+    if (fmatrix && !lu.fOrdered) return -3;  // not an F-matrix
+    *nnzL = (int64_t)lu.Li.size();
+    *nnzU = (int64_t)lu.Ui.size();
+    if (b && x) {
+      std::copy(b, b + n, x);
+      std::vector<double> w(n);
+      lu.solve(x, w.data());
+    }
+    return 0;
+  } catch (const std::exception&) {
+    return -1;
+  }
 }
 
 }  // extern "C"

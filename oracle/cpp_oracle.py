@@ -47,6 +47,8 @@ def load():
                                  C.POINTER(C.c_int), C.POINTER(C.c_double), vp, C.c_int, C.POINTER(C.c_int)]
         lib.ho_stats.argtypes = [vp, vp]
         lib.ho_get_reduced.argtypes = [vp, C.c_int, C.POINTER(i64), C.POINTER(i64), vp, vp, vp]
+        lib.ho_lu_fill.argtypes = [C.c_int, vp, vp, vp, C.c_int, vp, vp, C.POINTER(i64), C.POINTER(i64)]
+        lib.ho_set_subdomain_ordering.argtypes = [vp, C.c_int]
         _LIB = lib
     return _LIB
 
@@ -100,7 +102,7 @@ def maps_from_library(P):
 class Preconditioner:
     """HYMLS::Preconditioner(K, params, testVector) on the CPU (C++/OpenMP); same method names as oracle.hymls"""
 
-    def __init__(self, A, params, testvector, maps, threads=0, refine_steps=0):
+    def __init__(self, A, params, testvector, maps, threads=0, refine_steps=0, fmatrix_ordering=True):
         self.lib = load()
         A = sp.csr_matrix(A)
         A.sort_indices()
@@ -136,6 +138,10 @@ class Preconditioner:
         # refine_steps > 0: every direct solve is refined with extended-precision residuals (checker only: makes the
         # oracle as accurate as the exact-arithmetic algorithm where plain FP64 LU solves are not)
         self.lib.ho_set_refinement(self.h, int(refine_steps))
+        # subdomain solvers: the reference's F-matrix ordering + scaling + static pivots ("Custom Ordering" / "Custom
+        # Scaling", default true in src/HYMLS_SparseDirectSolver.cpp:238-239), or a general minimum-degree ordering
+        # with threshold partial pivoting
+        self.lib.ho_set_subdomain_ordering(self.h, 1 if fmatrix_ordering else 0)
 
     def __del__(self):
         try:
@@ -188,3 +194,27 @@ class Preconditioner:
         self._check(self.lib.ho_get_reduced(self.h, level, C.byref(n), C.byref(nnz), ptr.ctypes.data, col.ctypes.data,
                                             val.ctypes.data))
         return sp.csr_matrix((val, col, ptr), shape=(n.value, n.value))
+
+
+def lu_fill(A, b=None, fmatrix=False):
+    """nnz(L) (unit diagonal included), nnz(U) of the oracle's sparse LU of A, and A^-1 b (or None).
+    fmatrix: the reference's subdomain-solver ordering / scaling / static pivots (MatrixUtils::FillReducingOrdering)."""
+    lib = load()
+    Ac = sp.csc_matrix(A)
+    Ac.sort_indices()
+    n = Ac.shape[0]
+    ap = np.ascontiguousarray(Ac.indptr, dtype=np.int32)
+    ai = np.ascontiguousarray(Ac.indices, dtype=np.int32)
+    ax = np.ascontiguousarray(Ac.data, dtype=np.float64)
+    nl, nu = C.c_int64(), C.c_int64()
+    x = None
+    bp = xp = None
+    if b is not None:
+        bc = np.ascontiguousarray(b, dtype=np.float64)
+        x = np.zeros(n)
+        bp, xp = bc.ctypes.data, x.ctypes.data
+    rc = lib.ho_lu_fill(n, ap.ctypes.data, ai.ctypes.data, ax.ctypes.data, 1 if fmatrix else 0, bp, xp, C.byref(nl),
+                        C.byref(nu))
+    if rc != 0:
+        raise RuntimeError("ho_lu_fill failed (%d)" % rc)
+    return nl.value, nu.value, x

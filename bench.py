@@ -238,8 +238,8 @@ def reference_arm(args, workload):
     same = nx_cpu == args.nx
     scale = r["subdomains"] / float(num_subdomains(args.nx, args.sx))   # time is linear in the subdomain count
     v = scale / r["apply_s"]
-    sample = ("C++/OpenMP restatement of the reference's CPU path (oracle/cpp: sparse LU per subdomain, same "
-              "parameter list), %d threads, %d^3 grid = %d of %d subdomains%s: Compute %.1f s, %d timed ApplyInverse "
+    sample = ("C++/OpenMP restatement of the reference's CPU path (oracle/cpp: sparse LU per subdomain in the "
+              "reference's F-matrix ordering, same parameter list), %d threads, %d^3 grid = %d of %d subdomains%s: Compute %.1f s, %d timed ApplyInverse "
               "calls at %.1f ms" % (r["threads"], nx_cpu, r["subdomains"], num_subdomains(args.nx, args.sx),
                                     "" if same else " (rate scaled by the subdomain ratio)", r["compute_s"],
                                     args.steps, r["apply_s"] * 1e3))
@@ -463,7 +463,8 @@ def main():
         scale = r["subdomains"] / float(num_subdomains(nx, sx))
         out["cpu_baseline"] = {
             "value": scale / r["apply_s"], "unit": "1/s", "cores": r["threads"], "kind": "port",
-            "sample": "C++/OpenMP restatement (oracle/cpp, sparse LU per subdomain, same parameter list) on a %d^3 grid "
+            "sample": "C++/OpenMP restatement (oracle/cpp, sparse LU per subdomain in the reference's F-matrix ordering, "
+                      "same parameter list) on a %d^3 grid "
                       "= %d of %d subdomains, %d threads; 10 ApplyInverse calls at %.2f ms, rate scaled by the "
                       "subdomain ratio; `bench.py --impl reference` runs the full-size CPU arm"
                       % (snx, r["subdomains"], num_subdomains(nx, sx), r["threads"], r["apply_s"] * 1e3),

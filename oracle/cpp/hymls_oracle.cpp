@@ -17,8 +17,11 @@
 // integration targets); tests/test_oracle_cpp.py checks this file against them.  The index maps (interior
 // nodes and ordered separator groups per subdomain and level) are INPUT: from oracle/partitioner.py in the
 // tests, from the library's host partitioner (bit-exact with the former, tests/test_host_maps.py) at sizes the
-// Python partitioner cannot reach.  The per-subdomain solver is a left-looking sparse LU with partial
-// pivoting (Gilbert-Peierls, the algorithm inside KLU) on a minimum-degree ordering of A + A'.
+// Python partitioner cannot reach.  The per-subdomain solver is a left-looking sparse LU (Gilbert-Peierls, the
+// algorithm inside KLU) in the reference's F-matrix ordering with its scaling and static pivots
+//   MatrixUtils::FillReducingOrdering                  src/HYMLS_MatrixUtils.cpp:1311-1740
+//   SparseDirectSolver::ComputeScaling, KLU settings   src/HYMLS_SparseDirectSolver.cpp:238-254, 632-664
+// pinned to the reference's known-answer fill counts (unit_tests/HYMLS_SparseDirectSolver.cpp:117-152).
 // Not covered: bordering, deflation, non-default variants (oracle/hymls.py covers bordering at small sizes).
 #include <omp.h>
 
@@ -57,8 +60,9 @@ struct Csr {
 };
 
 // ---------------------------------------------------------------------------------------------
-// Sparse LU, left looking (Gilbert-Peierls), partial pivoting with a preference for the diagonal
-// (threshold 0.001 like KLU's default), column ordering = minimum degree on A + A'.
+// Sparse LU, left looking (Gilbert-Peierls).  General matrices (coarse solver): column ordering = minimum degree on
+// A + A', partial pivoting with a preference for the diagonal (threshold 0.001 like KLU's default).  Subdomain
+// matrices: the reference's F-matrix ordering, scaling and static pivots (fmatrixOrdering below).
 // ---------------------------------------------------------------------------------------------
 static std::vector<int> minimumDegreeOrderAdj(std::vector<std::vector<int>>& adj);
 static std::vector<int> minimumDegreeOrder(int n, const std::vector<int>& Ap, const std::vector<int>& Ai) {

@@ -86,3 +86,43 @@ def test_no_schedule_for_small_or_exact_problems(monkeypatch):
                                                         "Number of Levels": 1}), pattern_only=True)
     R.Initialize()
     assert R.Stats()["host_pipeline_state"] == -2      # switched off
+
+
+@pytest.mark.gpu
+def test_pipelined_host_apply_reproduces_the_serial_path(monkeypatch):
+    """On the GPU: pinned host vectors, the copies overlapped in chunks (forced on for a small problem), against the
+    serial copies on the same handle -- bitwise -- and against the pageable-buffer path; the handle's own first-call
+    check must have passed (state 1).  tools/host_pipeline_check.py does the same at 64^3 / 128^3 and times it."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location(
+        "host_pipeline_check", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools",
+                                            "host_pipeline_check.py"))
+    tool = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tool)
+    monkeypatch.setenv("HYMLS_B200_HOST_PIPELINE_MIN_ROWS", "0")
+    nx = 16
+    params = {"Problem": {"Equations": "Stokes-C", "Dimension": 3, "nx": nx, "ny": nx, "nz": nx},
+              "Preconditioner": {"Partitioner": "Skew Cartesian", "Separator Length": 4, "Number of Levels": 2,
+                                 "Coarsening Factor": 2}}
+    A = -hb.galeri.create_matrix("Stokes-C", 3, nx)
+    P = hb.Preconditioner(A, params, hb.galeri.create_testvector(A))
+    P.Initialize()
+    P.Compute()
+    n = A.shape[0]
+    b, xs, xp = tool.pinned(n), tool.pinned(n), tool.pinned(n)
+    b[:] = np.random.default_rng(5).uniform(-1, 1, n)
+    lib, h = P._lib, P._h
+    monkeypatch.setenv("HYMLS_B200_HOST_PIPELINE", "0")
+    assert lib.hymls_b200_apply_inverse(h, b.ctypes.data, n, xs.ctypes.data, n, 1, 0) == 0
+    assert P.Stats()["host_pipeline_state"] == -2
+    monkeypatch.setenv("HYMLS_B200_HOST_PIPELINE", "1")
+    calls = P.Stats()["num_apply_inverse"]
+    for _ in range(3):
+        xp[:] = 0
+        assert lib.hymls_b200_apply_inverse(h, b.ctypes.data, n, xp.ctypes.data, n, 1, 0) == 0
+    st = P.Stats()
+    assert st["host_pipeline_chunks"] >= 2 and st["host_pipeline_state"] == 1
+    assert st["num_apply_inverse"] == calls + 3          # the self-check of the first call is not counted
+    assert np.array_equal(xs, xp)
+    assert np.array_equal(P.ApplyInverse(np.array(b)), xp)   # pageable buffers: serial copies

@@ -348,7 +348,9 @@ def main():
     hb_in.copy_(torch.from_numpy(bh[rows]))
     bin_np, bout_np = hb_in.numpy(), hb_out.numpy()
     for _ in range(2):
-        lib.hymls_b200_apply_inverse_dist(h, bin_np.ctypes.data, bout_np.ctypes.data, 0)
+        rc = lib.hymls_b200_apply_inverse_dist(h, bin_np.ctypes.data, bout_np.ctypes.data, 0)
+        if rc != 0:
+            raise RuntimeError("apply_inverse_dist (host buffers): " + lib.hymls_b200_last_error().decode())
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):

@@ -344,14 +344,15 @@ HostPipePlan planHostPipe(const std::vector<int>& n, const std::vector<int>& nb,
   // smallest / largest matrix row of every matrix, work = bytes of its inverse
   std::vector<int64_t> lo(M, nRows), hi(M, -1);
   std::vector<double> cum(M + 1, 0.0);
-  for (int m = 0; m < M; ++m) {
-    for (int q = 0; q < n[m]; ++q) {
-      const int64_t r = intRow[vecOff[m] + q];
-      lo[m] = std::min(lo[m], r);
-      hi[m] = std::max(hi[m], r);
-    }
-    cum[m + 1] = cum[m] + (double)n[m] * (double)n[m];
-  }
+  parallelFor(M, [&](int64_t m0, int64_t m1, int) {
+    for (int64_t m = m0; m < m1; ++m)
+      for (int q = 0; q < n[m]; ++q) {
+        const int64_t r = intRow[vecOff[m] + q];
+        lo[m] = std::min(lo[m], r);
+        hi[m] = std::max(hi[m], r);
+      }
+  }, 64);
+  for (int m = 0; m < M; ++m) cum[m + 1] = cum[m] + (double)n[m] * (double)n[m];
   if (cum[M] <= 0.0) return P;
   // share of the work per chunk: equal, or tapered towards both ends (1 2 4 8 8 .. 8 4 2 1): the copy of b that the
   // FIRST chunk waits for and the copy of x that follows the LAST chunk are the parts that cannot be hidden
@@ -405,6 +406,7 @@ bool checkHostPipe(const HostPipePlan& P, const std::vector<int>& n, const std::
     return false;
   int64_t lead = 0, full = 0;
   int c = 0;
+  std::vector<int> chunkOf(M, -1);
   for (int m = 0; m < M; ++m) {
     while (c < K && m >= P.matStart[c + 1]) {  // chunk boundary: the work lists must be cut exactly here
       if (P.matStart[c + 1] <= P.matStart[c] || P.leadItem[c + 1] != lead || P.fullItem[c + 1] != full ||
@@ -413,16 +415,26 @@ bool checkHostPipe(const HostPipePlan& P, const std::vector<int>& n, const std::
       ++c;
     }
     if (c >= K) return false;
+    chunkOf[m] = c;
     for (int r0 = 0; r0 < nb[m]; r0 += rowsPerItem) ++lead;   // the loops of BatchedInverse::setup
     for (int r0 = 0; r0 < n[m]; r0 += rowsPerItem) ++full;
-    for (int q = 0; q < n[m]; ++q) {
-      const int64_t r = intRow[vecOff[m] + q];
-      if (r < 0 || r >= nRows) return false;
-      if (r >= P.inRows[c + 1]) return false;  // b[r] on the device before chunk c of the first pass starts
-      if (r < P.outRows[c]) return false;      // x[r] not copied out before chunk c of the last pass has written it
-    }
   }
-  return c == K - 1 && P.leadItem[K] == lead && P.fullItem[K] == full;
+  if (c != K - 1 || P.leadItem[K] != lead || P.fullItem[K] != full) return false;
+  std::vector<char> bad(64, 0);
+  parallelFor(M, [&](int64_t m0, int64_t m1, int t) {
+    for (int64_t m = m0; m < m1; ++m) {
+      const int cm = chunkOf[m];
+      for (int q = 0; q < n[m]; ++q) {
+        const int64_t r = intRow[vecOff[m] + q];
+        // b[r] on the device before chunk cm of the first pass starts; x[r] not copied out before chunk cm of the
+        // last pass has written it
+        if (r < 0 || r >= nRows || r >= P.inRows[cm + 1] || r < P.outRows[cm]) bad[t & 63] = 1;
+      }
+    }
+  }, 64);
+  for (char f : bad)
+    if (f) return false;
+  return true;
 }
 
 

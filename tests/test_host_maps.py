@@ -341,3 +341,27 @@ def test_initialize_is_independent_of_the_host_thread_count(monkeypatch):
     for a, b in zip(seen[0][0], seen[1][0]):
         assert np.array_equal(a, b)
     assert seen[0][1] == seen[1][1]
+
+
+def test_header_is_plain_c_and_the_ctypes_mirror_matches_it(tmp_path):
+    """The boundary is a C ABI: include/hymls_b200.h compiles as C99, and the ctypes mirrors of its structs
+    (hymls_b200/api.py) have the size and the field offsets the C compiler gives them."""
+    import subprocess
+    root = os.path.dirname(api._HERE)
+    src = tmp_path / "layout.c"
+    fields = [k for k, _ in api._Stats._fields_]
+    info = [k for k, _ in api._SolveInfo._fields_]
+    src.write_text(
+        '#include <stdio.h>\n#include <stddef.h>\n#include "hymls_b200.h"\nint main(void) {\n'
+        '  printf("%zu\\n", sizeof(hymls_b200_stats));\n'
+        + "".join('  printf("%%zu\\n", offsetof(hymls_b200_stats, %s));\n' % f for f in fields)
+        + '  printf("%zu\\n", sizeof(hymls_b200_solve_info));\n'
+        + "".join('  printf("%%zu\\n", offsetof(hymls_b200_solve_info, %s));\n' % f for f in info)
+        + "  return 0;\n}\n")
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror",
+                           "-I" + os.path.join(root, "include"), str(src), "-o", str(exe)])
+    out = [int(v) for v in subprocess.check_output([str(exe)]).split()]
+    want = [ctypes.sizeof(api._Stats)] + [getattr(api._Stats, f).offset for f in fields] + \
+           [ctypes.sizeof(api._SolveInfo)] + [getattr(api._SolveInfo, f).offset for f in info]
+    assert out == want

@@ -13,6 +13,9 @@ Parity status:
     fixtures (committed, reduced, under tests/golden/).
   * exact path (Number of Levels = 0): PINNED by the reference's "1 iteration"
     integration targets on the Stokes fixtures.
+  * subdomain solver of the timed CPU baseline (oracle/cpp): F-matrix ordering, scaling and static pivots of the
+    reference; its fill is PINNED to the known-answer counts of unit_tests/HYMLS_SparseDirectSolver.cpp
+    (78 / 397 / 2033 there, 78 / 396 / 2128 here: AMD vs exact minimum degree; tests/test_oracle_cpp.py).
   * approximate path (levels >= 1): the reference ships no golden ApplyInverse
     vectors; pinned only through iteration-count / residual targets of the
     reference's integration tests ("parity unpinned" beyond that).

@@ -89,8 +89,20 @@ def read_system(datadir):
     return K, vec["rhs"], vec["sol"]
 
 
+def _with_diagonal(K, diag_pos, values):
+    """K with its EXISTING diagonal entries replaced (Epetra_CrsMatrix::ReplaceDiagonalValues: rows without a stored
+    diagonal entry are left alone, so the sparsity pattern -- and the symbolic phase -- stays)"""
+    K2 = K.copy()
+    rows = np.nonzero(diag_pos >= 0)[0]
+    K2.data[diag_pos[rows]] = values[rows]
+    return K2
+
+
 def run(xml_text, overrides=None, comm=None, seed=42, verbose=True):
-    """One factorization + one solve; returns a dict with the numbers hymls_main prints.
+    """hymls_main (src/main.cpp:48-535): "Number of factorizations" x "Number of solves" (Driver sublist, default
+    1 x 1) factorizations / solves; every factorization after a "Diagonal Perturbation" / "Diagonal Shift" of the
+    matrix when those are set (:343-360) -- the same-pattern SetMatrix + Compute path NOX takes every Newton step.
+    Returns a dict with the numbers hymls_main prints for the LAST solve and the list of all of them in "runs".
     `comm` = (unique_id, rank, nranks) for the sharded (one process per GPU) run."""
     params = parse_parameter_list(xml_text)
     for path, v in (overrides or {}).items():
@@ -134,41 +146,72 @@ def run(xml_text, overrides=None, comm=None, seed=42, verbose=True):
     if kind != "None":
         V = create_nullspace(n, kind, problem)
         P.SetBorder(V)  # solver->SetBorder(nullSpace), main.cpp:363-366
-    t0 = time.time()
-    P.Compute()
-    t_compute = time.time() - t0
+    num_computes = max(1, int(driver.get("Number of factorizations", 1)))
+    num_solves = max(1, int(driver.get("Number of solves", 1)))
+    perturbation = float(driver.get("Diagonal Perturbation", 0.0))
+    diag_shift = float(driver.get("Diagonal Shift", 0.0))
+    K0 = K
+    perturb = perturbation != 0.0 or diag_shift != 0.0
+    if perturb:
+        K0.sort_indices()
+        diag_pos = np.full(n, -1, dtype=np.int64)   # position of every stored diagonal entry in K.data
+        rows = np.repeat(np.arange(n), np.diff(K0.indptr))
+        on_diag = np.nonzero(K0.indices == rows)[0]
+        diag_pos[rows[on_diag]] = on_diag
+        diag0 = K0.diagonal()
+        rng_pert = np.random.default_rng(seed + 1000)
     rng = np.random.default_rng(seed)
-    if rhs is None:
-        x_ex = rng.uniform(-1, 1, n)
-        if V is not None:
-            x_ex -= V @ (V.T @ x_ex)  # project the null space out of x_ex (main.cpp:401-409)
-        rhs = K @ x_ex
-    else:
-        x_ex = sol
     S = Solver(P)
-    t0 = time.time()
-    x = S.ApplyInverse(rhs, seed=seed + 1)
-    t_solve = time.time() - t0
-    res = np.linalg.norm(K @ x - rhs) / np.linalg.norm(rhs)
-    out = {"equations": eqn, "n": int(n), "nnz": int(K.nnz), "levels": P.NumLevels(),
-           "subdomains": P.NumMySubdomains(0), "iterations": S.num_iter, "converged": bool(S.info["converged"]),
-           "residual": float(res), "t_matrix_s": t_matrix, "t_initialize_s": t_init, "t_compute_s": t_compute,
-           "t_solve_s": t_solve, "t_solve_device_s": S.info["solve_seconds"], "border": 0 if V is None else V.shape[1],
-           "history": [float(h) for h in S.history]}
-    if x_ex is not None:
-        err = x - x_ex
-        if V is not None:
-            err -= V @ (V.T @ err)
-        elif eqn == "Stokes-C" and sol is not None:
-            pv = create_nullspace(n, "Constant P", problem)  # integration_tests.cpp:585-604
-            err -= pv @ (pv.T @ err)
-        out["error"] = float(np.linalg.norm(err) / np.linalg.norm(rhs))
-    if verbose and (comm is None or comm[1] == 0):
-        print("Residual Norm ||Ax-b||/||b||: %.8e" % out["residual"])
-        if "error" in out:
-            print("Error Norm ||x-x_ex||/||b||: %.8e" % out["error"])
-        print("iterations: %d  converged: %s  compute %.3f s  solve %.3f s" % (
-            out["iterations"], out["converged"], t_compute, out["t_solve_device_s"]))
+    read_rhs = rhs
+    runs = []
+    show = verbose and (comm is None or comm[1] == 0)
+    for f in range(num_computes):
+        if perturb:  # "change the matrix values just to see if that works" (main.cpp:343-358)
+            K = _with_diagonal(K0, diag_pos, diag0 + diag_shift + perturbation * rng_pert.uniform(-1, 1, n))
+            P.SetMatrix(K)          # same pattern: the symbolic phase of Initialize() is kept
+        if V is not None and f > 0:
+            P.SetBorder(V)          # solver->SetBorder(nullSpace) before every Compute (main.cpp:361-364)
+        t0 = time.time()
+        P.Compute()
+        t_compute = time.time() - t0
+        for s_ in range(num_solves):
+            if read_rhs is None:
+                x_ex = rng.uniform(-1, 1, n)
+                if V is not None:
+                    x_ex -= V @ (V.T @ x_ex)  # project the null space out of x_ex (main.cpp:401-409)
+                rhs = K @ x_ex
+            else:
+                x_ex = sol
+            t0 = time.time()
+            x = S.ApplyInverse(rhs, seed=seed + 1)
+            t_solve = time.time() - t0
+            res = np.linalg.norm(K @ x - rhs) / np.linalg.norm(rhs)
+            out = {"equations": eqn, "n": int(n), "nnz": int(K.nnz), "levels": P.NumLevels(),
+                   "subdomains": P.NumMySubdomains(0), "iterations": S.num_iter,
+                   "converged": bool(S.info["converged"]), "residual": float(res), "t_matrix_s": t_matrix,
+                   "t_initialize_s": t_init, "t_compute_s": t_compute, "t_solve_s": t_solve,
+                   "t_solve_device_s": S.info["solve_seconds"], "border": 0 if V is None else V.shape[1],
+                   "history": [float(h) for h in S.history]}
+            if x_ex is not None:
+                err = x - x_ex
+                if V is not None:
+                    err -= V @ (V.T @ err)
+                elif eqn == "Stokes-C" and sol is not None:
+                    pv = create_nullspace(n, "Constant P", problem)  # integration_tests.cpp:585-604
+                    err -= pv @ (pv.T @ err)
+                out["error"] = float(np.linalg.norm(err) / np.linalg.norm(rhs))
+            runs.append({"factorization": f + 1, "solve": s_ + 1, "iterations": out["iterations"],
+                         "converged": out["converged"], "residual": out["residual"], "error": out.get("error"),
+                         "t_compute_s": t_compute, "t_solve_device_s": out["t_solve_device_s"]})
+            if show:
+                if num_computes * num_solves > 1:
+                    print("Compute Preconditioner (%d)  Solve (%d)" % (f + 1, s_ + 1))
+                print("Residual Norm ||Ax-b||/||b||: %.8e" % out["residual"])
+                if "error" in out:
+                    print("Error Norm ||x-x_ex||/||b||: %.8e" % out["error"])
+                print("iterations: %d  converged: %s  compute %.3f s  solve %.3f s" % (
+                    out["iterations"], out["converged"], t_compute, out["t_solve_device_s"]))
+    out["runs"] = runs
     out["_objects"] = (K, P, S, x, rhs)
     return out
 

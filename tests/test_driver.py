@@ -5,6 +5,7 @@ import os
 
 import numpy as np
 import pytest
+import scipy.sparse as sp
 
 import hymls_b200 as hb
 from hymls_b200 import driver
@@ -141,3 +142,85 @@ def test_parameter_list_xml_details():
     assert out["Preconditioner"]["Coarse Solver"]["amesos: solver type"] == "Amesos_Klu & friends"
     with pytest.raises(hb.HymlsError):
         hb.Preconditioner(None, "<ParameterList name='x'><Parameter name='a' type='int' value='1'/>")  # not closed
+
+
+class _OraclePrec:
+    """Stand-in for hymls_b200.Preconditioner backed by the numpy ORACLE: lets the hymls_main flow of
+    hymls_b200/driver.py (factorization / solve loops, diagonal perturbation) run on a machine without a GPU.
+    Test infrastructure only."""
+    log = []
+
+    def __init__(self, K, params, tv):
+        from oracle import hymls as oh
+        from oracle.params import ParameterList
+
+        def to_pl(d):
+            pl = ParameterList()
+            for k, v in d.items():
+                pl[k] = to_pl(v) if isinstance(v, dict) else v
+            return pl
+        self._mk = lambda K_: oh.Preconditioner(K_, to_pl(params), tv)
+        self.K = K
+        self.O = self._mk(K)
+        _OraclePrec.log.append("create")
+
+    def Initialize(self):
+        self.O.initialize()
+        _OraclePrec.log.append("Initialize")
+
+    def SetMatrix(self, K):
+        assert np.array_equal(K.indptr, self.K.indptr) and np.array_equal(K.indices, self.K.indices)  # same pattern
+        self.K = K
+        self.O = self._mk(K)
+        self.O.initialize()
+        _OraclePrec.log.append("SetMatrix")
+
+    def Compute(self):
+        self.O.compute()
+        _OraclePrec.log.append("Compute")
+
+    def NumLevels(self):
+        return 1
+
+    def NumMySubdomains(self, level):
+        return len(self.O.hid.interior)
+
+
+class _OracleSolver:
+    def __init__(self, P):
+        self.P = P
+
+    def ApplyInverse(self, b, seed=0):
+        from oracle import krylov as ok
+        K, O = self.P.K, self.P.O
+        x, its, conv, h = ok.cg(lambda v: K @ v, b, np.zeros(len(b)), O.apply_inverse, tol=1e-10, max_iters=200)
+        self.num_iter, self.history = its, h
+        self.info = {"converged": conv, "solve_seconds": 0.0}
+        _OraclePrec.log.append("Solve")
+        return x
+
+
+def test_driver_factorization_and_solve_loops(monkeypatch):
+    """hymls_main's "Number of factorizations" x "Number of solves" loops with a "Diagonal Perturbation"
+    (src/main.cpp:341-470): Initialize once, then per factorization SetMatrix (same pattern) + Compute and the
+    solves, each with a fresh right-hand side."""
+    from hymls_b200 import driver
+    monkeypatch.setattr(driver, "Preconditioner", _OraclePrec)
+    monkeypatch.setattr(driver, "Solver", _OracleSolver)
+    _OraclePrec.log = []
+    xml = open(os.path.join(ROOT, "configs", "laplace.xml")).read()
+    over = {"Problem/nx": 16, "Problem/ny": 16, "Preconditioner/Number of Levels": 1,
+            "Driver/Number of factorizations": 2, "Driver/Number of solves": 3, "Driver/Diagonal Perturbation": 0.05}
+    out = driver.run(xml, over, verbose=False)
+    assert _OraclePrec.log == ["create", "Initialize"] + (["SetMatrix", "Compute"] + ["Solve"] * 3) * 2
+    assert [(r["factorization"], r["solve"]) for r in out["runs"]] == [(f, s) for f in (1, 2) for s in (1, 2, 3)]
+    assert all(r["converged"] and r["residual"] < 1e-9 and r["error"] < 1e-8 for r in out["runs"])
+    K = out["_objects"][0]
+    K0 = hb.galeri.create_matrix("Laplace", 2, 16)
+    d = K.diagonal() - K0.diagonal()
+    assert 0 < np.abs(d).max() <= 0.05 and (K - K0 - sp.diags(d)).nnz == 0    # only the diagonal moved
+    # defaults: one factorization, one solve, no SetMatrix -- the flow the GPU tests run
+    _OraclePrec.log = []
+    out1 = driver.run(xml, {"Problem/nx": 16, "Problem/ny": 16, "Preconditioner/Number of Levels": 1}, verbose=False)
+    assert _OraclePrec.log == ["create", "Initialize", "Compute", "Solve"] and len(out1["runs"]) == 1
+    assert out1["iterations"] == out1["runs"][0]["iterations"] and out1["residual"] < 1e-9

@@ -359,6 +359,27 @@ def main():
     e2e_ms = (time.perf_counter() - t0) * 1e3
     e2e_ok = bool(np.array_equal(bout_np, x_own.cpu().numpy()))
     clocks = sampler.stop()
+    st_e2e = P.Stats()   # (host_pipeline_state as the timed loop left it)
+    # the same loop with the copy / compute overlap of the host-buffer path switched off (one GPU; the switch is read
+    # at every call): the serial-copies figure next to the default one
+    e2e_serial_ms = None
+    if world == 1:
+        old_env = os.environ.get("HYMLS_B200_HOST_PIPELINE")
+        os.environ["HYMLS_B200_HOST_PIPELINE"] = "0"
+        try:
+            for _ in range(2):
+                lib.hymls_b200_apply_inverse_dist(h, bin_np.ctypes.data, bout_np.ctypes.data, 0)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                lib.hymls_b200_apply_inverse_dist(h, bin_np.ctypes.data, bout_np.ctypes.data, 0)
+            torch.cuda.synchronize()
+            e2e_serial_ms = (time.perf_counter() - t0) * 1e3
+        finally:
+            if old_env is None:
+                del os.environ["HYMLS_B200_HOST_PIPELINE"]
+            else:
+                os.environ["HYMLS_B200_HOST_PIPELINE"] = old_env
     # ---- dominant kernel (batched A11^-1 apply, level 0) via CUDA events inside the library ----
     ms_apply_lib, ms_a11 = P.TimeApply(max(5, min(args.steps, 20)))
     st2 = P.Stats()
@@ -435,8 +456,10 @@ def main():
                 "matches_device_result": e2e_ok,
                 # one GPU: the copies are overlapped with the two passes over the level-0 inverses in `chunks` pieces
                 # (state 1 = the first such call reproduced the serial path bit for bit)
-                "host_pipeline": {"chunks": int(st2.get("host_pipeline_chunks", 0)),
-                                  "state": int(st2.get("host_pipeline_state", 0))},
+                "host_pipeline": {"chunks": int(st_e2e.get("host_pipeline_chunks", 0)),
+                                  "state": int(st_e2e.get("host_pipeline_state", 0)),
+                                  "value_with_serial_copies": (args.steps / (e2e_serial_ms * 1e-3))
+                                  if e2e_serial_ms else None},
                 "call": "hymls_b200_apply_inverse_dist (pinned host rows this rank owns in / out)"},
         "gpu_launches": int(launches),
         "clocks": clocks,

@@ -18,5 +18,8 @@ Parity status:
     (78 / 397 / 2033 there, 78 / 396 / 2128 here: AMD vs exact minimum degree; tests/test_oracle_cpp.py).
   * approximate path (levels >= 1): the reference ships no golden ApplyInverse
     vectors; pinned only through iteration-count / residual targets of the
-    reference's integration tests ("parity unpinned" beyond that).
+    reference's integration tests ("parity unpinned" beyond that) -- on the shipped
+    fixtures (tests/test_oracle_solver.py, test_oracle_skew.py) and on the reference's
+    generated multi-level problems threeD1.xml (34 iterations, bound 35) and stokes6.xml
+    (28-29, bound 30) (tests/test_oracle_cpp.py).
 """

@@ -93,7 +93,7 @@ int hymls_b200_get_owned_subdomains(hymls_b200_t* h, int level, int32_t* sd, int
   HY_TRY
   if (!h->eng->initialized()) throw Error(HYMLS_B200_ERR_STATE, "not initialized");
   const std::vector<int>& v = h->eng->ownedSubdomains(level);
-  if (sd && cap >= (int)v.size()) std::memcpy(sd, v.data(), v.size() * sizeof(int));
+  if (sd && !v.empty() && cap >= (int)v.size()) std::memcpy(sd, v.data(), v.size() * sizeof(int));
   return (int)v.size();
   HY_CATCH
 }
@@ -271,7 +271,7 @@ int64_t hymls_b200_get_interior(hymls_b200_t* h, int level, int sd, int64_t* gid
   const HierarchicalMap& H = h->eng->sym(level).H;
   if (sd < 0 || sd >= H.nsd) throw Error(HYMLS_B200_ERR_ARG, "subdomain index out of range");
   int64_t a = H.intPtr[sd], z = H.intPtr[sd + 1];
-  if (gids && cap >= z - a) std::memcpy(gids, H.intGid.data() + a, (z - a) * sizeof(int64_t));
+  if (gids && z > a && cap >= z - a) std::memcpy(gids, H.intGid.data() + a, (z - a) * sizeof(int64_t));
   return z - a;
   HY_CATCH
 }
@@ -288,7 +288,7 @@ int hymls_b200_get_groups(hymls_b200_t* h, int level, int sd, int64_t* ptr, int3
   if (ptr && types && gids && cap >= z - a) {
     for (int64_t g = ga; g <= gz; ++g) ptr[g - ga] = H.grpPtr[g] - a;
     for (int64_t g = ga; g < gz; ++g) types[g - ga] = H.grpType[g];
-    std::memcpy(gids, H.grpGid.data() + a, (z - a) * sizeof(int64_t));
+    if (z > a) std::memcpy(gids, H.grpGid.data() + a, (z - a) * sizeof(int64_t));
   }
   return (int)(gz - ga);
   HY_CATCH
@@ -310,7 +310,7 @@ int64_t hymls_b200_get_map(hymls_b200_t* h, int level, int which, int64_t* gids,
       break;
     default: throw Error(HYMLS_B200_ERR_ARG, "unknown map");
   }
-  if (gids && cap >= (int64_t)v->size()) std::memcpy(gids, v->data(), v->size() * sizeof(int64_t));
+  if (gids && !v->empty() && cap >= (int64_t)v->size()) std::memcpy(gids, v->data(), v->size() * sizeof(int64_t));
   return (int64_t)v->size();
   HY_CATCH
 }
@@ -321,7 +321,7 @@ int hymls_b200_pid_map(const char* xml, int nprocs, int32_t* pid, int cap) {
   std::unique_ptr<CartesianPartitioner> part(makePartitioner(p, 0, nprocs, 0));
   part->partition();
   const std::vector<int>& m = part->pidMap();
-  if (pid && cap >= (int)m.size()) std::memcpy(pid, m.data(), m.size() * sizeof(int));
+  if (pid && !m.empty() && cap >= (int)m.size()) std::memcpy(pid, m.data(), m.size() * sizeof(int));
   return (int)m.size();
   HY_CATCH
 }
